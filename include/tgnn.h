@@ -1,0 +1,136 @@
+/*
+ * tgnn.h -- C ABI of the B200-native TilinGNN scoring path (libtgnn.so).
+ *
+ * The reference (xuhaocuhk/TilinGNN) has no FFI / plugin registry: its boundary
+ * for this path is a Python nn.Module call.  This header is the C-ABI a
+ * maintainer binds in its place (ctypes stub in INTEGRATION.md); every entry
+ * point cites the reference interface it replaces (paths relative to the
+ * reference root).  Plain pointers and sizes only -- no torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from tgnn_last_error(h) (or tgnn_last_error(NULL) for failures
+ *     of tgnn_create itself).  The Python wrapper raises RuntimeError with it,
+ *     which preserves the reference's contract that a failed forward surfaces
+ *     as a Python exception (graph_networks/network_utils.py:10-19).
+ *   - the caller owns every buffer passed in; the handle owns parameters,
+ *     graph structure, workspace.  Inputs are never written.
+ *   - all device work is ordered on the `stream` argument (a cudaStream_t
+ *     passed as void*; NULL = the legacy default stream).
+ *   - one handle is NOT thread-safe; distinct handles are independent.
+ *   - there is no CPU fallback: without a CUDA device tgnn_create fails.
+ */
+#ifndef TGNN_H_
+#define TGNN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGNN_ABI_VERSION 1
+
+#define TGNN_BN_TRAIN 0   /* batch statistics over the rows of THIS call -- the reference's
+                             behaviour: solver/ml_solver/ml_solver.py:129-131 ends in network.train() */
+#define TGNN_BN_EVAL  1   /* running statistics from the checkpoint (nn.Module.eval())               */
+
+typedef struct tgnn_handle tgnn_handle;
+
+/* Constructor arguments of TilinGNN.__init__ (graph_networks/networks/TilinGNN.py:14-20).
+ * width must be 32 (inputs/config.py:38; every shipped checkpoint). */
+typedef struct tgnn_cfg {
+    int32_t d_x;        /* node_features_dim   = environment.tile_count + 1            */
+    int32_t d_e;        /* adj_edge_features_dim                                       */
+    int32_t width;      /* network_width (32)                                          */
+    int32_t depth;      /* network_depth (20 shipped; 6 in the benchmark configs)      */
+    int32_t bn_mode;    /* TGNN_BN_TRAIN | TGNN_BN_EVAL                                */
+    int32_t device;     /* CUDA device ordinal                                         */
+} tgnn_cfg;
+
+int tgnn_abi_version(void);
+
+/* TilinGNN(...)  -- graph_networks/networks/TilinGNN.py:14-48 */
+int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out);
+int tgnn_destroy(tgnn_handle* h);
+
+/* network.load_state_dict(torch.load(path)) -- solver/ml_solver/ml_solver.py:129-130.
+ * One call per reference state_dict key (fp32 data, host or device pointer; shape checked).
+ * The aliased "...nnConv.nn.mlp.*" keys (graph_networks/layers/edge_conv.py:17-18 registers one
+ * MLP under two names) address the same tensor as "...mlp.mlp.*" (the last write wins);
+ * "...num_batches_tracked" keys are accepted and ignored (int64). */
+int tgnn_set_param(tgnn_handle* h, const char* ref_key, const void* data,
+                   const int64_t* shape, int32_t ndim);
+/* Number of reference keys still unset (0 = ready); writes the first missing key to buf. */
+int tgnn_missing_params(tgnn_handle* h, char* buf, int32_t buflen);
+/* nn.Module.train() / .eval() */
+int tgnn_set_bn_mode(tgnn_handle* h, int32_t bn_mode);
+
+/* The graph arguments of TilinGNN.forward (graph_networks/networks/TilinGNN.py:51):
+ * adj_e_index = [adj_src; adj_dst] and col_e_idx = [col_src; col_dst] in PyG
+ * source_to_target order, int64, as util/data_util.py:110-117 produces them;
+ * adj_feat = adj_e_features [E_a, d_e] fp32 row-major.  Device pointers.
+ * Builds the device-side structures (edge-type ids, typed adjacency tiles, collision CSR,
+ * per-layer edge-weight tables).  Collision self loops are dropped (PyG GINConv). */
+int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes,
+                   int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
+                   int64_t e_col, const int64_t* col_src, const int64_t* col_dst,
+                   void* stream);
+
+/* TilinGNN.forward(x, ...) -> scores  (graph_networks/networks/TilinGNN.py:51-78).
+ * x: [n_nodes, d_x] fp32 device; scores_out: [n_nodes] fp32 device (the [N,1] column). */
+int tgnn_forward(tgnn_handle* h, const float* x, float* scores_out, void* stream);
+
+/* ---- multi-GPU: node-range shards (new work; the reference is single-device) ------------ */
+/* 128-byte NCCL unique id; rank 0 creates it, the host side broadcasts it. */
+int tgnn_nccl_unique_id(void* out128);
+/* Join the communicator.  Must be called before tgnn_set_graph_shard. */
+int tgnn_shard_init(tgnn_handle* h, const void* unique_id128, int32_t rank, int32_t world);
+/* Sharded graph in LOCAL row numbering: rows [0, n_own) are this rank's nodes, rows
+ * [n_own, n_own + world*halo_slot) mirror the boundary rows every rank publishes (slot r holds
+ * rank r's send list, padded to halo_slot rows).  dst in [0, n_own), src in [0, n_rows).
+ * send_rows[n_send] (n_send <= halo_slot): this rank's own rows that peers read.
+ * n_global = total node count over all ranks (BatchNorm statistics are global). */
+int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_t halo_slot,
+                         int64_t n_send, const int64_t* send_rows,
+                         int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
+                         int64_t e_col, const int64_t* col_src, const int64_t* col_dst,
+                         void* stream);
+
+/* ---- introspection (tests, bench, profiling) --------------------------------------------- */
+typedef struct tgnn_info {
+    int64_t n_own, n_rows, n_global;
+    int64_t e_adj, e_col;          /* e_col after self-loop removal                          */
+    int64_t n_edge_types;          /* K distinct adjacency feature rows                      */
+    int64_t adj_slots;             /* padded slots of the typed adjacency tiles (>= e_adj)   */
+    int64_t launches_per_forward;  /* kernels of this library launched by one tgnn_forward   */
+    int64_t workspace_bytes;
+    int64_t collectives_per_forward;
+} tgnn_info;
+int tgnn_get_info(tgnn_handle* h, tgnn_info* out);
+
+/* Test hooks.  tgnn_debug_set_stop_layer(h, i >= 0): the next forwards stop after message-passing
+ * layer i (no final MLP, scores untouched); -1 restores the full forward.
+ * tgnn_debug_read copies an internal tensor of the LAST forward to `out` (device, fp32, [n_own,32]):
+ *   "mid_<k>"  middle_features[k] of TilinGNN.forward (k = 0 is the init MLP output, k = i+1 layer i's b1)
+ *   "pre1" / "pre2"  LeakyReLU(conv) of the last layer that ran, before BatchNorm
+ *   "g1" / "g2"      GraphConv / CollConv output (after BatchNorm) of the last layer that ran
+ * tgnn_debug_graph copies the built graph structures out (sizes: tgnn_get_info; null = skip):
+ *   cptr[n_tiles+1] ctype[n_chunks] csrc[adj_slots] cdst[adj_slots] inv_deg[n_own]
+ *   col_ptr[n_own+1] col_src[e_col] type_rows[n_edge_types*d_e];  n_tiles = ceil(n_own/64), n_chunks = adj_slots/16. */
+int tgnn_debug_set_stop_layer(tgnn_handle* h, int32_t layer);
+int tgnn_debug_read(tgnn_handle* h, const char* name, float* out, void* stream);
+int tgnn_debug_graph(tgnn_handle* h, int32_t* cptr, int32_t* ctype, int32_t* csrc, uint8_t* cdst, float* inv_deg,
+                     int32_t* col_ptr, int32_t* col_src, float* type_rows, void* stream);
+
+/* Per-kernel-family device time of the last forward (ms), measured with CUDA events on `stream`
+ * when enabled.  names: "init","conv","gin","bnfin","combine","final","score","halo". */
+int tgnn_set_profiling(tgnn_handle* h, int32_t enabled);
+int tgnn_get_profile(tgnn_handle* h, const char* name, float* ms_out, int32_t* launches_out);
+
+const char* tgnn_last_error(tgnn_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TGNN_H_ */

@@ -1,0 +1,696 @@
+// C-ABI entry points (include/tgnn.h), parameter store, workspace and the forward orchestration.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "tgnn_internal.h"
+
+// ---- NCCL, bound at run time from the copy torch already loaded (no link-time dependency, so the
+// ---- library also loads on machines without NCCL / without a GPU) --------------------------------
+namespace {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0 };
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.lib, "ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.lib, "ncclCommInitRank");
+        api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.lib, "ncclCommDestroy");
+        api.AllGather = (decltype(api.AllGather))dlsym(api.lib, "ncclAllGather");
+        api.AllReduce = (decltype(api.AllReduce))dlsym(api.lib, "ncclAllReduce");
+        api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.lib, "ncclGetErrorString");
+    });
+    return api;
+}
+void nccl_check(ncclResult_t r, const char* what) {
+    if (r != 0) {
+        const char* s = nccl().GetErrorString ? nccl().GetErrorString(r) : "?";
+        throw tgnn::Error(std::string(what) + ": NCCL error: " + s);
+    }
+}
+std::string g_create_error;
+}  // namespace
+
+namespace tgnn {
+
+struct Param {
+    std::vector<int64_t> shape;
+    DevBuf buf;
+    bool set = false;
+    size_t numel() const { size_t n = 1; for (auto d : shape) n *= (size_t)d; return n; }
+};
+
+struct ProfEntry { std::string fam; cudaEvent_t a, b; };
+
+}  // namespace tgnn
+
+using namespace tgnn;
+
+struct tgnn_handle {
+    tgnn_cfg cfg{};
+    int sm_count = 148;
+    std::string err;
+    std::map<std::string, Param> params;           // canonical reference keys
+    std::vector<std::string> key_order;
+    bool params_dirty = true, tables_dirty = true, graph_set = false;
+    Graph g;
+    Scratch scratch;
+
+    // derived parameter layouts
+    DevBuf init_w1t;
+    std::vector<std::unique_ptr<DevBuf>> gin_wt;    // 3 per layer
+    std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4
+    std::vector<float> gin_eps;
+    float fin_last_bias = 0.f;
+    DevBuf coef;                                    // all BatchNorm coefficient blocks
+    size_t coef_init[2]{}, coef_fin[4]{};
+    std::vector<size_t> coef_a, coef_c;
+    DevBuf tab;                                     // [L][K][32][32]
+
+    // workspace
+    std::vector<std::unique_ptr<DevBuf>> mid;
+    DevBuf pre1, pre2[2], fa[4], partA, partB, sums, slab_ptrs, halo;
+    size_t workspace_bytes = 0;
+
+    // sharding
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+
+    // bookkeeping
+    int64_t launches = 0, collectives = 0;
+    int stop_layer = -1;
+    int last_layer_run = -1;
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    std::map<std::string, std::pair<float, int>> prof_result;
+
+    float* P(const std::string& k) {
+        auto it = params.find(k);
+        TGNN_CHECK(it != params.end(), "internal: unknown parameter " + k);
+        return it->second.buf.as<float>();
+    }
+    float* C(size_t off) { return coef.as<float>() + off; }
+};
+
+namespace {
+
+std::string canonical_key(const std::string& k) {
+    // graph_networks/layers/edge_conv.py:17-18 registers self.mlp also as self.nnConv.nn
+    const std::string alias = ".nnConv.nn.mlp.";
+    size_t p = k.find(alias);
+    if (p == std::string::npos) return k;
+    return k.substr(0, p) + ".mlp.mlp." + k.substr(p + alias.size());
+}
+
+void add_param(tgnn_handle* h, const std::string& k, std::vector<int64_t> shape) {
+    h->params[k].shape = std::move(shape);
+    h->key_order.push_back(k);
+}
+void add_lt(tgnn_handle* h, const std::string& p, int in, int out, bool bn) {
+    add_param(h, p + ".linear.weight", {out, in});
+    add_param(h, p + ".linear.bias", {out});
+    if (bn) {
+        for (const char* s : {".batch_norm.weight", ".batch_norm.bias", ".batch_norm.running_mean", ".batch_norm.running_var"})
+            add_param(h, p + s, {out});
+    }
+}
+void add_bn(tgnn_handle* h, const std::string& p, int c) {
+    for (const char* s : {".weight", ".bias", ".running_mean", ".running_var"}) add_param(h, p + s, {c});
+}
+
+void declare_params(tgnn_handle* h) {
+    const int L = h->cfg.depth, dx = h->cfg.d_x, de = h->cfg.d_e;
+    add_lt(h, "init_node_feature_trans.mlp.0", dx, F, true);
+    add_lt(h, "init_node_feature_trans.mlp.1", F, F, true);
+    for (int i = 0; i < L; ++i) {
+        std::string p = "brch_1_graph_conv_layers." + std::to_string(i);
+        int dims[4] = {de, 32, 64, F * F};
+        for (int k = 0; k < 3; ++k) add_lt(h, p + ".mlp.mlp." + std::to_string(k), dims[k], dims[k + 1], false);
+        add_param(h, p + ".nnConv.root", {F, F});
+        add_param(h, p + ".nnConv.bias", {F});
+        add_bn(h, p + ".batch_norm", F);
+    }
+    for (int i = 0; i < L; ++i) {
+        std::string p = "brch_2_coll_conv_layers." + std::to_string(i);
+        add_param(h, p + ".ginConv.eps", {1});
+        int dims[4] = {F, 32, 64, F};
+        for (int k = 0; k < 3; ++k) add_lt(h, p + ".ginConv.nn.mlp." + std::to_string(k), dims[k], dims[k + 1], false);
+        add_bn(h, p + ".batch_norm", F);
+    }
+    int dims[5] = {F * (L + 1), 256, 128, 64, F};
+    for (int k = 0; k < 4; ++k) add_lt(h, "final_mlp.0.mlp." + std::to_string(k), dims[k], dims[k + 1], true);
+    add_lt(h, "final_mlp.1", F, 1, false);
+}
+
+bool ends_with(const std::string& s, const char* suf) {
+    size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+struct DeviceGuard {
+    int prev = 0;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); cudaSetDevice(dev); }
+    ~DeviceGuard() { cudaSetDevice(prev); }
+};
+
+const int FIN_DIMS[5] = {0, 256, 128, 64, 32};
+
+void pack_params(tgnn_handle* h, cudaStream_t st) {
+    if (!h->params_dirty) return;
+    for (auto& k : h->key_order) TGNN_CHECK(h->params[k].set, "parameter not set: " + k);
+    const int L = h->cfg.depth;
+    h->init_w1t.reserve(32 * 32 * sizeof(float));
+    launch_transpose(h->P("init_node_feature_trans.mlp.1.linear.weight"), h->init_w1t.as<float>(), 32, 32, st);
+    h->gin_wt.clear(); h->gin_eps.assign(L, 0.f);
+    for (int i = 0; i < L; ++i) {
+        std::string p = "brch_2_coll_conv_layers." + std::to_string(i);
+        int dims[4] = {F, 32, 64, F};
+        for (int k = 0; k < 3; ++k) {
+            h->gin_wt.emplace_back(new DevBuf());
+            h->gin_wt.back()->reserve((size_t)dims[k] * dims[k + 1] * sizeof(float));
+            launch_transpose(h->P(p + ".ginConv.nn.mlp." + std::to_string(k) + ".linear.weight"),
+                             h->gin_wt.back()->as<float>(), dims[k + 1], dims[k], st);
+        }
+        TGNN_CUDA(cudaMemcpyAsync(&h->gin_eps[i], h->P(p + ".ginConv.eps"), sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    h->fin_wt.clear();
+    int dims[5] = {F * (L + 1), 256, 128, 64, F};
+    for (int k = 0; k < 4; ++k) {
+        h->fin_wt.emplace_back(new DevBuf());
+        h->fin_wt.back()->reserve((size_t)dims[k] * dims[k + 1] * sizeof(float));
+        launch_transpose(h->P("final_mlp.0.mlp." + std::to_string(k) + ".linear.weight"), h->fin_wt.back()->as<float>(),
+                         dims[k + 1], dims[k], st);
+    }
+    TGNN_CUDA(cudaMemcpyAsync(&h->fin_last_bias, h->P("final_mlp.1.linear.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
+    // coefficient blocks
+    size_t off = 0;
+    auto take = [&](int c) { size_t o = off; off += 4 * (size_t)c; return o; };
+    h->coef_init[0] = take(32); h->coef_init[1] = take(32);
+    h->coef_a.resize(L); h->coef_c.resize(L);
+    for (int i = 0; i < L; ++i) { h->coef_a[i] = take(32); h->coef_c[i] = take(32); }
+    for (int k = 0; k < 4; ++k) h->coef_fin[k] = take(FIN_DIMS[k + 1]);
+    h->coef.reserve(off * sizeof(float));
+    TGNN_CUDA(cudaStreamSynchronize(st));
+    h->params_dirty = false;
+    h->tables_dirty = true;
+}
+
+void eval_coefs(tgnn_handle* h, cudaStream_t st) {
+    auto one = [&](const std::string& bn, size_t off, int c) {
+        launch_bn_coef_eval(h->P(bn + ".running_mean"), h->P(bn + ".running_var"), h->P(bn + ".weight"), h->P(bn + ".bias"),
+                            h->C(off), c, st);
+    };
+    const int L = h->cfg.depth;
+    one("init_node_feature_trans.mlp.0.batch_norm", h->coef_init[0], 32);
+    one("init_node_feature_trans.mlp.1.batch_norm", h->coef_init[1], 32);
+    for (int i = 0; i < L; ++i) {
+        one("brch_1_graph_conv_layers." + std::to_string(i) + ".batch_norm", h->coef_a[i], 32);
+        one("brch_2_coll_conv_layers." + std::to_string(i) + ".batch_norm", h->coef_c[i], 32);
+    }
+    for (int k = 0; k < 4; ++k) one("final_mlp.0.mlp." + std::to_string(k) + ".batch_norm", h->coef_fin[k], FIN_DIMS[k + 1]);
+}
+
+void build_tables(tgnn_handle* h, cudaStream_t st) {
+    if (!h->tables_dirty) return;
+    const int L = h->cfg.depth, K = h->g.n_types;
+    if (K > 0) {
+        h->tab.reserve((size_t)L * K * F * F * sizeof(float));
+        for (int i = 0; i < L; ++i) {
+            std::string p = "brch_1_graph_conv_layers." + std::to_string(i) + ".mlp.mlp.";
+            launch_edge_table(h->g.type_rows.as<float>(), K, h->cfg.d_e,
+                              h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
+                              h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
+                              h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"),
+                              h->tab.as<float>() + (size_t)i * K * F * F, st);
+        }
+    }
+    h->tables_dirty = false;
+}
+
+void alloc_workspace(tgnn_handle* h) {
+    const int L = h->cfg.depth;
+    const size_t rows = (size_t)h->g.n_rows, own = (size_t)h->g.n_own;
+    size_t total = 0;
+    auto res = [&](DevBuf& b, size_t bytes) { b.reserve(bytes); total += b.cap; };
+    while ((int)h->mid.size() < L + 1) h->mid.emplace_back(new DevBuf());
+    for (int i = 0; i <= L; ++i) res(*h->mid[i], rows * F * sizeof(float));
+    res(h->pre1, own * F * sizeof(float));
+    res(h->pre2[0], rows * F * sizeof(float));
+    res(h->pre2[1], rows * F * sizeof(float));
+    for (int k = 0; k < 4; ++k) res(h->fa[k], own * FIN_DIMS[k + 1] * sizeof(float));
+    size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->sm_count), (size_t)gin_num_parts((int)own, h->sm_count),
+                          (size_t)init_num_parts((int)own, h->sm_count)});
+    size_t part_bytes = std::max(np * 64, (size_t)dense_row_blocks((int)own) * 2 * 256) * sizeof(double);
+    res(h->partA, part_bytes);
+    res(h->partB, np * 64 * sizeof(double));
+    res(h->sums, 2 * 512 * sizeof(double));
+    res(h->slab_ptrs, (size_t)(L + 1) * sizeof(float*));
+    std::vector<const float*> slabs(L + 1);
+    for (int i = 0; i <= L; ++i) slabs[i] = h->mid[i]->as<float>();
+    TGNN_CUDA(cudaMemcpy(h->slab_ptrs.p, slabs.data(), slabs.size() * sizeof(float*), cudaMemcpyHostToDevice));
+    if (h->world > 1) res(h->halo, (size_t)h->world * h->g.halo_slot * 64 * sizeof(float));
+    h->workspace_bytes = total;
+}
+
+struct Launcher {
+    tgnn_handle* h; cudaStream_t st;
+    void begin(const char* fam) {
+        if (!h->profiling) return;
+        ProfEntry e; e.fam = fam;
+        cudaEventCreate(&e.a); cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, st);
+        h->prof.push_back(e);
+    }
+    void end(int n_launch) {
+        h->launches += n_launch;
+        if (!h->profiling) return;
+        cudaEventRecord(h->prof.back().b, st);
+        h->prof_result[h->prof.back().fam].second += n_launch;
+    }
+};
+
+void allreduce_sums(tgnn_handle* h, double* sums, int n, cudaStream_t st) {
+    if (h->world <= 1) return;
+    nccl_check(nccl().AllReduce(sums, sums, (size_t)n, ncclFloat64, ncclSum, h->comm, st), "BatchNorm all-reduce");
+    h->collectives += 1;
+}
+
+void halo_exchange(tgnn_handle* h, float* a, float* b, cudaStream_t st, Launcher& lz) {
+    if (h->world <= 1) return;
+    lz.begin("halo");
+    float* slot = h->halo.as<float>() + (size_t)h->rank * h->g.halo_slot * 64;
+    launch_halo_pack(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, slot, st);
+    nccl_check(nccl().AllGather(slot, h->halo.p, (size_t)h->g.halo_slot * 64, ncclFloat32, h->comm, st), "halo all-gather");
+    launch_halo_unpack(h->halo.as<float>(), h->world, h->rank, h->g.halo_slot, h->g.n_own, a, b, st);
+    h->collectives += 1;
+    lz.end(2);
+}
+
+void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st) {
+    TGNN_CHECK(h->graph_set, "tgnn_forward: no graph set (call tgnn_set_graph first)");
+    pack_params(h, st);
+    build_tables(h, st);
+    const int L = h->cfg.depth;
+    const bool train = h->cfg.bn_mode == TGNN_BN_TRAIN;
+    const int n_own = (int)h->g.n_own;
+    const double count = (double)h->g.n_global;
+    h->launches = 0; h->collectives = 0;
+    for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    h->prof.clear(); h->prof_result.clear();
+    Launcher lz{h, st};
+    double* sums = h->sums.as<double>();
+    if (!train) { lz.begin("bnfin"); eval_coefs(h, st); lz.end(2 + 2 * L + 4); }
+
+    auto finish_bn = [&](const double* part, int n_part, int c, const std::string& bn, size_t coef_off) {
+        launch_bn_reduce(part, n_part, c, sums, st);
+        allreduce_sums(h, sums, 2 * c, st);
+        launch_bn_coef(sums, count, h->P(bn + ".weight"), h->P(bn + ".bias"), h->C(coef_off), c, st);
+    };
+
+    // ---- init MLP ------------------------------------------------------------------------------
+    InitArgs ia{};
+    ia.x = x; ia.d_x = h->cfg.d_x;
+    ia.w0 = h->P("init_node_feature_trans.mlp.0.linear.weight"); ia.b0 = h->P("init_node_feature_trans.mlp.0.linear.bias");
+    ia.w1t = h->init_w1t.as<float>(); ia.b1 = h->P("init_node_feature_trans.mlp.1.linear.bias");
+    ia.coef0 = h->C(h->coef_init[0]); ia.coef1 = h->C(h->coef_init[1]);
+    ia.out = h->mid[0]->as<float>(); ia.part = h->partA.as<double>(); ia.n_own = n_own;
+    const int np_init = init_num_parts(n_own, h->sm_count);
+    if (train) {
+        lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.0.batch_norm", h->coef_init[0]); lz.end(2);
+        lz.begin("init"); launch_init(ia, 1, h->sm_count, st); lz.end(1);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.1.batch_norm", h->coef_init[1]); lz.end(2);
+    }
+    lz.begin("init"); launch_init(ia, 2, h->sm_count, st); lz.end(1);
+    halo_exchange(h, h->mid[0]->as<float>(), nullptr, st, lz);
+
+    // ---- message-passing layers ----------------------------------------------------------------
+    const int n_layers = h->stop_layer >= 0 ? std::min(L, h->stop_layer + 1) : L;
+    const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->sm_count), np_gin = gin_num_parts(n_own, h->sm_count);
+    for (int i = 0; i < n_layers; ++i) {
+        std::string pa = "brch_1_graph_conv_layers." + std::to_string(i);
+        std::string pc = "brch_2_coll_conv_layers." + std::to_string(i);
+        ConvArgs ca{};
+        ca.xin = h->mid[i]->as<float>();
+        ca.tab = h->tab.as<float>() + (size_t)i * h->g.n_types * F * F;
+        ca.root = h->P(pa + ".nnConv.root"); ca.bias = h->P(pa + ".nnConv.bias");
+        ca.cptr = h->g.cptr.as<int>(); ca.ctype = h->g.ctype.as<int>(); ca.csrc = h->g.csrc.as<int>();
+        ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->g.inv_deg.as<float>();
+        ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
+        ca.n_own = n_own; ca.n_tiles = h->g.n_tiles;
+        lz.begin("conv"); launch_conv_adj(ca, h->sm_count, st); lz.end(1);
+
+        GinArgs ga{};
+        ga.xin = i == 0 ? h->mid[0]->as<float>() : h->pre2[(i - 1) & 1].as<float>();
+        ga.in_coef = i == 0 ? nullptr : h->C(h->coef_c[i - 1]);
+        ga.col_ptr = h->g.col_ptr.as<int>(); ga.col_src = h->g.col_src.as<int>();
+        ga.w1t = h->gin_wt[3 * i + 0]->as<float>(); ga.b1 = h->P(pc + ".ginConv.nn.mlp.0.linear.bias");
+        ga.w2t = h->gin_wt[3 * i + 1]->as<float>(); ga.b2 = h->P(pc + ".ginConv.nn.mlp.1.linear.bias");
+        ga.w3t = h->gin_wt[3 * i + 2]->as<float>(); ga.b3 = h->P(pc + ".ginConv.nn.mlp.2.linear.bias");
+        ga.eps = h->gin_eps[i];
+        ga.out = h->pre2[i & 1].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
+        lz.begin("gin"); launch_gin(ga, h->sm_count, st); lz.end(1);
+
+        if (train) {
+            lz.begin("bnfin");
+            launch_bn_reduce(h->partA.as<double>(), np_conv, 32, sums, st);
+            launch_bn_reduce(h->partB.as<double>(), np_gin, 32, sums + 64, st);
+            allreduce_sums(h, sums, 128, st);
+            launch_bn_coef(sums, count, h->P(pa + ".batch_norm.weight"), h->P(pa + ".batch_norm.bias"), h->C(h->coef_a[i]), 32, st);
+            launch_bn_coef(sums + 64, count, h->P(pc + ".batch_norm.weight"), h->P(pc + ".batch_norm.bias"), h->C(h->coef_c[i]), 32, st);
+            lz.end(4);
+        }
+        lz.begin("combine");
+        launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[i & 1].as<float>(), h->C(h->coef_c[i]),
+                       i >= 2 ? h->mid[i - 2]->as<float>() : nullptr, h->mid[i + 1]->as<float>(), n_own, st);
+        lz.end(1);
+        if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[i & 1].as<float>(), st, lz);
+        h->last_layer_run = i;
+    }
+
+    // ---- final MLP -----------------------------------------------------------------------------
+    if (h->stop_layer < 0) {
+        int dims[5] = {F * (L + 1), 256, 128, 64, F};
+        for (int k = 0; k < 4; ++k) {
+            std::string p = "final_mlp.0.mlp." + std::to_string(k);
+            DenseArgs da{};
+            da.slabs = k == 0 ? h->slab_ptrs.as<const float*>() : nullptr;
+            da.a = k == 0 ? nullptr : h->fa[k - 1].as<float>();
+            da.virtual_concat = k == 0;
+            da.in_coef = k == 0 ? nullptr : h->C(h->coef_fin[k - 1]);
+            da.wt = h->fin_wt[k]->as<float>(); da.bias = h->P(p + ".linear.bias");
+            da.out = h->fa[k].as<float>(); da.part = train ? h->partA.as<double>() : nullptr;
+            da.n = n_own; da.K = dims[k]; da.n_out = dims[k + 1];
+            lz.begin("final"); launch_dense(da, st); lz.end(1);
+            if (train) {
+                lz.begin("bnfin");
+                finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], p + ".batch_norm", h->coef_fin[k]);
+                lz.end(2);
+            }
+        }
+        lz.begin("score");
+        launch_score(h->fa[3].as<float>(), h->C(h->coef_fin[3]), h->P("final_mlp.1.linear.weight"), h->fin_last_bias, scores,
+                     n_own, st);
+        lz.end(1);
+    }
+    if (h->profiling) {
+        TGNN_CUDA(cudaStreamSynchronize(st));
+        for (auto& e : h->prof) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e.a, e.b);
+            h->prof_result[e.fam].first += ms;
+        }
+    }
+}
+
+template <class Fn>
+int guarded(tgnn_handle* h, Fn&& fn) {
+    try {
+        fn();
+        return 0;
+    } catch (const std::exception& e) {
+        if (h) h->err = e.what(); else g_create_error = e.what();
+        return 1;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int tgnn_abi_version(void) { return TGNN_ABI_VERSION; }
+
+int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
+    return guarded(nullptr, [&] {
+        TGNN_CHECK(cfg && out, "tgnn_create: null argument");
+        TGNN_CHECK(cfg->width == F, "tgnn_create: network_width must be 32");
+        TGNN_CHECK(cfg->depth >= 1 && cfg->depth <= 64, "tgnn_create: network_depth must be in [1, 64]");
+        TGNN_CHECK(cfg->d_x >= 1 && cfg->d_x <= 1024 && cfg->d_e >= 1 && cfg->d_e <= 4096, "tgnn_create: bad feature dims");
+        TGNN_CHECK(cfg->bn_mode == TGNN_BN_TRAIN || cfg->bn_mode == TGNN_BN_EVAL, "tgnn_create: bad bn_mode");
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        TGNN_CHECK(e == cudaSuccess && ndev > 0,
+                   std::string("tgnn_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+        TGNN_CHECK(cfg->device >= 0 && cfg->device < ndev, "tgnn_create: bad device ordinal");
+        DeviceGuard dg(cfg->device);
+        cudaDeviceProp prop{};
+        TGNN_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+        TGNN_CHECK(prop.major >= 10, "tgnn_create: this build targets sm_100a (B200); found sm_" +
+                                         std::to_string(prop.major) + std::to_string(prop.minor));
+        std::unique_ptr<tgnn_handle> h(new tgnn_handle());
+        h->cfg = *cfg;
+        h->sm_count = prop.multiProcessorCount;
+        declare_params(h.get());
+        *out = h.release();
+    });
+}
+
+int tgnn_destroy(tgnn_handle* h) {
+    if (!h) return 0;
+    {
+        DeviceGuard dg(h->cfg.device);
+        for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
+        delete h;
+    }
+    return 0;
+}
+
+int tgnn_set_param(tgnn_handle* h, const char* ref_key, const void* data, const int64_t* shape, int32_t ndim) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && ref_key, "tgnn_set_param: null argument");
+        std::string key(ref_key);
+        if (ends_with(key, ".num_batches_tracked")) return;            // int64 counter, irrelevant to outputs
+        key = canonical_key(key);
+        auto it = h->params.find(key);
+        TGNN_CHECK(it != h->params.end(), "tgnn_set_param: unexpected key " + std::string(ref_key));
+        Param& p = it->second;
+        TGNN_CHECK(data != nullptr, "tgnn_set_param: null data for " + key);
+        bool ok = (int)p.shape.size() == ndim;
+        for (int i = 0; ok && i < ndim; ++i) ok = p.shape[i] == shape[i];
+        if (!ok) {
+            std::string want, got;
+            for (auto d : p.shape) want += std::to_string(d) + ",";
+            for (int i = 0; i < ndim; ++i) got += std::to_string(shape[i]) + ",";
+            throw Error("tgnn_set_param: size mismatch for " + key + ": expected [" + want + "] got [" + got + "]");
+        }
+        DeviceGuard dg(h->cfg.device);
+        size_t bytes = p.numel() * sizeof(float);
+        p.buf.reserve(bytes);
+        TGNN_CUDA(cudaMemcpy(p.buf.p, data, bytes, cudaMemcpyDefault));
+        p.set = true;
+        h->params_dirty = true;
+    });
+}
+
+int tgnn_missing_params(tgnn_handle* h, char* buf, int32_t buflen) {
+    if (!h) return -1;
+    int missing = 0;
+    for (auto& k : h->key_order)
+        if (!h->params[k].set) {
+            if (missing == 0 && buf && buflen > 0) { strncpy(buf, k.c_str(), buflen - 1); buf[buflen - 1] = 0; }
+            ++missing;
+        }
+    return missing;
+}
+
+int tgnn_set_bn_mode(tgnn_handle* h, int32_t bn_mode) {
+    return guarded(h, [&] {
+        TGNN_CHECK(bn_mode == TGNN_BN_TRAIN || bn_mode == TGNN_BN_EVAL, "tgnn_set_bn_mode: bad mode");
+        h->cfg.bn_mode = bn_mode;
+    });
+}
+
+int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst,
+                   const float* adj_feat, int64_t e_col, const int64_t* col_src, const int64_t* col_dst, void* stream) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h, "tgnn_set_graph: null handle");
+        TGNN_CHECK(h->world == 1, "tgnn_set_graph: handle is sharded, use tgnn_set_graph_shard");
+        DeviceGuard dg(h->cfg.device);
+        cudaStream_t st = (cudaStream_t)stream;
+        h->graph_set = false;
+        build_graph(h->g, h->scratch, h->cfg.d_e, n_nodes, n_nodes, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src,
+                    col_dst, st);
+        h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
+        alloc_workspace(h);
+        h->tables_dirty = true;
+        h->graph_set = true;
+    });
+}
+
+int tgnn_forward(tgnn_handle* h, const float* x, float* scores_out, void* stream) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && x && (scores_out || h->stop_layer >= 0), "tgnn_forward: null argument");
+        DeviceGuard dg(h->cfg.device);
+        forward_impl(h, x, scores_out, (cudaStream_t)stream);
+    });
+}
+
+int tgnn_nccl_unique_id(void* out128) {
+    return guarded(nullptr, [&] {
+        TGNN_CHECK(nccl().GetUniqueId, "NCCL is not available in this process (libnccl.so.2 not found)");
+        ncclUniqueId id;
+        nccl_check(nccl().GetUniqueId(&id), "ncclGetUniqueId");
+        memcpy(out128, &id, 128);
+    });
+}
+
+int tgnn_shard_init(tgnn_handle* h, const void* unique_id128, int32_t rank, int32_t world) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && unique_id128 && world >= 1 && rank >= 0 && rank < world, "tgnn_shard_init: bad arguments");
+        h->rank = rank; h->world = world;
+        if (world == 1) return;
+        TGNN_CHECK(nccl().CommInitRank, "NCCL is not available in this process (libnccl.so.2 not found)");
+        DeviceGuard dg(h->cfg.device);
+        ncclUniqueId id;
+        memcpy(&id, unique_id128, 128);
+        nccl_check(nccl().CommInitRank(&h->comm, world, id, rank), "ncclCommInitRank");
+    });
+}
+
+int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_t halo_slot, int64_t n_send,
+                         const int64_t* send_rows, int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst,
+                         const float* adj_feat, int64_t e_col, const int64_t* col_src, const int64_t* col_dst, void* stream) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h, "tgnn_set_graph_shard: null handle");
+        TGNN_CHECK(halo_slot >= 0 && n_send >= 0 && n_send <= halo_slot && n_global >= n_own, "tgnn_set_graph_shard: bad sizes");
+        DeviceGuard dg(h->cfg.device);
+        cudaStream_t st = (cudaStream_t)stream;
+        h->graph_set = false;
+        const int64_t n_rows = n_own + (h->world > 1 ? (int64_t)h->world * halo_slot : 0);
+        build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst, st);
+        h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
+        if (n_send > 0) {
+            std::vector<int64_t> rows64(n_send);
+            TGNN_CUDA(cudaMemcpyAsync(rows64.data(), send_rows, n_send * sizeof(int64_t), cudaMemcpyDefault, st));
+            TGNN_CUDA(cudaStreamSynchronize(st));
+            std::vector<int> rows32(n_send);
+            for (int64_t i = 0; i < n_send; ++i) {
+                TGNN_CHECK(rows64[i] >= 0 && rows64[i] < n_own, "tgnn_set_graph_shard: send row out of range");
+                rows32[i] = (int)rows64[i];
+            }
+            h->g.send_rows.reserve(n_send * sizeof(int));
+            TGNN_CUDA(cudaMemcpyAsync(h->g.send_rows.p, rows32.data(), n_send * sizeof(int), cudaMemcpyHostToDevice, st));
+            TGNN_CUDA(cudaStreamSynchronize(st));
+        }
+        alloc_workspace(h);
+        h->tables_dirty = true;
+        h->graph_set = true;
+    });
+}
+
+int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && out, "tgnn_get_info: null argument");
+        out->n_own = h->g.n_own; out->n_rows = h->g.n_rows; out->n_global = h->g.n_global;
+        out->e_adj = h->g.e_adj; out->e_col = h->g.e_col; out->n_edge_types = h->g.n_types;
+        out->adj_slots = (int64_t)h->g.n_chunks * CH;
+        out->launches_per_forward = h->launches;
+        out->workspace_bytes = (int64_t)h->workspace_bytes;
+        out->collectives_per_forward = h->collectives;
+    });
+}
+
+int tgnn_debug_set_stop_layer(tgnn_handle* h, int32_t layer) {
+    return guarded(h, [&] { h->stop_layer = layer; });
+}
+
+int tgnn_debug_read(tgnn_handle* h, const char* name, float* out, void* stream) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && name && out && h->graph_set, "tgnn_debug_read: bad arguments");
+        DeviceGuard dg(h->cfg.device);
+        cudaStream_t st = (cudaStream_t)stream;
+        std::string n(name);
+        const size_t bytes = (size_t)h->g.n_own * F * sizeof(float);
+        const int i = h->last_layer_run;
+        if (n.rfind("mid_", 0) == 0) {
+            int k = std::stoi(n.substr(4));
+            TGNN_CHECK(k >= 0 && k <= h->cfg.depth, "tgnn_debug_read: bad slab index");
+            TGNN_CUDA(cudaMemcpyAsync(out, h->mid[k]->p, bytes, cudaMemcpyDeviceToDevice, st));
+        } else if (n == "pre1") {
+            TGNN_CUDA(cudaMemcpyAsync(out, h->pre1.p, bytes, cudaMemcpyDeviceToDevice, st));
+        } else if (n == "pre2") {
+            TGNN_CHECK(i >= 0, "tgnn_debug_read: no layer has run");
+            TGNN_CUDA(cudaMemcpyAsync(out, h->pre2[i & 1].p, bytes, cudaMemcpyDeviceToDevice, st));
+        } else if (n == "g1" || n == "g2") {
+            // BN(pre) of the last layer that ran: combine with the other factor's BN replaced by identity
+            TGNN_CHECK(i >= 0, "tgnn_debug_read: no layer has run");
+            DevBuf ident;
+            ident.reserve(128 * sizeof(float));
+            std::vector<float> idc(128, 0.f);
+            for (int c = 0; c < 32; ++c) idc[64 + c] = 0.f, idc[96 + c] = 1.f;     // scale 0, beta 1 -> factor 1
+            TGNN_CUDA(cudaMemcpyAsync(ident.p, idc.data(), 128 * sizeof(float), cudaMemcpyHostToDevice, st));
+            if (n == "g1")
+                launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[i & 1].as<float>(), ident.as<float>(), nullptr, out,
+                               h->g.n_own, st);
+            else
+                launch_combine(h->pre1.as<float>(), ident.as<float>(), h->pre2[i & 1].as<float>(), h->C(h->coef_c[i]), nullptr, out,
+                               h->g.n_own, st);
+            TGNN_CUDA(cudaStreamSynchronize(st));
+        } else {
+            throw Error("tgnn_debug_read: unknown tensor " + n);
+        }
+    });
+}
+
+int tgnn_debug_graph(tgnn_handle* h, int32_t* cptr, int32_t* ctype, int32_t* csrc, uint8_t* cdst, float* inv_deg,
+                     int32_t* col_ptr, int32_t* col_src, float* type_rows, void* stream) {
+    // Copies the built graph structures to caller-provided DEVICE or HOST buffers (sizes from tgnn_get_info and the
+    // struct Graph comments); null pointers are skipped.  Test-only.
+    return guarded(h, [&] {
+        TGNN_CHECK(h && h->graph_set, "tgnn_debug_graph: no graph");
+        DeviceGuard dg(h->cfg.device);
+        cudaStream_t st = (cudaStream_t)stream;
+        auto cp = [&](void* dst, const DevBuf& b, size_t bytes) {
+            if (dst && bytes) TGNN_CUDA(cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDefault, st));
+        };
+        cp(cptr, h->g.cptr, (size_t)(h->g.n_tiles + 1) * 4);
+        cp(ctype, h->g.ctype, (size_t)h->g.n_chunks * 4);
+        cp(csrc, h->g.csrc, (size_t)h->g.n_chunks * CH * 4);
+        cp(cdst, h->g.cdst, (size_t)h->g.n_chunks * CH);
+        cp(inv_deg, h->g.inv_deg, (size_t)h->g.n_own * 4);
+        cp(col_ptr, h->g.col_ptr, (size_t)(h->g.n_own + 1) * 4);
+        cp(col_src, h->g.col_src, (size_t)h->g.e_col * 4);
+        cp(type_rows, h->g.type_rows, (size_t)h->g.n_types * h->cfg.d_e * 4);
+        TGNN_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int tgnn_set_profiling(tgnn_handle* h, int32_t enabled) {
+    return guarded(h, [&] { h->profiling = enabled != 0; });
+}
+
+int tgnn_get_profile(tgnn_handle* h, const char* name, float* ms_out, int32_t* launches_out) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && name, "tgnn_get_profile: null argument");
+        auto it = h->prof_result.find(name);
+        float ms = 0.f; int n = 0;
+        if (it != h->prof_result.end()) { ms = it->second.first; n = it->second.second; }
+        if (ms_out) *ms_out = ms;
+        if (launches_out) *launches_out = n;
+    });
+}
+
+const char* tgnn_last_error(tgnn_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+}  // extern "C"

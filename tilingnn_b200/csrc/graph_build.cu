@@ -1,0 +1,354 @@
+// Device-side construction of the graph structures the scoring kernels consume.
+//
+// Input is exactly what TilinGNN.forward receives (graph_networks/networks/TilinGNN.py:51 of the
+// reference): int64 COO edge lists in PyG source_to_target order and the fp32 adjacency edge
+// features.  Output (struct Graph):
+//   * edge-type ids: the reference runs a 3-layer MLP on every edge's feature row
+//     (graph_networks/layers/edge_conv.py:17-18); rows that are bitwise equal give equal weights,
+//     so edges are labelled with the id of their distinct row (K ids) and the MLP is evaluated K
+//     times per layer instead of E_a times.
+//   * typed adjacency tiles: destinations are cut into warp tiles of WN rows; the in-edges of a
+//     tile are grouped into chunks of CH slots that all share one edge type, and inside every
+//     8-slot group all destinations are distinct (so a warp can accumulate messages into shared
+//     memory without atomics).
+//   * collision CSR by destination with self loops removed (PyG GINConv.remove_self_loops).
+// Everything is sorts / scans (CUB) plus small kernels; summation orders derived from it are
+// deterministic (stable sorts keyed on content, ties broken by original edge order).
+#include <cub/cub.cuh>
+
+#include "tgnn_internal.h"
+
+namespace tgnn {
+namespace {
+
+constexpr int TPB = 256;
+inline int nblk(int64_t n) { return (int)((n + TPB - 1) / TPB); }
+
+struct MaxOp {
+    __device__ __forceinline__ int operator()(int a, int b) const { return a > b ? a : b; }
+};
+
+__global__ void k_validate(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e,
+                           int64_t n_rows, int64_t n_own, int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    int64_t s = src[i], d = dst[i];
+    if (s < 0 || s >= n_rows || d < 0 || d >= n_own) atomicOr(err, 1);
+}
+
+// 64-bit hash of one feature row (-0.0 canonicalised to +0.0 so numerically equal rows match).
+__global__ void k_hash_rows(const float* __restrict__ feat, int64_t e, int d_e,
+                            unsigned long long* __restrict__ h, int* __restrict__ eid) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const unsigned* row = reinterpret_cast<const unsigned*>(feat + i * d_e);
+    unsigned long long x = 0x9E3779B97F4A7C15ull;
+    for (int k = 0; k < d_e; ++k) {
+        unsigned w = row[k];
+        if (w == 0x80000000u) w = 0u;
+        x ^= (unsigned long long)w + 0x9E3779B97F4A7C15ull + (x << 6) + (x >> 2);
+        x *= 0xFF51AFD7ED558CCDull;
+        x ^= x >> 33;
+    }
+    h[i] = x;
+    eid[i] = (int)i;
+}
+
+__global__ void k_head_flags_u64(const unsigned long long* __restrict__ k, int64_t e, int* __restrict__ head) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    head[i] = (i == 0 || k[i] != k[i - 1]) ? 1 : 0;
+}
+
+// after inclusive scan of head flags: type of sorted position i is scan[i]-1
+__global__ void k_assign_types(const int* __restrict__ scan, const int* __restrict__ head,
+                               const int* __restrict__ eid_sorted, int64_t e,
+                               int* __restrict__ type_of_edge, int* __restrict__ rep_edge, int max_types) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    int t = scan[i] - 1;
+    type_of_edge[eid_sorted[i]] = t;
+    if (head[i] && t < max_types) rep_edge[t] = eid_sorted[i];
+}
+
+__global__ void k_verify_types(const float* __restrict__ feat, int64_t e, int d_e,
+                               const int* __restrict__ type_of_edge, const int* __restrict__ rep_edge,
+                               int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const unsigned* a = reinterpret_cast<const unsigned*>(feat + i * d_e);
+    const unsigned* b = reinterpret_cast<const unsigned*>(feat + (int64_t)rep_edge[type_of_edge[i]] * d_e);
+    bool bad = false;
+    for (int k = 0; k < d_e; ++k) {
+        unsigned x = a[k], y = b[k];
+        if (x == 0x80000000u) x = 0u;
+        if (y == 0x80000000u) y = 0u;
+        bad |= (x != y);
+    }
+    if (bad) atomicOr(err, 2);
+}
+
+__global__ void k_gather_type_rows(const float* __restrict__ feat, int d_e, const int* __restrict__ rep_edge,
+                                   int n_types, float* __restrict__ rows) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_types * d_e) return;
+    int t = i / d_e, k = i - t * d_e;
+    rows[i] = feat[(int64_t)rep_edge[t] * d_e + k];
+}
+
+// key = (warp tile << 22) | (type << 6) | local destination
+__global__ void k_adj_keys(const int64_t* __restrict__ dst, const int* __restrict__ type_of_edge, int64_t e,
+                           int64_t n_own, unsigned long long* __restrict__ key, int* __restrict__ eid, int* __restrict__ deg) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    long long d = dst[i];
+    if (d < 0 || d >= n_own) d = 0;                     // flagged by k_validate; keep the access in range
+    unsigned long long tile = (unsigned long long)(d / WN);
+    unsigned long long dl = (unsigned long long)(d % WN);
+    key[i] = (tile << 22) | ((unsigned long long)type_of_edge[i] << 6) | dl;
+    eid[i] = (int)i;
+    atomicAdd(&deg[d], 1);
+}
+
+__global__ void k_adj_flags(const unsigned long long* __restrict__ key, int64_t e,
+                            int* __restrict__ run_head, int* __restrict__ run_start_seed,
+                            int* __restrict__ grp_start_seed) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    bool rh = (i == 0) || ((key[i] >> 6) != (key[i - 1] >> 6));
+    bool gh = (i == 0) || (key[i] != key[i - 1]);
+    run_head[i] = rh ? 1 : 0;
+    run_start_seed[i] = rh ? (int)i : 0;
+    grp_start_seed[i] = gh ? (int)i : 0;
+}
+
+__global__ void k_adj_runs(const unsigned long long* __restrict__ key, int64_t e,
+                           const int* __restrict__ run_idx_incl, const int* __restrict__ run_head,
+                           const int* __restrict__ grp_start,
+                           int* __restrict__ run_pos, int* __restrict__ run_maxmult) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    int r = run_idx_incl[i] - 1;
+    if (run_head[i]) run_pos[r] = (int)i;
+    int mult = (int)i - grp_start[i] + 1;
+    if (mult > 1) atomicMax(&run_maxmult[r], mult);
+}
+
+__global__ void k_run_chunks(const int* __restrict__ run_pos, const int* __restrict__ run_maxmult,
+                             int n_runs, int e, int* __restrict__ run_chunks) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    int len = ((r + 1 < n_runs) ? run_pos[r + 1] : e) - run_pos[r];
+    int g = (len + GRP - 1) / GRP;
+    int mm = run_maxmult[r];
+    if (mm > g) g = mm;
+    g += g & 1;
+    run_chunks[r] = g / 2;
+}
+
+// per run: chunk types, and the end of the tile's chunk range if this is the tile's last run
+__global__ void k_run_fill(const unsigned long long* __restrict__ key, const int* __restrict__ run_pos,
+                           const int* __restrict__ run_chunks, const int* __restrict__ chunk_base,
+                           int n_runs, int* __restrict__ ctype, int* __restrict__ tile_end) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    unsigned long long k = key[run_pos[r]];
+    int type = (int)((k >> 6) & 0xFFFFull);
+    long long tile = (long long)(k >> 22);
+    int base = chunk_base[r], nc = run_chunks[r];
+    for (int c = 0; c < nc; ++c) ctype[base + c] = type;
+    bool last = (r + 1 == n_runs) || ((long long)(key[run_pos[r + 1]] >> 22) != tile);
+    if (last) tile_end[tile] = base + nc;
+}
+
+__global__ void k_adj_scatter(const unsigned long long* __restrict__ key, const int* __restrict__ eid_sorted,
+                              const int64_t* __restrict__ src, int64_t e,
+                              const int* __restrict__ run_idx_incl, const int* __restrict__ run_pos,
+                              const int* __restrict__ run_chunks, const int* __restrict__ chunk_base,
+                              int* __restrict__ csrc, uint8_t* __restrict__ cdst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    int r = run_idx_incl[i] - 1;
+    int p = (int)i - run_pos[r];
+    int g = 2 * run_chunks[r];
+    int64_t slot = (int64_t)chunk_base[r] * CH + (int64_t)(p % g) * GRP + p / g;
+    csrc[slot] = (int)src[eid_sorted[i]];
+    cdst[slot] = (uint8_t)(key[i] & 63ull);
+}
+
+__global__ void k_fill_int(int* __restrict__ p, int64_t n, int v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void k_inv_deg(const int* __restrict__ deg, int64_t n, float* __restrict__ inv) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) { int d = deg[i]; inv[i] = 1.0f / (float)(d > 1 ? d : 1); }
+}
+
+// cptr[0] = 0, cptr[t+1] = running max of tile_end (empty tiles inherit the previous end)
+__global__ void k_cptr_first(int* __restrict__ cptr) { if (threadIdx.x == 0 && blockIdx.x == 0) cptr[0] = 0; }
+
+__global__ void k_col_keys(const int64_t* __restrict__ src, const int64_t* __restrict__ dst, int64_t e, int n_own,
+                           unsigned* __restrict__ key, int* __restrict__ val, int* __restrict__ cnt) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    long long s = src[i], d = dst[i];
+    if (s == d || d < 0 || d >= n_own) { key[i] = (unsigned)n_own; val[i] = -1; }     // self loop: parked behind the last row
+    else { key[i] = (unsigned)d; val[i] = (int)s; atomicAdd(&cnt[d], 1); }
+}
+
+int bits_for(unsigned long long v) { int b = 1; while ((v >> b) != 0 && b < 64) ++b; return b; }
+
+template <class K, class V>
+void sort_pairs(Scratch& sc, const K* kin, K* kout, const V* vin, V* vout, int64_t n, int end_bit, cudaStream_t st) {
+    size_t tb = 0;
+    TGNN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, (int)n, 0, end_bit, st));
+    void* tmp = sc.get<char>(tb);
+    TGNN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, kin, kout, vin, vout, (int)n, 0, end_bit, st));
+}
+
+void incl_sum(Scratch& sc, const int* in, int* out, int64_t n, cudaStream_t st) {
+    size_t tb = 0;
+    TGNN_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, in, out, (int)n, st));
+    void* tmp = sc.get<char>(tb);
+    TGNN_CUDA(cub::DeviceScan::InclusiveSum(tmp, tb, in, out, (int)n, st));
+}
+void excl_sum(Scratch& sc, const int* in, int* out, int64_t n, cudaStream_t st) {
+    size_t tb = 0;
+    TGNN_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, (int)n, st));
+    void* tmp = sc.get<char>(tb);
+    TGNN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tb, in, out, (int)n, st));
+}
+void incl_max(Scratch& sc, const int* in, int* out, int64_t n, cudaStream_t st) {
+    size_t tb = 0;
+    TGNN_CUDA(cub::DeviceScan::InclusiveScan(nullptr, tb, in, out, MaxOp(), (int)n, st));
+    void* tmp = sc.get<char>(tb);
+    TGNN_CUDA(cub::DeviceScan::InclusiveScan(tmp, tb, in, out, MaxOp(), (int)n, st));
+}
+
+int read_int(const int* dptr, cudaStream_t st) {
+    int v = 0;
+    TGNN_CUDA(cudaMemcpyAsync(&v, dptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TGNN_CUDA(cudaStreamSynchronize(st));
+    return v;
+}
+
+}  // namespace
+
+void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
+                 int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, cudaStream_t st) {
+    TGNN_CHECK(n_own > 0 && n_rows >= n_own, "tgnn_set_graph: need n_nodes > 0");
+    TGNN_CHECK(n_rows < (1ll << 31) - 64, "tgnn_set_graph: more than 2^31 rows per GPU is not supported");
+    TGNN_CHECK(e_adj >= 0 && e_adj < (1ll << 31) - 64 && e_col >= 0 && e_col < (1ll << 31) - 64,
+               "tgnn_set_graph: edge count per GPU must be below 2^31");
+    sc.reset();
+    g.n_own = n_own; g.n_rows = n_rows;
+    g.n_tiles = (int)((n_own + WN - 1) / WN);
+    int* err = sc.get<int>(1);
+    TGNN_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
+
+    // ---------------- adjacency: edge types -----------------------------------------------------
+    g.cptr.reserve((size_t)(g.n_tiles + 1) * sizeof(int));
+    g.inv_deg.reserve((size_t)n_own * sizeof(float));
+    int* deg = sc.get<int>(n_own);
+    TGNN_CUDA(cudaMemsetAsync(deg, 0, (size_t)n_own * sizeof(int), st));
+    g.n_types = 0; g.n_chunks = 0; g.e_adj = e_adj;
+    if (e_adj > 0) {
+        k_validate<<<nblk(e_adj), TPB, 0, st>>>(adj_src, adj_dst, e_adj, n_rows, n_own, err);
+        unsigned long long* h0 = sc.get<unsigned long long>(e_adj);
+        unsigned long long* h1 = sc.get<unsigned long long>(e_adj);
+        int* id0 = sc.get<int>(e_adj);
+        int* id1 = sc.get<int>(e_adj);
+        k_hash_rows<<<nblk(e_adj), TPB, 0, st>>>(adj_feat, e_adj, d_e, h0, id0);
+        sort_pairs(sc, h0, h1, id0, id1, e_adj, 64, st);
+        int* head = sc.get<int>(e_adj);
+        int* scan = sc.get<int>(e_adj);
+        k_head_flags_u64<<<nblk(e_adj), TPB, 0, st>>>(h1, e_adj, head);
+        incl_sum(sc, head, scan, e_adj, st);
+        int n_types = read_int(scan + (e_adj - 1), st);
+        TGNN_CHECK(read_int(err, st) == 0, "tgnn_set_graph: adjacency edge index out of range");
+        TGNN_CHECK(n_types <= MAX_TYPES,
+                   "tgnn_set_graph: more than 65535 distinct adjacency edge-feature rows; the dense "
+                   "per-edge weight path for non-repeating edge features is not implemented");
+        g.n_types = n_types;
+        int* type_of_edge = sc.get<int>(e_adj);
+        int* rep_edge = sc.get<int>(n_types);
+        k_assign_types<<<nblk(e_adj), TPB, 0, st>>>(scan, head, id1, e_adj, type_of_edge, rep_edge, n_types);
+        k_verify_types<<<nblk(e_adj), TPB, 0, st>>>(adj_feat, e_adj, d_e, type_of_edge, rep_edge, err);
+        g.type_rows.reserve((size_t)n_types * d_e * sizeof(float));
+        k_gather_type_rows<<<nblk((int64_t)n_types * d_e), TPB, 0, st>>>(adj_feat, d_e, rep_edge, n_types,
+                                                                         g.type_rows.as<float>());
+
+        // ---------------- adjacency: typed tiles ---------------------------------------------------
+        unsigned long long* k0 = h0;      // reuse
+        unsigned long long* k1 = h1;
+        k_adj_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, k0, id0, deg);
+        int end_bit = 22 + bits_for((unsigned long long)g.n_tiles);
+        sort_pairs(sc, k0, k1, id0, id1, e_adj, end_bit, st);
+        int* run_head = head;
+        int* run_seed = sc.get<int>(e_adj);
+        int* grp_seed = sc.get<int>(e_adj);
+        k_adj_flags<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, run_head, run_seed, grp_seed);
+        int* run_idx = scan;
+        incl_sum(sc, run_head, run_idx, e_adj, st);
+        int* grp_start = sc.get<int>(e_adj);
+        incl_max(sc, grp_seed, grp_start, e_adj, st);
+        int n_runs = read_int(run_idx + (e_adj - 1), st);
+        int* run_pos = sc.get<int>(n_runs + 1);
+        int* run_maxmult = sc.get<int>(n_runs);
+        int* run_chunks = sc.get<int>(n_runs);
+        int* chunk_base = sc.get<int>(n_runs + 1);
+        TGNN_CUDA(cudaMemsetAsync(run_maxmult, 0, (size_t)n_runs * sizeof(int), st));
+        k_adj_runs<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, run_idx, run_head, grp_start, run_pos, run_maxmult);
+        k_run_chunks<<<nblk(n_runs), TPB, 0, st>>>(run_pos, run_maxmult, n_runs, (int)e_adj, run_chunks);
+        excl_sum(sc, run_chunks, chunk_base, n_runs, st);
+        int last_base = read_int(chunk_base + (n_runs - 1), st);
+        int last_cnt = read_int(run_chunks + (n_runs - 1), st);
+        int64_t n_chunks = (int64_t)last_base + last_cnt;
+        TGNN_CHECK(n_chunks * CH < (1ll << 31) - 64, "tgnn_set_graph: typed adjacency tiles exceed 2^31 slots");
+        g.n_chunks = (int)n_chunks;
+        g.ctype.reserve((size_t)n_chunks * sizeof(int));
+        g.csrc.reserve((size_t)n_chunks * CH * sizeof(int));
+        g.cdst.reserve((size_t)n_chunks * CH);
+        k_fill_int<<<nblk(n_chunks * CH), TPB, 0, st>>>(g.csrc.as<int>(), n_chunks * CH, -1);
+        TGNN_CUDA(cudaMemsetAsync(g.cdst.p, 0, (size_t)n_chunks * CH, st));
+        int* tile_end = sc.get<int>(g.n_tiles);
+        TGNN_CUDA(cudaMemsetAsync(tile_end, 0, (size_t)g.n_tiles * sizeof(int), st));
+        k_run_fill<<<nblk(n_runs), TPB, 0, st>>>(k1, run_pos, run_chunks, chunk_base, n_runs,
+                                                  g.ctype.as<int>(), tile_end);
+        k_cptr_first<<<1, 32, 0, st>>>(g.cptr.as<int>());
+        incl_max(sc, tile_end, g.cptr.as<int>() + 1, g.n_tiles, st);
+        k_adj_scatter<<<nblk(e_adj), TPB, 0, st>>>(k1, id1, adj_src, e_adj, run_idx, run_pos, run_chunks,
+                                                    chunk_base, g.csrc.as<int>(), g.cdst.as<uint8_t>());
+    } else {
+        TGNN_CUDA(cudaMemsetAsync(g.cptr.p, 0, (size_t)(g.n_tiles + 1) * sizeof(int), st));
+    }
+    k_inv_deg<<<nblk(n_own), TPB, 0, st>>>(deg, n_own, g.inv_deg.as<float>());
+
+    // ---------------- collision CSR -----------------------------------------------------------------
+    g.col_ptr.reserve((size_t)(n_own + 1) * sizeof(int));
+    g.e_col = 0;
+    if (e_col > 0) {
+        k_validate<<<nblk(e_col), TPB, 0, st>>>(col_src, col_dst, e_col, n_rows, n_own, err);
+        unsigned* ck0 = sc.get<unsigned>(e_col);
+        unsigned* ck1 = sc.get<unsigned>(e_col);
+        int* cv0 = sc.get<int>(e_col);
+        g.col_src.reserve((size_t)e_col * sizeof(int));
+        int* cnt = sc.get<int>(n_own + 1);
+        TGNN_CUDA(cudaMemsetAsync(cnt, 0, (size_t)(n_own + 1) * sizeof(int), st));
+        k_col_keys<<<nblk(e_col), TPB, 0, st>>>(col_src, col_dst, e_col, (int)n_own, ck0, cv0, cnt);
+        sort_pairs(sc, ck0, ck1, cv0, g.col_src.as<int>(), e_col, bits_for((unsigned long long)n_own), st);
+        excl_sum(sc, cnt, g.col_ptr.as<int>(), n_own + 1, st);
+        g.e_col = read_int(g.col_ptr.as<int>() + n_own, st);
+    } else {
+        TGNN_CUDA(cudaMemsetAsync(g.col_ptr.p, 0, (size_t)(n_own + 1) * sizeof(int), st));
+    }
+    int e = read_int(err, st);
+    TGNN_CHECK((e & 1) == 0, "tgnn_set_graph: edge index out of range");
+    TGNN_CHECK((e & 2) == 0, "tgnn_set_graph: 64-bit hash collision between distinct edge-feature rows");
+    TGNN_CUDA(cudaGetLastError());
+}
+
+}  // namespace tgnn

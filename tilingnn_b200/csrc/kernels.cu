@@ -1,0 +1,707 @@
+// Scoring kernels of the TilinGNN forward pass for sm_100a (fp32 arithmetic, fp64 BatchNorm sums).
+//
+// Layout in HBM: every node tensor is row-major [rows][32] fp32, one 128-byte line per node, so a
+// gather of a neighbour is exactly one coalesced line.  See DESIGN.md for the per-kernel byte model.
+#include <algorithm>
+
+#include "tgnn_internal.h"
+
+namespace tgnn {
+namespace {
+
+constexpr int XS = 36;          // padded shared-memory row stride (floats): 144 B keeps float4 alignment
+constexpr int WARPS = 8;        // warps per CTA in the warp-tile kernels
+constexpr int TPB = WARPS * 32;
+
+__device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
+__device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+
+__device__ __forceinline__ float4 ld_row4(const float* base, int row, int q) {
+    return __ldg(reinterpret_cast<const float4*>(base + (size_t)row * F) + q);
+}
+
+// 16-row x 32-col product on CUDA cores.  Thread (a = lane>>3, q = lane&7) owns rows a+4i (i<4) and
+// columns 4q..4q+3.  xs: [16][XS] in shared memory, W: [KDIM][ldw] (k-major) readable with float4 loads.
+template <int KDIM, bool W_GLOBAL>
+__device__ __forceinline__ void tile16_fma(const float* __restrict__ xs, int xstride, const float* __restrict__ W,
+                                           int ldw, int col0, int a, int q, float (&m)[4][4]) {
+#pragma unroll
+    for (int kk = 0; kk < KDIM / 4; ++kk) {
+        float4 xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            xv[i] = *reinterpret_cast<const float4*>(xs + (a + 4 * i) * xstride + 4 * kk);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            const float4* wp = reinterpret_cast<const float4*>(W + (size_t)(4 * kk + k2) * ldw + col0) + q;
+            float4 w = W_GLOBAL ? __ldg(wp) : *wp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float x = k2 == 0 ? xv[i].x : k2 == 1 ? xv[i].y : k2 == 2 ? xv[i].z : xv[i].w;
+                m[i][0] = fmaf(x, w.x, m[i][0]);
+                m[i][1] = fmaf(x, w.y, m[i][1]);
+                m[i][2] = fmaf(x, w.z, m[i][2]);
+                m[i][3] = fmaf(x, w.w, m[i][3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adjacency branch: typed NNConv(mean) + root + bias + LeakyReLU, BatchNorm partial sums.
+// (graph_networks/layers/edge_conv.py:24-27 of the reference; PyG NNConv semantics.)
+// One warp owns a tile of WN destination rows and walks its chunks; messages are accumulated in the
+// warp's private shared-memory tile (no atomics: destinations are distinct inside an 8-slot group).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TPB, 2)
+k_conv_adj(ConvArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* acc = smem + warp * (WN * XS + CH * XS);
+    float* xs = acc + WN * XS;
+    const int a = lane >> 3, q = lane & 7;
+    const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
+    double s1 = 0.0, s2 = 0.0;
+    const float bias_c = __ldg(A.bias + lane);
+
+    for (int tile = gwarp; tile < A.n_tiles; tile += nwarp) {
+        for (int i = lane; i < WN * XS; i += 32) acc[i] = 0.f;
+        const int c0 = __ldg(A.cptr + tile), c1 = __ldg(A.cptr + tile + 1);
+        // prefetch first chunk
+        float4 pre[4];
+        int psrc = -1, pdst = 0;
+        if (c0 < c1) {
+            psrc = __ldg(A.csrc + (size_t)c0 * CH + (lane & 15));
+            pdst = __ldg(A.cdst + (size_t)c0 * CH + (lane & 15));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int s = __shfl_sync(0xffffffffu, psrc, a + 4 * j);
+                pre[j] = s >= 0 ? ld_row4(A.xin, s, q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncwarp();
+        for (int c = c0; c < c1; ++c) {
+            const int csrc = psrc, cdst = pdst;
+            const int type = __ldg(A.ctype + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                *reinterpret_cast<float4*>(xs + (a + 4 * j) * XS + 4 * q) = pre[j];
+            __syncwarp();
+            if (c + 1 < c1) {
+                psrc = __ldg(A.csrc + (size_t)(c + 1) * CH + (lane & 15));
+                pdst = __ldg(A.cdst + (size_t)(c + 1) * CH + (lane & 15));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int s = __shfl_sync(0xffffffffu, psrc, a + 4 * j);
+                    pre[j] = s >= 0 ? ld_row4(A.xin, s, q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float m[4][4] = {};
+            tile16_fma<F, true>(xs, XS, A.tab + (size_t)type * (F * F), F, 0, a, q, m);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                int s = __shfl_sync(0xffffffffu, csrc, a + 4 * i);
+                int d = __shfl_sync(0xffffffffu, cdst, a + 4 * i);
+                if (s >= 0) {
+                    float4* p = reinterpret_cast<float4*>(acc + d * XS + 4 * q);
+                    float4 v = *p;
+                    v.x += m[i][0]; v.y += m[i][1]; v.z += m[i][2]; v.w += m[i][3];
+                    *p = v;
+                }
+                __syncwarp();
+            }
+        }
+        // mean over in-edges
+        const int node0 = tile * WN;
+        for (int r = 0; r < WN; ++r) {
+            int node = node0 + r;
+            if (node < A.n_own) acc[r * XS + lane] *= __ldg(A.inv_deg + node);
+        }
+        __syncwarp();
+        // root term: x_i @ root, four 16-row chunks of the tile's own rows
+        for (int rc = 0; rc < WN / CH; ++rc) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int node = node0 + rc * CH + a + 4 * j;
+                float4 v = node < A.n_own ? ld_row4(A.xin, node, q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(xs + (a + 4 * j) * XS + 4 * q) = v;
+            }
+            __syncwarp();
+            float m[4][4] = {};
+            tile16_fma<F, true>(xs, XS, A.root, F, 0, a, q, m);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4* p = reinterpret_cast<float4*>(acc + (rc * CH + a + 4 * i) * XS + 4 * q);
+                float4 v = *p;
+                v.x += m[i][0]; v.y += m[i][1]; v.z += m[i][2]; v.w += m[i][3];
+                *p = v;
+            }
+            __syncwarp();
+        }
+        // bias, LeakyReLU, store, statistics (lane = channel)
+        for (int r = 0; r < WN; ++r) {
+            int node = node0 + r;
+            if (node < A.n_own) {
+                float v = leaky(acc[r * XS + lane] + bias_c);
+                A.out[(size_t)node * F + lane] = v;
+                s1 += (double)v;
+                s2 += (double)v * (double)v;
+            }
+        }
+        __syncwarp();
+    }
+    if (A.part) {
+        A.part[(size_t)gwarp * 64 + lane] = s1;
+        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Collision branch: GINConv (sum over CSR neighbours + self) and its 32->32->64->32 sigmoid MLP,
+// LeakyReLU, BatchNorm partial sums.  (graph_networks/layers/coll_conv.py:24-27; PyG GINConv.)
+// The previous layer's BatchNorm is applied lazily on the gathered rows:
+//   sum_j BN(x_j) = scale * sum_j ((x_j - mu_hi) - mu_lo) + (#terms) * beta
+// ------------------------------------------------------------------------------------------------
+struct GinSmem {
+    float w1t[32 * 32]; float w2t[32 * 64]; float w3t[64 * 32];
+    float b1[32]; float b2[64]; float b3[32];
+};
+constexpr int GIN_WARP_FLOATS = CH * XS + CH * XS + CH * 68;
+
+__global__ void __launch_bounds__(TPB, 2)
+k_gin(GinArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    GinSmem* W = reinterpret_cast<GinSmem*>(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 32 * 32; i += TPB) W->w1t[i] = __ldg(A.w1t + i);
+    for (int i = threadIdx.x; i < 32 * 64; i += TPB) { W->w2t[i] = __ldg(A.w2t + i); W->w3t[i] = __ldg(A.w3t + i); }
+    if (threadIdx.x < 32) { W->b1[threadIdx.x] = __ldg(A.b1 + threadIdx.x); W->b3[threadIdx.x] = __ldg(A.b3 + threadIdx.x); }
+    if (threadIdx.x < 64) W->b2[threadIdx.x] = __ldg(A.b2 + threadIdx.x);
+    __syncthreads();
+    float* xs = smem + sizeof(GinSmem) / sizeof(float) + warp * GIN_WARP_FLOATS;
+    float* h1 = xs + CH * XS;
+    float* h2 = h1 + CH * XS;
+    const int a = lane >> 3, q = lane & 7;
+    const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
+    const int n_chunks = (A.n_own + CH - 1) / CH;
+    float mu_hi = 0.f, mu_lo = 0.f, scale = 1.f, beta = 0.f;
+    if (A.in_coef) {
+        mu_hi = __ldg(A.in_coef + lane); mu_lo = __ldg(A.in_coef + 32 + lane);
+        scale = __ldg(A.in_coef + 64 + lane); beta = __ldg(A.in_coef + 96 + lane);
+    }
+    const float self_w = 1.0f + A.eps;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+
+    for (int chunk = gwarp; chunk < n_chunks; chunk += nwarp) {
+        const int node0 = chunk * CH;
+        // gather + sum (lane = channel)
+        for (int r = 0; r < CH; ++r) {
+            const int node = node0 + r;
+            float h = 0.f;
+            if (node < A.n_own) {
+                const int e0 = __ldg(A.col_ptr + node), e1 = __ldg(A.col_ptr + node + 1);
+                float c = (__ldg(A.xin + (size_t)node * F + lane) - mu_hi) - mu_lo;
+                float sum = self_w * c;
+                for (int eb = e0; eb < e1; eb += 32) {
+                    const int cnt = min(32, e1 - eb);
+                    int idx = lane < cnt ? __ldg(A.col_src + eb + lane) : 0;
+                    int j = 0;
+                    for (; j + 4 <= cnt; j += 4) {
+                        int i0 = __shfl_sync(0xffffffffu, idx, j), i1 = __shfl_sync(0xffffffffu, idx, j + 1);
+                        int i2 = __shfl_sync(0xffffffffu, idx, j + 2), i3 = __shfl_sync(0xffffffffu, idx, j + 3);
+                        float v0 = __ldg(A.xin + (size_t)i0 * F + lane), v1 = __ldg(A.xin + (size_t)i1 * F + lane);
+                        float v2 = __ldg(A.xin + (size_t)i2 * F + lane), v3 = __ldg(A.xin + (size_t)i3 * F + lane);
+                        sum += (v0 - mu_hi) - mu_lo;
+                        sum += (v1 - mu_hi) - mu_lo;
+                        sum += (v2 - mu_hi) - mu_lo;
+                        sum += (v3 - mu_hi) - mu_lo;
+                    }
+                    for (; j < cnt; ++j) {
+                        int i0 = __shfl_sync(0xffffffffu, idx, j);
+                        sum += (__ldg(A.xin + (size_t)i0 * F + lane) - mu_hi) - mu_lo;
+                    }
+                }
+                h = fmaf(scale, sum, (self_w + (float)(e1 - e0)) * beta);
+            }
+            xs[r * XS + lane] = h;
+        }
+        __syncwarp();
+        // layer 1: 32 -> 32
+        {
+            float m[4][4] = {};
+            tile16_fma<32, false>(xs, XS, W->w1t, 32, 0, a, q, m);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float4 o;
+                o.x = sigmoidf_acc(m[i][0] + W->b1[4 * q + 0]); o.y = sigmoidf_acc(m[i][1] + W->b1[4 * q + 1]);
+                o.z = sigmoidf_acc(m[i][2] + W->b1[4 * q + 2]); o.w = sigmoidf_acc(m[i][3] + W->b1[4 * q + 3]);
+                *reinterpret_cast<float4*>(h1 + (a + 4 * i) * XS + 4 * q) = o;
+            }
+        }
+        __syncwarp();
+        // layer 2: 32 -> 64 (two column halves)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float m[4][4] = {};
+            tile16_fma<32, false>(h1, XS, W->w2t, 64, 32 * half, a, q, m);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float* bb = W->b2 + 32 * half + 4 * q;
+                float4 o;
+                o.x = sigmoidf_acc(m[i][0] + bb[0]); o.y = sigmoidf_acc(m[i][1] + bb[1]);
+                o.z = sigmoidf_acc(m[i][2] + bb[2]); o.w = sigmoidf_acc(m[i][3] + bb[3]);
+                *reinterpret_cast<float4*>(h2 + (a + 4 * i) * 68 + 32 * half + 4 * q) = o;
+            }
+        }
+        __syncwarp();
+        // layer 3: 64 -> 32, sigmoid, LeakyReLU, store, statistics
+        {
+            float m[4][4] = {};
+            tile16_fma<64, false>(h2, 68, W->w3t, 32, 0, a, q, m);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int node = node0 + a + 4 * i;
+                if (node < A.n_own) {
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        o[j] = leaky(sigmoidf_acc(m[i][j] + W->b3[4 * q + j]));
+                        s1[j] += (double)o[j];
+                        s2[j] += (double)o[j] * (double)o[j];
+                    }
+                    *reinterpret_cast<float4*>(A.out + (size_t)node * F + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    // fold the four row groups (lanes with equal q) in a fixed order, lanes 0..7 publish
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+    }
+    if (A.part && a == 0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            A.part[(size_t)gwarp * 64 + 4 * q + j] = s1[j];
+            A.part[(size_t)gwarp * 64 + 32 + 4 * q + j] = s2[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine: b1_new = BN_a(pre1) * BN_c(pre2) + middle[i-2]     (TilinGNN.py:64-69)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bn_apply(float x, const float* __restrict__ coef, int c, int C) {
+    return fmaf((x - coef[c]) - coef[C + c], coef[2 * C + c], coef[3 * C + c]);
+}
+
+__global__ void k_combine(const float4* __restrict__ pre1, const float* __restrict__ coef1,
+                          const float4* __restrict__ pre2, const float* __restrict__ coef2,
+                          const float4* __restrict__ res, float4* __restrict__ out, int64_t n4) {
+    __shared__ float c1[128], c2[128];
+    if (threadIdx.x < 128) { c1[threadIdx.x] = coef1[threadIdx.x]; c2[threadIdx.x] = coef2[threadIdx.x]; }
+    __syncthreads();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i & 7) * 4;
+        float4 p = __ldg(pre1 + i), g = __ldg(pre2 + i);
+        float4 o;
+        o.x = bn_apply(p.x, c1, c + 0, 32) * bn_apply(g.x, c2, c + 0, 32);
+        o.y = bn_apply(p.y, c1, c + 1, 32) * bn_apply(g.y, c2, c + 1, 32);
+        o.z = bn_apply(p.z, c1, c + 2, 32) * bn_apply(g.z, c2, c + 2, 32);
+        o.w = bn_apply(p.w, c1, c + 3, 32) * bn_apply(g.w, c2, c + 3, 32);
+        if (res) { float4 r = __ldg(res + i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+        out[i] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// init MLP (TilinGNN.py:31,54): two Linear -> LeakyReLU -> BN stages, recomputed from x per pass.
+// lane = channel, one warp per node (d_x is tiny).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_init(InitArgs A) {
+    __shared__ float w1t[32 * 33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (MODE >= 1) {
+        for (int i = threadIdx.x; i < 32 * 32; i += TPB) w1t[(i >> 5) * 33 + (i & 31)] = __ldg(A.w1t + i);
+        __syncthreads();
+    }
+    float w0[8];
+#pragma unroll
+    for (int d = 0; d < 8; ++d) w0[d] = d < A.d_x ? __ldg(A.w0 + lane * A.d_x + d) : 0.f;
+    const float b0 = __ldg(A.b0 + lane);
+    const float b1 = MODE >= 1 ? __ldg(A.b1 + lane) : 0.f;
+    const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
+    double s1 = 0.0, s2 = 0.0;
+    for (int node = gwarp; node < A.n_own; node += nwarp) {
+        float v = b0;
+        for (int d0 = 0; d0 < A.d_x; d0 += 8) {
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+                if (d0 + d < A.d_x) {
+                    float wv = d0 == 0 ? w0[d] : __ldg(A.w0 + lane * A.d_x + d0 + d);
+                    v = fmaf(__ldg(A.x + (size_t)node * A.d_x + d0 + d), wv, v);
+                }
+        }
+        v = leaky(v);
+        if (MODE >= 1) {
+            float y = bn_apply(v, A.coef0, lane, 32);
+            float o = b1;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o = fmaf(__shfl_sync(0xffffffffu, y, k), w1t[k * 33 + lane], o);
+            v = leaky(o);
+            if (MODE == 2) { A.out[(size_t)node * F + lane] = bn_apply(v, A.coef1, lane, 32); continue; }
+        }
+        s1 += (double)v;
+        s2 += (double)v * (double)v;
+    }
+    if (MODE < 2 && A.part) {
+        A.part[(size_t)gwarp * 64 + lane] = s1;
+        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense stage of the final MLP (TilinGNN.py:45-46,74-76): out = LeakyReLU(BN_in(A) @ Wt + b) and
+// per-column partial sums.  A is either a plain [n][K] matrix or the virtual concat of K/32 slabs.
+// CTA tile 128 rows x BN columns, k-chunks of 32, thread tile 8 x (BN/16).
+// ------------------------------------------------------------------------------------------------
+constexpr int DM = 128, DK = 32;
+
+template <int BN>
+__global__ void __launch_bounds__(256)
+k_dense(DenseArgs A) {
+    constexpr int TN = BN / 16;
+    __shared__ __align__(16) float As[DK][DM + 4];
+    __shared__ __align__(16) float Bs[DK][BN];
+    __shared__ double red[2][BN];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int row0 = blockIdx.x * DM, col0 = blockIdx.y * BN;
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < A.K; k0 += DK) {
+        const float* abase; int lda, koff;
+        if (A.virtual_concat) { abase = A.slabs[k0 / DK]; lda = F; koff = 0; }
+        else { abase = A.a; lda = A.K; koff = k0; }
+        // A tile: 128 rows x 32 k; thread loads float4 (row = tid/8 + 32*j, k4 = tid%8)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = (tid >> 3) + 32 * j, k4 = (tid & 7) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < A.n) v = __ldg(reinterpret_cast<const float4*>(abase + (size_t)(row0 + r) * lda + koff + k4));
+            if (A.in_coef) {
+                const float* cf = A.in_coef; const int C = A.K, c = k0 + k4;
+                v.x = bn_apply(v.x, cf, c + 0, C); v.y = bn_apply(v.y, cf, c + 1, C);
+                v.z = bn_apply(v.z, cf, c + 2, C); v.w = bn_apply(v.w, cf, c + 3, C);
+            }
+            As[k4 + 0][r] = v.x; As[k4 + 1][r] = v.y; As[k4 + 2][r] = v.z; As[k4 + 3][r] = v.w;
+        }
+        // B tile: 32 k x BN cols
+        for (int i = tid; i < DK * BN / 4; i += 256) {
+            const int k = i / (BN / 4), c4 = (i % (BN / 4)) * 4;
+            *reinterpret_cast<float4*>(&Bs[k][c4]) =
+                __ldg(reinterpret_cast<const float4*>(A.wt + (size_t)(k0 + k) * A.n_out + col0 + c4));
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < DK; ++k) {
+            float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+            float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+            float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            float bv[TN];
+#pragma unroll
+            for (int j = 0; j < TN; ++j) bv[j] = Bs[k][tx * TN + j];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // epilogue
+    if (tid < BN) { red[0][tid] = 0.0; red[1][tid] = 0.0; }
+    __syncthreads();
+    double cs1[TN], cs2[TN];
+#pragma unroll
+    for (int j = 0; j < TN; ++j) { cs1[j] = 0.0; cs2[j] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = row0 + ty * 8 + i;
+        if (row < A.n) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int col = col0 + tx * TN + j;
+                float v = leaky(acc[i][j] + __ldg(A.bias + col));
+                A.out[(size_t)row * A.n_out + col] = v;
+                cs1[j] += (double)v; cs2[j] += (double)v * (double)v;
+            }
+        }
+    }
+    // deterministic column reduction over the 16 row groups: ty-ordered accumulation in shared memory
+    for (int t = 0; t < 16; ++t) {
+        if (ty == t) {
+#pragma unroll
+            for (int j = 0; j < TN; ++j) { red[0][tx * TN + j] += cs1[j]; red[1][tx * TN + j] += cs2[j]; }
+        }
+        __syncthreads();
+    }
+    if (A.part && tid < BN) {
+        double* p = A.part + (size_t)blockIdx.x * 2 * A.n_out;
+        p[col0 + tid] = red[0][tid];
+        p[A.n_out + col0 + tid] = red[1][tid];
+    }
+}
+
+// final Linear(32 -> 1) + Sigmoid on BN(a3)   (TilinGNN.py:47)
+__global__ void k_score(const float* __restrict__ a3, const float* __restrict__ coef, const float* __restrict__ w,
+                        float b, float* __restrict__ out, int64_t n) {
+    const int lane = threadIdx.x & 31;
+    const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float wl = __ldg(w + lane);
+    for (int64_t node = gwarp; node < n; node += nwarp) {
+        float v = bn_apply(__ldg(a3 + node * F + lane), coef, lane, 32) * wl;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) out[node] = sigmoidf_acc(v + b);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void k_bn_reduce(const double* __restrict__ part, int n_part, int C2, double* __restrict__ sums) {
+    __shared__ double sh[256];
+    const int j = blockIdx.x;                        // one block per column of [sum | sumsq]
+    double s = 0.0;
+    for (int p = threadIdx.x; p < n_part; p += 256) s += part[(size_t)p * C2 + j];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sums[j] = sh[0];
+}
+
+__global__ void k_bn_coef(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float* __restrict__ coef, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = sums[c] / count;
+    double var = sums[C + c] / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + BN_EPS);
+    const float mh = (float)mean;
+    coef[c] = mh;
+    coef[C + c] = (float)(mean - (double)mh);
+    coef[2 * C + c] = (float)((double)gamma[c] * rstd);
+    coef[3 * C + c] = beta[c];
+}
+
+__global__ void k_bn_coef_eval(const float* __restrict__ rmean, const float* __restrict__ rvar,
+                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                               float* __restrict__ coef, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    coef[c] = rmean[c];
+    coef[C + c] = 0.f;
+    coef[2 * C + c] = (float)((double)gamma[c] / sqrt((double)rvar[c] + BN_EPS));
+    coef[3 * C + c] = beta[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-type edge weights: W_t = sigmoid(A3 sigmoid(A2 sigmoid(A1 e_t + a1) + a2) + a3), evaluated in
+// fp64 and rounded once to fp32  (graph_networks/layers/edge_conv.py:17; util.py:10-17).
+// grid = K types, block = 256.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_edge_table(const float* __restrict__ rows, int d_e,
+                             const float* __restrict__ a1, const float* __restrict__ c1,
+                             const float* __restrict__ a2, const float* __restrict__ c2,
+                             const float* __restrict__ a3, const float* __restrict__ c3,
+                             float* __restrict__ tab) {
+    __shared__ double h1[32], h2[64];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const float* e = rows + (size_t)t * d_e;
+    if (tid < 32) {
+        double s = (double)c1[tid];
+        for (int k = 0; k < d_e; ++k) s += (double)a1[tid * d_e + k] * (double)e[k];
+        h1[tid] = 1.0 / (1.0 + exp(-s));
+    }
+    __syncthreads();
+    if (tid < 64) {
+        double s = (double)c2[tid];
+        for (int k = 0; k < 32; ++k) s += (double)a2[tid * 32 + k] * h1[k];
+        h2[tid] = 1.0 / (1.0 + exp(-s));
+    }
+    __syncthreads();
+    for (int o = tid; o < F * F; o += 256) {
+        double s = (double)c3[o];
+        for (int k = 0; k < 64; ++k) s += (double)a3[(size_t)o * 64 + k] * h2[k];
+        tab[(size_t)t * (F * F) + o] = (float)(1.0 / (1.0 + exp(-s)));
+    }
+}
+
+__global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    int r = i / cols, c = i - r * cols;
+    out[(size_t)c * rows + r] = in[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// halo pack / unpack: rows of two [*, 32] tensors <-> [slot rows][64] exchange buffer
+// ------------------------------------------------------------------------------------------------
+__global__ void k_halo_pack(const float4* __restrict__ a, const float4* __restrict__ b, const int* __restrict__ rows,
+                            int n_send, float4* __restrict__ sendbuf) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_send * 16) return;
+    int r = (int)(i >> 4), c = (int)(i & 15);
+    int row = rows[r];
+    sendbuf[i] = c < 8 ? __ldg(a + (size_t)row * 8 + c) : (b ? __ldg(b + (size_t)row * 8 + (c - 8)) : make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+__global__ void k_halo_unpack(const float4* __restrict__ recv, int world, int rank, int64_t halo_slot, int64_t n_own,
+                              float4* __restrict__ a, float4* __restrict__ b) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)world * halo_slot * 16;
+    if (i >= total) return;
+    int64_t r = i >> 4; int c = (int)(i & 15);
+    if (r / halo_slot == rank) return;               // own slot: rows are read in place
+    float4 v = __ldg(recv + i);
+    if (c < 8) a[(size_t)(n_own + r) * 8 + c] = v; else if (b) b[(size_t)(n_own + r) * 8 + (c - 8)] = v;
+}
+
+int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_per_sm) {
+    int want = work_items_per_block_unit;
+    int cap = sm_count * blocks_per_sm;
+    return want < 1 ? 1 : (want < cap ? want : cap);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+static size_t conv_smem() { return (size_t)WARPS * (WN * XS + CH * XS) * sizeof(float); }
+static size_t gin_smem() { return sizeof(GinSmem) + (size_t)WARPS * GIN_WARP_FLOATS * sizeof(float); }
+
+static int conv_blocks(int n_tiles, int sm_count) { return persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2); }
+static int gin_blocks(int n_own, int sm_count) {
+    int chunks = (n_own + CH - 1) / CH;
+    return persistent_blocks((chunks + WARPS - 1) / WARPS, sm_count, 2);
+}
+static int init_blocks(int n_own, int sm_count) { return persistent_blocks((n_own + WARPS * 8 - 1) / (WARPS * 8), sm_count, 4); }
+
+int conv_adj_num_parts(int n_tiles, int sm_count) { return conv_blocks(n_tiles, sm_count) * WARPS; }
+int gin_num_parts(int n_own, int sm_count) { return gin_blocks(n_own, sm_count) * WARPS; }
+int init_num_parts(int n_own, int sm_count) { return init_blocks(n_own, sm_count) * WARPS; }
+int dense_row_blocks(int n) { return (n + DM - 1) / DM; }
+
+void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem()));
+        attr = true;
+    }
+    k_conv_adj<<<conv_blocks(a.n_tiles, sm_count), TPB, conv_smem(), st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        TGNN_CUDA(cudaFuncSetAttribute(k_gin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem()));
+        attr = true;
+    }
+    k_gin<<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(), st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
+                    const float* residual, float* out, int64_t n_own, cudaStream_t st) {
+    int64_t n4 = n_own * (F / 4);
+    int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
+    if (blocks < 1) blocks = 1;
+    k_combine<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(pre1), coef1,
+                                      reinterpret_cast<const float4*>(pre2), coef2,
+                                      reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), n4);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st) {
+    int blocks = init_blocks(a.n_own, sm_count);
+    if (mode == 0) k_init<0><<<blocks, TPB, 0, st>>>(a);
+    else if (mode == 1) k_init<1><<<blocks, TPB, 0, st>>>(a);
+    else k_init<2><<<blocks, TPB, 0, st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_dense(const DenseArgs& a, cudaStream_t st) {
+    TGNN_CHECK(a.K % DK == 0, "dense stage: K must be a multiple of 32");
+    dim3 grid(dense_row_blocks(a.n), 1);
+    if (a.n_out % 64 == 0) { grid.y = a.n_out / 64; k_dense<64><<<grid, 256, 0, st>>>(a); }
+    else if (a.n_out % 32 == 0) { grid.y = a.n_out / 32; k_dense<32><<<grid, 256, 0, st>>>(a); }
+    else TGNN_CHECK(false, "dense stage: n_out must be a multiple of 32");
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_score(const float* a3, const float* coef, const float* w, float b, float* out, int64_t n, cudaStream_t st) {
+    int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
+    if (blocks < 1) blocks = 1;
+    k_score<<<blocks, 256, 0, st>>>(a3, coef, w, b, out, n);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_bn_reduce(const double* part, int n_part, int C, double* sums_out, cudaStream_t st) {
+    k_bn_reduce<<<2 * C, 256, 0, st>>>(part, n_part, 2 * C, sums_out);
+    TGNN_CUDA(cudaGetLastError());
+}
+void launch_bn_coef(const double* sums, double count, const float* gamma, const float* beta, float* coef_out, int C,
+                    cudaStream_t st) {
+    k_bn_coef<<<(C + 63) / 64, 64, 0, st>>>(sums, count, gamma, beta, coef_out, C);
+    TGNN_CUDA(cudaGetLastError());
+}
+void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gamma, const float* beta, float* coef_out,
+                         int C, cudaStream_t st) {
+    k_bn_coef_eval<<<(C + 63) / 64, 64, 0, st>>>(rmean, rvar, gamma, beta, coef_out, C);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_edge_table(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
+                       const float* c2, const float* a3, const float* c3, float* tab, cudaStream_t st) {
+    if (n_types <= 0) return;
+    k_edge_table<<<n_types, 256, 0, st>>>(type_rows, d_e, a1, c1, a2, c2, a3, c3, tab);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st) {
+    k_transpose<<<(rows * cols + 255) / 256, 256, 0, st>>>(in, out, rows, cols);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_halo_pack(const float* a, const float* b, const int* rows, int n_send, float* sendbuf, cudaStream_t st) {
+    if (n_send <= 0) return;
+    int64_t n = (int64_t)n_send * 16;
+    k_halo_pack<<<(int)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(a),
+                                                        reinterpret_cast<const float4*>(b), rows, n_send,
+                                                        reinterpret_cast<float4*>(sendbuf));
+    TGNN_CUDA(cudaGetLastError());
+}
+void launch_halo_unpack(const float* recv, int world, int rank, int64_t halo_slot, int64_t n_own, float* a, float* b,
+                        cudaStream_t st) {
+    int64_t n = (int64_t)world * halo_slot * 16;
+    if (n <= 0) return;
+    k_halo_unpack<<<(int)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(recv), world, rank, halo_slot,
+                                                          n_own, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b));
+    TGNN_CUDA(cudaGetLastError());
+}
+
+}  // namespace tgnn

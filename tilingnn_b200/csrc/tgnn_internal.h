@@ -1,0 +1,190 @@
+// Internal declarations shared by the translation units of libtgnn.so.
+// Not part of the public ABI (that is include/tgnn.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tgnn.h"
+
+namespace tgnn {
+
+constexpr int F = 32;            // network_width (inputs/config.py:38 of the reference)
+constexpr int WN = 64;           // destination rows owned by one warp tile of the typed adjacency format
+constexpr int CH = 16;           // edge slots per chunk (all of one edge type)
+constexpr int GRP = 8;           // slots per group; destinations are distinct inside a group
+constexpr int MAX_TYPES = 65535; // edge-type ids are 16 bit inside the sort key
+constexpr float LEAKY = 0.01f;
+constexpr double BN_EPS = 1e-5;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define TGNN_CUDA(expr)                                                                       \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess)                                                                \
+            throw ::tgnn::Error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" +   \
+                                __FILE__ + ":" + std::to_string(__LINE__) + ")");             \
+    } while (0)
+
+#define TGNN_CHECK(cond, msg)                                                                 \
+    do {                                                                                      \
+        if (!(cond)) throw ::tgnn::Error(std::string(msg));                                   \
+    } while (0)
+
+// Owning device buffer (grow-only reuse keeps cudaMalloc out of repeated set_graph calls).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        TGNN_CUDA(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// BatchNorm coefficients as consumers apply them:  y = ((x - mu_hi) - mu_lo) * scale + beta
+// layout [4][C] floats: mu_hi, mu_lo, scale, beta.
+struct BnRef {
+    const float* coef = nullptr;   // device, [4][C]
+};
+
+// ----- graph structures (device) -------------------------------------------------------------
+struct Graph {
+    int64_t n_own = 0, n_rows = 0, n_global = 0;
+    int64_t e_adj = 0, e_col = 0;
+    int n_types = 0;
+    int n_tiles = 0;          // ceil(n_own / WN)
+    int n_chunks = 0;
+    // typed adjacency tiles
+    DevBuf cptr;              // int32 [n_tiles + 1]   chunk range per warp tile
+    DevBuf ctype;             // int32 [n_chunks]
+    DevBuf csrc;              // int32 [n_chunks * CH] source row, -1 = empty slot
+    DevBuf cdst;              // uint8 [n_chunks * CH] local destination row in the tile
+    DevBuf inv_deg;           // float [n_own]         1 / max(1, in-degree)
+    DevBuf type_rows;         // float [n_types * d_e] representative feature row per type
+    // collision CSR by destination (self loops removed)
+    DevBuf col_ptr;           // int32 [n_own + 1]
+    DevBuf col_src;           // int32 [e_col]
+    // halo (sharded mode)
+    int64_t halo_slot = 0, n_send = 0;
+    DevBuf send_rows;         // int32 [n_send]
+};
+
+struct Scratch {
+    std::vector<std::unique_ptr<DevBuf>> bufs;
+    size_t next = 0;
+    void reset() { next = 0; }
+    template <class T> T* get(size_t count) {
+        if (next == bufs.size()) bufs.emplace_back(new DevBuf());
+        DevBuf& b = *bufs[next++];
+        b.reserve(count * sizeof(T) + 16);
+        return b.as<T>();
+    }
+};
+
+// graph_build.cu
+void build_graph(Graph& g, Scratch& scratch, int d_e, int64_t n_own, int64_t n_rows,
+                 int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, cudaStream_t st);
+
+// ----- kernels.cu launchers --------------------------------------------------------------------
+struct ConvArgs {
+    const float* xin;        // [n_rows][32]  b1 of the previous layer (materialised)
+    const float* tab;        // [K][32][32]   per-type edge weight, [k_in][k_out]
+    const float* root;       // [32][32]      nnConv.root  [in][out]
+    const float* bias;       // [32]
+    const int* cptr; const int* ctype; const int* csrc; const uint8_t* cdst;
+    const float* inv_deg;
+    float* out;              // pre1 [n_own][32]  LeakyReLU(conv), before BatchNorm
+    double* part;            // [n_part][64]  per-warp partial sums (sum, sum of squares)
+    int n_own, n_tiles;
+};
+int conv_adj_num_parts(int n_tiles, int sm_count);
+void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
+
+struct GinArgs {
+    const float* xin;        // [n_rows][32]  pre-BN activations of the previous collision layer (or h0)
+    const float* in_coef;    // [4][32] BN coefficients to apply lazily to xin; nullptr = identity
+    const int* col_ptr; const int* col_src;
+    const float* w1t; const float* b1;   // [32][32] (k-major), [32]
+    const float* w2t; const float* b2;   // [32][64], [64]
+    const float* w3t; const float* b3;   // [64][32], [32]
+    float eps;
+    float* out;              // pre2 [n_own][32]
+    double* part;            // [n_part][64]
+    int n_own;
+};
+int gin_num_parts(int n_own, int sm_count);
+void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st);
+
+// b1_new = BN(pre1) * BN(pre2) + residual
+void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
+                    const float* residual, float* out, int64_t n_own, cudaStream_t st);
+
+// init MLP: mode 0 = stats of layer 0, 1 = stats of layer 1, 2 = write h0
+struct InitArgs {
+    const float* x; int d_x;
+    const float* w0; const float* b0;    // [32][d_x], [32]
+    const float* w1t; const float* b1;   // [32][32] k-major, [32]
+    const float* coef0; const float* coef1;
+    float* out; double* part; int n_own;
+};
+int init_num_parts(int n_own, int sm_count);
+void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st);
+
+// dense stage of the final MLP: out = LeakyReLU( BN_in(A) @ Wt + b ), plus column statistics
+struct DenseArgs {
+    const float* const* slabs;  // device array of slab pointers when virtual_concat, else nullptr
+    const float* a;             // [n][K] when not virtual_concat
+    int virtual_concat;         // A = concat of K/32 slabs of [n_rows][32]
+    const float* in_coef;       // [4][K] or nullptr
+    const float* wt;            // [K][N_out] k-major
+    const float* bias;          // [N_out]
+    float* out;                 // [n][N_out]
+    double* part;               // [row_blocks][2][N_out]
+    int n, K, n_out;
+};
+int dense_row_blocks(int n);
+void launch_dense(const DenseArgs& a, cudaStream_t st);
+
+void launch_score(const float* a3, const float* coef, const float* w, float b, float* out,
+                  int64_t n, cudaStream_t st);
+
+// BatchNorm statistics: reduce partials (fixed order, fp64) and turn them into coefficients.
+// part layout: [n_part][2*C] (sum[C], sumsq[C]).  sums_out: [2*C] doubles.
+void launch_bn_reduce(const double* part, int n_part, int C, double* sums_out, cudaStream_t st);
+void launch_bn_coef(const double* sums, double count, const float* gamma, const float* beta,
+                    float* coef_out, int C, cudaStream_t st);
+// eval mode: coefficients from running statistics
+void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gamma, const float* beta,
+                         float* coef_out, int C, cudaStream_t st);
+
+// per-type edge weight table: tab[t] = sigmoid MLP(type_rows[t]) in fp64, rounded to fp32
+void launch_edge_table(const float* type_rows, int n_types, int d_e,
+                       const float* a1, const float* c1, const float* a2, const float* c2,
+                       const float* a3, const float* c3, float* tab, cudaStream_t st);
+
+void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);  // out[c][r] = in[r][c]
+
+// halo pack / unpack (sharded mode)
+void launch_halo_pack(const float* a, const float* b, const int* rows, int n_send, float* sendbuf, cudaStream_t st);
+void launch_halo_unpack(const float* recv, int world, int rank, int64_t halo_slot, int64_t n_own,
+                        float* a, float* b, cudaStream_t st);
+
+}  // namespace tgnn

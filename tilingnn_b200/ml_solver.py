@@ -1,0 +1,78 @@
+"""``ML_Solver`` -- the caller side of the scoring path, mirroring
+/root/reference/solver/ml_solver/ml_solver.py:13-81,129-136 (``predict``, ``get_predict_probs``,
+``load_saved_network``) and ``get_network_prediction``
+(/root/reference/graph_networks/network_utils.py:4-21) for the ``tilingnn_b200.TilinGNN`` module.
+
+A "layout" is anything with the five numpy attributes of the reference's ``BrickLayout``
+(/root/reference/tiling/brick_layout.py:22-31): ``node_feature``, ``align_edge_index``,
+``align_edge_features``, ``collide_edge_index``, ``collide_edge_features`` --
+``tilingnn_b200.tile_graph_io.SuperGraph`` is one.
+"""
+from __future__ import annotations
+
+import traceback
+from copy import deepcopy
+
+import numpy as np
+import torch
+
+
+def get_network_prediction(network, x, adj_e_index, adj_e_features, col_e_idx, col_e_features=None):
+    """network_utils.py:4-21: keyword call, print the traceback and re-raise, return probs only."""
+    try:
+        probs, *_ = network(x=x, adj_e_index=adj_e_index, adj_e_features=adj_e_features,
+                            col_e_idx=col_e_idx, col_e_features=col_e_features)
+    except Exception:
+        print(traceback.format_exc())
+        raise
+    return probs
+
+
+def to_torch_tensor(device, node_feature, align_edge_index, align_edge_features, collide_edge_index,
+                    collide_edge_features=None):
+    """util/data_util.py:110-117 -- except that the collision edge FEATURES, which the network never
+    reads (TilinGNN.py:51,63), are not uploaded (9.3 MB of the reference's 16 MB per call on the
+    30-60-90 complete graph)."""
+    pin = device.type == "cuda"
+
+    def up(a, dt):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+        if pin and t.numel() > 0:
+            t = t.pin_memory()
+        return t.to(device, non_blocking=True)
+    return (up(node_feature, torch.float32), up(align_edge_index, torch.int64),
+            up(align_edge_features, torch.float32), up(collide_edge_index, torch.int64), None)
+
+
+class ML_Solver:
+    def __init__(self, debugger, device, complete_graph, network, num_prob_maps=1):
+        if num_prob_maps != 1:
+            raise ValueError("the reference only ever uses num_prob_maps = 1 (Tiling-Shape.py:37)")
+        self.debugger = debugger
+        self.device = torch.device(device)
+        self.complete_graph = complete_graph
+        self.network = network
+        self.random_network = deepcopy(self.network)      # ml_solver.py:26
+        self.num_prob_maps = num_prob_maps
+
+    def predict(self, brick_layout):
+        """ml_solver.py:29-49.  Returns ``np.ndarray[N]`` float32."""
+        n = brick_layout.node_feature.shape[0]
+        if len(brick_layout.collide_edge_index) == 0 or len(brick_layout.align_edge_index) == 0:
+            return np.ones(n, dtype=np.float32)                                   # :31-32
+        x, ai, af, ci, _ = to_torch_tensor(self.device, brick_layout.node_feature, brick_layout.align_edge_index,
+                                           brick_layout.align_edge_features, brick_layout.collide_edge_index)
+        predictions, *_ = self.network(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci, col_e_features=None)
+        # get_best_prob_map (:46,133-136) is argsort over num_prob_maps = 1 losses: always column 0
+        return predictions[:, 0].detach().cpu().numpy()
+
+    def get_predict_probs(self, brick_layout):
+        """ml_solver.py:69-81."""
+        x, ai, af, ci, _ = to_torch_tensor(self.device, brick_layout.node_feature, brick_layout.align_edge_index,
+                                           brick_layout.align_edge_features, brick_layout.collide_edge_index)
+        return get_network_prediction(self.network, x, ai, af, ci)
+
+    def load_saved_network(self, net_path):
+        """ml_solver.py:129-131 -- including the ``.train()`` that makes inference use batch statistics."""
+        self.network.load_state_dict(torch.load(net_path, map_location=self.device, weights_only=True))
+        self.network.train()
