@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the TilinGNN scoring forward pass (BASELINE.json: node-scores/sec on a 1M-node,
+avg-degree-32 super-graph; HBM GB/s vs roofline).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU algorithm (oracle port)
+
+A "step" is one full forward (6 message-passing layers + init/final MLP, train-mode BatchNorm --
+the reference's behaviour) over one synthetic super-graph of ``--nodes`` nodes per GPU (weak
+scaling: every rank owns ``--nodes`` nodes of an N x larger lattice graph, halo all-gather + BN
+all-reduce per layer).  ``value`` is timed with CUDA events with the graph resident in HBM;
+``e2e`` goes through the reference-facing call (host numpy arrays in, host scores out, graph
+structures rebuilt every call as the reference's per-call topology requires).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "node-scores/sec"
+UNIT = "node-scores/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="tilingnn", choices=["tilingnn", "reference"])
+    ap.add_argument("--nodes", type=int, default=1_000_000, help="nodes per GPU")
+    ap.add_argument("--deg", type=int, default=32, help="adjacency and collision stencil size")
+    ap.add_argument("--depth", type=int, default=6)
+    ap.add_argument("--bn", default="train", choices=["train", "eval"])
+    ap.add_argument("--graph", default="lattice", choices=["lattice", "random"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample-nodes", type=int, default=0, help="0 = calibrate to ~15 s")
+    return ap.parse_args()
+
+
+D_X, D_E = 3, 19
+
+
+def bytes_per_node_model(L, d_adj, d_col, bn):
+    """ALGORITHMIC bytes per node-score (SURVEY.md §8d / BASELINE.md §3)."""
+    if bn == "train":
+        return L * (1032 + 8 * d_adj + 4 * d_col) - 256 + (8 * D_X + 128) + (128 * (L + 1) + 3844)
+    return L * (648 + 8 * d_adj + 4 * d_col) - 256 + (4 * D_X + 128) + (128 * (L + 1) + 4)
+
+
+def kernel_bytes_model(fam, n, e_adj, e_col, L):
+    """ALGORITHMIC bytes of ONE launch of a kernel family."""
+    if fam == "conv":      # read b1 rows once, write pre1, 8 B per adjacency edge (index + type/dst), 4 B/row
+        return n * 260 + 8 * e_adj
+    if fam == "gin":       # read pre2 rows once, write pre2', 4 B per collision edge, row pointers
+        return n * 260 + 4 * e_col
+    if fam == "combine":   # pre1, pre2, residual in; b1 out
+        return n * 512
+    if fam == "final":     # averaged over the four dense stages: 128(L+1) + 2*4*(256+128+64+32) - 128 (a3 read by score)
+        return n * (128 * (L + 1) + 8 * 480 - 128) / 4
+    if fam == "init":
+        return n * (8 * D_X + 128) / 3
+    return 0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        for r in rows:
+            f = [s.strip() for s in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def seeded_state_dict(depth):
+    """Random-init weights of the benchmarked architecture (torch default init, seed 0) under the
+    reference's keys -- shared by the CUDA arm and the CPU baseline."""
+    import torch
+    from tilingnn_b200 import TilinGNN
+    torch.manual_seed(0)
+    net = TilinGNN(D_E, depth, 32, node_features_dim=D_X)
+    return net, {k: v.clone() for k, v in net.state_dict().items()}
+
+
+def make_graph(args, n_global, lo, hi, device):
+    from tilingnn_b200 import synthetic as syn
+    if args.graph == "random":
+        assert lo == 0 and hi == n_global, "random graphs are single-GPU only"
+        return syn.random_graph(n_global, args.deg, args.deg, D_X, D_E, seed=0, device=device)
+    return syn.lattice_graph(n_global, args.deg, args.deg, D_X, D_E, seed=0, device=device, lo=lo, hi=hi)
+
+
+def cpu_reference_rate(args, steps, warmup, sample_nodes=0, budget_s=15.0):
+    """The reference's algorithm (per-edge MLP -> [E,1024] weights, scatter-mean, GIN, train-BN) as
+    restated in oracle/tilingnn_oracle.py, fp32, torch CPU with all host threads."""
+    import torch
+    from oracle import tilingnn_oracle as orc
+    from tilingnn_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    _, sd = seeded_state_dict(args.depth)
+
+    def one(n):
+        x, ai, af, ci = syn.lattice_graph(n, args.deg, args.deg, D_X, D_E, seed=0)
+        t = time.perf_counter()
+        with torch.no_grad():
+            orc.forward(sd, x, ai, af, ci, depth=args.depth, bn_mode=args.bn, dtype=torch.float32)
+        return time.perf_counter() - t
+    n = sample_nodes
+    if n <= 0:
+        one(500)                                              # thread-pool / allocator warm-up
+        t_cal = one(2000)
+        per_step = budget_s / max(1, steps + warmup)
+        n = int(min(args.nodes, max(1000, 2000 * per_step / max(t_cal, 1e-3))))
+    for _ in range(warmup):
+        one(n)
+    ts = [one(n) for _ in range(max(1, steps))]
+    mean = sum(ts) / len(ts)
+    return {"value": n / mean, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n}-node lattice, deg {args.deg}+{args.deg}, depth {args.depth}, fp32, {args.bn}-BN, "
+                      f"{len(ts)} step(s) of {mean:.2f} s on {cores} threads (oracle/tilingnn_oracle.py)"}, mean, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, mean, n = cpu_reference_rate(args, args.steps, args.warmup, args.cpu_sample_nodes, budget_s=120.0)
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic lattice super-graph, avg-deg {args.deg} adj + {args.deg} col, "
+                                   f"{args.depth} layers, width 32, {args.bn}-mode BatchNorm; CPU sample of {n} nodes "
+                                   f"(the reference materialises [E,1024] fp32 per layer: 131 GB at 1M nodes)"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0 and not os.path.exists(ge.LIB):
+        ge.build()                                   # normally prebuilt in-tree and shipped with the snapshot
+    if world > 1:
+        dist.barrier()
+    from tilingnn_b200 import shard as shard_mod
+    warmup = max(3, args.warmup)
+
+    n_global = args.nodes * world
+    bounds = shard_mod.even_bounds(n_global, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    net, sd = seeded_state_dict(args.depth)
+    net = net.to(dev)
+    net.train() if args.bn == "train" else net.eval()
+    x, ai, af, ci = make_graph(args, n_global, lo, hi, dev)
+    e_adj, e_col, n_own = ai.shape[1], ci.shape[1], hi - lo
+    plan = None
+    if world > 1:
+        net.shard_init()
+        plan = shard_mod.make_plan(n_global, bounds, ai, ci)
+        net.set_graph_shard(plan, af)
+    else:
+        net.set_graph(n_own, ai, af, ci)
+    out = torch.empty(n_own, dtype=torch.float32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        net.score(x, out=out)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        net.score(x, out=out)
+    ev1.record()
+    barrier()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_global / (ms_step * 1e-3)
+    info = net.info()
+    assert bool(torch.isfinite(out).all()), "non-finite scores"
+
+    # ---- per-kernel-family device times (CUDA events on the launch stream, inside the library) ----
+    net.set_profiling(True)
+    fam_ms = {}
+    reps = 3
+    for _ in range(reps):
+        net.score(x, out=out)
+        for fam, (ms, nl) in net.profile().items():
+            a = fam_ms.setdefault(fam, [0.0, 0])
+            a[0] += ms / reps; a[1] = nl
+    net.set_profiling(False)
+    torch.cuda.synchronize()
+    peak, peak_src = measured_peaks()
+    dom = max(fam_ms, key=lambda f: fam_ms[f][0])
+    dom_ms, dom_launches = fam_ms[dom]
+    per_launch_ms = dom_ms / max(1, dom_launches)
+    kb = kernel_bytes_model(dom, n_own, e_adj, e_col, args.depth)
+    achieved = kb / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+    traffic = None
+    prof_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(prof_json):
+        try:
+            traffic = json.load(open(prof_json)).get("traffic_bytes_per_launch", {}).get(dom)
+        except Exception:
+            traffic = None
+    bpn = bytes_per_node_model(args.depth, e_adj / n_own, e_col / n_own, args.bn)
+    fwd_gbs = bpn * n_own / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the reference-facing call, HOST buffers in / out -----------------------
+    e2e = None
+    if not args.no_e2e:
+        h = [t.cpu().pin_memory() for t in (x, ai, af, ci)]
+        h2d = sum(t.numel() * t.element_size() for t in h)
+        host_out = torch.empty(n_own, dtype=torch.float32).pin_memory()
+        del ai, af, ci
+        torch.cuda.empty_cache()
+
+        def e2e_step():
+            d = [t.to(dev, non_blocking=True) for t in h]
+            if world > 1:
+                p = shard_mod.make_plan(n_global, bounds, d[1], d[3])
+                net.set_graph_shard(p, d[2])
+                s = net.score(d[0])
+            else:
+                s = net(x=d[0], adj_e_index=d[1], adj_e_features=d[2], col_e_idx=d[3])[0][:, 0]
+            host_out.copy_(s, non_blocking=True)
+        e2e_step()
+        barrier()
+        t_a = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t_a) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n_global / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_own * 4),
+               "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "note": "pinned host arrays -> H2D -> graph structures rebuilt -> forward -> D2H scores, per step; per rank bytes"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _, _ = cpu_reference_rate(args, steps=1, warmup=0, sample_nodes=args.cpu_sample_nodes)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"synthetic {args.graph} super-graph, {args.nodes} nodes per GPU ({n_global} total), "
+                                   f"avg-deg {e_adj / n_own:.1f} adj + {e_col / n_own:.1f} col, {args.depth} layers, width 32, "
+                                   f"{args.bn}-mode BatchNorm (reference behaviour), {info['n_edge_types']} edge types",
+                       "nodes_per_gpu": args.nodes, "deg": args.deg, "depth": args.depth, "bn": args.bn,
+                       "parallelism": f"node-range shards x{world}" if world > 1 else "single GPU",
+                       "l2_policy": f"no flush needed: per-step working set {info['workspace_bytes'] / 1e9:.1f} GB >> 126 MB L2"},
+            "roofline": {"bound": "hbm", "kernel": {"conv": "k_conv_adj", "gin": "k_gin", "final": "k_dense",
+                                                    "combine": "k_combine"}.get(dom, dom),
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": kb, "ms_per_launch": per_launch_ms,
+                         "share_of_step": dom_ms / max(1e-9, sum(v[0] for v in fam_ms.values())),
+                         "forward": {"algorithmic_bytes_per_node": bpn, "achieved": fwd_gbs, "frac": fwd_gbs / peak}},
+            "kernel_ms": {f: round(v[0], 4) for f, v in fam_ms.items()},
+            "cpu_baseline": cpu_baseline,
+            "e2e": e2e,
+            "gpu_launches": int(info["launches_per_forward"]) * args.steps,
+            "collectives_per_step": int(info["collectives_per_forward"]),
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

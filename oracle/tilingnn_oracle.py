@@ -36,6 +36,7 @@ from __future__ import annotations
 
 import torch
 
+_BN_CAPTURE = None      # set by forward(_capture_bn=True): {bn prefix: (mean, biased var)}
 LEAKY_SLOPE = 0.01      # torch.nn.LeakyReLU() default, TilinGNN.py:31,46
 BN_EPS = 1e-5           # torch.nn.BatchNorm1d default
 
@@ -54,6 +55,8 @@ def batch_norm(h, p, prefix, bn_mode):
     if bn_mode == "train":
         mu = h.mean(dim=0)
         var = ((h - mu) ** 2).mean(dim=0)          # biased, as F.batch_norm uses for normalisation
+        if _BN_CAPTURE is not None:
+            _BN_CAPTURE[prefix] = (mu.clone(), var.clone())
     else:
         mu = p[prefix + ".running_mean"]
         var = p[prefix + ".running_var"]
@@ -118,7 +121,7 @@ def ginconv(x, edge_index, p, prefix):
 
 def forward(params, x, adj_e_index, adj_e_features, col_e_idx, *, depth,
             bn_mode="train", dtype=torch.float64, return_intermediates=False,
-            edge_chunk=1 << 16):
+            edge_chunk=1 << 16, _capture_bn=False):
     """``TilinGNN.forward`` (TilinGNN.py:51-78).  Returns scores ``[N, 1]``.
 
     ``params``: reference state_dict (tensors, any float dtype); cast to ``dtype``.
@@ -130,6 +133,8 @@ def forward(params, x, adj_e_index, adj_e_features, col_e_idx, *, depth,
     adj_e_index = adj_e_index.long()
     col_e_idx = col_e_idx.long()
     inter = {}
+    global _BN_CAPTURE
+    _BN_CAPTURE = {} if _capture_bn else None
 
     h = mlp(x, p, "init_node_feature_trans", 2, "leaky", True, bn_mode)     # TilinGNN.py:54
     b1 = b2 = h
@@ -155,10 +160,26 @@ def forward(params, x, adj_e_index, adj_e_features, col_e_idx, *, depth,
     z = torch.cat(middle, 1)                                               # TilinGNN.py:74
     z = mlp(z, p, "final_mlp.0", 4, "leaky", True, bn_mode)                # TilinGNN.py:45-46
     score = linear_trans(z, p, "final_mlp.1", "sigmoid", False, bn_mode)   # TilinGNN.py:47
+    if _capture_bn:
+        inter["bn_stats"], _BN_CAPTURE = _BN_CAPTURE, None
     if return_intermediates:
         inter["h0"] = h
         return score, inter
     return score
+
+
+def calibrate_running_stats(params, x, adj_e_index, adj_e_features, col_e_idx, *, depth):
+    """Copy of ``params`` whose BatchNorm running statistics are the (biased) batch statistics of a
+    train-mode fp64 forward on this graph -- so that an eval-mode forward of a synthetic network is
+    not saturated (with arbitrary running statistics it is: SURVEY.md §8c) and equals the train-mode
+    one up to rounding."""
+    _, it = forward(params, x, adj_e_index, adj_e_features, col_e_idx, depth=depth, bn_mode="train",
+                    dtype=torch.float64, return_intermediates=True, _capture_bn=True)
+    out = dict(params)
+    for k, (mu, var) in it["bn_stats"].items():
+        out[k + ".running_mean"] = mu.to(torch.float32)
+        out[k + ".running_var"] = var.to(torch.float32)
+    return out
 
 
 def predict(params, node_feature, align_edge_index, align_edge_features,

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Run on the B200 box (under gpurun): headline bench, ncu launch list, ncu --set full on the top kernels.
+# Outputs land in gpurun_out/ ; the summaries that matter are copied to profiles/ afterwards.
+set -u
+OUT=gpurun_out; mkdir -p $OUT
+TAG=${1:-r1}
+python bench.py --steps 10 --warmup 3 > $OUT/bench_${TAG}.json 2> $OUT/bench_${TAG}.err
+tail -c 3000 $OUT/bench_${TAG}.json; tail -5 $OUT/bench_${TAG}.err
+for cfg in "10000 8" "100000 32" "1000000 8"; do
+  set -- $cfg
+  python bench.py --steps 20 --warmup 3 --nodes $1 --deg $2 --no-cpu-baseline --e2e-steps 2 > $OUT/bench_${TAG}_n$1_d$2.json 2>> $OUT/bench_${TAG}.err
+done
+# every launch with its device time (cold cache, serialised: compare SHARES)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_${TAG}.csv \
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_${TAG}.log 2>&1
+# full capture of the three heaviest kernels (one forward's worth each)
+ncu --set full --clock-control none --import-source on -k regex:'k_conv_adj|k_gin|k_dense' -s 12 -c 6 \
+    -o $OUT/prof_${TAG} -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_full_${TAG}.log 2>&1
+ls -la $OUT

@@ -144,7 +144,10 @@ def test_synthetic_configs_vs_oracle(dev, n, deg, mode):
     from tilingnn_b200 import synthetic as syn
     x, ai, af, ci = syn.lattice_graph(n, deg, deg, seed=0)
     p = orc.make_params(3, 19, 6, seed=0)
+    if mode == "eval":      # running statistics = this graph's batch statistics, else the net saturates to 0
+        p = orc.calibrate_running_stats(p, x, ai, af, ci, depth=6)
     gold = orc.forward(p, x, ai, af, ci, depth=6, bn_mode=mode, dtype=torch.float64)[:, 0].numpy()
+    assert gold.std() > 0.05
     net = make_net(p, 3, 19, 6, dev, mode)
     s = run(net, x, ai, af, ci, dev)
     err = np.abs(s - gold).max()

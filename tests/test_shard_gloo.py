@@ -1,0 +1,81 @@
+"""world_size-2 (and 3) gloo tests of the node-range sharding plan (host logic of the N>1 path)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, deg, q):
+    try:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from tilingnn_b200 import shard, synthetic as syn
+        bounds = shard.even_bounds(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        x, ai, af, ci = syn.lattice_graph(n, deg, deg, seed=1, lo=lo, hi=hi)
+        plan = shard.make_plan(n, bounds, ai, ci)
+        gid = plan.global_id_of_local_rows()
+        # every remapped source points at a local row that mirrors the right global node
+        assert torch.equal(gid[plan.adj_src_local], ai[0])
+        assert torch.equal(gid[plan.col_src_local], ci[0])
+        assert torch.equal(plan.adj_dst_local + lo, ai[1]) and torch.equal(plan.col_dst_local + lo, ci[1])
+        assert plan.adj_dst_local.min() >= 0 and plan.adj_dst_local.max() < plan.n_own
+        # the send list is made of own rows only, sorted, and equals what this rank publishes
+        assert (plan.send_rows >= 0).all() and (plan.send_rows < plan.n_own).all()
+        assert torch.equal(plan.send_rows + lo, plan.publish_lists[rank])
+        assert all(p.numel() <= plan.halo_slot for p in plan.publish_lists)
+        # halo is a boundary effect on a lattice: far smaller than the shard
+        assert plan.send_rows.numel() < 0.5 * plan.n_own
+        # emulate one halo exchange with gloo and check a gather through local rows
+        feat = torch.arange(lo, hi, dtype=torch.float32).unsqueeze(1).repeat(1, 4)     # row i holds its global id
+        local = torch.zeros(plan.n_rows, 4)
+        local[: plan.n_own] = feat
+        slot = torch.zeros(plan.halo_slot, 4)
+        slot[: plan.send_rows.numel()] = feat[plan.send_rows]
+        slots = [torch.zeros_like(slot) for _ in range(world)]
+        dist.all_gather(slots, slot)
+        local[plan.n_own:] = torch.cat(slots)
+        assert torch.equal(local[plan.adj_src_local][:, 0], ai[0].float())
+        assert torch.equal(local[plan.col_src_local][:, 0], ci[0].float())
+        q.put((rank, "ok", int(plan.halo_slot), int(plan.n_own)))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc(), 0, 0))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,deg", [(2, 6000, 8), (3, 5000, 32)])
+def test_shard_plan_gloo(world, n, deg):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, deg, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+    assert sum(r[3] for r in res) == n
+
+
+def test_even_bounds():
+    from tilingnn_b200 import shard
+    for n, w in ((1000000, 8), (10000, 2), (100, 4), (63, 2)):
+        b = shard.even_bounds(n, w)
+        assert b[0] == 0 and b[-1] == n and len(b) == w + 1
+        assert all(b[i] <= b[i + 1] for i in range(w))
+        assert all(x % 64 == 0 or x == n for x in b[:-1])

@@ -260,6 +260,50 @@ class TilinGNN(nn.Module):
         _lib.check(nat.h, rc, "tgnn_forward")
         return out
 
+    # ---- multi-GPU: node-range shards --------------------------------------------
+    def shard_init(self, group=None):
+        """Join this module's handle to an NCCL communicator of its own (one process per GPU).
+        ``torch.distributed`` must be initialised; it only carries the 128-byte unique id."""
+        import torch.distributed as dist
+        nat = self._sync()
+        lib = _lib.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        dev = self._device()
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            _lib.check(None, lib.tgnn_nccl_unique_id(buf), "tgnn_nccl_unique_id")
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        carrier = uid.to(dev) if dist.get_backend(group) == "nccl" else uid
+        dist.broadcast(carrier, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(carrier.cpu().tolist())
+        with torch.cuda.device(dev):
+            rc = lib.tgnn_shard_init(nat.h, C.c_char_p(raw), rank, world)
+        _lib.check(nat.h, rc, "tgnn_shard_init")
+        nat.shard = (rank, world)
+
+    def set_graph_shard(self, plan, adj_e_features):
+        """``plan``: tilingnn_b200.shard.ShardPlan for this rank; ``adj_e_features`` [E_a, d_e] of the
+        rank's own adjacency edges (same order as the plan's edge arrays)."""
+        nat = self._sync()
+        if nat.shard is None:
+            raise RuntimeError("set_graph_shard: call shard_init() first")
+        lib = _lib.load()
+        dev = self._device()
+        mv = lambda t: t.to(dev).to(torch.int64).contiguous()
+        a_src, a_dst = mv(plan.adj_src_local), mv(plan.adj_dst_local)
+        c_src, c_dst = mv(plan.col_src_local), mv(plan.col_dst_local)
+        send = mv(plan.send_rows)
+        feat = adj_e_features.to(dev).to(torch.float32).contiguous() if a_src.numel() else None
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = lib.tgnn_set_graph_shard(nat.h, plan.n_own, plan.n_global, plan.halo_slot, send.numel(), _ptr(send),
+                                          a_src.numel(), _ptr(a_src), _ptr(a_dst), _ptr(feat),
+                                          c_src.numel(), _ptr(c_src), _ptr(c_dst), C.c_void_p(st))
+        nat.graph_key = None
+        _lib.check(nat.h, rc, "tgnn_set_graph_shard")
+        nat.num_nodes = plan.n_own
+
     # ---- the reference signature ---------------------------------------------------------------
     def forward(self, x, adj_e_index, adj_e_features, col_e_idx, col_e_features=None):
         nat = self._ensure_handle()
