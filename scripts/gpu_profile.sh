@@ -11,7 +11,7 @@ for cfg in "10000 8" "100000 32" "1000000 8"; do
   python bench.py --steps 20 --warmup 3 --nodes $1 --deg $2 --no-cpu-baseline --e2e-steps 2 > $OUT/bench_${TAG}_n$1_d$2.json 2>> $OUT/bench_${TAG}.err
 done
 # every launch with its device time (cold cache, serialised: compare SHARES)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_${TAG}.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'^k_|k_conv|k_gin|k_dense|k_init|k_bn|k_comb|k_score' -c 400 --csv --log-file $OUT/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_${TAG}.log 2>&1
 # full capture of the three heaviest kernels (one forward's worth each)
 ncu --set full --clock-control none --import-source on -k regex:'k_conv_adj|k_gin|k_dense' -s 12 -c 6 \

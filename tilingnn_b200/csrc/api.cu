@@ -78,14 +78,14 @@ struct tgnn_handle {
 
     // derived parameter layouts
     DevBuf init_w1t;
-    std::vector<std::unique_ptr<DevBuf>> gin_wt;    // 3 per layer
+    std::vector<std::unique_ptr<DevBuf>> gin_wt;    // per layer: frag tables W1|W2|W3 and biases b1|b2|b3
     std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4
     std::vector<float> gin_eps;
     float fin_last_bias = 0.f;
     DevBuf coef;                                    // all BatchNorm coefficient blocks
     size_t coef_init[2]{}, coef_fin[4]{};
     std::vector<size_t> coef_a, coef_c;
-    DevBuf tab;                                     // [L][K][32][32]
+    DevBuf tab;                                     // [L][K+1][2048] frag tables (entry K = root)
 
     // workspace
     std::vector<std::unique_ptr<DevBuf>> mid;
@@ -182,14 +182,25 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
     h->init_w1t.reserve(32 * 32 * sizeof(float));
     launch_transpose(h->P("init_node_feature_trans.mlp.1.linear.weight"), h->init_w1t.as<float>(), 32, 32, st);
     h->gin_wt.clear(); h->gin_eps.assign(L, 0.f);
+    DevBuf tmp_t;
     for (int i = 0; i < L; ++i) {
         std::string p = "brch_2_coll_conv_layers." + std::to_string(i);
         int dims[4] = {F, 32, 64, F};
+        h->gin_wt.emplace_back(new DevBuf());
+        h->gin_wt.back()->reserve((size_t)TG_GIN_WFLOATS * sizeof(float));
+        float* wf = h->gin_wt.back()->as<float>();
+        const size_t off[3] = {0, 2048, 2048 + 4096};
+        const int kmap[3] = {TG_KMAP_NATURAL, TG_KMAP_CHAIN, TG_KMAP_CHAIN};
+        const int nmap[3] = {TG_NMAP_NATURAL, TG_NMAP_NATURAL, TG_NMAP_CONTIG8};
+        float* boff = wf + 2048 + 4096 + 4096;
         for (int k = 0; k < 3; ++k) {
-            h->gin_wt.emplace_back(new DevBuf());
-            h->gin_wt.back()->reserve((size_t)dims[k] * dims[k + 1] * sizeof(float));
-            launch_transpose(h->P(p + ".ginConv.nn.mlp." + std::to_string(k) + ".linear.weight"),
-                             h->gin_wt.back()->as<float>(), dims[k + 1], dims[k], st);
+            const std::string lin = p + ".ginConv.nn.mlp." + std::to_string(k) + ".linear";
+            tmp_t.reserve((size_t)dims[k] * dims[k + 1] * sizeof(float));
+            launch_transpose(h->P(lin + ".weight"), tmp_t.as<float>(), dims[k + 1], dims[k], st);       // -> [K][N]
+            launch_frag_pack(tmp_t.as<float>(), dims[k], dims[k + 1], kmap[k], nmap[k], wf + off[k], st);
+            TGNN_CUDA(cudaMemcpyAsync(boff, h->P(lin + ".bias"), dims[k + 1] * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            boff += dims[k + 1];
+            TGNN_CUDA(cudaStreamSynchronize(st));                                                        // tmp_t is reused
         }
         TGNN_CUDA(cudaMemcpyAsync(&h->gin_eps[i], h->P(p + ".ginConv.eps"), sizeof(float), cudaMemcpyDeviceToHost, st));
     }
@@ -233,16 +244,17 @@ void eval_coefs(tgnn_handle* h, cudaStream_t st) {
 void build_tables(tgnn_handle* h, cudaStream_t st) {
     if (!h->tables_dirty) return;
     const int L = h->cfg.depth, K = h->g.n_types;
-    if (K > 0) {
-        h->tab.reserve((size_t)L * K * F * F * sizeof(float));
-        for (int i = 0; i < L; ++i) {
-            std::string p = "brch_1_graph_conv_layers." + std::to_string(i) + ".mlp.mlp.";
-            launch_edge_table(h->g.type_rows.as<float>(), K, h->cfg.d_e,
-                              h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
-                              h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
-                              h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"),
-                              h->tab.as<float>() + (size_t)i * K * F * F, st);
-        }
+    h->tab.reserve((size_t)L * (K + 1) * TG_FRAG32 * sizeof(float));
+    for (int i = 0; i < L; ++i) {
+        const std::string c = "brch_1_graph_conv_layers." + std::to_string(i);
+        const std::string p = c + ".mlp.mlp.";
+        float* base = h->tab.as<float>() + (size_t)i * (K + 1) * TG_FRAG32;
+        launch_edge_table(h->g.type_rows.as<float>(), K, h->cfg.d_e,
+                          h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
+                          h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
+                          h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), base, st);
+        // nnConv.root is [in][out] = k-major already
+        launch_frag_pack(h->P(c + ".nnConv.root"), F, F, TG_KMAP_GATHER, TG_NMAP_CONTIG8, base + (size_t)K * TG_FRAG32, st);
     }
     h->tables_dirty = false;
 }
@@ -352,8 +364,8 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         std::string pc = "brch_2_coll_conv_layers." + std::to_string(i);
         ConvArgs ca{};
         ca.xin = h->mid[i]->as<float>();
-        ca.tab = h->tab.as<float>() + (size_t)i * h->g.n_types * F * F;
-        ca.root = h->P(pa + ".nnConv.root"); ca.bias = h->P(pa + ".nnConv.bias");
+        ca.tabF = h->tab.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32;
+        ca.n_types = h->g.n_types; ca.bias = h->P(pa + ".nnConv.bias");
         ca.cptr = h->g.cptr.as<int>(); ca.ctype = h->g.ctype.as<int>(); ca.csrc = h->g.csrc.as<int>();
         ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->g.inv_deg.as<float>();
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
@@ -364,9 +376,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ga.xin = i == 0 ? h->mid[0]->as<float>() : h->pre2[(i - 1) & 1].as<float>();
         ga.in_coef = i == 0 ? nullptr : h->C(h->coef_c[i - 1]);
         ga.col_ptr = h->g.col_ptr.as<int>(); ga.col_src = h->g.col_src.as<int>();
-        ga.w1t = h->gin_wt[3 * i + 0]->as<float>(); ga.b1 = h->P(pc + ".ginConv.nn.mlp.0.linear.bias");
-        ga.w2t = h->gin_wt[3 * i + 1]->as<float>(); ga.b2 = h->P(pc + ".ginConv.nn.mlp.1.linear.bias");
-        ga.w3t = h->gin_wt[3 * i + 2]->as<float>(); ga.b3 = h->P(pc + ".ginConv.nn.mlp.2.linear.bias");
+        ga.wfrag = h->gin_wt[i]->as<float>();
         ga.eps = h->gin_eps[i];
         ga.out = h->pre2[i & 1].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
         lz.begin("gin"); launch_gin(ga, h->sm_count, st); lz.end(1);

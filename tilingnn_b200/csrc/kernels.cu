@@ -16,6 +16,72 @@ constexpr int TPB = WARPS * 32;
 __device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
 __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-core building block: mma.sync m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi),
+// which keeps fp32-level accuracy (dropped term ~2^-22) -- needed for the 1e-4 parity bar, single
+// TF32 (2^-11) is not enough.  The irregular 16-row chunks of this path (16 gathered edges of one
+// type; 16 nodes of the GIN MLP) are below tcgen05's minimum M of 64, so they use the warp-level
+// mma.sync path; operands are laid out so that NO shared-memory staging of A is needed:
+//   * K is permuted so a lane's two float4 loads of a gathered row ARE its A fragments,
+//   * N is permuted so a lane ends up with 8 contiguous output channels (float4 RMW / stores),
+//   * chained layers use the previous C fragments directly as the next A fragments.
+// B fragments come from tables pre-split into hi/lo and stored in fragment order ("frag tables"):
+//   float4 index ((ks*2 + hl) * (N/16) + j) * 32 + lane ; float4 = {b0,b1 of n-tile 2j, b0,b1 of n-tile 2j+1}
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rna(x);
+    lo = tf32_rna(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// 3xTF32 update of one n-tile pair held in a float4 of hi and a float4 of lo B fragments
+__device__ __forceinline__ void mma3(float (&c0)[4], float (&c1)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
+                                     const float4& bh, const float4& bl) {
+    mma_tf32(c0, alo, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    mma_tf32(c0, ahi, __float_as_uint(bl.x), __float_as_uint(bl.y));
+    mma_tf32(c0, ahi, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    mma_tf32(c1, alo, __float_as_uint(bh.z), __float_as_uint(bh.w));
+    mma_tf32(c1, ahi, __float_as_uint(bl.z), __float_as_uint(bl.w));
+    mma_tf32(c1, ahi, __float_as_uint(bh.z), __float_as_uint(bh.w));
+}
+
+// K / N index maps of the frag tables.
+//  KMAP_GATHER : A comes from two float4 loads per row (cols 4t.., 16+4t..): k-step ks, slot kk=tt+4e  <-> col 16(ks>>1)+4tt+2(ks&1)+e
+//  KMAP_NATURAL: A comes from shared memory, col = 8ks + kk
+//  KMAP_CHAIN  : A is the previous layer's C fragment: k-step ks = previous n-tile, slot kk=tt+4e <-> unit 8ks + 2tt + e
+//  NMAP_NATURAL: unit = 8nt + g          NMAP_CONTIG8: channel = 8(g>>1) + 2nt + (g&1)   (N = 32 only)
+enum { KMAP_GATHER = 0, KMAP_NATURAL = 1, KMAP_CHAIN = 2, NMAP_NATURAL = 0, NMAP_CONTIG8 = 1 };
+
+__host__ __device__ __forceinline__ void frag_coords(int k, int n, int kmap, int nmap, int& ks, int& tt, int& e, int& nt, int& g) {
+    if (kmap == KMAP_GATHER) { int r = k & 15; ks = 2 * (k >> 4) + ((r >> 1) & 1); tt = r >> 2; e = r & 1; }
+    else if (kmap == KMAP_NATURAL) { ks = k >> 3; int kk = k & 7; tt = kk & 3; e = kk >> 2; }
+    else { ks = k >> 3; int r = k & 7; tt = r >> 1; e = r & 1; }
+    if (nmap == NMAP_NATURAL) { nt = n >> 3; g = n & 7; }
+    else { int r = n & 7; nt = r >> 1; g = 2 * (n >> 3) + (r & 1); }
+}
+// float index of element (k, n), hi (hl=0) or lo (hl=1) part, in a frag table of an [K x N] matrix
+__host__ __device__ __forceinline__ size_t frag_index(int k, int n, int N, int kmap, int nmap, int hl) {
+    int ks, tt, e, nt, g;
+    frag_coords(k, n, kmap, nmap, ks, tt, e, nt, g);
+    const int lane = g * 4 + tt, j = nt >> 1, comp = 2 * (nt & 1) + e;
+    return ((((size_t)ks * 2 + hl) * (N / 16) + j) * 32 + lane) * 4 + comp;
+}
+__device__ __forceinline__ void frag_store(float* tab, int k, int n, int N, int kmap, int nmap, double w) {
+    const uint32_t hi = tf32_rna((float)w);
+    const uint32_t lo = tf32_rna((float)(w - (double)__uint_as_float(hi)));
+    tab[frag_index(k, n, N, kmap, nmap, 0)] = __uint_as_float(hi);
+    tab[frag_index(k, n, N, kmap, nmap, 1)] = __uint_as_float(lo);
+}
+
 __device__ __forceinline__ float4 ld_row4(const float* base, int row, int q) {
     return __ldg(reinterpret_cast<const float4*>(base + (size_t)row * F) + q);
 }
@@ -50,66 +116,104 @@ __device__ __forceinline__ void tile16_fma(const float* __restrict__ xs, int xst
 // ------------------------------------------------------------------------------------------------
 // Adjacency branch: typed NNConv(mean) + root + bias + LeakyReLU, BatchNorm partial sums.
 // (graph_networks/layers/edge_conv.py:24-27 of the reference; PyG NNConv semantics.)
-// One warp owns a tile of WN destination rows and walks its chunks; messages are accumulated in the
-// warp's private shared-memory tile (no atomics: destinations are distinct inside an 8-slot group).
+// One warp owns a tile of WN destination rows and walks its chunks of 16 same-type edges:
+//   gather (2 x LDG.128 per row per lane, straight into A fragments) -> 48 mma.sync (3xTF32) against the
+//   type's B fragments held in registers -> accumulate the 16 messages into the warp's private
+//   shared-memory tile (float4 read-modify-write, no atomics: destinations are distinct per 8-slot group).
 // ------------------------------------------------------------------------------------------------
+constexpr int FRAG32 = 2048;    // floats of one 32x32 frag table (hi + lo)
+
+struct BFrag32 { float4 h[4][2], l[4][2]; };
+
+__device__ __forceinline__ void load_bfrag32(BFrag32& b, const float* __restrict__ tab, int lane) {
+    const float4* p = reinterpret_cast<const float4*>(tab) + lane;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            b.h[ks][j] = __ldg(p + ((ks * 2 + 0) * 2 + j) * 32);
+            b.l[ks][j] = __ldg(p + ((ks * 2 + 1) * 2 + j) * 32);
+        }
+}
+
+// rows[0..1] = the lane's two float4 of row g, rows[2..3] = of row g+8 (KMAP_GATHER)
+__device__ __forceinline__ void chunk_mma32(const float4 (&rows)[4], const BFrag32& b, float (&c)[4][4]) {
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        const float4 lo4 = rows[ks >> 1], hi4 = rows[2 + (ks >> 1)];
+        float av[4];
+        av[0] = (ks & 1) ? lo4.z : lo4.x;   // (row g,   k = t)
+        av[1] = (ks & 1) ? hi4.z : hi4.x;   // (row g+8, k = t)
+        av[2] = (ks & 1) ? lo4.w : lo4.y;   // (row g,   k = t+4)
+        av[3] = (ks & 1) ? hi4.w : hi4.y;   // (row g+8, k = t+4)
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+        mma3(c[0], c[1], ah, al, b.h[ks][0], b.l[ks][0]);
+        mma3(c[2], c[3], ah, al, b.h[ks][1], b.l[ks][1]);
+    }
+}
+
+__device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int half) {
+    float4* p = reinterpret_cast<float4*>(row);
+    float4 v0 = p[0], v1 = p[1];
+    v0.x += c[0][2 * half]; v0.y += c[0][2 * half + 1]; v0.z += c[1][2 * half]; v0.w += c[1][2 * half + 1];
+    v1.x += c[2][2 * half]; v1.y += c[2][2 * half + 1]; v1.z += c[3][2 * half]; v1.w += c[3][2 * half + 1];
+    p[0] = v0; p[1] = v1;
+}
+
 __global__ void __launch_bounds__(TPB, 2)
 k_conv_adj(ConvArgs A) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* acc = smem + warp * (WN * XS + CH * XS);
-    float* xs = acc + WN * XS;
-    const int a = lane >> 3, q = lane & 7;
+    float* acc = smem + warp * (WN * XS);
+    const int g = lane >> 2, t = lane & 3;
     const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
     double s1 = 0.0, s2 = 0.0;
     const float bias_c = __ldg(A.bias + lane);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    BFrag32 bf;
+    int cur_type = -1;
 
     for (int tile = gwarp; tile < A.n_tiles; tile += nwarp) {
         for (int i = lane; i < WN * XS; i += 32) acc[i] = 0.f;
         const int c0 = __ldg(A.cptr + tile), c1 = __ldg(A.cptr + tile + 1);
-        // prefetch first chunk
         float4 pre[4];
-        int psrc = -1, pdst = 0;
+        int psrc = -1, pdst = 0, ptype = 0;
         if (c0 < c1) {
             psrc = __ldg(A.csrc + (size_t)c0 * CH + (lane & 15));
             pdst = __ldg(A.cdst + (size_t)c0 * CH + (lane & 15));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int s = __shfl_sync(0xffffffffu, psrc, a + 4 * j);
-                pre[j] = s >= 0 ? ld_row4(A.xin, s, q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            ptype = __ldg(A.ctype + c0);
+            const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
+            pre[0] = sa >= 0 ? ld_row4(A.xin, sa, t) : zero4; pre[1] = sa >= 0 ? ld_row4(A.xin, sa, 4 + t) : zero4;
+            pre[2] = sb >= 0 ? ld_row4(A.xin, sb, t) : zero4; pre[3] = sb >= 0 ? ld_row4(A.xin, sb, 4 + t) : zero4;
         }
         __syncwarp();
         for (int c = c0; c < c1; ++c) {
-            const int csrc = psrc, cdst = pdst;
-            const int type = __ldg(A.ctype + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                *reinterpret_cast<float4*>(xs + (a + 4 * j) * XS + 4 * q) = pre[j];
-            __syncwarp();
+            const float4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
+            const int csrc = psrc, cdst = pdst, type = ptype;
             if (c + 1 < c1) {
                 psrc = __ldg(A.csrc + (size_t)(c + 1) * CH + (lane & 15));
                 pdst = __ldg(A.cdst + (size_t)(c + 1) * CH + (lane & 15));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    int s = __shfl_sync(0xffffffffu, psrc, a + 4 * j);
-                    pre[j] = s >= 0 ? ld_row4(A.xin, s, q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                ptype = __ldg(A.ctype + c + 1);
+                const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
+                pre[0] = sa >= 0 ? ld_row4(A.xin, sa, t) : zero4; pre[1] = sa >= 0 ? ld_row4(A.xin, sa, 4 + t) : zero4;
+                pre[2] = sb >= 0 ? ld_row4(A.xin, sb, t) : zero4; pre[3] = sb >= 0 ? ld_row4(A.xin, sb, 4 + t) : zero4;
             }
+            if (type != cur_type) { load_bfrag32(bf, A.tabF + (size_t)type * FRAG32, lane); cur_type = type; }
             float m[4][4] = {};
-            tile16_fma<F, true>(xs, XS, A.tab + (size_t)type * (F * F), F, 0, a, q, m);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int s = __shfl_sync(0xffffffffu, csrc, a + 4 * i);
-                int d = __shfl_sync(0xffffffffu, cdst, a + 4 * i);
-                if (s >= 0) {
-                    float4* p = reinterpret_cast<float4*>(acc + d * XS + 4 * q);
-                    float4 v = *p;
-                    v.x += m[i][0]; v.y += m[i][1]; v.z += m[i][2]; v.w += m[i][3];
-                    *p = v;
-                }
-                __syncwarp();
+            chunk_mma32(cur, bf, m);
+            // rows 0..7 (group 0), then rows 8..15 (group 1): destinations are distinct inside a group
+            {
+                const int s = __shfl_sync(0xffffffffu, csrc, g), d = __shfl_sync(0xffffffffu, cdst, g);
+                if (s >= 0) acc_add8(acc + d * XS + 8 * t, m, 0);
             }
+            __syncwarp();
+            {
+                const int s = __shfl_sync(0xffffffffu, csrc, g + 8), d = __shfl_sync(0xffffffffu, cdst, g + 8);
+                if (s >= 0) acc_add8(acc + d * XS + 8 * t, m, 1);
+            }
+            __syncwarp();
         }
         // mean over in-edges
         const int node0 = tile * WN;
@@ -118,26 +222,19 @@ k_conv_adj(ConvArgs A) {
             if (node < A.n_own) acc[r * XS + lane] *= __ldg(A.inv_deg + node);
         }
         __syncwarp();
-        // root term: x_i @ root, four 16-row chunks of the tile's own rows
+        // root term: x_i @ root as four 16-row chunks of the tile's own rows (frag table entry n_types)
+        if (cur_type != A.n_types) { load_bfrag32(bf, A.tabF + (size_t)A.n_types * FRAG32, lane); cur_type = A.n_types; }
         for (int rc = 0; rc < WN / CH; ++rc) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int node = node0 + rc * CH + a + 4 * j;
-                float4 v = node < A.n_own ? ld_row4(A.xin, node, q) : make_float4(0.f, 0.f, 0.f, 0.f);
-                *reinterpret_cast<float4*>(xs + (a + 4 * j) * XS + 4 * q) = v;
-            }
-            __syncwarp();
+            const int na = node0 + rc * CH + g, nb = na + 8;
+            float4 cur[4];
+            cur[0] = na < A.n_own ? ld_row4(A.xin, na, t) : zero4; cur[1] = na < A.n_own ? ld_row4(A.xin, na, 4 + t) : zero4;
+            cur[2] = nb < A.n_own ? ld_row4(A.xin, nb, t) : zero4; cur[3] = nb < A.n_own ? ld_row4(A.xin, nb, 4 + t) : zero4;
             float m[4][4] = {};
-            tile16_fma<F, true>(xs, XS, A.root, F, 0, a, q, m);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4* p = reinterpret_cast<float4*>(acc + (rc * CH + a + 4 * i) * XS + 4 * q);
-                float4 v = *p;
-                v.x += m[i][0]; v.y += m[i][1]; v.z += m[i][2]; v.w += m[i][3];
-                *p = v;
-            }
-            __syncwarp();
+            chunk_mma32(cur, bf, m);
+            acc_add8(acc + (rc * CH + g) * XS + 8 * t, m, 0);
+            acc_add8(acc + (rc * CH + g + 8) * XS + 8 * t, m, 1);
         }
+        __syncwarp();
         // bias, LeakyReLU, store, statistics (lane = channel)
         for (int r = 0; r < WN; ++r) {
             int node = node0 + r;
@@ -161,131 +258,164 @@ k_conv_adj(ConvArgs A) {
 // LeakyReLU, BatchNorm partial sums.  (graph_networks/layers/coll_conv.py:24-27; PyG GINConv.)
 // The previous layer's BatchNorm is applied lazily on the gathered rows:
 //   sum_j BN(x_j) = scale * sum_j ((x_j - mu_hi) - mu_lo) + (#terms) * beta
+// Gather: four 8-lane groups each stream every 4th neighbour row with LDG.128 (4 rows per instruction,
+// 16 in flight per warp).  MLP: three chained mma.sync 3xTF32 layers on 16-node chunks; layer k's C
+// fragments are layer k+1's A fragments (KMAP_CHAIN), weights are frag tables in shared memory.
 // ------------------------------------------------------------------------------------------------
-struct GinSmem {
-    float w1t[32 * 32]; float w2t[32 * 64]; float w3t[64 * 32];
-    float b1[32]; float b2[64]; float b3[32];
-};
-constexpr int GIN_WARP_FLOATS = CH * XS + CH * XS + CH * 68;
+constexpr int GIN_W1 = 2048, GIN_W2 = 4096, GIN_W3 = 4096;                 // floats (hi + lo)
+constexpr int GIN_WFLOATS = GIN_W1 + GIN_W2 + GIN_W3 + 128;                // + b1[32] b2[64] b3[32]
+constexpr int GIN_WARP_FLOATS = CH * XS;
+
+__device__ __forceinline__ float4 center4(float4 v, const float4& mh, const float4& ml) {
+    v.x = (v.x - mh.x) - ml.x; v.y = (v.y - mh.y) - ml.y; v.z = (v.z - mh.z) - ml.z; v.w = (v.w - mh.w) - ml.w;
+    return v;
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 __global__ void __launch_bounds__(TPB, 2)
 k_gin(GinArgs A) {
     extern __shared__ __align__(16) float smem[];
-    GinSmem* W = reinterpret_cast<GinSmem*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 32 * 32; i += TPB) W->w1t[i] = __ldg(A.w1t + i);
-    for (int i = threadIdx.x; i < 32 * 64; i += TPB) { W->w2t[i] = __ldg(A.w2t + i); W->w3t[i] = __ldg(A.w3t + i); }
-    if (threadIdx.x < 32) { W->b1[threadIdx.x] = __ldg(A.b1 + threadIdx.x); W->b3[threadIdx.x] = __ldg(A.b3 + threadIdx.x); }
-    if (threadIdx.x < 64) W->b2[threadIdx.x] = __ldg(A.b2 + threadIdx.x);
+    for (int i = threadIdx.x; i < GIN_WFLOATS / 4; i += TPB)
+        reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(A.wfrag) + i);
     __syncthreads();
-    float* xs = smem + sizeof(GinSmem) / sizeof(float) + warp * GIN_WARP_FLOATS;
-    float* h1 = xs + CH * XS;
-    float* h2 = h1 + CH * XS;
-    const int a = lane >> 3, q = lane & 7;
+    const float4* W1 = reinterpret_cast<const float4*>(smem);
+    const float4* W2 = reinterpret_cast<const float4*>(smem + GIN_W1);
+    const float4* W3 = reinterpret_cast<const float4*>(smem + GIN_W1 + GIN_W2);
+    const float* b1 = smem + GIN_W1 + GIN_W2 + GIN_W3;
+    const float* b2 = b1 + 32;
+    const float* b3 = b2 + 64;
+    float* xs = smem + GIN_WFLOATS + warp * GIN_WARP_FLOATS;
+    const int a = lane >> 3, q = lane & 7;       // gather roles
+    const int g = lane >> 2, t = lane & 3;       // mma roles
     const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
     const int n_chunks = (A.n_own + CH - 1) / CH;
-    float mu_hi = 0.f, mu_lo = 0.f, scale = 1.f, beta = 0.f;
+    float4 mh = make_float4(0.f, 0.f, 0.f, 0.f), ml = mh, sc = make_float4(1.f, 1.f, 1.f, 1.f), be = mh;
     if (A.in_coef) {
-        mu_hi = __ldg(A.in_coef + lane); mu_lo = __ldg(A.in_coef + 32 + lane);
-        scale = __ldg(A.in_coef + 64 + lane); beta = __ldg(A.in_coef + 96 + lane);
+        mh = __ldg(reinterpret_cast<const float4*>(A.in_coef) + q);
+        ml = __ldg(reinterpret_cast<const float4*>(A.in_coef + 32) + q);
+        sc = __ldg(reinterpret_cast<const float4*>(A.in_coef + 64) + q);
+        be = __ldg(reinterpret_cast<const float4*>(A.in_coef + 96) + q);
     }
     const float self_w = 1.0f + A.eps;
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    double s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
 
     for (int chunk = gwarp; chunk < n_chunks; chunk += nwarp) {
         const int node0 = chunk * CH;
-        // gather + sum (lane = channel)
+        // ---- gather + sum ---------------------------------------------------------------------
         for (int r = 0; r < CH; ++r) {
             const int node = node0 + r;
-            float h = 0.f;
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            int deg = 0;
             if (node < A.n_own) {
                 const int e0 = __ldg(A.col_ptr + node), e1 = __ldg(A.col_ptr + node + 1);
-                float c = (__ldg(A.xin + (size_t)node * F + lane) - mu_hi) - mu_lo;
-                float sum = self_w * c;
-                for (int eb = e0; eb < e1; eb += 32) {
-                    const int cnt = min(32, e1 - eb);
-                    int idx = lane < cnt ? __ldg(A.col_src + eb + lane) : 0;
-                    int j = 0;
-                    for (; j + 4 <= cnt; j += 4) {
-                        int i0 = __shfl_sync(0xffffffffu, idx, j), i1 = __shfl_sync(0xffffffffu, idx, j + 1);
-                        int i2 = __shfl_sync(0xffffffffu, idx, j + 2), i3 = __shfl_sync(0xffffffffu, idx, j + 3);
-                        float v0 = __ldg(A.xin + (size_t)i0 * F + lane), v1 = __ldg(A.xin + (size_t)i1 * F + lane);
-                        float v2 = __ldg(A.xin + (size_t)i2 * F + lane), v3 = __ldg(A.xin + (size_t)i3 * F + lane);
-                        sum += (v0 - mu_hi) - mu_lo;
-                        sum += (v1 - mu_hi) - mu_lo;
-                        sum += (v2 - mu_hi) - mu_lo;
-                        sum += (v3 - mu_hi) - mu_lo;
-                    }
-                    for (; j < cnt; ++j) {
-                        int i0 = __shfl_sync(0xffffffffu, idx, j);
-                        sum += (__ldg(A.xin + (size_t)i0 * F + lane) - mu_hi) - mu_lo;
-                    }
+                deg = e1 - e0;
+                if (a == 0) {
+                    float4 c = center4(ld_row4(A.xin, node, q), mh, ml);
+                    sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
                 }
-                h = fmaf(scale, sum, (self_w + (float)(e1 - e0)) * beta);
+                int e = e0 + a;
+                for (; e + 12 < e1; e += 16) {
+                    const int i0 = __ldg(A.col_src + e), i1 = __ldg(A.col_src + e + 4);
+                    const int i2 = __ldg(A.col_src + e + 8), i3 = __ldg(A.col_src + e + 12);
+                    const float4 v0 = ld_row4(A.xin, i0, q), v1 = ld_row4(A.xin, i1, q);
+                    const float4 v2 = ld_row4(A.xin, i2, q), v3 = ld_row4(A.xin, i3, q);
+                    add4(sum, center4(v0, mh, ml)); add4(sum, center4(v1, mh, ml));
+                    add4(sum, center4(v2, mh, ml)); add4(sum, center4(v3, mh, ml));
+                }
+                for (; e < e1; e += 4) add4(sum, center4(ld_row4(A.xin, __ldg(A.col_src + e), q), mh, ml));
             }
-            xs[r * XS + lane] = h;
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 8);  sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 8);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, 8);  sum.w += __shfl_xor_sync(0xffffffffu, sum.w, 8);
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 16); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 16);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, 16); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, 16);
+            if (a == 0) {
+                const float nt = node < A.n_own ? self_w + (float)deg : 0.f;
+                float4 h;
+                h.x = fmaf(sc.x, sum.x, nt * be.x); h.y = fmaf(sc.y, sum.y, nt * be.y);
+                h.z = fmaf(sc.z, sum.z, nt * be.z); h.w = fmaf(sc.w, sum.w, nt * be.w);
+                *reinterpret_cast<float4*>(xs + r * XS + 4 * q) = h;
+            }
         }
         __syncwarp();
-        // layer 1: 32 -> 32
-        {
-            float m[4][4] = {};
-            tile16_fma<32, false>(xs, XS, W->w1t, 32, 0, a, q, m);
+        // ---- layer 1: 32 -> 32, A from shared memory (natural K order) -------------------------------
+        float c1[4][4] = {};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float4 o;
-                o.x = sigmoidf_acc(m[i][0] + W->b1[4 * q + 0]); o.y = sigmoidf_acc(m[i][1] + W->b1[4 * q + 1]);
-                o.z = sigmoidf_acc(m[i][2] + W->b1[4 * q + 2]); o.w = sigmoidf_acc(m[i][3] + W->b1[4 * q + 3]);
-                *reinterpret_cast<float4*>(h1 + (a + 4 * i) * XS + 4 * q) = o;
-            }
+        for (int ks = 0; ks < 4; ++ks) {
+            float av[4] = {xs[g * XS + 8 * ks + t], xs[(g + 8) * XS + 8 * ks + t],
+                           xs[g * XS + 8 * ks + t + 4], xs[(g + 8) * XS + 8 * ks + t + 4]};
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                mma3(c1[2 * j], c1[2 * j + 1], ah, al, W1[((ks * 2 + 0) * 2 + j) * 32 + lane], W1[((ks * 2 + 1) * 2 + j) * 32 + lane]);
         }
         __syncwarp();
-        // layer 2: 32 -> 64 (two column halves)
+        // ---- layer 2: 32 -> 64, A = sigmoid(c1 + b1) straight from the C fragments ------------------
+        float c2[8][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const float bA = b1[8 * ks + 2 * t], bB = b1[8 * ks + 2 * t + 1];
+            float av[4] = {sigmoidf_acc(c1[ks][0] + bA), sigmoidf_acc(c1[ks][2] + bA),
+                           sigmoidf_acc(c1[ks][1] + bB), sigmoidf_acc(c1[ks][3] + bB)};
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                mma3(c2[2 * j], c2[2 * j + 1], ah, al, W2[((ks * 2 + 0) * 4 + j) * 32 + lane], W2[((ks * 2 + 1) * 4 + j) * 32 + lane]);
+        }
+        // ---- layer 3: 64 -> 32 (output channels 8t..8t+7 per lane) ----------------------------------
+        float c3[4][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+            const float bA = b2[8 * ks + 2 * t], bB = b2[8 * ks + 2 * t + 1];
+            float av[4] = {sigmoidf_acc(c2[ks][0] + bA), sigmoidf_acc(c2[ks][2] + bA),
+                           sigmoidf_acc(c2[ks][1] + bB), sigmoidf_acc(c2[ks][3] + bB)};
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                mma3(c3[2 * j], c3[2 * j + 1], ah, al, W3[((ks * 2 + 0) * 2 + j) * 32 + lane], W3[((ks * 2 + 1) * 2 + j) * 32 + lane]);
+        }
+        // ---- sigmoid, LeakyReLU, store, statistics ------------------------------------------------
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            float m[4][4] = {};
-            tile16_fma<32, false>(h1, XS, W->w2t, 64, 32 * half, a, q, m);
+            const int node = node0 + g + 8 * half;
+            float o[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float* bb = W->b2 + 32 * half + 4 * q;
-                float4 o;
-                o.x = sigmoidf_acc(m[i][0] + bb[0]); o.y = sigmoidf_acc(m[i][1] + bb[1]);
-                o.z = sigmoidf_acc(m[i][2] + bb[2]); o.w = sigmoidf_acc(m[i][3] + bb[3]);
-                *reinterpret_cast<float4*>(h2 + (a + 4 * i) * 68 + 32 * half + 4 * q) = o;
-            }
-        }
-        __syncwarp();
-        // layer 3: 64 -> 32, sigmoid, LeakyReLU, store, statistics
-        {
-            float m[4][4] = {};
-            tile16_fma<64, false>(h2, 68, W->w3t, 32, 0, a, q, m);
+            for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int node = node0 + a + 4 * i;
-                if (node < A.n_own) {
-                    float o[4];
+                for (int e = 0; e < 2; ++e)
+                    o[2 * nt + e] = leaky(sigmoidf_acc(c3[nt][2 * half + e] + b3[8 * t + 2 * nt + e]));
+            if (node < A.n_own) {
+                float4* dst = reinterpret_cast<float4*>(A.out + (size_t)node * F + 8 * t);
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        o[j] = leaky(sigmoidf_acc(m[i][j] + W->b3[4 * q + j]));
-                        s1[j] += (double)o[j];
-                        s2[j] += (double)o[j] * (double)o[j];
-                    }
-                    *reinterpret_cast<float4*>(A.out + (size_t)node * F + 4 * q) = make_float4(o[0], o[1], o[2], o[3]);
-                }
+                for (int j = 0; j < 8; ++j) { s1[j] += (double)o[j]; s2[j] += (double)o[j] * (double)o[j]; }
             }
         }
         __syncwarp();
     }
-    // fold the four row groups (lanes with equal q) in a fixed order, lanes 0..7 publish
+    // fold the eight row groups (lanes with equal t) in a fixed order; lanes 0..3 publish channels 8t..8t+7
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
-        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
     }
-    if (A.part && a == 0) {
+    if (A.part && g == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            A.part[(size_t)gwarp * 64 + 4 * q + j] = s1[j];
-            A.part[(size_t)gwarp * 64 + 32 + 4 * q + j] = s2[j];
+        for (int j = 0; j < 8; ++j) {
+            A.part[(size_t)gwarp * 64 + 8 * t + j] = s1[j];
+            A.part[(size_t)gwarp * 64 + 32 + 8 * t + j] = s2[j];
         }
     }
 }
@@ -545,7 +675,8 @@ __global__ void k_edge_table(const float* __restrict__ rows, int d_e,
     for (int o = tid; o < F * F; o += 256) {
         double s = (double)c3[o];
         for (int k = 0; k < 64; ++k) s += (double)a3[(size_t)o * 64 + k] * h2[k];
-        tab[(size_t)t * (F * F) + o] = (float)(1.0 / (1.0 + exp(-s)));
+        // o = k_in * 32 + k_out  (NNConv: weight.view(-1, in, out))
+        frag_store(tab + (size_t)t * FRAG32, o >> 5, o & 31, 32, KMAP_GATHER, NMAP_CONTIG8, 1.0 / (1.0 + exp(-s)));
     }
 }
 
@@ -554,6 +685,13 @@ __global__ void k_transpose(const float* __restrict__ in, float* __restrict__ ou
     if (i >= rows * cols) return;
     int r = i / cols, c = i - r * cols;
     out[(size_t)c * rows + r] = in[i];
+}
+
+// frag table of a k-major [K][N] fp32 matrix (root weights, GIN MLP weights)
+__global__ void k_frag_pack(const float* __restrict__ w, int K, int N, int kmap, int nmap, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    frag_store(out, i / N, i % N, N, kmap, nmap, (double)w[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,8 +728,8 @@ int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_pe
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static size_t conv_smem() { return (size_t)WARPS * (WN * XS + CH * XS) * sizeof(float); }
-static size_t gin_smem() { return sizeof(GinSmem) + (size_t)WARPS * GIN_WARP_FLOATS * sizeof(float); }
+static size_t conv_smem() { return (size_t)WARPS * (WN * XS) * sizeof(float); }
+static size_t gin_smem() { return (size_t)(GIN_WFLOATS + WARPS * GIN_WARP_FLOATS) * sizeof(float); }
 
 static int conv_blocks(int n_tiles, int sm_count) { return persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2); }
 static int gin_blocks(int n_own, int sm_count) {
@@ -679,6 +817,11 @@ void launch_edge_table(const float* type_rows, int n_types, int d_e, const float
                        const float* c2, const float* a3, const float* c3, float* tab, cudaStream_t st) {
     if (n_types <= 0) return;
     k_edge_table<<<n_types, 256, 0, st>>>(type_rows, d_e, a1, c1, a2, c2, a3, c3, tab);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_frag_pack(const float* w_kn, int K, int N, int kmap, int nmap, float* out, cudaStream_t st) {
+    k_frag_pack<<<(K * N + 255) / 256, 256, 0, st>>>(w_kn, K, N, kmap, nmap, out);
     TGNN_CUDA(cudaGetLastError());
 }
 

@@ -106,8 +106,8 @@ void build_graph(Graph& g, Scratch& scratch, int d_e, int64_t n_own, int64_t n_r
 // ----- kernels.cu launchers --------------------------------------------------------------------
 struct ConvArgs {
     const float* xin;        // [n_rows][32]  b1 of the previous layer (materialised)
-    const float* tab;        // [K][32][32]   per-type edge weight, [k_in][k_out]
-    const float* root;       // [32][32]      nnConv.root  [in][out]
+    const float* tabF;       // [K+1][2048]   frag tables (hi|lo) of the per-type edge weights; entry K = nnConv.root
+    int n_types;             // K
     const float* bias;       // [32]
     const int* cptr; const int* ctype; const int* csrc; const uint8_t* cdst;
     const float* inv_deg;
@@ -122,9 +122,7 @@ struct GinArgs {
     const float* xin;        // [n_rows][32]  pre-BN activations of the previous collision layer (or h0)
     const float* in_coef;    // [4][32] BN coefficients to apply lazily to xin; nullptr = identity
     const int* col_ptr; const int* col_src;
-    const float* w1t; const float* b1;   // [32][32] (k-major), [32]
-    const float* w2t; const float* b2;   // [32][64], [64]
-    const float* w3t; const float* b3;   // [64][32], [32]
+    const float* wfrag;      // frag tables W1[2048] W2[4096] W3[4096] then b1[32] b2[64] b3[32]
     float eps;
     float* out;              // pre2 [n_own][32]
     double* part;            // [n_part][64]
@@ -181,6 +179,11 @@ void launch_edge_table(const float* type_rows, int n_types, int d_e,
                        const float* a3, const float* c3, float* tab, cudaStream_t st);
 
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);  // out[c][r] = in[r][c]
+// frag table (tensor-core B fragments, hi|lo TF32 split) of a k-major [K][N] matrix; maps: see kernels.cu
+enum { TG_KMAP_GATHER = 0, TG_KMAP_NATURAL = 1, TG_KMAP_CHAIN = 2, TG_NMAP_NATURAL = 0, TG_NMAP_CONTIG8 = 1 };
+constexpr int TG_FRAG32 = 2048;          // floats of a 32x32 frag table
+constexpr int TG_GIN_WFLOATS = 2048 + 4096 + 4096 + 128;
+void launch_frag_pack(const float* w_kn, int K, int N, int kmap, int nmap, float* out, cudaStream_t st);
 
 // halo pack / unpack (sharded mode)
 void launch_halo_pack(const float* a, const float* b, const int* rows, int n_send, float* sendbuf, cudaStream_t st);
