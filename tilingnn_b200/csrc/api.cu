@@ -2,6 +2,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -79,7 +80,10 @@ struct tgnn_handle {
     // derived parameter layouts
     DevBuf init_w1t;
     std::vector<std::unique_ptr<DevBuf>> gin_wt;    // per layer: frag tables W1|W2|W3 and biases b1|b2|b3
-    std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4
+    std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4: k-major transposes (CUDA-core path)
+    std::vector<std::unique_ptr<DevBuf>> fin_whl;   // 4: [hi | lo] TF32 split of the [N_out][K] weights (tcgen05 path)
+    DevBuf dev_error;                               // int: device-side error flag (pipeline timeouts)
+    bool dense_ffma = false;                        // TGNN_DENSE=ffma selects the CUDA-core dense stage (debug A/B)
     std::vector<float> gin_eps;
     float fin_last_bias = 0.f;
     DevBuf coef;                                    // all BatchNorm coefficient blocks
@@ -101,6 +105,7 @@ struct tgnn_handle {
     int stop_layer = -1;
     int last_layer_run = -1;
     bool profiling = false;
+    bool check_errors = getenv("TGNN_CHECK") != nullptr;     // synchronous device-error check after every forward
     std::vector<ProfEntry> prof;
     std::map<std::string, std::pair<float, int>> prof_result;
 
@@ -204,14 +209,22 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
         }
         TGNN_CUDA(cudaMemcpyAsync(&h->gin_eps[i], h->P(p + ".ginConv.eps"), sizeof(float), cudaMemcpyDeviceToHost, st));
     }
-    h->fin_wt.clear();
+    h->fin_wt.clear(); h->fin_whl.clear();
     int dims[5] = {F * (L + 1), 256, 128, 64, F};
     for (int k = 0; k < 4; ++k) {
+        const float* w = h->P("final_mlp.0.mlp." + std::to_string(k) + ".linear.weight");
+        const size_t ne = (size_t)dims[k] * dims[k + 1];
         h->fin_wt.emplace_back(new DevBuf());
-        h->fin_wt.back()->reserve((size_t)dims[k] * dims[k + 1] * sizeof(float));
-        launch_transpose(h->P("final_mlp.0.mlp." + std::to_string(k) + ".linear.weight"), h->fin_wt.back()->as<float>(),
-                         dims[k + 1], dims[k], st);
+        h->fin_wt.back()->reserve(ne * sizeof(float));
+        launch_transpose(w, h->fin_wt.back()->as<float>(), dims[k + 1], dims[k], st);
+        h->fin_whl.emplace_back(new DevBuf());
+        h->fin_whl.back()->reserve(2 * ne * sizeof(float));
+        launch_split_tf32(w, h->fin_whl.back()->as<float>(), h->fin_whl.back()->as<float>() + ne, (int)ne, st);
     }
+    h->dev_error.reserve(sizeof(int));
+    TGNN_CUDA(cudaMemsetAsync(h->dev_error.p, 0, sizeof(int), st));
+    const char* dsel = getenv("TGNN_DENSE");
+    h->dense_ffma = dsel && std::string(dsel) == "ffma";
     TGNN_CUDA(cudaMemcpyAsync(&h->fin_last_bias, h->P("final_mlp.1.linear.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
     // coefficient blocks
     size_t off = 0;
@@ -411,7 +424,13 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             da.wt = h->fin_wt[k]->as<float>(); da.bias = h->P(p + ".linear.bias");
             da.out = h->fa[k].as<float>(); da.part = train ? h->partA.as<double>() : nullptr;
             da.n = n_own; da.K = dims[k]; da.n_out = dims[k + 1];
-            lz.begin("final"); launch_dense(da, st); lz.end(1);
+            lz.begin("final");
+            if (h->dense_ffma) launch_dense(da, st);
+            else {
+                const size_t ne = (size_t)dims[k] * dims[k + 1];
+                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->fin_whl[k]->as<float>() + ne, h->dev_error.as<int>(), st);
+            }
+            lz.end(1);
             if (train) {
                 lz.begin("bnfin");
                 finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], p + ".batch_norm", h->coef_fin[k]);
@@ -423,8 +442,13 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
                      n_own, st);
         lz.end(1);
     }
-    if (h->profiling) {
+    if (h->profiling || h->check_errors) {
         TGNN_CUDA(cudaStreamSynchronize(st));
+        int e = 0;
+        TGNN_CUDA(cudaMemcpy(&e, h->dev_error.p, sizeof(int), cudaMemcpyDeviceToHost));
+        TGNN_CHECK(e == 0, "tgnn_forward: device-side pipeline timeout in k_dense_tc (mbarrier wait exceeded its bound)");
+    }
+    if (h->profiling) {
         for (auto& e : h->prof) {
             float ms = 0.f;
             cudaEventElapsedTime(&ms, e.a, e.b);

@@ -1,0 +1,322 @@
+// Dense stages of the final MLP (TilinGNN.py:45-46,74-76 of the reference) on the 5th-generation
+// tensor cores:  out = LeakyReLU( BN_in(A) @ W^T + b )  and per-column BatchNorm partial sums.
+//
+// One CTA = one tile of 128 rows x all N_out columns.  The fp32 accumulator lives in TMEM
+// (128 lanes x N_out columns).  K is walked in slabs of 32 (= one 128-byte SWIZZLE_128B atom row):
+//   producers (warps 0-3): A slab  global -> registers -> lazy BatchNorm -> hi/lo TF32 split -> swizzled smem
+//                          W slab  (pre-split hi / lo, [N_out][K] = the checkpoint's own layout, K-major)
+//                                  cp.async -> swizzled smem
+//   MMA issuer (warp 4, one lane): 12 x tcgen05.mma.kind::tf32 per slab (4 K-steps of 8 x {lo*hi, hi*lo, hi*hi}),
+//                          tcgen05.commit -> mbarrier frees the smem stage / publishes the accumulator
+//   epilogue (warps 0-3):  tcgen05.ld 32 columns at a time -> bias, LeakyReLU -> global, column sums in fp64.
+// 3xTF32 keeps fp32-level accuracy (single-pass TF32 would break the 1e-4 parity bar).
+// Every mbarrier wait is bounded: on a timeout the kernel raises a device-side error flag and exits instead of
+// hanging the GPU.
+#include <algorithm>
+
+#include "tgnn_internal.h"
+
+namespace tgnn {
+namespace {
+
+constexpr int BM = 128;           // rows per tile (UMMA M)
+constexpr int BK = 32;            // K per slab (128 bytes of tf32)
+constexpr int STAGES = 2;
+constexpr int A_TILE_BYTES = BM * BK * 4;            // 16 KB
+constexpr int NTHREADS = 160;                        // 4 producer/epilogue warps + 1 MMA warp
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// bounded wait: false on timeout (~2 s)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+        if (clock64() - t0 > 4000000000ll) return false;
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows at 128 B pitch,
+// 8-row groups at 1024 B (SBO), LBO = 1 (unused for swizzled K-major), version 1 (Blackwell), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                   "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// byte offset of 16-byte chunk c of row r inside a SWIZZLE_128B K-major tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct DenseTcArgs {
+    const float* const* slabs;  // virtual concat: K/32 slab pointers [n_rows][32]
+    const float* a;             // else plain [n][K]
+    int virtual_concat;
+    const float* in_coef;       // [4][K] lazy BatchNorm of the input, or nullptr
+    const float* w_hi;          // [N_out][K] tf32-rounded weights
+    const float* w_lo;          // [N_out][K] tf32-rounded residuals
+    const float* bias;          // [N_out]
+    float* out;                 // [n][N_out]
+    double* part;               // [gridDim.x][2][N_out] or nullptr
+    int* error_flag;
+    int n, K;
+};
+
+template <int NOUT>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_dense_tc(DenseTcArgs A) {
+    constexpr int B_TILE_BYTES = NOUT * BK * 4;
+    constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    constexpr uint32_t IDESC = umma_idesc_tf32(NOUT);
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+    __shared__ uint32_t tmem_base_smem;
+    __shared__ int timeout_flag;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]), bar_acc = smem_u32(&bars[2 * STAGES]);
+    const int row0 = blockIdx.x * BM;
+    const int n_slabs = A.K / BK;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, 128); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_acc, 1);
+        timeout_flag = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(NOUT));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_smem;
+
+    if (warp < 4) {
+        // ===================== producers =====================
+        for (int s = 0; s < n_slabs; ++s) {
+            const int st = s % STAGES;
+            if (s >= STAGES) {
+                if (!mbar_wait(bar_empty + 8 * st, ((s / STAGES) - 1) & 1)) { timeout_flag = 1; break; }
+            }
+            uint8_t* sa_hi = smem + st * STAGE_BYTES;
+            uint8_t* sa_lo = sa_hi + A_TILE_BYTES;
+            const uint32_t sb_hi = smem_base + st * STAGE_BYTES + 2 * A_TILE_BYTES;
+            const uint32_t sb_lo = sb_hi + B_TILE_BYTES;
+            // W slab: rows n = 0..NOUT-1, 8 chunks of 16 B each, hi and lo
+            const int k0 = s * BK;
+            for (int i = tid; i < NOUT * 8; i += 128) {
+                const int r = i >> 3, c = i & 7;
+                const float* gh = A.w_hi + (size_t)r * A.K + k0 + 4 * c;
+                const float* gl = A.w_lo + (size_t)r * A.K + k0 + 4 * c;
+                const uint32_t off = sw128_off(r, c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_hi + off), "l"(gh) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_lo + off), "l"(gl) : "memory");
+            }
+            // A slab: 128 rows x 8 chunks; 8 lanes per row -> coalesced 128-byte rows
+            const float* abase; size_t lda; int koff;
+            if (A.virtual_concat) { abase = A.slabs[s]; lda = F; koff = 0; }
+            else { abase = A.a; lda = (size_t)A.K; koff = k0; }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = (tid >> 3) + 16 * j, c = tid & 7;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < A.n) v = __ldg(reinterpret_cast<const float4*>(abase + (size_t)(row0 + r) * lda + koff) + c);
+                if (A.in_coef) {
+                    const float* cf = A.in_coef + k0 + 4 * c;
+                    const int C = A.K;
+                    v.x = fmaf((v.x - cf[0]) - cf[C + 0], cf[2 * C + 0], cf[3 * C + 0]);
+                    v.y = fmaf((v.y - cf[1]) - cf[C + 1], cf[2 * C + 1], cf[3 * C + 1]);
+                    v.z = fmaf((v.z - cf[2]) - cf[C + 2], cf[2 * C + 2], cf[3 * C + 2]);
+                    v.w = fmaf((v.w - cf[3]) - cf[C + 3], cf[2 * C + 3], cf[3 * C + 3]);
+                    if (row0 + r >= A.n) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                uint4 hi, lo;
+                hi.x = tf32_rna(v.x); lo.x = tf32_rna(v.x - __uint_as_float(hi.x));
+                hi.y = tf32_rna(v.y); lo.y = tf32_rna(v.y - __uint_as_float(hi.y));
+                hi.z = tf32_rna(v.z); lo.z = tf32_rna(v.z - __uint_as_float(hi.z));
+                hi.w = tf32_rna(v.w); lo.w = tf32_rna(v.w - __uint_as_float(hi.w));
+                const uint32_t off = sw128_off(r, c);
+                *reinterpret_cast<uint4*>(sa_hi + off) = hi;
+                *reinterpret_cast<uint4*>(sa_lo + off) = lo;
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+            mbar_arrive(bar_full + 8 * st);
+        }
+    } else if (lane == 0) {
+        // ===================== MMA issuer (one thread) =====================
+        bool ok = true;
+        for (int s = 0; s < n_slabs && ok; ++s) {
+            const int st = s % STAGES;
+            ok = mbar_wait(bar_full + 8 * st, (s / STAGES) & 1);
+            if (!ok) { timeout_flag = 1; break; }
+            tc_fence_after();
+            const uint32_t a_hi = smem_base + st * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
+            const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+            for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint32_t kb = ks * 32;           // 8 tf32 = 32 bytes along K inside the swizzle atom
+                const uint64_t dah = umma_desc_sw128(a_hi + kb), dal = umma_desc_sw128(a_lo + kb);
+                const uint64_t dbh = umma_desc_sw128(b_hi + kb), dbl = umma_desc_sw128(b_lo + kb);
+                umma_tf32(tmem_base, dal, dbh, IDESC, (s > 0 || ks > 0) ? 1u : 0u);
+                umma_tf32(tmem_base, dah, dbl, IDESC, 1u);
+                umma_tf32(tmem_base, dah, dbh, IDESC, 1u);
+            }
+            umma_commit(bar_empty + 8 * st);           // smem stage reusable once these MMAs have read it
+        }
+        umma_commit(bar_acc);                          // accumulator complete
+    }
+
+    // ===================== epilogue (warps 0-3; TMEM lane = 32*warp + lane = tile row) =====================
+    double* red = reinterpret_cast<double*>(smem);      // [4 warps][2][NOUT] -- the stage buffers are free by now
+    bool acc_ok = true;
+    if (warp < 4) {
+        acc_ok = mbar_wait(bar_acc, 0);
+        if (!acc_ok) timeout_flag = 1;
+        tc_fence_after();
+        const int row = row0 + 32 * warp + lane;
+        const bool live = row < A.n && acc_ok;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NOUT; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(32 * warp) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(leaky(__uint_as_float(v[j]) + __ldg(A.bias + c0 + j)));
+            if (live) {
+                float4* dst = reinterpret_cast<float4*>(A.out + (size_t)row * NOUT + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+            if (A.part) {
+                // transpose-reduce over the warp's 32 rows (fp64): after 5 halving steps lane j holds column c0+j.
+                // Two passes (sum, then sum of squares) to keep the register footprint down.
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double sv[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const double o = live ? (double)__uint_as_float(v[j]) : 0.0;
+                        sv[j] = q == 0 ? o : o * o;
+                    }
+#pragma unroll
+                    for (int w = 16; w >= 1; w >>= 1) {
+                        const bool upper = (lane & w) != 0;
+#pragma unroll
+                        for (int j = 0; j < w; ++j) {
+                            const double send = upper ? sv[j] : sv[j + w];
+                            const double keep = upper ? sv[j + w] : sv[j];
+                            sv[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+                        }
+                    }
+                    red[(warp * 2 + q) * NOUT + c0 + lane] = sv[0];
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (A.part && acc_ok) {
+        double* p = A.part + (size_t)blockIdx.x * 2 * NOUT;
+        for (int i = tid; i < 2 * NOUT; i += NTHREADS) {
+            const int q = i / NOUT, c = i % NOUT;
+            p[i] = ((red[(0 * 2 + q) * NOUT + c] + red[(1 * 2 + q) * NOUT + c]) + red[(2 * 2 + q) * NOUT + c]) + red[(3 * 2 + q) * NOUT + c];
+        }
+    }
+    if (timeout_flag && tid == 0) atomicExch(A.error_flag, 1);
+    if (warp == 4) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NOUT));
+    }
+}
+
+__global__ void k_split_tf32(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = w[i];
+    const uint32_t h = tf32_rna(x);
+    hi[i] = __uint_as_float(h);
+    lo[i] = __uint_as_float(tf32_rna(x - __uint_as_float(h)));
+}
+
+template <int NOUT>
+void launch_one(const DenseTcArgs& a, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * A_TILE_BYTES + 2 * NOUT * BK * 4) + 1024;
+    static bool attr = false;
+    if (!attr) {
+        TGNN_CUDA(cudaFuncSetAttribute(k_dense_tc<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    k_dense_tc<NOUT><<<(a.n + BM - 1) / BM, NTHREADS, smem, st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+void launch_split_tf32(const float* w, float* hi, float* lo, int n, cudaStream_t st) {
+    k_split_tf32<<<(n + 255) / 256, 256, 0, st>>>(w, hi, lo, n);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+int dense_tc_row_blocks(int n) { return (n + BM - 1) / BM; }
+
+void launch_dense_tc(const DenseArgs& d, const float* w_hi, const float* w_lo, int* error_flag, cudaStream_t st) {
+    TGNN_CHECK(d.K % BK == 0, "dense stage: K must be a multiple of 32");
+    DenseTcArgs a{};
+    a.slabs = d.slabs; a.a = d.a; a.virtual_concat = d.virtual_concat; a.in_coef = d.in_coef;
+    a.w_hi = w_hi; a.w_lo = w_lo; a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag;
+    a.n = d.n; a.K = d.K;
+    switch (d.n_out) {
+        case 256: launch_one<256>(a, st); break;
+        case 128: launch_one<128>(a, st); break;
+        case 64: launch_one<64>(a, st); break;
+        case 32: launch_one<32>(a, st); break;
+        default: TGNN_CHECK(false, "dense stage: n_out must be 32, 64, 128 or 256");
+    }
+}
+
+}  // namespace tgnn
