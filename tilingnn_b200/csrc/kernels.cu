@@ -43,15 +43,22 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// 3xTF32 update of one n-tile pair held in a float4 of hi and a float4 of lo B fragments
+// 3xTF32 update of one n-tile pair held in a float4 of hi and a float4 of lo B fragments.
+// Tensor cores accumulate with round-toward-zero; chaining every MMA into one accumulator builds a
+// one-sided error of ~1 ulp per instruction that train-mode BatchNorm cancels but eval-mode BatchNorm
+// amplifies.  So each k-step's three products go into a zeroed temporary (small terms first) and are
+// added to the running sum with an IEEE round-to-nearest FADD (Ootomo & Yokota's 3xTF32 recipe).
 __device__ __forceinline__ void mma3(float (&c0)[4], float (&c1)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
                                      const float4& bh, const float4& bl) {
-    mma_tf32(c0, alo, __float_as_uint(bh.x), __float_as_uint(bh.y));
-    mma_tf32(c0, ahi, __float_as_uint(bl.x), __float_as_uint(bl.y));
-    mma_tf32(c0, ahi, __float_as_uint(bh.x), __float_as_uint(bh.y));
-    mma_tf32(c1, alo, __float_as_uint(bh.z), __float_as_uint(bh.w));
-    mma_tf32(c1, ahi, __float_as_uint(bl.z), __float_as_uint(bl.w));
-    mma_tf32(c1, ahi, __float_as_uint(bh.z), __float_as_uint(bh.w));
+    float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+    mma_tf32(t0, alo, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    mma_tf32(t0, ahi, __float_as_uint(bl.x), __float_as_uint(bl.y));
+    mma_tf32(t0, ahi, __float_as_uint(bh.x), __float_as_uint(bh.y));
+    mma_tf32(t1, alo, __float_as_uint(bh.z), __float_as_uint(bh.w));
+    mma_tf32(t1, ahi, __float_as_uint(bl.z), __float_as_uint(bl.w));
+    mma_tf32(t1, ahi, __float_as_uint(bh.z), __float_as_uint(bh.w));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c0[i] += t0[i]; c1[i] += t1[i]; }
 }
 
 // K / N index maps of the frag tables.
