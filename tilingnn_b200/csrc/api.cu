@@ -428,7 +428,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             if (h->dense_ffma) launch_dense(da, st);
             else {
                 const size_t ne = (size_t)dims[k] * dims[k + 1];
-                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->fin_whl[k]->as<float>() + ne, h->dev_error.as<int>(), st);
+                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->fin_whl[k]->as<float>() + ne, h->dev_error.as<int>(), h->sm_count, st);
             }
             lz.end(1);
             if (train) {
