@@ -90,6 +90,8 @@ struct tgnn_handle {
     size_t coef_init[2]{}, coef_fin[4]{};
     std::vector<size_t> coef_a, coef_c;
     DevBuf tab;                                     // [L][K+1][2048] frag tables (entry K = root)
+    DevBuf tabS;                                    // [L][K+1][2048] transposed hi|lo tables of the tcgen05 conv kernel
+    bool conv_chunk_only = false;                   // TGNN_CONV=chunk forces the mma.sync edge-chunk kernel
 
     // workspace
     std::vector<std::unique_ptr<DevBuf>> mid;
@@ -221,8 +223,6 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
         h->fin_whl.back()->reserve(2 * ne * sizeof(float));
         launch_split_tf32(w, h->fin_whl.back()->as<float>(), h->fin_whl.back()->as<float>() + ne, (int)ne, st);
     }
-    h->dev_error.reserve(sizeof(int));
-    TGNN_CUDA(cudaMemsetAsync(h->dev_error.p, 0, sizeof(int), st));
     const char* dsel = getenv("TGNN_DENSE");
     h->dense_ffma = dsel && std::string(dsel) == "ffma";
     TGNN_CUDA(cudaMemcpyAsync(&h->fin_last_bias, h->P("final_mlp.1.linear.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -268,6 +268,14 @@ void build_tables(tgnn_handle* h, cudaStream_t st) {
                           h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), base, st);
         // nnConv.root is [in][out] = k-major already
         launch_frag_pack(h->P(c + ".nnConv.root"), F, F, TG_KMAP_GATHER, TG_NMAP_CONTIG8, base + (size_t)K * TG_FRAG32, st);
+        if (h->g.has_s) {
+            h->tabS.reserve((size_t)L * (K + 1) * TG_FRAG32 * sizeof(float));
+            launch_edge_table_s(h->g.type_rows.as<float>(), K, h->cfg.d_e,
+                                h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
+                                h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
+                                h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), h->P(c + ".nnConv.root"),
+                                h->tabS.as<float>() + (size_t)i * (K + 1) * TG_FRAG32, st);
+        }
     }
     h->tables_dirty = false;
 }
@@ -283,7 +291,7 @@ void alloc_workspace(tgnn_handle* h) {
     res(h->pre2[0], rows * F * sizeof(float));
     res(h->pre2[1], rows * F * sizeof(float));
     for (int k = 0; k < 4; ++k) res(h->fa[k], own * FIN_DIMS[k + 1] * sizeof(float));
-    size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->sm_count), (size_t)gin_num_parts((int)own, h->sm_count),
+    size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->sm_count), (size_t)h->g.s_tiles, (size_t)gin_num_parts((int)own, h->sm_count),
                           (size_t)init_num_parts((int)own, h->sm_count)});
     size_t part_bytes = std::max(np * 64, (size_t)dense_row_blocks((int)own) * 2 * 256) * sizeof(double);
     res(h->partA, part_bytes);
@@ -383,7 +391,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->g.inv_deg.as<float>();
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles;
-        lz.begin("conv"); launch_conv_adj(ca, h->sm_count, st); lz.end(1);
+        lz.begin("conv");
+        if (h->g.has_s)
+            launch_conv_s(ca, h->g, h->tabS.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32, h->dev_error.as<int>(), st);
+        else
+            launch_conv_adj(ca, h->sm_count, st);
+        lz.end(1);
 
         GinArgs ga{};
         ga.xin = i == 0 ? h->mid[0]->as<float>() : h->pre2[(i - 1) & 1].as<float>();
@@ -396,7 +409,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
 
         if (train) {
             lz.begin("bnfin");
-            launch_bn_reduce(h->partA.as<double>(), np_conv, 32, sums, st);
+            launch_bn_reduce(h->partA.as<double>(), h->g.has_s ? h->g.s_tiles : np_conv, 32, sums, st);
             launch_bn_reduce(h->partB.as<double>(), np_gin, 32, sums + 64, st);
             allreduce_sums(h, sums, 128, st);
             launch_bn_coef(sums, count, h->P(pa + ".batch_norm.weight"), h->P(pa + ".batch_norm.bias"), h->C(h->coef_a[i]), 32, st);
@@ -446,7 +459,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         TGNN_CUDA(cudaStreamSynchronize(st));
         int e = 0;
         TGNN_CUDA(cudaMemcpy(&e, h->dev_error.p, sizeof(int), cudaMemcpyDeviceToHost));
-        TGNN_CHECK(e == 0, "tgnn_forward: device-side pipeline timeout in k_dense_tc (mbarrier wait exceeded its bound)");
+        TGNN_CHECK(e == 0, "tgnn_forward: device-side pipeline timeout in a tcgen05 kernel (mbarrier wait exceeded its bound)");
     }
     if (h->profiling) {
         for (auto& e : h->prof) {
@@ -494,6 +507,10 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         std::unique_ptr<tgnn_handle> h(new tgnn_handle());
         h->cfg = *cfg;
         h->sm_count = prop.multiProcessorCount;
+        const char* csel = getenv("TGNN_CONV");
+        h->conv_chunk_only = csel && std::string(csel) == "chunk";
+        h->dev_error.reserve(sizeof(int));
+        TGNN_CUDA(cudaMemset(h->dev_error.p, 0, sizeof(int)));
         declare_params(h.get());
         *out = h.release();
     });
@@ -564,7 +581,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         cudaStream_t st = (cudaStream_t)stream;
         h->graph_set = false;
         build_graph(h->g, h->scratch, h->cfg.d_e, n_nodes, n_nodes, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src,
-                    col_dst, st);
+                    col_dst, !h->conv_chunk_only, st);
         h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
         alloc_workspace(h);
         h->tables_dirty = true;
@@ -612,7 +629,8 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
         cudaStream_t st = (cudaStream_t)stream;
         h->graph_set = false;
         const int64_t n_rows = n_own + (h->world > 1 ? (int64_t)h->world * halo_slot : 0);
-        build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst, st);
+        build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst,
+                    !h->conv_chunk_only, st);
         h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
         if (n_send > 0) {
             std::vector<int64_t> rows64(n_send);

@@ -198,6 +198,58 @@ __global__ void k_col_keys(const int64_t* __restrict__ src, const int64_t* __res
     else { key[i] = (unsigned)d; val[i] = (int)s; atomicAdd(&cnt[d], 1); }
 }
 
+// ---- S format ------------------------------------------------------------------------------------------
+// key = (tile128 << 23) | (type << 7) | local destination row
+__global__ void k_s_keys(const int64_t* __restrict__ dst, const int* __restrict__ type_of_edge, int64_t e, int64_t n_own,
+                         unsigned long long* __restrict__ key, int* __restrict__ eid) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    long long d = dst[i];
+    if (d < 0 || d >= n_own) d = 0;
+    key[i] = ((unsigned long long)(d / S_BM) << 23) | ((unsigned long long)type_of_edge[i] << 7) | (unsigned long long)(d % S_BM);
+    eid[i] = (int)i;
+}
+__global__ void k_s_flags(const unsigned long long* __restrict__ key, int64_t e, int* __restrict__ run_head) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    run_head[i] = ((i == 0) || ((key[i] >> 7) != (key[i - 1] >> 7))) ? 1 : 0;
+}
+__global__ void k_s_heads(const unsigned long long* __restrict__ key, int64_t e, const int* __restrict__ run_idx_incl,
+                          const int* __restrict__ run_head, int* __restrict__ pbase, int* __restrict__ ptype,
+                          int* __restrict__ tile_end) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const int pass = run_idx_incl[i] - 1;
+    if (run_head[i]) { pbase[pass] = (int)i; ptype[pass] = (int)((key[i] >> 7) & 0xFFFFull); }
+    const bool last_of_tile = (i + 1 == e) || ((key[i + 1] >> 23) != (key[i] >> 23));
+    if (last_of_tile) tile_end[key[i] >> 23] = pass + 1;
+    if (i + 1 == e) pbase[pass + 1] = (int)e;
+}
+// off[pass][r] = number of edges of the pass whose destination row is < r  (r = 0..128)
+__global__ void k_s_offsets(const unsigned long long* __restrict__ key, const int* __restrict__ eid_sorted,
+                            const int64_t* __restrict__ src, int64_t e, const int* __restrict__ run_idx_incl,
+                            const int* __restrict__ run_head, const int* __restrict__ pbase,
+                            unsigned short* __restrict__ off, int* __restrict__ s_src, int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    s_src[i] = (int)src[eid_sorted[i]];
+    const int pass = run_idx_incl[i] - 1;
+    const int p = (int)i - pbase[pass];
+    const int d = (int)(key[i] & 127ull);
+    unsigned short* o = off + (size_t)pass * S_OFF_STRIDE;
+    const bool grp_head = run_head[i] || (key[i] != key[i - 1]);
+    if (grp_head) {
+        const int d_prev = run_head[i] ? -1 : (int)(key[i - 1] & 127ull);
+        for (int r = d_prev + 1; r <= d; ++r) o[r] = (unsigned short)p;
+    }
+    const bool last_of_run = (i + 1 == e) || run_head[i + 1];
+    if (last_of_run) {
+        const int len = p + 1;
+        if (len > 65535) atomicOr(err, 4);
+        for (int r = d + 1; r <= S_BM; ++r) o[r] = (unsigned short)len;
+    }
+}
+
 int bits_for(unsigned long long v) { int b = 1; while ((v >> b) != 0 && b < 64) ++b; return b; }
 
 template <class K, class V>
@@ -238,7 +290,7 @@ int read_int(const int* dptr, cudaStream_t st) {
 
 void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
-                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, cudaStream_t st) {
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, cudaStream_t st) {
     TGNN_CHECK(n_own > 0 && n_rows >= n_own, "tgnn_set_graph: need n_nodes > 0");
     TGNN_CHECK(n_rows < (1ll << 31) - 64, "tgnn_set_graph: more than 2^31 rows per GPU is not supported");
     TGNN_CHECK(e_adj >= 0 && e_adj < (1ll << 31) - 64 && e_col >= 0 && e_col < (1ll << 31) - 64,
@@ -322,7 +374,32 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         incl_max(sc, tile_end, g.cptr.as<int>() + 1, g.n_tiles, st);
         k_adj_scatter<<<nblk(e_adj), TPB, 0, st>>>(k1, id1, adj_src, e_adj, run_idx, run_pos, run_chunks,
                                                     chunk_base, g.csrc.as<int>(), g.cdst.as<uint8_t>());
+        // ---------------- adjacency: S format (tcgen05 kernel) -----------------------------------------
+        g.has_s = false;
+        if (want_s && n_types <= S_MAX_TYPES) {
+            g.s_tiles = (int)((n_own + S_BM - 1) / S_BM);
+            k_s_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, k0, id0);
+            sort_pairs(sc, k0, k1, id0, id1, e_adj, 23 + bits_for((unsigned long long)g.s_tiles), st);
+            k_s_flags<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, run_head);
+            incl_sum(sc, run_head, run_idx, e_adj, st);
+            const int n_pass = read_int(run_idx + (e_adj - 1), st);
+            g.s_passes = n_pass;
+            g.s_pptr.reserve((size_t)(g.s_tiles + 1) * sizeof(int));
+            g.s_ptype.reserve((size_t)n_pass * sizeof(int));
+            g.s_pbase.reserve((size_t)(n_pass + 1) * sizeof(int));
+            g.s_off.reserve((size_t)n_pass * S_OFF_STRIDE * sizeof(unsigned short));
+            g.s_src.reserve((size_t)e_adj * sizeof(int));
+            int* s_tile_end = sc.get<int>(g.s_tiles);
+            TGNN_CUDA(cudaMemsetAsync(s_tile_end, 0, (size_t)g.s_tiles * sizeof(int), st));
+            k_s_heads<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, run_idx, run_head, g.s_pbase.as<int>(), g.s_ptype.as<int>(), s_tile_end);
+            k_s_offsets<<<nblk(e_adj), TPB, 0, st>>>(k1, id1, adj_src, e_adj, run_idx, run_head, g.s_pbase.as<int>(),
+                                                      g.s_off.as<unsigned short>(), g.s_src.as<int>(), err);
+            k_cptr_first<<<1, 32, 0, st>>>(g.s_pptr.as<int>());
+            incl_max(sc, s_tile_end, g.s_pptr.as<int>() + 1, g.s_tiles, st);
+            g.has_s = true;
+        }
     } else {
+        g.has_s = false;
         TGNN_CUDA(cudaMemsetAsync(g.cptr.p, 0, (size_t)(g.n_tiles + 1) * sizeof(int), st));
     }
     k_inv_deg<<<nblk(n_own), TPB, 0, st>>>(deg, n_own, g.inv_deg.as<float>());
@@ -348,6 +425,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
     int e = read_int(err, st);
     TGNN_CHECK((e & 1) == 0, "tgnn_set_graph: edge index out of range");
     TGNN_CHECK((e & 2) == 0, "tgnn_set_graph: 64-bit hash collision between distinct edge-feature rows");
+    TGNN_CHECK((e & 4) == 0, "tgnn_set_graph: more than 65535 same-type in-edges in one 128-row tile");
     TGNN_CUDA(cudaGetLastError());
 }
 

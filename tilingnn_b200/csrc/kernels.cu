@@ -271,7 +271,8 @@ k_conv_adj(ConvArgs A) {
 // ------------------------------------------------------------------------------------------------
 constexpr int GIN_W1 = 2048, GIN_W2 = 4096, GIN_W3 = 4096;                 // floats (hi + lo)
 constexpr int GIN_WFLOATS = GIN_W1 + GIN_W2 + GIN_W3 + 128;                // + b1[32] b2[64] b3[32]
-constexpr int GIN_WARP_FLOATS = CH * XS;
+constexpr int GIN_IDX_CAP = 1024;                                         // staged neighbour indices per 16-node chunk
+constexpr int GIN_WARP_FLOATS = CH * XS + GIN_IDX_CAP;
 
 __device__ __forceinline__ float4 center4(float4 v, const float4& mh, const float4& ml) {
     v.x = (v.x - mh.x) - ml.x; v.y = (v.y - mh.y) - ml.y; v.z = (v.z - mh.z) - ml.z; v.w = (v.w - mh.w) - ml.w;
@@ -293,6 +294,7 @@ k_gin(GinArgs A) {
     const float* b2 = b1 + 32;
     const float* b3 = b2 + 64;
     float* xs = smem + GIN_WFLOATS + warp * GIN_WARP_FLOATS;
+    int* sidx = reinterpret_cast<int*>(xs + CH * XS);
     const int a = lane >> 3, q = lane & 7;       // gather roles
     const int g = lane >> 2, t = lane & 3;       // mma roles
     const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
@@ -311,40 +313,39 @@ k_gin(GinArgs A) {
 
     for (int chunk = gwarp; chunk < n_chunks; chunk += nwarp) {
         const int node0 = chunk * CH;
-        // ---- gather + sum ---------------------------------------------------------------------
-        for (int r = 0; r < CH; ++r) {
-            const int node = node0 + r;
+        // ---- gather + sum: each 8-lane group owns nodes 4i+a of the chunk and keeps 8 neighbour rows in flight;
+        // ---- the chunk's neighbour indices are staged in shared memory first (no dependent global load) -----
+        int p = 0;
+        if (lane <= CH) p = __ldg(A.col_ptr + min(node0 + lane, A.n_own));
+        const int e_lo = __shfl_sync(0xffffffffu, p, 0), e_hi = __shfl_sync(0xffffffffu, p, CH);
+        const bool staged = (e_hi - e_lo) <= GIN_IDX_CAP;
+        if (staged) for (int i = lane; i < e_hi - e_lo; i += 32) sidx[i] = __ldg(A.col_src + e_lo + i);
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < CH / 4; ++i) {
+            const int r = 4 * i + a, node = node0 + r;
+            const int e0 = __shfl_sync(0xffffffffu, p, r), e1 = __shfl_sync(0xffffffffu, p, r + 1);
             float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-            int deg = 0;
-            if (node < A.n_own) {
-                const int e0 = __ldg(A.col_ptr + node), e1 = __ldg(A.col_ptr + node + 1);
-                deg = e1 - e0;
-                if (a == 0) {
-                    float4 c = center4(ld_row4(A.xin, node, q), mh, ml);
-                    sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
-                }
-                int e = e0 + a;
-                for (; e + 12 < e1; e += 16) {
-                    const int i0 = __ldg(A.col_src + e), i1 = __ldg(A.col_src + e + 4);
-                    const int i2 = __ldg(A.col_src + e + 8), i3 = __ldg(A.col_src + e + 12);
-                    const float4 v0 = ld_row4(A.xin, i0, q), v1 = ld_row4(A.xin, i1, q);
-                    const float4 v2 = ld_row4(A.xin, i2, q), v3 = ld_row4(A.xin, i3, q);
-                    add4(sum, center4(v0, mh, ml)); add4(sum, center4(v1, mh, ml));
-                    add4(sum, center4(v2, mh, ml)); add4(sum, center4(v3, mh, ml));
-                }
-                for (; e < e1; e += 4) add4(sum, center4(ld_row4(A.xin, __ldg(A.col_src + e), q), mh, ml));
+            const bool live = node < A.n_own;
+            if (live) {
+                float4 c = center4(ld_row4(A.xin, node, q), mh, ml);
+                sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
             }
-            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 8);  sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 8);
-            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, 8);  sum.w += __shfl_xor_sync(0xffffffffu, sum.w, 8);
-            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, 16); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, 16);
-            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, 16); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, 16);
-            if (a == 0) {
-                const float nt = node < A.n_own ? self_w + (float)deg : 0.f;
-                float4 h;
-                h.x = fmaf(sc.x, sum.x, nt * be.x); h.y = fmaf(sc.y, sum.y, nt * be.y);
-                h.z = fmaf(sc.z, sum.z, nt * be.z); h.w = fmaf(sc.w, sum.w, nt * be.w);
-                *reinterpret_cast<float4*>(xs + r * XS + 4 * q) = h;
+            for (int e = live ? e0 : e1; e < e1; e += 8) {
+                int idx[8];
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) idx[k] = e + k < e1 ? (staged ? sidx[e + k - e_lo] : __ldg(A.col_src + e + k)) : -1;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = idx[k] >= 0 ? ld_row4(A.xin, idx[k], q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) if (idx[k] >= 0) add4(sum, center4(v[k], mh, ml));
             }
+            const float nt = live ? self_w + (float)(e1 - e0) : 0.f;
+            float4 h;
+            h.x = fmaf(sc.x, sum.x, nt * be.x); h.y = fmaf(sc.y, sum.y, nt * be.y);
+            h.z = fmaf(sc.z, sum.z, nt * be.z); h.w = fmaf(sc.w, sum.w, nt * be.w);
+            *reinterpret_cast<float4*>(xs + r * XS + 4 * q) = h;
         }
         __syncwarp();
         // ---- layer 1: 32 -> 32, A from shared memory (natural K order) -------------------------------

@@ -78,6 +78,15 @@ struct Graph {
     DevBuf cdst;              // uint8 [n_chunks * CH] local destination row in the tile
     DevBuf inv_deg;           // float [n_own]         1 / max(1, in-degree)
     DevBuf type_rows;         // float [n_types * d_e] representative feature row per type
+    // "S" format for the tcgen05 adjacency kernel: destinations in tiles of 128 rows; a tile's in-edges sorted by
+    // (type, destination row); one PASS per distinct type present in the tile
+    bool has_s = false;
+    int s_tiles = 0, s_passes = 0;
+    DevBuf s_pptr;            // int32  [s_tiles + 1]      pass range per tile
+    DevBuf s_ptype;           // int32  [s_passes]         edge type of the pass
+    DevBuf s_pbase;           // int32  [s_passes + 1]     first edge of the pass in s_src
+    DevBuf s_off;             // uint16 [s_passes * 136]   per pass: edge offset of row r (r = 0..128) inside the pass
+    DevBuf s_src;             // int32  [e_adj]            source rows in (tile, type, row) order
     // collision CSR by destination (self loops removed)
     DevBuf col_ptr;           // int32 [n_own + 1]
     DevBuf col_src;           // int32 [e_col]
@@ -101,7 +110,10 @@ struct Scratch {
 // graph_build.cu
 void build_graph(Graph& g, Scratch& scratch, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
-                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, cudaStream_t st);
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, cudaStream_t st);
+constexpr int S_BM = 128;         // destination rows per tile of the S format
+constexpr int S_OFF_STRIDE = 136; // uint16 per pass (129 used; 272 B keeps 16-byte alignment)
+constexpr int S_MAX_TYPES = 120;  // the S path is chosen only when K + 1 (root) passes fit its per-tile tables
 
 // ----- kernels.cu launchers --------------------------------------------------------------------
 struct ConvArgs {
@@ -117,6 +129,11 @@ struct ConvArgs {
 };
 int conv_adj_num_parts(int n_tiles, int sm_count);
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
+
+// tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
+void launch_edge_table_s(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
+                         const float* c2, const float* a3, const float* c3, const float* root, float* tab, cudaStream_t st);
+void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, cudaStream_t st);
 
 struct GinArgs {
     const float* xin;        // [n_rows][32]  pre-BN activations of the previous collision layer (or h0)
