@@ -393,7 +393,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles;
         lz.begin("conv");
         if (h->g.has_s)
-            launch_conv_s(ca, h->g, h->tabS.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32, h->dev_error.as<int>(), st);
+            launch_conv_s(ca, h->g, h->tabS.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
         else
             launch_conv_adj(ca, h->sm_count, st);
         lz.end(1);

@@ -8,13 +8,16 @@
 // atomics, cost per (destination, type) instead of per edge, and M = 128 is what tcgen05 wants.  (The edge-chunk
 // mma.sync kernel in kernels.cu remains the path for graphs with many edge types, where K passes do not pay.)
 //
-// CTA = one tile of 128 destinations, 2 CTAs per SM.
-//   producer group g (4 warps, passes p = g, g+2, ...): gather + pre-sum the source rows into registers (the
-//     pass's row offsets, source indices and weight tiles were prefetched one pass ahead with cp.async), then
-//     wait for its smem stage, hi/lo TF32 split, swizzled store, fence, mbarrier arrive
-//   MMA warp: per pass 12 x tcgen05.mma.kind::tf32 (M=128, N=32; 3xTF32), commit -> stage empty
-//   the root term x_i root is one more pass into a second accumulator (columns 32..63)
-//   epilogue (warps 0-3): tcgen05.ld, * 1/deg + root + bias, LeakyReLU, store, BatchNorm partial sums (fp64)
+// Persistent CTAs (one per SM) walk tiles of 128 destinations; 17 warps, warp specialised:
+//   loaders (4 warps, pass s -> warp s%4): cp.async the pass's source rows into a 608-row shared-memory ring,
+//     its weight tiles and row-offset table into a slot ring; completion is signalled asynchronously with
+//     cp.async.mbarrier.arrive, so up to 6 passes of gathers are in flight without holding registers
+//   transformers (8 warps): per (row, 16-byte chunk) sum the row's sources from the ring, hi/lo TF32 split,
+//     swizzled store into the A operand stage, fence, mbarrier arrive
+//   MMA warp: per pass 12 x tcgen05.mma.kind::tf32 (M=128, N=32; 3xTF32), commits free the stage and the slot
+//   the root term x_i root is one more pass into a second accumulator (columns 32..63); TMEM is double buffered
+//   epilogue (4 warps): tcgen05.ld, * 1/deg + root + bias, LeakyReLU, store, BatchNorm partial sums (fp64),
+//     overlapping the next tile's passes
 #include <algorithm>
 
 #include "tc_common.cuh"
@@ -26,17 +29,24 @@ using namespace tc;
 
 constexpr int SA_TILE = 16384;                 // bytes of one A tile (hi or lo): 128 rows x 128 B
 constexpr int SB_TILE = 4096;                  // bytes of one B tile (hi or lo): 32 rows x 128 B
-constexpr int IDX_CAP = 512;                   // staged source indices per pass
-constexpr int CS_THREADS = 9 * 32;             // 2 producer groups x 4 warps + MMA warp
-constexpr int OFF_A = 0;                                   // [2 stages][hi|lo]
-constexpr int OFF_B = OFF_A + 4 * SA_TILE;                 // [2 groups][2 slots][hi|lo]
-constexpr int OFF_IDX = OFF_B + 8 * SB_TILE;               // [2 groups][2 slots][IDX_CAP] int
-constexpr int OFF_OFFB = OFF_IDX + 4 * IDX_CAP * 4;        // [2 groups][2 slots][S_OFF_STRIDE] uint16
-constexpr int OFF_SCAL = OFF_OFFB + 4 * S_OFF_STRIDE * 2;  // ptype[128], pbase[129]
-constexpr int CS_SMEM = OFF_SCAL + (128 + 132) * 4 + 1024;
+constexpr int D_SLOTS = 6;                     // passes in flight (ring of weight tiles / offset rows / barriers)
+constexpr int RING_ROWS = 608;                 // gathered source rows in flight (76 KB)
+constexpr int N_LOAD = 4, N_XFORM = 8;         // loader warps, transformer warps
+constexpr int W_MMA = N_LOAD + N_XFORM, W_EPI0 = W_MMA + 1;
+constexpr int CS_THREADS = (W_EPI0 + 4) * 32;  // 17 warps
+constexpr int OFF_A = 0;                                        // [2 stages][hi|lo]
+constexpr int OFF_B = OFF_A + 4 * SA_TILE;                      // [D_SLOTS][hi|lo]
+constexpr int OFF_RING = OFF_B + D_SLOTS * 2 * SB_TILE;         // [RING_ROWS][128 B]
+constexpr int OFF_OFFB = OFF_RING + RING_ROWS * 128;            // [D_SLOTS][S_OFF_STRIDE] uint16
+constexpr int OFF_META = OFF_OFFB + D_SLOTS * S_OFF_STRIDE * 2; // [D_SLOTS] int4 {first ring row of the pass, root flag, -, -}
+constexpr int OFF_EPI = OFF_META + D_SLOTS * 16;                // scratch [4][32*33] float, red [4][2][32] double
+constexpr int CS_SMEM = OFF_EPI + 4 * 32 * 33 * 4 + 4 * 2 * 32 * 8 + 1024;
 
 __device__ __forceinline__ float4 ld_row4(const float* base, int row, int q) {
     return __ldg(reinterpret_cast<const float4*>(base + (size_t)row * F) + q);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
 struct ConvSArgs {
@@ -46,36 +56,32 @@ struct ConvSArgs {
     const int* pptr; const int* ptype; const int* pbase; const unsigned short* off; const int* ssrc;
     const float* inv_deg; const float* bias;
     float* out; double* part; int* error_flag;
-    int n_own, n_tiles;
+    int n_own, n_tiles, d_eff;   // d_eff: passes in flight such that d_eff * (longest pass) <= RING_ROWS
 };
 
-__global__ void __launch_bounds__(CS_THREADS, 2)
+__global__ void __launch_bounds__(CS_THREADS, 1)
 k_conv_s(ConvSArgs A) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[5];          // full[2], empty[2], acc
+    __shared__ __align__(8) uint64_t bars[2 * D_SLOTS + 4 + 4];   // raw_full[D], raw_empty[D], a_full[2], a_empty[2], acc_full[2], acc_empty[2]
     __shared__ uint32_t tmem_base_smem;
     __shared__ int timeout_flag;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
-    int* s_ptype = reinterpret_cast<int*>(smem + OFF_SCAL);
-    int* s_pbase = s_ptype + 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[2]), bar_acc = smem_u32(&bars[4]);
-    const int tile = blockIdx.x;
-    const int p0 = __ldg(A.pptr + tile), np = __ldg(A.pptr + tile + 1) - p0;   // typed passes of this tile
+    const uint32_t bar_rf = smem_u32(&bars[0]), bar_re = smem_u32(&bars[D_SLOTS]);
+    const uint32_t bar_af = smem_u32(&bars[2 * D_SLOTS]), bar_ae = smem_u32(&bars[2 * D_SLOTS + 2]);
+    const uint32_t bar_cf = smem_u32(&bars[2 * D_SLOTS + 4]), bar_ce = smem_u32(&bars[2 * D_SLOTS + 6]);
+    const int D = A.d_eff;
 
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_full + 8 * s, 4); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_acc, 1);
+        for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 33); mbar_init(bar_re + 8 * i, N_XFORM + 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_af + 8 * i, N_XFORM); mbar_init(bar_ae + 8 * i, 1);
+                                      mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4); }
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i <= np && i < 129; i += CS_THREADS) {
-        if (i < np) s_ptype[i] = __ldg(A.ptype + p0 + i);
-        s_pbase[i] = __ldg(A.pbase + p0 + i);
-    }
-    if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(64));
+    if (warp == W_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(128));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -83,167 +89,246 @@ k_conv_s(ConvSArgs A) {
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
 
-    if (warp < 8) {
-        // ===================== producers =====================
-        const int g = warp >> 2, gt = tid & 127, c = gt & 7, rbase = gt >> 3;
-        const uint32_t bar_id = 2 + g;
-        auto prefetch = [&](int q, int slot) {
-            if (q > np) return;
-            const int type = q < np ? s_ptype[q] : A.n_types;
-            const uint32_t bdst = smem_base + OFF_B + (uint32_t)((g * 2 + slot) * 2) * SB_TILE;
-            for (int i = gt; i < 512; i += 128) {
+    if (warp < N_LOAD) {
+        // ===================== loaders: warp w takes passes s = w, w+4, ... of the CTA's pass sequence ==========
+        // Per tile the pass table (pbase, ptype) sits in registers (lane i holds entries i, i+32, ...); the source
+        // indices of a pass are requested one own-pass ahead of their use (two register buffers), so the loader
+        // itself only ever blocks on the ring-slot barrier.
+        const int c = lane & 7, sub = lane >> 3;
+        int s = 0, rows = 0;                               // pass counter / ring rows consumed so far
+        int idxA[10], idxB[10];                            // source indices of a pass (<= 320 edges)
+        bool par = false;                                  // pending pass's indices live in (par ? idxA : idxB)
+        int pd_tile = -1, pd_off = 0, pd_len = 0, pd_type = 0, pd_s = 0, pd_rows = 0;
+        auto issue = [&]() -> bool {
+            const bool root = pd_len < 0;
+            const int len = root ? S_BM : pd_len;
+            const int slot = pd_s % D;
+            if (!mbar_wait(bar_re + 8 * slot, (uint32_t)(((pd_s / D) & 1) ^ 1))) return false;
+            const uint32_t bdst = smem_base + OFF_B + (uint32_t)slot * 2 * SB_TILE;
+#pragma unroll 4
+            for (int i = lane; i < 512; i += 32) {
                 const int hl = i >> 8, n = (i >> 3) & 31, cc = i & 7;
-                const float* src = A.tabS + ((size_t)(type * 2 + hl) * 32 + n) * 32 + 4 * cc;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(bdst + hl * SB_TILE + sw128_off(n, cc)), "l"(src) : "memory");
+                cp_async16(bdst + hl * SB_TILE + sw128_off(n, cc), A.tabS + ((size_t)(pd_type * 2 + hl) * 32 + n) * 32 + 4 * cc);
             }
-            if (q < np) {
-                const uint32_t odst = smem_base + OFF_OFFB + (uint32_t)(g * 2 + slot) * S_OFF_STRIDE * 2;
-                if (gt < 17) {
-                    const unsigned short* src = A.off + (size_t)(p0 + q) * S_OFF_STRIDE + gt * 8;
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(odst + gt * 16), "l"(src) : "memory");
+            const int ring0 = pd_rows % RING_ROWS;
+            if (!root) {
+                if (lane < 17)
+                    cp_async16(smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2 + lane * 16,
+                               A.off + (size_t)pd_off * S_OFF_STRIDE + lane * 8);
+#pragma unroll
+                for (int jb = 0; jb < 10; ++jb) {
+                    if (32 * jb < len) {
+                        const int mine = par ? idxA[jb] : idxB[jb];
+                        const int cnt = min(32, len - 32 * jb);
+                        for (int j = 0; j < cnt; j += 4) {
+                            const int src = __shfl_sync(0xffffffffu, mine, (j + sub) & 31);
+                            if (j + sub < cnt) {
+                                int rr = ring0 + 32 * jb + j + sub; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                                cp_async16(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16, A.xin + (size_t)src * F + 4 * c);
+                            }
+                        }
+                    }
                 }
-                const int base = s_pbase[q], len = s_pbase[q + 1] - base;
-                if (len <= IDX_CAP) {
-                    const uint32_t idst = smem_base + OFF_IDX + (uint32_t)(g * 2 + slot) * IDX_CAP * 4;
-                    for (int i = gt; i < len; i += 128)
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(idst + i * 4), "l"(A.ssrc + base + i) : "memory");
+            } else {
+                const int node0 = pd_tile * S_BM;
+                for (int j = 0; j < S_BM; j += 4) {
+                    const int node = node0 + j + sub;
+                    if (node < A.n_own) {
+                        int rr = ring0 + j + sub; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                        cp_async16(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16, A.xin + (size_t)node * F + 4 * c);
+                    }
                 }
             }
+            if (lane == 0) {
+                *reinterpret_cast<int4*>(smem + OFF_META + slot * 16) = make_int4(ring0, root ? 1 : 0, 0, 0);
+                mbar_arrive(bar_rf + 8 * slot);            // releases the metadata store
+            }
+            // asynchronous arrive: counts once all cp.async issued by this lane have landed
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_rf + 8 * slot) : "memory");
+            return true;
         };
-        prefetch(g, 0);
         bool ok = true;
-        for (int q = g, k = 0; q <= np && ok; q += 2, ++k) {
-            const int slot = k & 1;
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-            // ---- gather + pre-sum into registers (overlaps the MMAs of earlier passes) ----
-            float4 v[8];
-            if (q < np) {
-                const unsigned short* ob = reinterpret_cast<const unsigned short*>(smem + OFF_OFFB) + (g * 2 + slot) * S_OFF_STRIDE;
-                const int* ib = reinterpret_cast<const int*>(smem + OFF_IDX) + (g * 2 + slot) * IDX_CAP;
-                const int base = s_pbase[q];
-                const bool staged = (s_pbase[q + 1] - base) <= IDX_CAP;
-                int es[8], ee[8];
+        for (int tile = blockIdx.x; tile < A.n_tiles && ok; tile += gridDim.x) {
+            const int p0 = __ldg(A.pptr + tile), np = __ldg(A.pptr + tile + 1) - p0;
+            int pb[4], pt[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { es[j] = ob[rbase + 16 * j]; ee[j] = ob[rbase + 16 * j + 1]; }
+            for (int j = 0; j < 4; ++j) {
+                pb[j] = (32 * j + lane <= np) ? __ldg(A.pbase + p0 + 32 * j + lane) : 0;
+                pt[j] = (32 * j + lane < np) ? __ldg(A.ptype + p0 + 32 * j + lane) : 0;
+            }
+            auto lookup = [&](const int (&arr)[4], int i) {
+                const int v0 = __shfl_sync(0xffffffffu, arr[0], i & 31), v1 = __shfl_sync(0xffffffffu, arr[1], i & 31);
+                const int v2 = __shfl_sync(0xffffffffu, arr[2], i & 31), v3 = __shfl_sync(0xffffffffu, arr[3], i & 31);
+                const int j = i >> 5;
+                return j == 0 ? v0 : (j == 1 ? v1 : (j == 2 ? v2 : v3));
+            };
+            for (int q = 0; q <= np && ok; ++q, ++s) {
+                const bool root = q == np;
+                const int base = root ? 0 : lookup(pb, q);
+                const int len = root ? S_BM : lookup(pb, q + 1) - base;
+                const int type = root ? A.n_types : lookup(pt, q);
+                if (s % N_LOAD == warp) {
+                    if (!root) {                            // request this pass's indices into the free buffer
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (es[j] < ee[j]) {
-                        const int idx = staged ? ib[es[j]] : __ldg(A.ssrc + base + es[j]);
-                        v[j] = ld_row4(A.xin, idx, c);
+                        for (int j = 0; j < 10; ++j) {
+                            const int v = (32 * j + lane < len) ? __ldg(A.ssrc + base + 32 * j + lane) : 0;
+                            if (par) idxB[j] = v; else idxA[j] = v;
+                        }
                     }
+                    if (pd_tile >= 0) ok = issue();         // issue the pass requested one own-pass ago
+                    pd_tile = tile; pd_off = p0 + q; pd_len = root ? -1 : len; pd_type = type; pd_s = s; pd_rows = rows;
+                    par = !par;
                 }
+                rows += len;
+            }
+        }
+        if (ok && pd_tile >= 0) ok = issue();
+        if (!ok) timeout_flag = 1;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp < W_MMA) {
+        // ===================== transformers: item (row = tt/8 + 32 j, chunk = tt%8) =====================
+        const int tt = tid - N_LOAD * 32, c = tt & 7, rbase = tt >> 3;
+        int s = 0;
+        for (int tile = blockIdx.x; tile < A.n_tiles;) {
+            const int slot = s % D, st = s & 1;
+            if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { timeout_flag = 1; break; }
+            const int4 meta = *reinterpret_cast<const int4*>(smem + OFF_META + slot * 16);
+            const int ring0 = meta.x;
+            const bool root = meta.y != 0;
+            float4 v[4];
+            if (!root) {
+                const unsigned short* ob = reinterpret_cast<const unsigned short*>(smem + OFF_OFFB) + slot * S_OFF_STRIDE;
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    for (int t = es[j] + 1; t < ee[j]; ++t) {
-                        const int idx = staged ? ib[t] : __ldg(A.ssrc + base + t);
-                        const float4 w = ld_row4(A.xin, idx, c);
-                        v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w;
+                for (int j = 0; j < 4; ++j) {
+                    const int r = rbase + 32 * j;
+                    const int es = ob[r], ee = ob[r + 1];
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int t = es; t < ee; ++t) {
+                        int rr = ring0 + t; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                        const float4 w = *reinterpret_cast<const float4*>(smem + OFF_RING + rr * 128 + c * 16);
+                        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
                     }
+                    v[j] = acc;
+                }
             } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int node = tile * S_BM + rbase + 16 * j;
-                    v[j] = node < A.n_own ? ld_row4(A.xin, node, c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int j = 0; j < 4; ++j) {
+                    const int r = rbase + 32 * j;
+                    int rr = ring0 + r; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                    v[j] = tile * S_BM + r < A.n_own ? *reinterpret_cast<const float4*>(smem + OFF_RING + rr * 128 + c * 16)
+                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
-            // ---- stage g is free once the MMAs of pass q-2 have read it ----
-            if (!mbar_wait(bar_empty + 8 * g, (k & 1) ^ 1)) { timeout_flag = 1; ok = false; break; }
-            prefetch(q + 2, slot ^ 1);
-            uint8_t* sa_hi = smem + OFF_A + (g * 2) * SA_TILE;
+            if (!mbar_wait(bar_ae + 8 * st, (uint32_t)(((s >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
+            uint8_t* sa_hi = smem + OFF_A + (st * 2) * SA_TILE;
             uint8_t* sa_lo = sa_hi + SA_TILE;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < 4; ++j) {
                 uint4 hi, lo;
                 hi.x = tf32_rna(v[j].x); lo.x = tf32_rna(v[j].x - __uint_as_float(hi.x));
                 hi.y = tf32_rna(v[j].y); lo.y = tf32_rna(v[j].y - __uint_as_float(hi.y));
                 hi.z = tf32_rna(v[j].z); lo.z = tf32_rna(v[j].z - __uint_as_float(hi.z));
                 hi.w = tf32_rna(v[j].w); lo.w = tf32_rna(v[j].w - __uint_as_float(hi.w));
-                const uint32_t o = sw128_off(rbase + 16 * j, c);
+                const uint32_t o = sw128_off(rbase + 32 * j, c);
                 *reinterpret_cast<uint4*>(sa_hi + o) = hi;
                 *reinterpret_cast<uint4*>(sa_lo + o) = lo;
             }
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full + 8 * g);
+            if (lane == 0) { mbar_arrive(bar_af + 8 * st); mbar_arrive(bar_re + 8 * slot); }
+            ++s;
+            if (root) tile += gridDim.x;
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (lane == 0) {
+    } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
-        constexpr uint32_t IDESC = umma_idesc_tf32(32);
-        for (int q = 0; q <= np; ++q) {
-            const int g = q & 1, k = q >> 1, slot = k & 1;
-            if (!mbar_wait(bar_full + 8 * g, k & 1)) { timeout_flag = 1; break; }
-            tc_fence_after();
-            const uint32_t a_hi = smem_base + OFF_A + (g * 2) * SA_TILE, a_lo = a_hi + SA_TILE;
-            const uint32_t b_hi = smem_base + OFF_B + (uint32_t)((g * 2 + slot) * 2) * SB_TILE, b_lo = b_hi + SB_TILE;
-            const bool root = q == np;
-            const uint32_t tmem_d = tmem_base + (root ? 32u : 0u);
+        if (lane == 0) {
+            constexpr uint32_t IDESC = umma_idesc_tf32(32);
+            int s = 0, it = 0, q = 0;
+            for (int tile = blockIdx.x; tile < A.n_tiles;) {
+                const int slot = s % D, st = s & 1, ab = it & 1;
+                if (q == 0 && !mbar_wait(bar_ce + 8 * ab, (uint32_t)(((it >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
+                if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { timeout_flag = 1; break; }
+                const bool root = reinterpret_cast<const int4*>(smem + OFF_META + slot * 16)->y != 0;
+                if (!mbar_wait(bar_af + 8 * st, (uint32_t)((s >> 1) & 1))) { timeout_flag = 1; break; }
+                fence_proxy_async();                   // weight tiles were written by the loaders' cp.async
+                tc_fence_after();
+                const uint32_t a_hi = smem_base + OFF_A + (st * 2) * SA_TILE, a_lo = a_hi + SA_TILE;
+                const uint32_t b_hi = smem_base + OFF_B + (uint32_t)slot * 2 * SB_TILE, b_lo = b_hi + SB_TILE;
+                const uint32_t tmem_d = tmem_base + (uint32_t)(ab * 64) + (root ? 32u : 0u);
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t kb = ks * 32;
-                const uint64_t dah = umma_desc_sw128(a_hi + kb), dal = umma_desc_sw128(a_lo + kb);
-                const uint64_t dbh = umma_desc_sw128(b_hi + kb), dbl = umma_desc_sw128(b_lo + kb);
-                umma_tf32(tmem_d, dal, dbh, IDESC, (ks > 0 || (!root && q > 0)) ? 1u : 0u);
-                umma_tf32(tmem_d, dah, dbl, IDESC, 1u);
-                umma_tf32(tmem_d, dah, dbh, IDESC, 1u);
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t kb = ks * 32;
+                    const uint64_t dah = umma_desc_sw128(a_hi + kb), dal = umma_desc_sw128(a_lo + kb);
+                    const uint64_t dbh = umma_desc_sw128(b_hi + kb), dbl = umma_desc_sw128(b_lo + kb);
+                    umma_tf32(tmem_d, dal, dbh, IDESC, (ks > 0 || (!root && q > 0)) ? 1u : 0u);
+                    umma_tf32(tmem_d, dah, dbl, IDESC, 1u);
+                    umma_tf32(tmem_d, dah, dbh, IDESC, 1u);
+                }
+                umma_commit(bar_ae + 8 * st);          // operand stage free
+                umma_commit(bar_re + 8 * slot);        // weight tile / ring rows of the slot free
+                ++s; ++q;
+                if (root) { umma_commit(bar_cf + 8 * ab); tile += gridDim.x; ++it; q = 0; }
             }
-            umma_commit(bar_empty + 8 * g);
         }
-        umma_commit(bar_acc);
-    }
-
-    // ===================== epilogue: warps 0-3, tile row = 32 * warp + lane =====================
-    float* scratch = reinterpret_cast<float*>(smem + OFF_A);                    // [4][32*33] floats
-    double* red = reinterpret_cast<double*>(smem + OFF_A + 4 * 32 * 33 * 4);    // [4][2][32]
-    bool acc_ok = true;
-    if (warp < 4) {
-        acc_ok = mbar_wait(bar_acc, 0);
-        if (!acc_ok) timeout_flag = 1;
-        tc_fence_after();
-        const int row = tile * S_BM + 32 * warp + lane;
-        const bool live = row < A.n_own && acc_ok;
-        uint32_t vt[32], vr[32];
-        tmem_ld32(tmem_base + ((uint32_t)(32 * warp) << 16) + 32u, vr);
-        if (np > 0) tmem_ld32(tmem_base + ((uint32_t)(32 * warp) << 16), vt);
-        const float idg = live ? __ldg(A.inv_deg + row) : 0.f;
-        float o[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float t = np > 0 ? __uint_as_float(vt[j]) : 0.f;
-            o[j] = leaky(fmaf(t, idg, __uint_as_float(vr[j])) + __ldg(A.bias + j));
-        }
-        if (live) {
-            float4* dst = reinterpret_cast<float4*>(A.out + (size_t)row * F);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        }
-        if (A.part) {
-            float* sc = scratch + warp * (32 * 33);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = o[j];
+    } else {
+        // ===================== epilogue warps: TMEM lane quarter q4 = warp % 4 =====================
+        const int q4 = warp & 3, etid = (warp - W_EPI0) * 32 + lane;
+        float* sc = reinterpret_cast<float*>(smem + OFF_EPI) + q4 * (32 * 33);
+        double* red = reinterpret_cast<double*>(smem + OFF_EPI + 4 * 32 * 33 * 4);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++it) {
+            const int ab = it & 1;
+            const int np = __ldg(A.pptr + tile + 1) - __ldg(A.pptr + tile);
+            if (!mbar_wait(bar_cf + 8 * ab, (uint32_t)((it >> 1) & 1))) { timeout_flag = 1; break; }
+            tc_fence_after();
+            const int row = tile * S_BM + 32 * q4 + lane;
+            const bool live = row < A.n_own;
+            uint32_t vt[32], vr[32];
+            const uint32_t tbase = tmem_base + ((uint32_t)(32 * q4) << 16) + (uint32_t)(ab * 64);
+            tmem_ld32(tbase + 32u, vr);
+            if (np > 0) tmem_ld32(tbase, vt);
+            tc_fence_before();
             __syncwarp();
-            int nv = A.n_own - (tile * S_BM + 32 * warp);
-            nv = (!acc_ok || nv < 0) ? 0 : (nv > 32 ? 32 : nv);
-            double s1 = 0.0, s2 = 0.0;
-            for (int r = 0; r < nv; ++r) { const double x = (double)sc[r * 33 + lane]; s1 += x; s2 += x * x; }
-            red[(warp * 2 + 0) * 32 + lane] = s1;
-            red[(warp * 2 + 1) * 32 + lane] = s2;
+            if (lane == 0) mbar_arrive(bar_ce + 8 * ab);          // accumulator buffer free for the tile after next
+            const float idg = live ? __ldg(A.inv_deg + row) : 0.f;
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float t = np > 0 ? __uint_as_float(vt[j]) : 0.f;
+                o[j] = leaky(fmaf(t, idg, __uint_as_float(vr[j])) + __ldg(A.bias + j));
+            }
+            if (live) {
+                float4* dst = reinterpret_cast<float4*>(A.out + (size_t)row * F);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+            if (A.part) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = o[j];
+                __syncwarp();
+                int nv = A.n_own - (tile * S_BM + 32 * q4);
+                nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+                double s1 = 0.0, s2 = 0.0;
+                for (int r = 0; r < nv; ++r) { const double x = (double)sc[r * 33 + lane]; s1 += x; s2 += x * x; }
+                red[(q4 * 2 + 0) * 32 + lane] = s1;
+                red[(q4 * 2 + 1) * 32 + lane] = s2;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (etid < 64) {
+                    const int qq = etid >> 5, cc = etid & 31;
+                    A.part[(size_t)tile * 64 + etid] = ((red[(0 * 2 + qq) * 32 + cc] + red[(1 * 2 + qq) * 32 + cc]) +
+                                                        red[(2 * 2 + qq) * 32 + cc]) + red[(3 * 2 + qq) * 32 + cc];
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
-    if (A.part && tid < 64) {
-        const int qq = tid >> 5, cc = tid & 31;
-        A.part[(size_t)tile * 64 + tid] = ((red[(0 * 2 + qq) * 32 + cc] + red[(1 * 2 + qq) * 32 + cc]) + red[(2 * 2 + qq) * 32 + cc]) +
-                                          red[(3 * 2 + qq) * 32 + cc];
-    }
     if (timeout_flag && tid == 0) atomicExch(A.error_flag, 1);
-    if (warp == 8) {
+    if (warp == W_MMA) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(64));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128));
     }
 }
 
@@ -298,7 +383,7 @@ void launch_edge_table_s(const float* type_rows, int n_types, int d_e, const flo
     TGNN_CUDA(cudaGetLastError());
 }
 
-void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, cudaStream_t st) {
+void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_s, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
@@ -310,7 +395,10 @@ void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* er
     a.off = g.s_off.as<unsigned short>(); a.ssrc = g.s_src.as<int>();
     a.inv_deg = c.inv_deg; a.bias = c.bias; a.out = c.out; a.part = c.part; a.error_flag = error_flag;
     a.n_own = c.n_own; a.n_tiles = g.s_tiles;
-    k_conv_s<<<g.s_tiles, CS_THREADS, CS_SMEM, st>>>(a);
+    const int longest = std::max(g.s_max_pass, S_BM);              // the root pass stages 128 rows
+    a.d_eff = std::min(D_SLOTS, RING_ROWS / longest);
+    TGNN_CHECK(a.d_eff >= 2, "conv_s: pass too long for the shared-memory ring");
+    k_conv_s<<<std::min(g.s_tiles, sm_count), CS_THREADS, CS_SMEM, st>>>(a);
     TGNN_CUDA(cudaGetLastError());
 }
 

@@ -229,7 +229,8 @@ __global__ void k_s_heads(const unsigned long long* __restrict__ key, int64_t e,
 __global__ void k_s_offsets(const unsigned long long* __restrict__ key, const int* __restrict__ eid_sorted,
                             const int64_t* __restrict__ src, int64_t e, const int* __restrict__ run_idx_incl,
                             const int* __restrict__ run_head, const int* __restrict__ pbase,
-                            unsigned short* __restrict__ off, int* __restrict__ s_src, int* __restrict__ err) {
+                            unsigned short* __restrict__ off, int* __restrict__ s_src, int* __restrict__ err,
+                            int* __restrict__ max_len) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= e) return;
     s_src[i] = (int)src[eid_sorted[i]];
@@ -246,6 +247,7 @@ __global__ void k_s_offsets(const unsigned long long* __restrict__ key, const in
     if (last_of_run) {
         const int len = p + 1;
         if (len > 65535) atomicOr(err, 4);
+        atomicMax(max_len, len);
         for (int r = d + 1; r <= S_BM; ++r) o[r] = (unsigned short)len;
     }
 }
@@ -392,11 +394,14 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
             int* s_tile_end = sc.get<int>(g.s_tiles);
             TGNN_CUDA(cudaMemsetAsync(s_tile_end, 0, (size_t)g.s_tiles * sizeof(int), st));
             k_s_heads<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, run_idx, run_head, g.s_pbase.as<int>(), g.s_ptype.as<int>(), s_tile_end);
+            int* s_maxlen = sc.get<int>(1);
+            TGNN_CUDA(cudaMemsetAsync(s_maxlen, 0, sizeof(int), st));
             k_s_offsets<<<nblk(e_adj), TPB, 0, st>>>(k1, id1, adj_src, e_adj, run_idx, run_head, g.s_pbase.as<int>(),
-                                                      g.s_off.as<unsigned short>(), g.s_src.as<int>(), err);
+                                                      g.s_off.as<unsigned short>(), g.s_src.as<int>(), err, s_maxlen);
             k_cptr_first<<<1, 32, 0, st>>>(g.s_pptr.as<int>());
             incl_max(sc, s_tile_end, g.s_pptr.as<int>() + 1, g.s_tiles, st);
-            g.has_s = true;
+            g.s_max_pass = read_int(s_maxlen, st);
+            g.has_s = g.s_max_pass <= 304;          // at least two passes must fit the kernel's 608-row ring
         }
     } else {
         g.has_s = false;

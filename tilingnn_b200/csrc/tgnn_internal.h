@@ -81,7 +81,7 @@ struct Graph {
     // "S" format for the tcgen05 adjacency kernel: destinations in tiles of 128 rows; a tile's in-edges sorted by
     // (type, destination row); one PASS per distinct type present in the tile
     bool has_s = false;
-    int s_tiles = 0, s_passes = 0;
+    int s_tiles = 0, s_passes = 0, s_max_pass = 0;   // s_max_pass: most edges in one pass
     DevBuf s_pptr;            // int32  [s_tiles + 1]      pass range per tile
     DevBuf s_ptype;           // int32  [s_passes]         edge type of the pass
     DevBuf s_pbase;           // int32  [s_passes + 1]     first edge of the pass in s_src
@@ -133,7 +133,7 @@ void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
 // tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
 void launch_edge_table_s(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
                          const float* c2, const float* a3, const float* c3, const float* root, float* tab, cudaStream_t st);
-void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, cudaStream_t st);
+void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st);
 
 struct GinArgs {
     const float* xin;        // [n_rows][32]  pre-BN activations of the previous collision layer (or h0)
