@@ -140,7 +140,7 @@ k_conv_s(ConvSArgs A) {
                 }
             }
             if (lane == 0) {
-                *reinterpret_cast<int4*>(smem + OFF_META + slot * 16) = make_int4(ring0, root ? 1 : 0, 0, 0);
+                sts128i(smem_base + OFF_META + slot * 16, make_int4(ring0, root ? 1 : 0, 0, 0));
                 mbar_arrive(bar_rf + 8 * slot);            // releases the metadata store
             }
             // asynchronous arrive: counts once all cp.async issued by this lane have landed
@@ -192,20 +192,24 @@ k_conv_s(ConvSArgs A) {
         for (int tile = blockIdx.x; tile < A.n_tiles;) {
             const int slot = s % D, st = s & 1;
             if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { timeout_flag = 1; break; }
-            const int4 meta = *reinterpret_cast<const int4*>(smem + OFF_META + slot * 16);
+            const int4 meta = lds128i(smem_base + OFF_META + slot * 16);
             const int ring0 = meta.x;
             const bool root = meta.y != 0;
             float4 v[4];
             if (!root) {
-                const unsigned short* ob = reinterpret_cast<const unsigned short*>(smem + OFF_OFFB) + slot * S_OFF_STRIDE;
+                const uint32_t ob = smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2;
+                int es[4], ee[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int r = rbase + 32 * j;
-                    const int es = ob[r], ee = ob[r + 1];
+                    es[j] = (int)lds_u16(ob + 2 * (rbase + 32 * j));
+                    ee[j] = (int)lds_u16(ob + 2 * (rbase + 32 * j + 1));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int t = es; t < ee; ++t) {
+                    for (int t = es[j]; t < ee[j]; ++t) {
                         int rr = ring0 + t; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                        const float4 w = *reinterpret_cast<const float4*>(smem + OFF_RING + rr * 128 + c * 16);
+                        const float4 w = lds128f(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16);
                         acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
                     }
                     v[j] = acc;
@@ -215,13 +219,12 @@ k_conv_s(ConvSArgs A) {
                 for (int j = 0; j < 4; ++j) {
                     const int r = rbase + 32 * j;
                     int rr = ring0 + r; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                    v[j] = tile * S_BM + r < A.n_own ? *reinterpret_cast<const float4*>(smem + OFF_RING + rr * 128 + c * 16)
+                    v[j] = tile * S_BM + r < A.n_own ? lds128f(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16)
                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
             if (!mbar_wait(bar_ae + 8 * st, (uint32_t)(((s >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
-            uint8_t* sa_hi = smem + OFF_A + (st * 2) * SA_TILE;
-            uint8_t* sa_lo = sa_hi + SA_TILE;
+            const uint32_t sa_hi = smem_base + OFF_A + (st * 2) * SA_TILE, sa_lo = sa_hi + SA_TILE;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 hi, lo;
@@ -230,8 +233,8 @@ k_conv_s(ConvSArgs A) {
                 hi.z = tf32_rna(v[j].z); lo.z = tf32_rna(v[j].z - __uint_as_float(hi.z));
                 hi.w = tf32_rna(v[j].w); lo.w = tf32_rna(v[j].w - __uint_as_float(hi.w));
                 const uint32_t o = sw128_off(rbase + 32 * j, c);
-                *reinterpret_cast<uint4*>(sa_hi + o) = hi;
-                *reinterpret_cast<uint4*>(sa_lo + o) = lo;
+                sts128(sa_hi + o, hi);
+                sts128(sa_lo + o, lo);
             }
             fence_proxy_async();
             __syncwarp();
@@ -248,7 +251,7 @@ k_conv_s(ConvSArgs A) {
                 const int slot = s % D, st = s & 1, ab = it & 1;
                 if (q == 0 && !mbar_wait(bar_ce + 8 * ab, (uint32_t)(((it >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
                 if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { timeout_flag = 1; break; }
-                const bool root = reinterpret_cast<const int4*>(smem + OFF_META + slot * 16)->y != 0;
+                const bool root = lds128i(smem_base + OFF_META + slot * 16).y != 0;
                 if (!mbar_wait(bar_af + 8 * st, (uint32_t)((s >> 1) & 1))) { timeout_flag = 1; break; }
                 fence_proxy_async();                   // weight tiles were written by the loaders' cp.async
                 tc_fence_after();
@@ -273,8 +276,8 @@ k_conv_s(ConvSArgs A) {
     } else {
         // ===================== epilogue warps: TMEM lane quarter q4 = warp % 4 =====================
         const int q4 = warp & 3, etid = (warp - W_EPI0) * 32 + lane;
-        float* sc = reinterpret_cast<float*>(smem + OFF_EPI) + q4 * (32 * 33);
-        double* red = reinterpret_cast<double*>(smem + OFF_EPI + 4 * 32 * 33 * 4);
+        const uint32_t sc = smem_base + OFF_EPI + (uint32_t)q4 * (32 * 33 * 4);
+        const uint32_t red = smem_base + OFF_EPI + 4 * 32 * 33 * 4;
         int it = 0;
         for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
@@ -304,19 +307,19 @@ k_conv_s(ConvSArgs A) {
             }
             if (A.part) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = o[j];
+                for (int j = 0; j < 32; ++j) sts_f32(sc + 4 * (lane * 33 + j), o[j]);
                 __syncwarp();
                 int nv = A.n_own - (tile * S_BM + 32 * q4);
                 nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
                 double s1 = 0.0, s2 = 0.0;
-                for (int r = 0; r < nv; ++r) { const double x = (double)sc[r * 33 + lane]; s1 += x; s2 += x * x; }
-                red[(q4 * 2 + 0) * 32 + lane] = s1;
-                red[(q4 * 2 + 1) * 32 + lane] = s2;
+                for (int r = 0; r < nv; ++r) { const double x = (double)lds_f32(sc + 4 * (r * 33 + lane)); s1 += x; s2 += x * x; }
+                sts_f64(red + 8 * ((q4 * 2 + 0) * 32 + lane), s1);
+                sts_f64(red + 8 * ((q4 * 2 + 1) * 32 + lane), s2);
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (etid < 64) {
                     const int qq = etid >> 5, cc = etid & 31;
-                    A.part[(size_t)tile * 64 + etid] = ((red[(0 * 2 + qq) * 32 + cc] + red[(1 * 2 + qq) * 32 + cc]) +
-                                                        red[(2 * 2 + qq) * 32 + cc]) + red[(3 * 2 + qq) * 32 + cc];
+                    A.part[(size_t)tile * 64 + etid] = ((lds_f64(red + 8 * ((0 * 2 + qq) * 32 + cc)) + lds_f64(red + 8 * ((1 * 2 + qq) * 32 + cc))) +
+                                                        lds_f64(red + 8 * ((2 * 2 + qq) * 32 + cc))) + lds_f64(red + 8 * ((3 * 2 + qq) * 32 + cc));
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }

@@ -68,10 +68,10 @@ k_dense_tc(DenseTcArgs A) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
-    uint8_t* epi = smem + STAGES * STAGE_BYTES;
-    float* scratch_all = reinterpret_cast<float*>(epi);
-    double* red = reinterpret_cast<double*>(epi + 4 * SCRATCH_FLOATS * 4);          // [4][2][NOUT]
-    float* bias_s = reinterpret_cast<float*>(epi + 4 * SCRATCH_FLOATS * 4 + 4 * 2 * NOUT * 8);
+    const uint32_t epi = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t scratch_all = epi;                                                // [4][32*33] float
+    const uint32_t red = epi + 4 * SCRATCH_FLOATS * 4;                               // [4][2][NOUT] double
+    const uint32_t bias_s = epi + 4 * SCRATCH_FLOATS * 4 + 4 * 2 * NOUT * 8;         // [NOUT] float
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
     const uint32_t bar_accf = smem_u32(&bars[2 * STAGES]), bar_acce = smem_u32(&bars[2 * STAGES + 2]);
     const int n_slabs = A.K / BK;
@@ -83,7 +83,7 @@ k_dense_tc(DenseTcArgs A) {
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < NOUT; i += NTHREADS) bias_s[i] = __ldg(A.bias + i);
+    for (int i = tid; i < NOUT; i += NTHREADS) sts_f32(bias_s + 4 * i, __ldg(A.bias + i));
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -117,8 +117,7 @@ k_dense_tc(DenseTcArgs A) {
             for (int s = 0; s < n_slabs; ++s, ++g) {
                 const int st = g % STAGES;
                 if (!mbar_wait(bar_empty + 8 * st, ((g / STAGES) & 1) ^ 1)) { timeout_flag = 1; ok = false; break; }
-                uint8_t* sa_hi = smem + st * STAGE_BYTES;
-                uint8_t* sa_lo = sa_hi + A_TILE_BYTES;
+                const uint32_t sa_hi = smem_base + st * STAGE_BYTES, sa_lo = sa_hi + A_TILE_BYTES;
                 const uint32_t sb_hi = smem_base + st * STAGE_BYTES + 2 * A_TILE_BYTES;
                 const uint32_t sb_lo = sb_hi + B_TILE_BYTES;
                 const int k0 = s * BK;
@@ -154,8 +153,8 @@ k_dense_tc(DenseTcArgs A) {
                     hi.z = tf32_rna(v.z); lo.z = tf32_rna(v.z - __uint_as_float(hi.z));
                     hi.w = tf32_rna(v.w); lo.w = tf32_rna(v.w - __uint_as_float(hi.w));
                     const uint32_t off = sw128_off(r, c);
-                    *reinterpret_cast<uint4*>(sa_hi + off) = hi;
-                    *reinterpret_cast<uint4*>(sa_lo + off) = lo;
+                    sts128(sa_hi + off, hi);
+                    sts128(sa_lo + off, lo);
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -196,7 +195,7 @@ k_dense_tc(DenseTcArgs A) {
     } else {
         // ===================== epilogue warps: TMEM lane quarter q = warp % 4, tile row = 32 q + lane =====================
         const int q = warp & 3, etid = (warp - EPI_WARP0) * 32 + lane;
-        float* sc = scratch_all + q * SCRATCH_FLOATS;
+        const uint32_t sc = scratch_all + (uint32_t)q * SCRATCH_FLOATS * 4;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
@@ -211,7 +210,7 @@ k_dense_tc(DenseTcArgs A) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ab * NOUT + c0), v);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(leaky(__uint_as_float(v[j]) + bias_s[c0 + j]));
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(leaky(__uint_as_float(v[j]) + lds_f32(bias_s + 4 * (c0 + j))));
                 if (live) {
                     float4* dst = reinterpret_cast<float4*>(A.out + (size_t)row * NOUT + c0);
 #pragma unroll
@@ -222,15 +221,15 @@ k_dense_tc(DenseTcArgs A) {
                 if (A.part) {
                     // column sums over this warp's rows through a padded 32x32 scratch block (lane = column)
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = __uint_as_float(v[j]);
+                    for (int j = 0; j < 32; ++j) sts_f32(sc + 4 * (lane * 33 + j), __uint_as_float(v[j]));
                     __syncwarp();
                     double s1 = 0.0, s2 = 0.0;
                     for (int r = 0; r < nv; ++r) {
-                        const double o = (double)sc[r * 33 + lane];
+                        const double o = (double)lds_f32(sc + 4 * (r * 33 + lane));
                         s1 += o; s2 += o * o;
                     }
-                    red[(q * 2 + 0) * NOUT + c0 + lane] = s1;
-                    red[(q * 2 + 1) * NOUT + c0 + lane] = s2;
+                    sts_f64(red + 8 * ((q * 2 + 0) * NOUT + c0 + lane), s1);
+                    sts_f64(red + 8 * ((q * 2 + 1) * NOUT + c0 + lane), s2);
                     __syncwarp();
                 }
             }
@@ -243,8 +242,8 @@ k_dense_tc(DenseTcArgs A) {
                 double* p = A.part + (size_t)tile * 2 * NOUT;
                 for (int i = etid; i < 2 * NOUT; i += 128) {
                     const int qq = i / NOUT, cc = i % NOUT;
-                    p[i] = ((red[(0 * 2 + qq) * NOUT + cc] + red[(1 * 2 + qq) * NOUT + cc]) + red[(2 * 2 + qq) * NOUT + cc]) +
-                           red[(3 * 2 + qq) * NOUT + cc];
+                    p[i] = ((lds_f64(red + 8 * ((0 * 2 + qq) * NOUT + cc)) + lds_f64(red + 8 * ((1 * 2 + qq) * NOUT + cc))) +
+                            lds_f64(red + 8 * ((2 * 2 + qq) * NOUT + cc))) + lds_f64(red + 8 * ((3 * 2 + qq) * NOUT + cc));
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
