@@ -29,8 +29,8 @@ using namespace tc;
 
 constexpr int SA_TILE = 16384;                 // bytes of one A tile (hi or lo): 128 rows x 128 B
 constexpr int SB_TILE = 4096;                  // bytes of one B tile (hi or lo): 32 rows x 128 B
-constexpr int D_SLOTS = 6;                     // passes in flight (ring of weight tiles / offset rows / barriers)
-constexpr int RING_ROWS = 608;                 // gathered source rows in flight (76 KB)
+constexpr int D_SLOTS = 4;                     // passes in flight (ring of weight tiles / offset rows / barriers)
+constexpr int RING_ROWS = 640;                 // gathered source rows in flight (80 KB): 4 passes of <= 160 rows
 constexpr int N_LOAD = 4, N_XFORM = 8;         // loader warps, transformer warps
 constexpr int W_MMA = N_LOAD + N_XFORM, W_EPI0 = W_MMA + 1;
 constexpr int CS_THREADS = (W_EPI0 + 4) * 32;  // 17 warps
@@ -71,7 +71,7 @@ k_conv_s(ConvSArgs A) {
     const uint32_t bar_rf = smem_u32(&bars[0]), bar_re = smem_u32(&bars[D_SLOTS]);
     const uint32_t bar_af = smem_u32(&bars[2 * D_SLOTS]), bar_ae = smem_u32(&bars[2 * D_SLOTS + 2]);
     const uint32_t bar_cf = smem_u32(&bars[2 * D_SLOTS + 4]), bar_ce = smem_u32(&bars[2 * D_SLOTS + 6]);
-    const int D = A.d_eff;
+    constexpr int D = D_SLOTS;
 
     if (tid == 0) {
         for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 33); mbar_init(bar_re + 8 * i, N_XFORM + 1); }
@@ -103,7 +103,7 @@ k_conv_s(ConvSArgs A) {
             const bool root = pd_len < 0;
             const int len = root ? S_BM : pd_len;
             const int slot = pd_s % D;
-            if (!mbar_wait(bar_re + 8 * slot, (uint32_t)(((pd_s / D) & 1) ^ 1))) return false;
+            if (!mbar_wait_relaxed(bar_re + 8 * slot, (uint32_t)(((pd_s / D) & 1) ^ 1))) return false;
             const uint32_t bdst = smem_base + OFF_B + (uint32_t)slot * 2 * SB_TILE;
 #pragma unroll 4
             for (int i = lane; i < 512; i += 32) {
@@ -188,29 +188,33 @@ k_conv_s(ConvSArgs A) {
     } else if (warp < W_MMA) {
         // ===================== transformers: item (row = tt/8 + 32 j, chunk = tt%8) =====================
         const int tt = tid - N_LOAD * 32, c = tt & 7, rbase = tt >> 3;
+        const uint32_t item_off = sw128_off(rbase, c);          // + 4096 j for row rbase + 32 j (same row & 7)
+        const uint32_t ring_c = smem_base + OFF_RING + c * 16;
+        uint32_t dirty[2] = {0xFu, 0xFu};                       // per stage: items whose last stored value was non-zero
         int s = 0;
         for (int tile = blockIdx.x; tile < A.n_tiles;) {
-            const int slot = s % D, st = s & 1;
+            const int slot = s & (D - 1), st = s & 1;
             if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { timeout_flag = 1; break; }
             const int4 meta = lds128i(smem_base + OFF_META + slot * 16);
             const int ring0 = meta.x;
             const bool root = meta.y != 0;
             float4 v[4];
+            uint32_t nz = 0;
             if (!root) {
-                const uint32_t ob = smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2;
+                const uint32_t ob = smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2 + 2 * rbase;
                 int es[4], ee[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    es[j] = (int)lds_u16(ob + 2 * (rbase + 32 * j));
-                    ee[j] = (int)lds_u16(ob + 2 * (rbase + 32 * j + 1));
-                }
+                for (int j = 0; j < 4; ++j) { es[j] = (int)lds_u16(ob + 64 * j); ee[j] = (int)lds_u16(ob + 64 * j + 2); }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int t = es[j]; t < ee[j]; ++t) {
-                        int rr = ring0 + t; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                        const float4 w = lds128f(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16);
-                        acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+                    if (es[j] < ee[j]) {
+                        nz |= 1u << j;
+                        for (int t = es[j]; t < ee[j]; ++t) {
+                            int rr = ring0 + t; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                            const float4 w = lds128f(ring_c + (uint32_t)rr * 128);
+                            acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+                        }
                     }
                     v[j] = acc;
                 }
@@ -219,23 +223,28 @@ k_conv_s(ConvSArgs A) {
                 for (int j = 0; j < 4; ++j) {
                     const int r = rbase + 32 * j;
                     int rr = ring0 + r; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                    v[j] = tile * S_BM + r < A.n_own ? lds128f(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16)
-                                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (tile * S_BM + r < A.n_own) { v[j] = lds128f(ring_c + (uint32_t)rr * 128); nz |= 1u << j; }
                 }
             }
             if (!mbar_wait(bar_ae + 8 * st, (uint32_t)(((s >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
-            const uint32_t sa_hi = smem_base + OFF_A + (st * 2) * SA_TILE, sa_lo = sa_hi + SA_TILE;
+            const uint32_t sa_hi = smem_base + OFF_A + (st * 2) * SA_TILE + item_off, sa_lo = sa_hi + SA_TILE;
+            const uint32_t need = nz | dirty[st];               // rows that are and stay zero need no store at all
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                uint4 hi, lo;
-                hi.x = tf32_rna(v[j].x); lo.x = tf32_rna(v[j].x - __uint_as_float(hi.x));
-                hi.y = tf32_rna(v[j].y); lo.y = tf32_rna(v[j].y - __uint_as_float(hi.y));
-                hi.z = tf32_rna(v[j].z); lo.z = tf32_rna(v[j].z - __uint_as_float(hi.z));
-                hi.w = tf32_rna(v[j].w); lo.w = tf32_rna(v[j].w - __uint_as_float(hi.w));
-                const uint32_t o = sw128_off(rbase + 32 * j, c);
-                sts128(sa_hi + o, hi);
-                sts128(sa_lo + o, lo);
+                if (need & (1u << j)) {
+                    // truncation split: hi keeps the top 19 bits (what kind::tf32 reads), lo = x - hi is exact and the
+                    // tensor core truncates it to TF32 itself (relative residual ~2^-21)
+                    uint4 hi, lo;
+                    hi.x = __float_as_uint(v[j].x) & 0xFFFFE000u; lo.x = __float_as_uint(v[j].x - __uint_as_float(hi.x));
+                    hi.y = __float_as_uint(v[j].y) & 0xFFFFE000u; lo.y = __float_as_uint(v[j].y - __uint_as_float(hi.y));
+                    hi.z = __float_as_uint(v[j].z) & 0xFFFFE000u; lo.z = __float_as_uint(v[j].z - __uint_as_float(hi.z));
+                    hi.w = __float_as_uint(v[j].w) & 0xFFFFE000u; lo.w = __float_as_uint(v[j].w - __uint_as_float(hi.w));
+                    sts128(sa_hi + 4096 * j, hi);
+                    sts128(sa_lo + 4096 * j, lo);
+                }
             }
+            dirty[st] = nz;
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) { mbar_arrive(bar_af + 8 * st); mbar_arrive(bar_re + 8 * slot); }
@@ -248,7 +257,7 @@ k_conv_s(ConvSArgs A) {
             constexpr uint32_t IDESC = umma_idesc_tf32(32);
             int s = 0, it = 0, q = 0;
             for (int tile = blockIdx.x; tile < A.n_tiles;) {
-                const int slot = s % D, st = s & 1, ab = it & 1;
+                const int slot = s & (D - 1), st = s & 1, ab = it & 1;
                 if (q == 0 && !mbar_wait(bar_ce + 8 * ab, (uint32_t)(((it >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
                 if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { timeout_flag = 1; break; }
                 const bool root = lds128i(smem_base + OFF_META + slot * 16).y != 0;
@@ -282,7 +291,7 @@ k_conv_s(ConvSArgs A) {
         for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
             const int np = __ldg(A.pptr + tile + 1) - __ldg(A.pptr + tile);
-            if (!mbar_wait(bar_cf + 8 * ab, (uint32_t)((it >> 1) & 1))) { timeout_flag = 1; break; }
+            if (!mbar_wait_relaxed(bar_cf + 8 * ab, (uint32_t)((it >> 1) & 1))) { timeout_flag = 1; break; }
             tc_fence_after();
             const int row = tile * S_BM + 32 * q4 + lane;
             const bool live = row < A.n_own;
@@ -398,9 +407,8 @@ void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* er
     a.off = g.s_off.as<unsigned short>(); a.ssrc = g.s_src.as<int>();
     a.inv_deg = c.inv_deg; a.bias = c.bias; a.out = c.out; a.part = c.part; a.error_flag = error_flag;
     a.n_own = c.n_own; a.n_tiles = g.s_tiles;
-    const int longest = std::max(g.s_max_pass, S_BM);              // the root pass stages 128 rows
-    a.d_eff = std::min(D_SLOTS, RING_ROWS / longest);
-    TGNN_CHECK(a.d_eff >= 2, "conv_s: pass too long for the shared-memory ring");
+    a.d_eff = D_SLOTS;
+    TGNN_CHECK(g.s_max_pass * D_SLOTS <= RING_ROWS, "conv_s: pass too long for the shared-memory ring");
     k_conv_s<<<std::min(g.s_tiles, sm_count), CS_THREADS, CS_SMEM, st>>>(a);
     TGNN_CUDA(cudaGetLastError());
 }

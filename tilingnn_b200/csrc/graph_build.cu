@@ -401,7 +401,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
             k_cptr_first<<<1, 32, 0, st>>>(g.s_pptr.as<int>());
             incl_max(sc, s_tile_end, g.s_pptr.as<int>() + 1, g.s_tiles, st);
             g.s_max_pass = read_int(s_maxlen, st);
-            g.has_s = g.s_max_pass <= 304;          // at least two passes must fit the kernel's 608-row ring
+            g.has_s = g.s_max_pass <= 160;          // four passes in flight must fit the kernel's 640-row ring
         }
     } else {
         g.has_s = false;

@@ -38,6 +38,20 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
         else if (clock64() - t0 > 4000000000ll) return false;
     }
 }
+// Same, for roles that are not on the critical path (loaders waiting for ring space, epilogue waiting for a whole
+// tile): back off with nanosleep so they do not compete for issue slots with the working warps.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    long long t0 = 0;
+    for (int it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return true;
+        __nanosleep(250);
+        if (it == 0) t0 = clock64();
+        else if ((it & 63) == 0 && clock64() - t0 > 4000000000ll) return false;
+    }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
