@@ -51,7 +51,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 
 struct ConvSArgs {
     const float* xin;            // [n_rows][32]
-    const float* tabS;           // [K+1][hi|lo][32 n][32 k]  W_t transposed (entry K = root transposed)
+    const float* tabS;           // [K+1][hi|lo] swizzled smem images of W_t^T [32 n][32 k]  (entry K = root^T)
     int n_types;
     const int* pptr; const int* ptype; const int* pbase; const unsigned short* off; const int* ssrc;
     const float* inv_deg; const float* bias;
@@ -74,7 +74,7 @@ k_conv_s(ConvSArgs A) {
     constexpr int D = D_SLOTS;
 
     if (tid == 0) {
-        for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 33); mbar_init(bar_re + 8 * i, N_XFORM + 1); }
+        for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 1); mbar_init(bar_re + 8 * i, N_XFORM + 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_af + 8 * i, N_XFORM); mbar_init(bar_ae + 8 * i, 1);
                                       mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4); }
         timeout_flag = 0;
@@ -94,57 +94,36 @@ k_conv_s(ConvSArgs A) {
         // Per tile the pass table (pbase, ptype) sits in registers (lane i holds entries i, i+32, ...); the source
         // indices of a pass are requested one own-pass ahead of their use (two register buffers), so the loader
         // itself only ever blocks on the ring-slot barrier.
-        const int c = lane & 7, sub = lane >> 3;
         int s = 0, rows = 0;                               // pass counter / ring rows consumed so far
         int idxA[10], idxB[10];                            // source indices of a pass (<= 320 edges)
         bool par = false;                                  // pending pass's indices live in (par ? idxA : idxB)
         int pd_tile = -1, pd_off = 0, pd_len = 0, pd_type = 0, pd_s = 0, pd_rows = 0;
         auto issue = [&]() -> bool {
             const bool root = pd_len < 0;
-            const int len = root ? S_BM : pd_len;
-            const int slot = pd_s % D;
+            const int slot = pd_s & (D - 1);
+            const uint32_t bar = bar_rf + 8 * slot;
             if (!mbar_wait_relaxed(bar_re + 8 * slot, (uint32_t)(((pd_s / D) & 1) ^ 1))) return false;
-            const uint32_t bdst = smem_base + OFF_B + (uint32_t)slot * 2 * SB_TILE;
-#pragma unroll 4
-            for (int i = lane; i < 512; i += 32) {
-                const int hl = i >> 8, n = (i >> 3) & 31, cc = i & 7;
-                cp_async16(bdst + hl * SB_TILE + sw128_off(n, cc), A.tabS + ((size_t)(pd_type * 2 + hl) * 32 + n) * 32 + 4 * cc);
-            }
             const int ring0 = pd_rows % RING_ROWS;
-            if (!root) {
-                if (lane < 17)
-                    cp_async16(smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2 + lane * 16,
-                               A.off + (size_t)pd_off * S_OFF_STRIDE + lane * 8);
-#pragma unroll
-                for (int jb = 0; jb < 10; ++jb) {
-                    if (32 * jb < len) {
-                        const int mine = par ? idxA[jb] : idxB[jb];
-                        const int cnt = min(32, len - 32 * jb);
-                        for (int j = 0; j < cnt; j += 4) {
-                            const int src = __shfl_sync(0xffffffffu, mine, (j + sub) & 31);
-                            if (j + sub < cnt) {
-                                int rr = ring0 + 32 * jb + j + sub; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                                cp_async16(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16, A.xin + (size_t)src * F + 4 * c);
-                            }
-                        }
-                    }
-                }
-            } else {
-                const int node0 = pd_tile * S_BM;
-                for (int j = 0; j < S_BM; j += 4) {
-                    const int node = node0 + j + sub;
-                    if (node < A.n_own) {
-                        int rr = ring0 + j + sub; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                        cp_async16(smem_base + OFF_RING + (uint32_t)rr * 128 + c * 16, A.xin + (size_t)node * F + 4 * c);
-                    }
-                }
-            }
+            int len = pd_len;
+            if (root) { len = A.n_own - pd_tile * S_BM; len = len > S_BM ? S_BM : len; }
             if (lane == 0) {
                 sts128i(smem_base + OFF_META + slot * 16, make_int4(ring0, root ? 1 : 0, 0, 0));
-                mbar_arrive(bar_rf + 8 * slot);            // releases the metadata store
+                // one arrival + the bytes the TMA engine will deliver: weight tiles, offset row, gathered rows
+                mbar_arrive_expect_tx(bar, (uint32_t)(2 * SB_TILE + (root ? 0 : S_OFF_STRIDE * 2) + len * 128));
+                bulk_g2s(smem_base + OFF_B + (uint32_t)slot * 2 * SB_TILE, A.tabS + (size_t)pd_type * 2048, 2 * SB_TILE, bar);
+                if (!root) bulk_g2s(smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2, A.off + (size_t)pd_off * S_OFF_STRIDE,
+                                    S_OFF_STRIDE * 2, bar);
             }
-            // asynchronous arrive: counts once all cp.async issued by this lane have landed
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar_rf + 8 * slot) : "memory");
+            __syncwarp();
+#pragma unroll
+            for (int jb = 0; jb < 10; ++jb) {
+                const int e = 32 * jb + lane;
+                if (e < len) {
+                    const int src = root ? pd_tile * S_BM + e : (par ? idxA[jb] : idxB[jb]);
+                    int rr = ring0 + e; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                    bulk_g2s(smem_base + OFF_RING + (uint32_t)rr * 128, A.xin + (size_t)src * F, 128, bar);
+                }
+            }
             return true;
         };
         bool ok = true;
@@ -184,7 +163,6 @@ k_conv_s(ConvSArgs A) {
         }
         if (ok && pd_tile >= 0) ok = issue();
         if (!ok) timeout_flag = 1;
-        asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp < W_MMA) {
         // ===================== transformers: item (row = tt/8 + 32 j, chunk = tt%8) =====================
         const int tt = tid - N_LOAD * 32, c = tt & 7, rbase = tt >> 3;
@@ -344,7 +322,12 @@ k_conv_s(ConvSArgs A) {
     }
 }
 
-// per-type edge weights for the S kernel: tabS[t][hi|lo][n][k] = TF32 split of W_t[k][n], W_t evaluated in fp64
+// float index of element (row n, column k) inside the SWIZZLE_128B shared-memory IMAGE of a [32 x 32] tf32 tile:
+// the tables are stored in global memory pre-swizzled so that one bulk copy drops a ready-to-use operand tile.
+__host__ __device__ __forceinline__ int tile_pos(int n, int k) { return n * 32 + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3)); }
+
+// per-type edge weights for the S kernel: tabS[t][hi|lo] = swizzled image of W_t^T (row n = out, col k = in), TF32
+// split of W_t evaluated in fp64
 __global__ void k_edge_table_s(const float* __restrict__ rows, int d_e, const float* __restrict__ a1, const float* __restrict__ c1,
                                const float* __restrict__ a2, const float* __restrict__ c2, const float* __restrict__ a3,
                                const float* __restrict__ c3, float* __restrict__ tab) {
@@ -371,8 +354,9 @@ __global__ void k_edge_table_s(const float* __restrict__ rows, int d_e, const fl
         const int kin = o >> 5, n = o & 31;                   // NNConv: weight.view(-1, in, out)
         const uint32_t hi = tf32_rna((float)w);
         const uint32_t lo = tf32_rna((float)(w - (double)__uint_as_float(hi)));
-        out[n * 32 + kin] = __uint_as_float(hi);
-        out[1024 + n * 32 + kin] = __uint_as_float(lo);
+        const int pos = tile_pos(n, kin);
+        out[pos] = __uint_as_float(hi);
+        out[1024 + pos] = __uint_as_float(lo);
     }
 }
 // root [in][out] -> [hi|lo][n = out][k = in]
@@ -382,8 +366,9 @@ __global__ void k_root_table_s(const float* __restrict__ root, float* __restrict
     const int kin = o >> 5, n = o & 31;
     const float w = root[o];
     const uint32_t hi = tf32_rna(w);
-    out[n * 32 + kin] = __uint_as_float(hi);
-    out[1024 + n * 32 + kin] = __uint_as_float(tf32_rna(w - __uint_as_float(hi)));
+    const int pos = tile_pos(n, kin);
+    out[pos] = __uint_as_float(hi);
+    out[1024 + pos] = __uint_as_float(tf32_rna(w - __uint_as_float(hi)));
 }
 
 }  // namespace
