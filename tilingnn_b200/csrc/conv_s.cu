@@ -8,12 +8,12 @@
 // atomics, cost per (destination, type) instead of per edge, and M = 128 is what tcgen05 wants.  (The edge-chunk
 // mma.sync kernel in kernels.cu remains the path for graphs with many edge types, where K passes do not pay.)
 //
-// Persistent CTAs (one per SM) walk tiles of 128 destinations; 17 warps, warp specialised:
-//   loaders (4 warps, pass s -> warp s%4): cp.async the pass's source rows into a 608-row shared-memory ring,
-//     its weight tiles and row-offset table into a slot ring; completion is signalled asynchronously with
-//     cp.async.mbarrier.arrive, so up to 6 passes of gathers are in flight without holding registers
-//   transformers (8 warps): per (row, 16-byte chunk) sum the row's sources from the ring, hi/lo TF32 split,
-//     swizzled store into the A operand stage, fence, mbarrier arrive
+// Persistent CTAs (one per SM) walk tiles of 128 destinations; 22 warps, warp specialised:
+//   loader (1 warp): TMA bulk copies (cp.async.bulk, one per gathered 128-byte source row, one for the pass's
+//     pre-swizzled weight tiles, one for its row-offset table) into a 640-row ring / 4-slot ring; completion is
+//     counted in mbarrier transaction bytes, so 4 passes of gathers are in flight without holding registers
+//   transformers (2 groups x 8 warps, group g = passes with parity g = A stage g): per (row, 16-byte chunk) sum the
+//     row's sources from the ring, hi/lo TF32 split, swizzled store into the A operand stage, fence, arrive
 //   MMA warp: per pass 12 x tcgen05.mma.kind::tf32 (M=128, N=32; 3xTF32), commits free the stage and the slot
 //   the root term x_i root is one more pass into a second accumulator (columns 32..63); TMEM is double buffered
 //   epilogue (4 warps): tcgen05.ld, * 1/deg + root + bias, LeakyReLU, store, BatchNorm partial sums (fp64),
@@ -31,9 +31,9 @@ constexpr int SA_TILE = 16384;                 // bytes of one A tile (hi or lo)
 constexpr int SB_TILE = 4096;                  // bytes of one B tile (hi or lo): 32 rows x 128 B
 constexpr int D_SLOTS = 4;                     // passes in flight (ring of weight tiles / offset rows / barriers)
 constexpr int RING_ROWS = 640;                 // gathered source rows in flight (80 KB): 4 passes of <= 160 rows
-constexpr int N_LOAD = 4, N_XFORM = 8;         // loader warps, transformer warps
+constexpr int N_LOAD = 1, N_XGRP = 8, N_XFORM = 2 * N_XGRP;   // loader warp; two transformer groups of 8 warps (one per A stage)
 constexpr int W_MMA = N_LOAD + N_XFORM, W_EPI0 = W_MMA + 1;
-constexpr int CS_THREADS = (W_EPI0 + 4) * 32;  // 17 warps
+constexpr int CS_THREADS = (W_EPI0 + 4) * 32;  // 22 warps
 constexpr int OFF_A = 0;                                        // [2 stages][hi|lo]
 constexpr int OFF_B = OFF_A + 4 * SA_TILE;                      // [D_SLOTS][hi|lo]
 constexpr int OFF_RING = OFF_B + D_SLOTS * 2 * SB_TILE;         // [RING_ROWS][128 B]
@@ -74,8 +74,8 @@ k_conv_s(ConvSArgs A) {
     constexpr int D = D_SLOTS;
 
     if (tid == 0) {
-        for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 1); mbar_init(bar_re + 8 * i, N_XFORM + 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_af + 8 * i, N_XFORM); mbar_init(bar_ae + 8 * i, 1);
+        for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 1); mbar_init(bar_re + 8 * i, N_XGRP + 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_af + 8 * i, N_XGRP); mbar_init(bar_ae + 8 * i, 1);
                                       mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4); }
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -164,71 +164,83 @@ k_conv_s(ConvSArgs A) {
         if (ok && pd_tile >= 0) ok = issue();
         if (!ok) timeout_flag = 1;
     } else if (warp < W_MMA) {
-        // ===================== transformers: item (row = tt/8 + 32 j, chunk = tt%8) =====================
-        const int tt = tid - N_LOAD * 32, c = tt & 7, rbase = tt >> 3;
+        // ===================== transformers: group xg owns A stage xg and the passes with (s & 1) == xg ==========
+        // item (row = tt/8 + 32 j, chunk = tt%8), tt = thread index inside the group
+        const int xg = (warp - N_LOAD) / N_XGRP;
+        const int tt = tid - (N_LOAD + xg * N_XGRP) * 32, c = tt & 7, rbase = tt >> 3;
         const uint32_t item_off = sw128_off(rbase, c);          // + 4096 j for row rbase + 32 j (same row & 7)
         const uint32_t ring_c = smem_base + OFF_RING + c * 16;
-        uint32_t dirty[2] = {0xFu, 0xFu};                       // per stage: items whose last stored value was non-zero
+        const uint32_t sa_hi = smem_base + OFF_A + (xg * 2) * SA_TILE + item_off, sa_lo = sa_hi + SA_TILE;
+        uint32_t dirty = 0xFu;                                  // items whose last stored value was non-zero
         int s = 0;
-        for (int tile = blockIdx.x; tile < A.n_tiles;) {
-            const int slot = s & (D - 1), st = s & 1;
-            if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { timeout_flag = 1; break; }
-            const int4 meta = lds128i(smem_base + OFF_META + slot * 16);
-            const int ring0 = meta.x;
-            const bool root = meta.y != 0;
-            float4 v[4];
-            uint32_t nz = 0;
-            if (!root) {
-                const uint32_t ob = smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2 + 2 * rbase;
-                int es[4], ee[4];
+        bool ok = true;
+        int np_next = (int)blockIdx.x < A.n_tiles ? __ldg(A.pptr + blockIdx.x + 1) - __ldg(A.pptr + blockIdx.x) : 0;
+        for (int tile = blockIdx.x; tile < A.n_tiles && ok; tile += gridDim.x) {
+            const int np = np_next;
+            const int ntile = tile + gridDim.x;
+            if (ntile < A.n_tiles) np_next = __ldg(A.pptr + ntile + 1) - __ldg(A.pptr + ntile);
+            for (int q = 0; q <= np; ++q, ++s) {
+                if ((s & 1) != xg) continue;
+                const int slot = s & (D - 1);
+                if (!mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1))) { ok = false; break; }
+                const int ring0 = lds128i(smem_base + OFF_META + slot * 16).x;
+                const bool root = q == np;
+                float4 v[4];
+                uint32_t nz = 0;
+                if (!root) {
+                    const uint32_t ob = smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2 + 2 * rbase;
+                    int es[4], cnt[4], mx = 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { es[j] = (int)lds_u16(ob + 64 * j); ee[j] = (int)lds_u16(ob + 64 * j + 2); }
+                    for (int j = 0; j < 4; ++j) {
+                        es[j] = (int)lds_u16(ob + 64 * j);
+                        cnt[j] = (int)lds_u16(ob + 64 * j + 2) - es[j];
+                        mx = max(mx, cnt[j]);
+                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (cnt[j] > 0) nz |= 1u << j;
+                        es[j] += ring0;
+                    }
+                    for (int t = 0; t < mx; ++t) {              // the four items' loads are independent -> in flight together
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (es[j] < ee[j]) {
-                        nz |= 1u << j;
-                        for (int t = es[j]; t < ee[j]; ++t) {
-                            int rr = ring0 + t; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                            const float4 w = lds128f(ring_c + (uint32_t)rr * 128);
-                            acc.x += w.x; acc.y += w.y; acc.z += w.z; acc.w += w.w;
+                        for (int j = 0; j < 4; ++j) {
+                            if (t < cnt[j]) {
+                                int rr = es[j] + t; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                                const float4 w = lds128f(ring_c + (uint32_t)rr * 128);
+                                v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w;
+                            }
                         }
                     }
-                    v[j] = acc;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = rbase + 32 * j;
+                        int rr = ring0 + r; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (tile * S_BM + r < A.n_own) { v[j] = lds128f(ring_c + (uint32_t)rr * 128); nz |= 1u << j; }
+                    }
                 }
-            } else {
+                if (!mbar_wait(bar_ae + 8 * xg, (uint32_t)(((s >> 1) & 1) ^ 1))) { ok = false; break; }
+                const uint32_t need = nz | dirty;               // rows that are and stay zero need no store at all
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int r = rbase + 32 * j;
-                    int rr = ring0 + r; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (tile * S_BM + r < A.n_own) { v[j] = lds128f(ring_c + (uint32_t)rr * 128); nz |= 1u << j; }
+                    if (need & (1u << j)) {
+                        // truncation split: hi keeps the top 19 bits (what kind::tf32 reads), lo = x - hi is exact and
+                        // the tensor core truncates it to TF32 itself (relative residual ~2^-21)
+                        uint4 hi, lo;
+                        hi.x = __float_as_uint(v[j].x) & 0xFFFFE000u; lo.x = __float_as_uint(v[j].x - __uint_as_float(hi.x));
+                        hi.y = __float_as_uint(v[j].y) & 0xFFFFE000u; lo.y = __float_as_uint(v[j].y - __uint_as_float(hi.y));
+                        hi.z = __float_as_uint(v[j].z) & 0xFFFFE000u; lo.z = __float_as_uint(v[j].z - __uint_as_float(hi.z));
+                        hi.w = __float_as_uint(v[j].w) & 0xFFFFE000u; lo.w = __float_as_uint(v[j].w - __uint_as_float(hi.w));
+                        sts128(sa_hi + 4096 * j, hi);
+                        sts128(sa_lo + 4096 * j, lo);
+                    }
                 }
+                dirty = nz;
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(bar_af + 8 * xg); mbar_arrive(bar_re + 8 * slot); }
             }
-            if (!mbar_wait(bar_ae + 8 * st, (uint32_t)(((s >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
-            const uint32_t sa_hi = smem_base + OFF_A + (st * 2) * SA_TILE + item_off, sa_lo = sa_hi + SA_TILE;
-            const uint32_t need = nz | dirty[st];               // rows that are and stay zero need no store at all
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (need & (1u << j)) {
-                    // truncation split: hi keeps the top 19 bits (what kind::tf32 reads), lo = x - hi is exact and the
-                    // tensor core truncates it to TF32 itself (relative residual ~2^-21)
-                    uint4 hi, lo;
-                    hi.x = __float_as_uint(v[j].x) & 0xFFFFE000u; lo.x = __float_as_uint(v[j].x - __uint_as_float(hi.x));
-                    hi.y = __float_as_uint(v[j].y) & 0xFFFFE000u; lo.y = __float_as_uint(v[j].y - __uint_as_float(hi.y));
-                    hi.z = __float_as_uint(v[j].z) & 0xFFFFE000u; lo.z = __float_as_uint(v[j].z - __uint_as_float(hi.z));
-                    hi.w = __float_as_uint(v[j].w) & 0xFFFFE000u; lo.w = __float_as_uint(v[j].w - __uint_as_float(hi.w));
-                    sts128(sa_hi + 4096 * j, hi);
-                    sts128(sa_lo + 4096 * j, lo);
-                }
-            }
-            dirty[st] = nz;
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(bar_af + 8 * st); mbar_arrive(bar_re + 8 * slot); }
-            ++s;
-            if (root) tile += gridDim.x;
         }
+        if (!ok) timeout_flag = 1;
     } else if (warp == W_MMA) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
