@@ -8,10 +8,12 @@
 // atomics, cost per (destination, type) instead of per edge, and M = 128 is what tcgen05 wants.  (The edge-chunk
 // mma.sync kernel in kernels.cu remains the path for graphs with many edge types, where K passes do not pay.)
 //
-// Persistent CTAs (one per SM) walk tiles of 128 destinations; 22 warps, warp specialised:
-//   loader (1 warp): TMA bulk copies (cp.async.bulk, one per gathered 128-byte source row, one for the pass's
-//     pre-swizzled weight tiles, one for its row-offset table) into a 640-row ring / 4-slot ring; completion is
-//     counted in mbarrier transaction bytes, so 4 passes of gathers are in flight without holding registers
+// Persistent CTAs (one per SM) walk tiles of 128 destinations; 23 warps, warp specialised:
+//   loaders (2 warps): per pass one TMA bulk copy (cp.async.bulk) for the pre-swizzled weight tiles, one for the
+//     row-offset table (and the root pass's contiguous rows), 16-byte cp.async for the scattered source rows, into
+//     a 640-row ring / 4-slot ring; completion = mbarrier transaction bytes + cp.async.mbarrier.arrive, so 4 passes
+//     of gathers are in flight without holding registers.  (Per-row bulk copies were measured 2.6x slower: the
+//     instruction is uniform-datapath, 32 lanes with different addresses serialise.)
 //   transformers (2 groups x 8 warps, group g = passes with parity g = A stage g): per (row, 16-byte chunk) sum the
 //     row's sources from the ring, hi/lo TF32 split, swizzled store into the A operand stage, fence, arrive
 //   MMA warp: per pass 12 x tcgen05.mma.kind::tf32 (M=128, N=32; 3xTF32), commits free the stage and the slot
@@ -31,9 +33,9 @@ constexpr int SA_TILE = 16384;                 // bytes of one A tile (hi or lo)
 constexpr int SB_TILE = 4096;                  // bytes of one B tile (hi or lo): 32 rows x 128 B
 constexpr int D_SLOTS = 4;                     // passes in flight (ring of weight tiles / offset rows / barriers)
 constexpr int RING_ROWS = 640;                 // gathered source rows in flight (80 KB): 4 passes of <= 160 rows
-constexpr int N_LOAD = 1, N_XGRP = 8, N_XFORM = 2 * N_XGRP;   // loader warp; two transformer groups of 8 warps (one per A stage)
+constexpr int N_LOAD = 2, N_XGRP = 8, N_XFORM = 2 * N_XGRP;   // loader warp; two transformer groups of 8 warps (one per A stage)
 constexpr int W_MMA = N_LOAD + N_XFORM, W_EPI0 = W_MMA + 1;
-constexpr int CS_THREADS = (W_EPI0 + 4) * 32;  // 22 warps
+constexpr int CS_THREADS = (W_EPI0 + 4) * 32;  // 23 warps
 constexpr int OFF_A = 0;                                        // [2 stages][hi|lo]
 constexpr int OFF_B = OFF_A + 4 * SA_TILE;                      // [D_SLOTS][hi|lo]
 constexpr int OFF_RING = OFF_B + D_SLOTS * 2 * SB_TILE;         // [RING_ROWS][128 B]
@@ -74,7 +76,7 @@ k_conv_s(ConvSArgs A) {
     constexpr int D = D_SLOTS;
 
     if (tid == 0) {
-        for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 1); mbar_init(bar_re + 8 * i, N_XGRP + 1); }
+        for (int i = 0; i < D_SLOTS; ++i) { mbar_init(bar_rf + 8 * i, 33); mbar_init(bar_re + 8 * i, N_XGRP + 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_af + 8 * i, N_XGRP); mbar_init(bar_ae + 8 * i, 1);
                                       mbar_init(bar_cf + 8 * i, 1); mbar_init(bar_ce + 8 * i, 4); }
         timeout_flag = 0;
@@ -98,6 +100,9 @@ k_conv_s(ConvSArgs A) {
         int idxA[10], idxB[10];                            // source indices of a pass (<= 320 edges)
         bool par = false;                                  // pending pass's indices live in (par ? idxA : idxB)
         int pd_tile = -1, pd_off = 0, pd_len = 0, pd_type = 0, pd_s = 0, pd_rows = 0;
+        const int c = lane & 7, sub = lane >> 3;
+        const uint32_t ring_c = smem_base + OFF_RING + c * 16;
+        const float* xin_c = A.xin + 4 * c;
         auto issue = [&]() -> bool {
             const bool root = pd_len < 0;
             const int slot = pd_s & (D - 1);
@@ -107,23 +112,38 @@ k_conv_s(ConvSArgs A) {
             int len = pd_len;
             if (root) { len = A.n_own - pd_tile * S_BM; len = len > S_BM ? S_BM : len; }
             if (lane == 0) {
+                // big contiguous pieces go through the TMA engine (one bulk copy each), counted in transaction bytes:
+                // the pre-swizzled weight image, the offset row, and for the root pass the tile's own (contiguous) rows
                 sts128i(smem_base + OFF_META + slot * 16, make_int4(ring0, root ? 1 : 0, 0, 0));
-                // one arrival + the bytes the TMA engine will deliver: weight tiles, offset row, gathered rows
-                mbar_arrive_expect_tx(bar, (uint32_t)(2 * SB_TILE + (root ? 0 : S_OFF_STRIDE * 2) + len * 128));
+                mbar_arrive_expect_tx(bar, (uint32_t)(2 * SB_TILE + (root ? len * 128 : S_OFF_STRIDE * 2)));
                 bulk_g2s(smem_base + OFF_B + (uint32_t)slot * 2 * SB_TILE, A.tabS + (size_t)pd_type * 2048, 2 * SB_TILE, bar);
-                if (!root) bulk_g2s(smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2, A.off + (size_t)pd_off * S_OFF_STRIDE,
-                                    S_OFF_STRIDE * 2, bar);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int jb = 0; jb < 10; ++jb) {
-                const int e = 32 * jb + lane;
-                if (e < len) {
-                    const int src = root ? pd_tile * S_BM + e : (par ? idxA[jb] : idxB[jb]);
-                    int rr = ring0 + e; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                    bulk_g2s(smem_base + OFF_RING + (uint32_t)rr * 128, A.xin + (size_t)src * F, 128, bar);
+                if (!root) {
+                    bulk_g2s(smem_base + OFF_OFFB + (uint32_t)slot * S_OFF_STRIDE * 2, A.off + (size_t)pd_off * S_OFF_STRIDE,
+                             S_OFF_STRIDE * 2, bar);
+                } else {
+                    const int first = min(len, RING_ROWS - ring0);
+                    const float* src = A.xin + (size_t)pd_tile * S_BM * F;
+                    bulk_g2s(smem_base + OFF_RING + (uint32_t)ring0 * 128, src, first * 128, bar);
+                    if (len > first) bulk_g2s(smem_base + OFF_RING, src + (size_t)first * F, (len - first) * 128, bar);
                 }
             }
+            if (!root) {
+                // scattered source rows: 16-byte cp.async, 8 lanes per row, 4 rows per instruction
+#pragma unroll
+                for (int jb = 0; jb < 10; ++jb) {
+                    if (32 * jb < len) {
+                        const int mine = par ? idxA[jb] : idxB[jb];
+                        const int cnt = min(32, len - 32 * jb);
+                        for (int j = sub; j < cnt; j += 4) {
+                            const int src = __shfl_sync(0xffffffffu, mine, j);
+                            int rr = ring0 + 32 * jb + j; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                            cp_async16(ring_c + (uint32_t)rr * 128, xin_c + (size_t)src * F);
+                        }
+                    }
+                }
+            }
+            // asynchronous arrive: counts once all cp.async issued by this lane have landed
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
             return true;
         };
         bool ok = true;
