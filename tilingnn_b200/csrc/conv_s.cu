@@ -134,10 +134,13 @@ k_conv_s(ConvSArgs A) {
                     if (32 * jb < len) {
                         const int mine = par ? idxA[jb] : idxB[jb];
                         const int cnt = min(32, len - 32 * jb);
-                        for (int j = sub; j < cnt; j += 4) {
-                            const int src = __shfl_sync(0xffffffffu, mine, j);
-                            int rr = ring0 + 32 * jb + j; if (rr >= RING_ROWS) rr -= RING_ROWS;
-                            cp_async16(ring_c + (uint32_t)rr * 128, xin_c + (size_t)src * F);
+                        for (int j0 = 0; j0 < cnt; j0 += 4) {          // warp-uniform trip count (shuffle inside)
+                            const int j = j0 + sub;
+                            const int src = __shfl_sync(0xffffffffu, mine, j & 31);
+                            if (j < cnt) {
+                                int rr = ring0 + 32 * jb + j; if (rr >= RING_ROWS) rr -= RING_ROWS;
+                                cp_async16(ring_c + (uint32_t)rr * 128, xin_c + (size_t)src * F);
+                            }
                         }
                     }
                 }
