@@ -92,6 +92,8 @@ struct tgnn_handle {
     DevBuf tab;                                     // [L][K+1][2048] frag tables (entry K = root)
     DevBuf tabS;                                    // [L][K+1][2048] transposed hi|lo tables of the tcgen05 conv kernel
     bool conv_chunk_only = false;                   // TGNN_CONV=chunk forces the mma.sync edge-chunk kernel
+    bool conv_s_only = false;                       // TGNN_CONV=s forces the tcgen05 S kernel whenever its format exists
+    bool use_s = false;                             // decided per graph in set_graph
 
     // workspace
     std::vector<std::unique_ptr<DevBuf>> mid;
@@ -280,6 +282,13 @@ void build_tables(tgnn_handle* h, cudaStream_t st) {
     h->tables_dirty = false;
 }
 
+// Cost model from B200 measurements (1M nodes, deg 32, 51 types): the edge-chunk mma.sync kernel costs ~72 ps per
+// adjacency edge, the tcgen05 S kernel ~5.9 ns per (128-row tile, edge type) pass -> S pays off when the tiles see
+// few types relative to their edge count (the shipped tile graphs: 20-41 types), chunk when types are many.
+void choose_conv_kernel(tgnn_handle* h) {
+    h->use_s = h->g.has_s && (h->conv_s_only || (double)h->g.s_passes * 82.0 < (double)h->g.e_adj);
+}
+
 void alloc_workspace(tgnn_handle* h) {
     const int L = h->cfg.depth;
     const size_t rows = (size_t)h->g.n_rows, own = (size_t)h->g.n_own;
@@ -392,7 +401,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles;
         lz.begin("conv");
-        if (h->g.has_s)
+        if (h->use_s)
             launch_conv_s(ca, h->g, h->tabS.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
         else
             launch_conv_adj(ca, h->sm_count, st);
@@ -409,7 +418,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
 
         if (train) {
             lz.begin("bnfin");
-            launch_bn_reduce(h->partA.as<double>(), h->g.has_s ? h->g.s_tiles : np_conv, 32, sums, st);
+            launch_bn_reduce(h->partA.as<double>(), h->use_s ? h->g.s_tiles : np_conv, 32, sums, st);
             launch_bn_reduce(h->partB.as<double>(), np_gin, 32, sums + 64, st);
             allreduce_sums(h, sums, 128, st);
             launch_bn_coef(sums, count, h->P(pa + ".batch_norm.weight"), h->P(pa + ".batch_norm.bias"), h->C(h->coef_a[i]), 32, st);
@@ -509,6 +518,7 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->sm_count = prop.multiProcessorCount;
         const char* csel = getenv("TGNN_CONV");
         h->conv_chunk_only = csel && std::string(csel) == "chunk";
+        h->conv_s_only = csel && std::string(csel) == "s";
         h->dev_error.reserve(sizeof(int));
         TGNN_CUDA(cudaMemset(h->dev_error.p, 0, sizeof(int)));
         declare_params(h.get());
@@ -583,6 +593,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         build_graph(h->g, h->scratch, h->cfg.d_e, n_nodes, n_nodes, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src,
                     col_dst, !h->conv_chunk_only, st);
         h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
+        choose_conv_kernel(h);
         alloc_workspace(h);
         h->tables_dirty = true;
         h->graph_set = true;
@@ -632,6 +643,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
         build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst,
                     !h->conv_chunk_only, st);
         h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
+        choose_conv_kernel(h);
         if (n_send > 0) {
             std::vector<int64_t> rows64(n_send);
             TGNN_CUDA(cudaMemcpyAsync(rows64.data(), send_rows, n_send * sizeof(int64_t), cudaMemcpyDefault, st));

@@ -208,6 +208,13 @@ k_conv_adj(ConvArgs A) {
                 pre[2] = sb >= 0 ? ld_row4(A.xin, sb, t) : zero4; pre[3] = sb >= 0 ? ld_row4(A.xin, sb, 4 + t) : zero4;
             }
             if (type != cur_type) { load_bfrag32(bf, A.tabF + (size_t)type * FRAG32, lane); cur_type = type; }
+            // the next chunk's type is already known (ptype): pull its 8 KB fragment table towards L1 now, so the
+            // reload at the type change does not expose an L2 round trip (64 lines of 128 B, two per lane)
+            if (ptype != type && c + 1 < c1) {
+                const char* nt = reinterpret_cast<const char*>(A.tabF + (size_t)ptype * FRAG32);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nt + lane * 128));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nt + (lane + 32) * 128));
+            }
             float m[4][4] = {};
             chunk_mma32(cur, bf, m);
             // rows 0..7 (group 0), then rows 8..15 (group 1): destinations are distinct inside a group
