@@ -81,7 +81,7 @@ struct tgnn_handle {
     DevBuf init_w1t;
     std::vector<std::unique_ptr<DevBuf>> gin_wt;    // per layer: frag tables W1|W2|W3 and biases b1|b2|b3
     std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4: k-major transposes (CUDA-core path)
-    std::vector<std::unique_ptr<DevBuf>> fin_whl;   // 4: [hi | lo] TF32 split of the [N_out][K] weights (tcgen05 path)
+    std::vector<std::unique_ptr<DevBuf>> fin_whl;   // 4: pre-swizzled hi|lo slab images of the weights (tcgen05 path)
     DevBuf dev_error;                               // int: device-side error flag (pipeline timeouts)
     bool dense_ffma = false;                        // TGNN_DENSE=ffma selects the CUDA-core dense stage (debug A/B)
     std::vector<float> gin_eps;
@@ -223,7 +223,7 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
         launch_transpose(w, h->fin_wt.back()->as<float>(), dims[k + 1], dims[k], st);
         h->fin_whl.emplace_back(new DevBuf());
         h->fin_whl.back()->reserve(2 * ne * sizeof(float));
-        launch_split_tf32(w, h->fin_whl.back()->as<float>(), h->fin_whl.back()->as<float>() + ne, (int)ne, st);
+        launch_weight_image(w, h->fin_whl.back()->as<float>(), dims[k + 1], dims[k], st);
     }
     const char* dsel = getenv("TGNN_DENSE");
     h->dense_ffma = dsel && std::string(dsel) == "ffma";
@@ -449,8 +449,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             lz.begin("final");
             if (h->dense_ffma) launch_dense(da, st);
             else {
-                const size_t ne = (size_t)dims[k] * dims[k + 1];
-                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->fin_whl[k]->as<float>() + ne, h->dev_error.as<int>(), h->sm_count, st);
+                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->dev_error.as<int>(), h->sm_count, st);
             }
             lz.end(1);
             if (train) {

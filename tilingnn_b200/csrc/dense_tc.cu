@@ -4,8 +4,7 @@
 // Persistent CTAs (one per SM) walk tiles of 128 rows x all N_out columns.  The fp32 accumulator lives in
 // TMEM (128 lanes x N_out columns), double buffered so the epilogue of one tile overlaps the next main loop.  K is walked in slabs of 32 (= one 128-byte SWIZZLE_128B atom row):
 //   producers (warps 0-7): A slab  global -> registers -> lazy BatchNorm -> hi/lo TF32 split -> swizzled smem
-//                          W slab  (pre-split hi / lo, [N_out][K] = the checkpoint's own layout, K-major)
-//                                  cp.async -> swizzled smem
+//   bulk warp (warp 8, one lane): W slab = ONE TMA bulk copy of the pre-swizzled hi|lo image (mbarrier tx bytes)
 //   MMA issuer (warp 8, one lane): 12 x tcgen05.mma.kind::tf32 per slab (4 K-steps of 8 x {lo*hi, hi*lo, hi*hi}),
 //                          tcgen05.commit -> mbarrier frees the smem stage / publishes the accumulator
 //   epilogue (warps 9-12): tcgen05.ld 32 columns at a time -> bias, LeakyReLU -> global, column sums in fp64.
@@ -13,6 +12,8 @@
 // Every mbarrier wait is bounded: on a timeout the kernel raises a device-side error flag and exits instead of
 // hanging the GPU.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 #include "tgnn_internal.h"
@@ -23,9 +24,10 @@ namespace {
 constexpr int BM = 128;           // rows per tile (UMMA M)
 constexpr int BK = 32;            // K per slab (128 bytes of tf32)
 constexpr int A_TILE_BYTES = BM * BK * 4;            // 16 KB
-constexpr int N_PROD_WARPS = 8, MMA_WARP = 8, EPI_WARP0 = 9;
-constexpr int NTHREADS = 13 * 32;                    // 8 producer warps, 1 MMA warp, 4 epilogue warps
-constexpr int SCRATCH_FLOATS = 32 * 33;              // per epilogue warp: one 32x32 block, padded
+constexpr int N_PROD_WARPS = 8, BULK_WARP = 8, MMA_WARP = 9, EPI_WARP0 = 10;
+constexpr int N_EPI_WARPS = 4;
+constexpr int NTHREADS = (EPI_WARP0 + N_EPI_WARPS) * 32;   // 8 A-producer warps, 1 bulk (TMA) warp, 1 MMA warp, 4 epilogue warps
+constexpr int SCRATCH_FLOATS = 32 * 36;              // per epilogue warp: one 32x32 block, row stride 36 (16-B aligned, conflict-free)
 
 using namespace tc;
 
@@ -34,12 +36,12 @@ struct DenseTcArgs {
     const float* a;             // else plain [n][K]
     int virtual_concat;
     const float* in_coef;       // [4][K] lazy BatchNorm of the input, or nullptr
-    const float* w_hi;          // [N_out][K] tf32-rounded weights
-    const float* w_lo;          // [N_out][K] tf32-rounded residuals
+    const float* w_img;         // [K/32 slabs][hi|lo][N_out x 128 B] SWIZZLE_128B images of the TF32-split weights
     const float* bias;          // [N_out]
     float* out;                 // [n][N_out]
     double* part;               // [gridDim.x][2][N_out] or nullptr
     int* error_flag;
+    long long* dbg;             // optional per-role wait counters of CTA 0 (TGNN_DENSE_DBG=1)
     int n, K;
 };
 
@@ -47,15 +49,19 @@ template <int NOUT> struct DenseCfg {
     static constexpr int B_TILE_BYTES = NOUT * BK * 4;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
     static constexpr int STAGES = NOUT >= 256 ? 2 : (NOUT >= 128 ? 3 : 4);
-    static constexpr int EPI_BYTES = 4 * SCRATCH_FLOATS * 4 + 4 * 2 * NOUT * 8 + NOUT * 4;   // scratch, red (fp64), bias
+    static constexpr int EPI_BYTES = N_EPI_WARPS * SCRATCH_FLOATS * 4 + 4 * 2 * NOUT * 4 + NOUT * 4;   // scratch, red (fp32 block sums), bias
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024;
 };
 
 // Persistent, warp-specialised:  producers (warps 0-7) -> smem ring -> MMA warp -> TMEM (double buffered)
 // -> epilogue warps (9-12).  The epilogue of tile i overlaps the main loop of tile i+1.
+#define DTIMED(acc, expr) ([&]() { const long long _t = clock64(); const bool _r = (expr); (acc) += clock64() - _t; return _r; })()
+
 template <int NOUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dense_tc(DenseTcArgs A) {
+    long long w0 = 0, w1 = 0;
+    const long long t_start = clock64();
     using Cfg = DenseCfg<NOUT>;
     constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, B_TILE_BYTES = Cfg::B_TILE_BYTES;
     constexpr uint32_t IDESC = umma_idesc_tf32(NOUT);
@@ -64,22 +70,24 @@ k_dense_tc(DenseTcArgs A) {
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
     __shared__ uint32_t tmem_base_smem;
     __shared__ int timeout_flag;
+    __shared__ const float* slab_ptr[32];              // virtual concat: slab base pointers (no dependent global load per slab)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (A.virtual_concat && tid < A.K / BK && tid < 32) slab_ptr[tid] = A.slabs[tid];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t epi = smem_base + STAGES * STAGE_BYTES;
     const uint32_t scratch_all = epi;                                                // [4][32*33] float
-    const uint32_t red = epi + 4 * SCRATCH_FLOATS * 4;                               // [4][2][NOUT] double
-    const uint32_t bias_s = epi + 4 * SCRATCH_FLOATS * 4 + 4 * 2 * NOUT * 8;         // [NOUT] float
+    const uint32_t red = epi + N_EPI_WARPS * SCRATCH_FLOATS * 4;                     // [4][2][NOUT] float (32-row block sums)
+    const uint32_t bias_s = epi + N_EPI_WARPS * SCRATCH_FLOATS * 4 + 4 * 2 * NOUT * 4;   // [NOUT] float
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]);
     const uint32_t bar_accf = smem_u32(&bars[2 * STAGES]), bar_acce = smem_u32(&bars[2 * STAGES + 2]);
     const int n_slabs = A.K / BK;
     const int n_tiles = (A.n + BM - 1) / BM;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, N_PROD_WARPS); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, 4); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_full + 8 * s, N_PROD_WARPS + 1); mbar_init(bar_empty + 8 * s, 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, N_EPI_WARPS); }
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -99,67 +107,97 @@ k_dense_tc(DenseTcArgs A) {
         auto load_a = [&](int tile, int s, float4 (&v)[4]) {
             const int row0 = tile * BM;
             const float* abase; size_t lda; int koff;
-            if (A.virtual_concat) { abase = A.slabs[s]; lda = F; koff = 0; }
+            if (A.virtual_concat) { abase = slab_ptr[s]; lda = F; koff = 0; }
             else { abase = A.a; lda = (size_t)A.K; koff = s * BK; }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = row0 + rbase + 32 * j;
-                v[j] = r < A.n ? __ldg(reinterpret_cast<const float4*>(abase + (size_t)r * lda + koff) + c)
-                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                // zero first, then a PREDICATED load straight into the destination registers: `cond ? ldg : 0` becomes
+                // load-to-temp + dependent move, which makes the "prefetch" wait for its data right here
+                v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < A.n) v[j] = __ldg(reinterpret_cast<const float4*>(abase + (size_t)r * lda + koff) + c);
             }
         };
-        float4 pre[4];
-        int g = 0;
-        bool ok = true;
-        if ((int)blockIdx.x < n_tiles) load_a(blockIdx.x, 0, pre);
-        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-            const int row0 = tile * BM;
-            for (int s = 0; s < n_slabs; ++s, ++g) {
-                const int st = g % STAGES;
-                if (!mbar_wait(bar_empty + 8 * st, ((g / STAGES) & 1) ^ 1)) { timeout_flag = 1; ok = false; break; }
-                const uint32_t sa_hi = smem_base + st * STAGE_BYTES, sa_lo = sa_hi + A_TILE_BYTES;
-                const uint32_t sb_hi = smem_base + st * STAGE_BYTES + 2 * A_TILE_BYTES;
-                const uint32_t sb_lo = sb_hi + B_TILE_BYTES;
-                const int k0 = s * BK;
-                for (int i = tid; i < NOUT * 8; i += N_PROD_WARPS * 32) {
-                    const int r = i >> 3, cc = i & 7;
-                    const uint32_t off = sw128_off(r, cc);
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_hi + off), "l"(A.w_hi + (size_t)r * A.K + k0 + 4 * cc) : "memory");
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb_lo + off), "l"(A.w_lo + (size_t)r * A.K + k0 + 4 * cc) : "memory");
-                }
-                float4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
-                // prefetch the next slab's rows (possibly the next tile's first slab) while this one is transformed
-                {
-                    int nt = tile, ns = s + 1;
-                    if (ns == n_slabs) { ns = 0; nt = tile + gridDim.x; }
-                    if (nt < n_tiles) load_a(nt, ns, pre);
-                }
+        // A rows are prefetched THREE slabs ahead in registers (three statically named buffers used round-robin --
+        // no register copies, a MOV of a register with a load in flight would wait for it): one slab ahead (16 KB per
+        // SM in flight) caps the stream at ~2.4 TB/s chip-wide, well below HBM speed.
+        float4 pre0[4], pre1[4], pre2[4];
+        int la_tile = blockIdx.x, la_s = 0;                 // look-ahead position (next slab to request)
+        auto request = [&](float4 (&dst)[4]) {
+            if (la_tile < n_tiles) {
+                load_a(la_tile, la_s, dst);
+                if (++la_s == n_slabs) { la_s = 0; la_tile += gridDim.x; }
+            }
+        };
+        int g = 0, tile = blockIdx.x, s = 0;
+        float4 nmh = make_float4(0.f, 0.f, 0.f, 0.f), nml = nmh, nsc = nmh, nbe = nmh;
+        if (A.in_coef) {
+            const float4* cf = reinterpret_cast<const float4*>(A.in_coef) + c;
+            const int C4 = A.K / 4;
+            nmh = __ldg(cf); nml = __ldg(cf + C4); nsc = __ldg(cf + 2 * C4); nbe = __ldg(cf + 3 * C4);
+        }
+        auto process = [&](float4 (&buf)[4]) -> bool {
+            const int st = g % STAGES, row0 = tile * BM, k0 = s * BK;
+            if (!DTIMED(w0, mbar_wait(bar_empty + 8 * st, ((g / STAGES) & 1) ^ 1))) return false;
+            const uint32_t sa_hi = smem_base + st * STAGE_BYTES, sa_lo = sa_hi + A_TILE_BYTES;
+            // BatchNorm coefficients of this thread's 4 columns (lazy BN of the input), fetched one slab ahead
+            const float4 cmh = nmh, cml = nml, csc = nsc, cbe = nbe;
+            if (A.in_coef) {
+                const int ns = (s + 1 == n_slabs) ? 0 : s + 1;
+                const float4* cf = reinterpret_cast<const float4*>(A.in_coef + ns * BK) + c;
+                const int C4 = A.K / 4;
+                nmh = __ldg(cf); nml = __ldg(cf + C4); nsc = __ldg(cf + 2 * C4); nbe = __ldg(cf + 3 * C4);
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = rbase + 32 * j;
-                    float4 v = cur[j];
-                    if (A.in_coef) {
-                        const float* cf = A.in_coef + k0 + 4 * c;
-                        const int C = A.K;
-                        v.x = fmaf((v.x - cf[0]) - cf[C + 0], cf[2 * C + 0], cf[3 * C + 0]);
-                        v.y = fmaf((v.y - cf[1]) - cf[C + 1], cf[2 * C + 1], cf[3 * C + 1]);
-                        v.z = fmaf((v.z - cf[2]) - cf[C + 2], cf[2 * C + 2], cf[3 * C + 2]);
-                        v.w = fmaf((v.w - cf[3]) - cf[C + 3], cf[2 * C + 3], cf[3 * C + 3]);
-                        if (row0 + r >= A.n) v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    uint4 hi, lo;
-                    hi.x = tf32_rna(v.x); lo.x = tf32_rna(v.x - __uint_as_float(hi.x));
-                    hi.y = tf32_rna(v.y); lo.y = tf32_rna(v.y - __uint_as_float(hi.y));
-                    hi.z = tf32_rna(v.z); lo.z = tf32_rna(v.z - __uint_as_float(hi.z));
-                    hi.w = tf32_rna(v.w); lo.w = tf32_rna(v.w - __uint_as_float(hi.w));
-                    const uint32_t off = sw128_off(r, c);
-                    sts128(sa_hi + off, hi);
-                    sts128(sa_lo + off, lo);
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + 32 * j;
+                float4 v = buf[j];
+                if (A.in_coef) {
+                    v.x = fmaf((v.x - cmh.x) - cml.x, csc.x, cbe.x);
+                    v.y = fmaf((v.y - cmh.y) - cml.y, csc.y, cbe.y);
+                    v.z = fmaf((v.z - cmh.z) - cml.z, csc.z, cbe.z);
+                    v.w = fmaf((v.w - cmh.w) - cml.w, csc.w, cbe.w);
+                    if (row0 + r >= A.n) v = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                asm volatile("cp.async.wait_all;" ::: "memory");
-                fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core (async proxy)
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_full + 8 * st);
+                // truncation split: hi = top 19 bits (what kind::tf32 reads), lo = x - hi exact; the tensor core
+                // truncates lo to TF32 itself (relative residual ~2^-21)
+                uint4 hi, lo;
+                hi.x = __float_as_uint(v.x) & 0xFFFFE000u; lo.x = __float_as_uint(v.x - __uint_as_float(hi.x));
+                hi.y = __float_as_uint(v.y) & 0xFFFFE000u; lo.y = __float_as_uint(v.y - __uint_as_float(hi.y));
+                hi.z = __float_as_uint(v.z) & 0xFFFFE000u; lo.z = __float_as_uint(v.z - __uint_as_float(hi.z));
+                hi.w = __float_as_uint(v.w) & 0xFFFFE000u; lo.w = __float_as_uint(v.w - __uint_as_float(hi.w));
+                const uint32_t off = sw128_off(r, c);
+                sts128(sa_hi + off, hi);
+                sts128(sa_lo + off, lo);
+            }
+            request(buf);                              // the buffer is free again: fetch the slab three positions ahead
+            fence_proxy_async();                       // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + 8 * st);
+            ++g;
+            if (++s == n_slabs) { s = 0; tile += gridDim.x; }
+            return true;
+        };
+        request(pre0); request(pre1); request(pre2);
+        bool ok = true;
+        while (ok && tile < n_tiles) {
+            ok = process(pre0);
+            if (ok && tile < n_tiles) ok = process(pre1);
+            if (ok && tile < n_tiles) ok = process(pre2);
+        }
+        if (!ok) timeout_flag = 1;
+    } else if (warp == BULK_WARP) {
+        // ===================== weight slabs: ONE TMA bulk copy per slab (hi and lo tiles are adjacent) =============
+        if (lane == 0) {
+            int g = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < n_slabs; ++s, ++g) {
+                    const int st = g % STAGES;
+                    if (!DTIMED(w0, mbar_wait_relaxed(bar_empty + 8 * st, ((g / STAGES) & 1) ^ 1))) { timeout_flag = 1; break; }
+                    mbar_arrive_expect_tx(bar_full + 8 * st, 2 * B_TILE_BYTES);
+                    bulk_g2s(smem_base + st * STAGE_BYTES + 2 * A_TILE_BYTES, A.w_img + (size_t)s * 2 * NOUT * BK, 2 * B_TILE_BYTES,
+                             bar_full + 8 * st);
+                }
             }
         }
     } else if (warp == MMA_WARP) {
@@ -169,12 +207,12 @@ k_dense_tc(DenseTcArgs A) {
             bool ok = true;
             for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++it) {
                 const int ab = it & 1;
-                if (!mbar_wait(bar_acce + 8 * ab, ((it >> 1) & 1) ^ 1)) { timeout_flag = 1; break; }
+                if (!DTIMED(w1, mbar_wait(bar_acce + 8 * ab, ((it >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(ab * NOUT);
                 for (int s = 0; s < n_slabs; ++s, ++g) {
                     const int st = g % STAGES;
-                    if (!mbar_wait(bar_full + 8 * st, (g / STAGES) & 1)) { timeout_flag = 1; ok = false; break; }
+                    if (!DTIMED(w0, mbar_wait(bar_full + 8 * st, (g / STAGES) & 1))) { timeout_flag = 1; ok = false; break; }
                     tc_fence_after();
                     const uint32_t a_hi = smem_base + st * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
@@ -194,12 +232,12 @@ k_dense_tc(DenseTcArgs A) {
         }
     } else {
         // ===================== epilogue warps: TMEM lane quarter q = warp % 4, tile row = 32 q + lane =====================
-        const int q = warp & 3, etid = (warp - EPI_WARP0) * 32 + lane;
-        const uint32_t sc = scratch_all + (uint32_t)q * SCRATCH_FLOATS * 4;
+        const int q = warp & 3, ew = warp - EPI_WARP0, etid = ew * 32 + lane;
+        const uint32_t sc = scratch_all + (uint32_t)ew * SCRATCH_FLOATS * 4;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int ab = it & 1;
-            if (!mbar_wait(bar_accf + 8 * ab, (it >> 1) & 1)) { timeout_flag = 1; break; }
+            if (!DTIMED(w0, mbar_wait(bar_accf + 8 * ab, (it >> 1) & 1))) { timeout_flag = 1; break; }
             tc_fence_after();
             const int row0 = tile * BM, row = row0 + 32 * q + lane;
             const bool live = row < A.n;
@@ -209,29 +247,38 @@ k_dense_tc(DenseTcArgs A) {
             for (int c0 = 0; c0 < NOUT; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ab * NOUT + c0), v);
+                // transpose through the warp's 32x36 scratch block (8 x STS.128 per lane): every global store below is ONE
+                // coalesced 128-byte row segment (lane = column); bias, LeakyReLU and the column sums happen in the same
+                // loop.  Sums are fp32 over the block's 32 rows, then fp64 across blocks / tiles (these BatchNorms are
+                // well conditioned; the ill-conditioned conv/GIN ones keep fp64 throughout).
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(leaky(__uint_as_float(v[j]) + lds_f32(bias_s + 4 * (c0 + j))));
-                if (live) {
-                    float4* dst = reinterpret_cast<float4*>(A.out + (size_t)row * NOUT + c0);
+                for (int j = 0; j < 8; ++j)
+                    sts128(sc + 4 * (lane * 36 + 4 * j), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+                __syncwarp();
+                const float bias_c = lds_f32(bias_s + 4 * (c0 + lane));
+                float s1f[4] = {0.f, 0.f, 0.f, 0.f}, s2f[4] = {0.f, 0.f, 0.f, 0.f};
+                float* orow = A.out + (size_t)(row0 + 32 * q) * NOUT + c0 + lane;
+                int r = 0;
+                for (; r + 4 <= nv; r += 4) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                    for (int u = 0; u < 4; ++u) {
+                        float o = lds_f32(sc + 4 * ((r + u) * 36 + lane)) + bias_c;
+                        o = fmaxf(o, o * LEAKY);
+                        orow[(size_t)(r + u) * NOUT] = o;
+                        s1f[u] += o; s2f[u] = fmaf(o, o, s2f[u]);
+                    }
+                }
+                for (; r < nv; ++r) {
+                    float o = lds_f32(sc + 4 * (r * 36 + lane)) + bias_c;
+                    o = fmaxf(o, o * LEAKY);
+                    orow[(size_t)r * NOUT] = o;
+                    s1f[0] += o; s2f[0] = fmaf(o, o, s2f[0]);
                 }
                 if (A.part) {
-                    // column sums over this warp's rows through a padded 32x32 scratch block (lane = column)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sts_f32(sc + 4 * (lane * 33 + j), __uint_as_float(v[j]));
-                    __syncwarp();
-                    double s1 = 0.0, s2 = 0.0;
-                    for (int r = 0; r < nv; ++r) {
-                        const double o = (double)lds_f32(sc + 4 * (r * 33 + lane));
-                        s1 += o; s2 += o * o;
-                    }
-                    sts_f64(red + 8 * ((q * 2 + 0) * NOUT + c0 + lane), s1);
-                    sts_f64(red + 8 * ((q * 2 + 1) * NOUT + c0 + lane), s2);
-                    __syncwarp();
+                    sts_f32(red + 4 * ((q * 2 + 0) * NOUT + c0 + lane), (s1f[0] + s1f[1]) + (s1f[2] + s1f[3]));
+                    sts_f32(red + 4 * ((q * 2 + 1) * NOUT + c0 + lane), (s2f[0] + s2f[1]) + (s2f[2] + s2f[3]));
                 }
+                __syncwarp();
             }
             // all tcgen05.ld of this accumulator are complete (wait::ld inside tmem_ld32): hand the buffer back
             tc_fence_before();
@@ -242,13 +289,14 @@ k_dense_tc(DenseTcArgs A) {
                 double* p = A.part + (size_t)tile * 2 * NOUT;
                 for (int i = etid; i < 2 * NOUT; i += 128) {
                     const int qq = i / NOUT, cc = i % NOUT;
-                    p[i] = ((lds_f64(red + 8 * ((0 * 2 + qq) * NOUT + cc)) + lds_f64(red + 8 * ((1 * 2 + qq) * NOUT + cc))) +
-                            lds_f64(red + 8 * ((2 * 2 + qq) * NOUT + cc))) + lds_f64(red + 8 * ((3 * 2 + qq) * NOUT + cc));
+                    p[i] = (((double)lds_f32(red + 4 * ((0 * 2 + qq) * NOUT + cc)) + (double)lds_f32(red + 4 * ((1 * 2 + qq) * NOUT + cc))) +
+                            (double)lds_f32(red + 4 * ((2 * 2 + qq) * NOUT + cc))) + (double)lds_f32(red + 4 * ((3 * 2 + qq) * NOUT + cc));
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
         }
     }
+    if (A.dbg && blockIdx.x == 0 && lane == 0) { long long* d = A.dbg + warp * 4; d[0] = clock64() - t_start; d[1] = w0; d[2] = w1; }
     tc_fence_before();
     __syncthreads();
     if (timeout_flag && tid == 0) atomicExch(A.error_flag, 1);
@@ -259,13 +307,19 @@ k_dense_tc(DenseTcArgs A) {
     }
 }
 
-__global__ void k_split_tf32(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// w: [N_out][K] (the checkpoint layout).  img: per 32-wide K slab, the hi tile then the lo tile, each the
+// SWIZZLE_128B shared-memory image [N_out rows x 128 B] -- so a slab's B operand is one contiguous bulk copy.
+__global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ img, int n_out, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out * K) return;
+    const int n = i / K, k = i - n * K, slab = k >> 5, kk = k & 31;
     const float x = w[i];
     const uint32_t h = tf32_rna(x);
-    hi[i] = __uint_as_float(h);
-    lo[i] = __uint_as_float(tf32_rna(x - __uint_as_float(h)));
+    const uint32_t l = tf32_rna(x - __uint_as_float(h));
+    const size_t base = (size_t)slab * 2 * n_out * 32;
+    const int pos = n * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
+    img[base + pos] = __uint_as_float(h);
+    img[base + (size_t)n_out * 32 + pos] = __uint_as_float(l);
 }
 
 template <int NOUT>
@@ -277,24 +331,39 @@ void launch_one(const DenseTcArgs& a, int sm_count, cudaStream_t st) {
         attr = true;
     }
     const int n_tiles = (a.n + BM - 1) / BM;
-    k_dense_tc<NOUT><<<std::min(n_tiles, sm_count), NTHREADS, smem, st>>>(a);
+    static long long* dbg = nullptr;
+    static const bool want_dbg = getenv("TGNN_DENSE_DBG") != nullptr;
+    if (want_dbg && !dbg) TGNN_CUDA(cudaMalloc(&dbg, 16 * 4 * sizeof(long long)));
+    DenseTcArgs b = a;
+    b.dbg = dbg;
+    k_dense_tc<NOUT><<<std::min(n_tiles, sm_count), NTHREADS, smem, st>>>(b);
     TGNN_CUDA(cudaGetLastError());
+    if (want_dbg) {
+        static int calls = 0;
+        if (++calls == 8) {
+            long long h[16 * 4];
+            TGNN_CUDA(cudaStreamSynchronize(st));
+            TGNN_CUDA(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+            for (int w = 0; w < NTHREADS / 32; ++w)
+                fprintf(stderr, "dense<%d> dbg warp %2d total %9lld wait0 %9lld wait1 %9lld\n", NOUT, w, h[4 * w], h[4 * w + 1], h[4 * w + 2]);
+        }
+    }
 }
 
 }  // namespace
 
-void launch_split_tf32(const float* w, float* hi, float* lo, int n, cudaStream_t st) {
-    k_split_tf32<<<(n + 255) / 256, 256, 0, st>>>(w, hi, lo, n);
+void launch_weight_image(const float* w, float* img, int n_out, int K, cudaStream_t st) {
+    k_weight_image<<<(n_out * K + 255) / 256, 256, 0, st>>>(w, img, n_out, K);
     TGNN_CUDA(cudaGetLastError());
 }
 
 int dense_tc_row_blocks(int n) { return (n + BM - 1) / BM; }
 
-void launch_dense_tc(const DenseArgs& d, const float* w_hi, const float* w_lo, int* error_flag, int sm_count, cudaStream_t st) {
+void launch_dense_tc(const DenseArgs& d, const float* w_img, int* error_flag, int sm_count, cudaStream_t st) {
     TGNN_CHECK(d.K % BK == 0, "dense stage: K must be a multiple of 32");
     DenseTcArgs a{};
     a.slabs = d.slabs; a.a = d.a; a.virtual_concat = d.virtual_concat; a.in_coef = d.in_coef;
-    a.w_hi = w_hi; a.w_lo = w_lo; a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag;
+    a.w_img = w_img; a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag;
     a.n = d.n; a.K = d.K;
     switch (d.n_out) {
         case 256: launch_one<256>(a, sm_count, st); break;

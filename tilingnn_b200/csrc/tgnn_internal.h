@@ -179,8 +179,8 @@ int dense_row_blocks(int n);
 void launch_dense(const DenseArgs& a, cudaStream_t st);
 
 // tcgen05 (tensor-core) version of the dense stage: w_hi / w_lo = TF32 split of the [N_out][K] weight
-void launch_split_tf32(const float* w, float* hi, float* lo, int n, cudaStream_t st);
-void launch_dense_tc(const DenseArgs& a, const float* w_hi, const float* w_lo, int* error_flag, int sm_count, cudaStream_t st);
+void launch_weight_image(const float* w, float* img, int n_out, int K, cudaStream_t st);   // pre-swizzled hi|lo slabs
+void launch_dense_tc(const DenseArgs& a, const float* w_img, int* error_flag, int sm_count, cudaStream_t st);
 
 void launch_score(const float* a3, const float* coef, const float* w, float b, float* out,
                   int64_t n, cudaStream_t st);
