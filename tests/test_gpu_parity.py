@@ -155,6 +155,26 @@ def test_synthetic_configs_vs_oracle(dev, n, deg, mode):
     assert err <= TOL
 
 
+@pytest.mark.parametrize("kernel", ["chunk", "s"])
+def test_both_adjacency_kernels(dev, kernel, monkeypatch):
+    """The mma.sync edge-chunk kernel and the tcgen05 S kernel are selected per graph by a cost model; force each
+    (TGNN_CONV) on the shipped checkpoint (20 edge types) and on a synthetic graph (51 types)."""
+    monkeypatch.setenv("TGNN_CONV", kernel)
+    from tilingnn_b200 import synthetic as syn
+    z, x, ai, af, ci = load_graph("c1_complete.npz")
+    net = make_net(load_ckpt(), 3, 19, 20, dev, "train")
+    s = run(net, x, ai, af, ci, dev)
+    gold = z["ref_train_f64"]
+    assert np.abs(s - gold).max() <= max(TOL, 1.5 * np.abs(z["ref_train_f32"] - gold).max())
+    x, ai, af, ci = syn.lattice_graph(6000, 32, 32, seed=3)
+    p = orc.make_params(3, 19, 4, seed=3)
+    gold = orc.forward(p, x, ai, af, ci, depth=4, dtype=torch.float64)[:, 0].numpy()
+    net = make_net(p, 3, 19, 4, dev)
+    err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
+    print(f"TGNN_CONV={kernel}: max err {err:.2e}")
+    assert err <= TOL
+
+
 def test_random_graph_and_many_edge_types(dev):
     """uniform random sources (duplicates, self loops) and continuous features (one type per edge)."""
     from tilingnn_b200 import synthetic as syn

@@ -49,8 +49,9 @@ def _worker(rank, world, port, n, deg, depth, mode, q):
 
 
 @pytest.mark.parametrize("mode", ["train"])
-@pytest.mark.parametrize("n,deg", [(20000, 8), (6000, 32)])
-def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, mode):
+@pytest.mark.parametrize("n,deg,conv", [(20000, 8, "chunk"), (6000, 32, "s"), (6000, 32, "chunk")])
+def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, mode, monkeypatch):
+    monkeypatch.setenv("TGNN_CONV", conv)          # inherited by the spawned ranks
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from oracle import tilingnn_oracle as orc

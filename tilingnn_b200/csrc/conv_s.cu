@@ -322,6 +322,10 @@ k_conv_s(ConvSArgs A) {
         // ===================== MMA issuer =====================
         if (lane == 0) {
             constexpr uint32_t IDESC = umma_idesc_tf32(32);
+            // One thread issues every MMA of the CTA, so its scalar instruction stream bounds the pass rate: all
+            // descriptors are "base + small integer" (the address field is bits 0..13 in 16-byte units and every
+            // operand lives below 256 KB, so plain 64-bit adds never carry out of the field).
+            const uint64_t dA = umma_desc_sw128(smem_base + OFF_A), dB = umma_desc_sw128(smem_base + OFF_B);
             int s = 0, it = 0, q = 0;
             for (int tile = blockIdx.x; tile < A.n_tiles;) {
                 const int slot = s & (D - 1), st = s & 1, ab = it & 1;
@@ -329,19 +333,19 @@ k_conv_s(ConvSArgs A) {
                 if (!TIMED(w0, mbar_wait(bar_rf + 8 * slot, (uint32_t)((s / D) & 1)))) { timeout_flag = 1; break; }
                 const bool root = lds128i(smem_base + OFF_META + slot * 16).y != 0;
                 if (!TIMED(w1, mbar_wait(bar_af + 8 * st, (uint32_t)((s >> 1) & 1)))) { timeout_flag = 1; break; }
-                fence_proxy_async();                   // weight tiles were written by the loaders' cp.async
+                fence_proxy_async();                   // weight tiles were written by the TMA engine / loaders' cp.async
                 tc_fence_after();
-                const uint32_t a_hi = smem_base + OFF_A + (st * 2) * SA_TILE, a_lo = a_hi + SA_TILE;
-                const uint32_t b_hi = smem_base + OFF_B + (uint32_t)slot * 2 * SB_TILE, b_lo = b_hi + SB_TILE;
+                const uint64_t dah = dA + (uint64_t)(st * (2 * SA_TILE / 16)), dal = dah + SA_TILE / 16;
+                const uint64_t dbh = dB + (uint64_t)(slot * (2 * SB_TILE / 16)), dbl = dbh + SB_TILE / 16;
                 const uint32_t tmem_d = tmem_base + (uint32_t)(ab * 64) + (root ? 32u : 0u);
+                if (root || q == 0) umma_tf32_ovw(tmem_d, dal, dbh, IDESC); else umma_tf32_acc(tmem_d, dal, dbh, IDESC);
+                umma_tf32_acc(tmem_d, dah, dbl, IDESC);
+                umma_tf32_acc(tmem_d, dah, dbh, IDESC);
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t kb = ks * 32;
-                    const uint64_t dah = umma_desc_sw128(a_hi + kb), dal = umma_desc_sw128(a_lo + kb);
-                    const uint64_t dbh = umma_desc_sw128(b_hi + kb), dbl = umma_desc_sw128(b_lo + kb);
-                    umma_tf32(tmem_d, dal, dbh, IDESC, (ks > 0 || (!root && q > 0)) ? 1u : 0u);
-                    umma_tf32(tmem_d, dah, dbl, IDESC, 1u);
-                    umma_tf32(tmem_d, dah, dbh, IDESC, 1u);
+                for (int ks = 1; ks < 4; ++ks) {       // 8 tf32 = 32 bytes = 2 descriptor units along K inside the swizzle atom
+                    umma_tf32_acc(tmem_d, dal + 2 * ks, dbh + 2 * ks, IDESC);
+                    umma_tf32_acc(tmem_d, dah + 2 * ks, dbl + 2 * ks, IDESC);
+                    umma_tf32_acc(tmem_d, dah + 2 * ks, dbh + 2 * ks, IDESC);
                 }
                 umma_commit(bar_re + 8 * slot);        // pass done: operand stage, weight tile and ring rows are free
                 ++s; ++q;

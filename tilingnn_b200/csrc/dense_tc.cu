@@ -55,7 +55,11 @@ template <int NOUT> struct DenseCfg {
 
 // Persistent, warp-specialised:  producers (warps 0-7) -> smem ring -> MMA warp -> TMEM (double buffered)
 // -> epilogue warps (9-12).  The epilogue of tile i overlaps the main loop of tile i+1.
+#ifdef TGNN_DENSE_TIMING     // role wait counters (build with TGNN_NVCC_EXTRA=-DTGNN_DENSE_TIMING, run with TGNN_DENSE_DBG=1)
 #define DTIMED(acc, expr) ([&]() { const long long _t = clock64(); const bool _r = (expr); (acc) += clock64() - _t; return _r; })()
+#else
+#define DTIMED(acc, expr) (expr)
+#endif
 
 template <int NOUT>
 __global__ void __launch_bounds__(NTHREADS, 1)
