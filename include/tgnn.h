@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGNN_ABI_VERSION 1
+#define TGNN_ABI_VERSION 2
 
 #define TGNN_BN_TRAIN 0   /* batch statistics over the rows of THIS call -- the reference's
                              behaviour: solver/ml_solver/ml_solver.py:129-131 ends in network.train() */
@@ -106,6 +106,10 @@ typedef struct tgnn_info {
     int64_t launches_per_forward;  /* kernels of this library launched by one tgnn_forward   */
     int64_t workspace_bytes;
     int64_t collectives_per_forward;
+    int64_t conv_kernel;           /* adjacency kernel chosen for this graph: 0 = 3xTF32 edge-chunk (mma.sync),
+                                      1 = tcgen05 S formulation, 2 = fp16-split edge-chunk (mma.sync.f16)      */
+    int64_t range_fallback_layers; /* layers of the LAST forward that kernel 2 handed to kernel 0 because an
+                                      activation or root weight was outside the fp16 range (synchronises)      */
 } tgnn_info;
 int tgnn_get_info(tgnn_handle* h, tgnn_info* out);
 

@@ -155,10 +155,10 @@ def test_synthetic_configs_vs_oracle(dev, n, deg, mode):
     assert err <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["chunk", "s"])
-def test_both_adjacency_kernels(dev, kernel, monkeypatch):
-    """The mma.sync edge-chunk kernel and the tcgen05 S kernel are selected per graph by a cost model; force each
-    (TGNN_CONV) on the shipped checkpoint (20 edge types) and on a synthetic graph (51 types)."""
+@pytest.mark.parametrize("kernel", ["chunk", "s", "h"])
+def test_all_adjacency_kernels(dev, kernel, monkeypatch):
+    """The fp16-split edge-chunk kernel, its 3xTF32 twin and the tcgen05 S kernel are selected per graph by a cost
+    model; force each (TGNN_CONV) on the shipped checkpoint (20 edge types) and on a synthetic graph (51 types)."""
     monkeypatch.setenv("TGNN_CONV", kernel)
     from tilingnn_b200 import synthetic as syn
     z, x, ai, af, ci = load_graph("c1_complete.npz")
@@ -172,6 +172,26 @@ def test_both_adjacency_kernels(dev, kernel, monkeypatch):
     net = make_net(p, 3, 19, 4, dev)
     err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
     print(f"TGNN_CONV={kernel}: max err {err:.2e}")
+    assert err <= TOL
+    info = net.info()
+    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2}[kernel] and info["range_fallback_layers"] == 0
+
+
+def test_fp16_range_guard_hands_layers_to_the_tf32_kernel(dev, monkeypatch):
+    """k_conv_h works on fp16-split operands; activations beyond +-60000 (here: a BatchNorm gain of 1e6 in layer 0)
+    and root weights beyond it (layer 2) must raise the range flags so the 3xTF32 kernel takes those layers."""
+    monkeypatch.setenv("TGNN_CONV", "h")
+    from tilingnn_b200 import synthetic as syn
+    x, ai, af, ci = syn.lattice_graph(3000, 8, 8, seed=4)
+    p = dict(orc.make_params(3, 19, 4, seed=4))
+    p["brch_1_graph_conv_layers.0.batch_norm.weight"] = p["brch_1_graph_conv_layers.0.batch_norm.weight"] * 1e6
+    p["brch_1_graph_conv_layers.2.nnConv.root"] = p["brch_1_graph_conv_layers.2.nnConv.root"] * 1e6
+    gold = orc.forward(p, x, ai, af, ci, depth=4, dtype=torch.float64)[:, 0].numpy()
+    net = make_net(p, 3, 19, 4, dev)
+    err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
+    info = net.info()
+    print(f"range guard: max err {err:.2e}, fallback layers {info['range_fallback_layers']}")
+    assert info["conv_kernel"] == 2 and info["range_fallback_layers"] >= 2
     assert err <= TOL
 
 

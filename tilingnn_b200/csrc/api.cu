@@ -91,13 +91,19 @@ struct tgnn_handle {
     std::vector<size_t> coef_a, coef_c;
     DevBuf tab;                                     // [L][K+1][2048] frag tables (entry K = root)
     DevBuf tabS;                                    // [L][K+1][2048] transposed hi|lo tables of the tcgen05 conv kernel
-    bool conv_chunk_only = false;                   // TGNN_CONV=chunk forces the mma.sync edge-chunk kernel
+    DevBuf tabH;                                    // [L][K+1][1024] fp16 hi|lo fragment tables of k_conv_h
+    DevBuf hflags;                                  // int [L+1] activation range flags (per forward) | [L] weight range flags
+    bool conv_chunk_only = false;                   // TGNN_CONV=chunk forces the 3xTF32 mma.sync edge-chunk kernel
     bool conv_s_only = false;                       // TGNN_CONV=s forces the tcgen05 S kernel whenever its format exists
-    bool use_s = false;                             // decided per graph in set_graph
+    bool conv_h_only = false;                       // TGNN_CONV=h forces the fp16-split edge-chunk kernel (never S)
+    bool use_s = false, use_h = false;              // decided per graph in set_graph
 
     // workspace
     std::vector<std::unique_ptr<DevBuf>> mid;
     DevBuf pre1, pre2[2], fa[4], partA, partB, sums, slab_ptrs, halo;
+    DevBuf xh;                                      // [n_rows][8] uint4: fp16-split copy of the current layer's b1
+    int* rflag(int i) { return hflags.as<int>() + i; }
+    int* wflag(int i) { return hflags.as<int>() + cfg.depth + 1 + i; }
     size_t workspace_bytes = 0;
 
     // sharding
@@ -270,6 +276,15 @@ void build_tables(tgnn_handle* h, cudaStream_t st) {
                           h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), base, st);
         // nnConv.root is [in][out] = k-major already
         launch_frag_pack(h->P(c + ".nnConv.root"), F, F, TG_KMAP_GATHER, TG_NMAP_CONTIG8, base + (size_t)K * TG_FRAG32, st);
+        if (h->use_h) {
+            h->tabH.reserve((size_t)L * (K + 1) * TG_HFRAG32 * sizeof(uint32_t));
+            if (i == 0) TGNN_CUDA(cudaMemsetAsync(h->wflag(0), 0, (size_t)L * sizeof(int), st));
+            launch_edge_table_h(h->g.type_rows.as<float>(), K, h->cfg.d_e,
+                                h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
+                                h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
+                                h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), h->P(c + ".nnConv.root"),
+                                h->tabH.as<uint32_t>() + (size_t)i * (K + 1) * TG_HFRAG32, h->wflag(i), st);
+        }
         if (h->g.has_s) {
             h->tabS.reserve((size_t)L * (K + 1) * TG_FRAG32 * sizeof(float));
             launch_edge_table_s(h->g.type_rows.as<float>(), K, h->cfg.d_e,
@@ -286,7 +301,8 @@ void build_tables(tgnn_handle* h, cudaStream_t st) {
 // adjacency edge, the tcgen05 S kernel ~5.9 ns per (128-row tile, edge type) pass -> S pays off when the tiles see
 // few types relative to their edge count (the shipped tile graphs: 20-41 types), chunk when types are many.
 void choose_conv_kernel(tgnn_handle* h) {
-    h->use_s = h->g.has_s && (h->conv_s_only || (double)h->g.s_passes * 82.0 < (double)h->g.e_adj);
+    h->use_s = h->g.has_s && !h->conv_h_only && (h->conv_s_only || (double)h->g.s_passes * 164.0 < (double)h->g.e_adj);
+    h->use_h = !h->use_s && !h->conv_chunk_only;
 }
 
 void alloc_workspace(tgnn_handle* h) {
@@ -297,6 +313,7 @@ void alloc_workspace(tgnn_handle* h) {
     while ((int)h->mid.size() < L + 1) h->mid.emplace_back(new DevBuf());
     for (int i = 0; i <= L; ++i) res(*h->mid[i], rows * F * sizeof(float));
     res(h->pre1, own * F * sizeof(float));
+    if (h->use_h) res(h->xh, rows * F * sizeof(float));
     res(h->pre2[0], rows * F * sizeof(float));
     res(h->pre2[1], rows * F * sizeof(float));
     for (int k = 0; k < 4; ++k) res(h->fa[k], own * FIN_DIMS[k + 1] * sizeof(float));
@@ -337,13 +354,14 @@ void allreduce_sums(tgnn_handle* h, double* sums, int n, cudaStream_t st) {
     h->collectives += 1;
 }
 
-void halo_exchange(tgnn_handle* h, float* a, float* b, cudaStream_t st, Launcher& lz) {
+void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t st, Launcher& lz) {
     if (h->world <= 1) return;
     lz.begin("halo");
     float* slot = h->halo.as<float>() + (size_t)h->rank * h->g.halo_slot * 64;
     launch_halo_pack(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, slot, st);
     nccl_check(nccl().AllGather(slot, h->halo.p, (size_t)h->g.halo_slot * 64, ncclFloat32, h->comm, st), "halo all-gather");
-    launch_halo_unpack(h->halo.as<float>(), h->world, h->rank, h->g.halo_slot, h->g.n_own, a, b, st);
+    launch_halo_unpack(h->halo.as<float>(), h->world, h->rank, h->g.halo_slot, h->g.n_own, a, b,
+                       h->use_h ? h->xh.as<uint4>() : nullptr, flag, st);
     h->collectives += 1;
     lz.end(2);
 }
@@ -362,6 +380,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     Launcher lz{h, st};
     double* sums = h->sums.as<double>();
     if (!train) { lz.begin("bnfin"); eval_coefs(h, st); lz.end(2 + 2 * L + 4); }
+    if (h->use_h) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
 
     auto finish_bn = [&](const double* part, int n_part, int c, const std::string& bn, size_t coef_off) {
         launch_bn_reduce(part, n_part, c, sums, st);
@@ -376,6 +395,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     ia.w1t = h->init_w1t.as<float>(); ia.b1 = h->P("init_node_feature_trans.mlp.1.linear.bias");
     ia.coef0 = h->C(h->coef_init[0]); ia.coef1 = h->C(h->coef_init[1]);
     ia.out = h->mid[0]->as<float>(); ia.part = h->partA.as<double>(); ia.n_own = n_own;
+    ia.xh = h->use_h ? h->xh.as<uint32_t>() : nullptr; ia.flag = h->use_h ? h->rflag(0) : nullptr;
     const int np_init = init_num_parts(n_own, h->sm_count);
     if (train) {
         lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
@@ -384,7 +404,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.1.batch_norm", h->coef_init[1]); lz.end(2);
     }
     lz.begin("init"); launch_init(ia, 2, h->sm_count, st); lz.end(1);
-    halo_exchange(h, h->mid[0]->as<float>(), nullptr, st, lz);
+    halo_exchange(h, h->mid[0]->as<float>(), nullptr, h->rflag(0), st, lz);
 
     // ---- message-passing layers ----------------------------------------------------------------
     const int n_layers = h->stop_layer >= 0 ? std::min(L, h->stop_layer + 1) : L;
@@ -401,11 +421,21 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles;
         lz.begin("conv");
-        if (h->use_s)
+        if (h->use_s) {
             launch_conv_s(ca, h->g, h->tabS.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
-        else
+            lz.end(1);
+        } else if (h->use_h) {
+            // fp16-split kernel; k_conv_adj right behind it takes the layer only if a range flag is raised
+            ca.xh = h->xh.as<uint4>();
+            ca.tabH = h->tabH.as<uint32_t>() + (size_t)i * (h->g.n_types + 1) * TG_HFRAG32;
+            ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
+            launch_conv_h(ca, h->sm_count, st);
             launch_conv_adj(ca, h->sm_count, st);
-        lz.end(1);
+            lz.end(2);
+        } else {
+            launch_conv_adj(ca, h->sm_count, st);
+            lz.end(1);
+        }
 
         GinArgs ga{};
         ga.xin = i == 0 ? h->mid[0]->as<float>() : h->pre2[(i - 1) & 1].as<float>();
@@ -427,9 +457,10 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         }
         lz.begin("combine");
         launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[i & 1].as<float>(), h->C(h->coef_c[i]),
-                       i >= 2 ? h->mid[i - 2]->as<float>() : nullptr, h->mid[i + 1]->as<float>(), n_own, st);
+                       i >= 2 ? h->mid[i - 2]->as<float>() : nullptr, h->mid[i + 1]->as<float>(),
+                       h->use_h ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), n_own, st);
         lz.end(1);
-        if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[i & 1].as<float>(), st, lz);
+        if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[i & 1].as<float>(), h->rflag(i + 1), st, lz);
         h->last_layer_run = i;
     }
 
@@ -518,6 +549,9 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         const char* csel = getenv("TGNN_CONV");
         h->conv_chunk_only = csel && std::string(csel) == "chunk";
         h->conv_s_only = csel && std::string(csel) == "s";
+        h->conv_h_only = csel && std::string(csel) == "h";
+        h->hflags.reserve((size_t)(2 * cfg->depth + 1) * sizeof(int));
+        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 1) * sizeof(int)));
         h->dev_error.reserve(sizeof(int));
         TGNN_CUDA(cudaMemset(h->dev_error.p, 0, sizeof(int)));
         declare_params(h.get());
@@ -671,6 +705,16 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         out->launches_per_forward = h->launches;
         out->workspace_bytes = (int64_t)h->workspace_bytes;
         out->collectives_per_forward = h->collectives;
+        out->conv_kernel = h->use_s ? 1 : (h->use_h ? 2 : 0);
+        out->range_fallback_layers = 0;
+        if (h->use_h && h->graph_set) {
+            DeviceGuard dg(h->cfg.device);
+            const int L = h->cfg.depth;
+            std::vector<int> f(2 * L + 1);
+            TGNN_CUDA(cudaDeviceSynchronize());
+            TGNN_CUDA(cudaMemcpy(f.data(), h->hflags.p, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < L; ++i) out->range_fallback_layers += (f[i] | f[L + 1 + i]) ? 1 : 0;
+        }
     });
 }
 
@@ -705,10 +749,10 @@ int tgnn_debug_read(tgnn_handle* h, const char* name, float* out, void* stream) 
             TGNN_CUDA(cudaMemcpyAsync(ident.p, idc.data(), 128 * sizeof(float), cudaMemcpyHostToDevice, st));
             if (n == "g1")
                 launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[i & 1].as<float>(), ident.as<float>(), nullptr, out,
-                               h->g.n_own, st);
+                               nullptr, nullptr, h->g.n_own, st);
             else
                 launch_combine(h->pre1.as<float>(), ident.as<float>(), h->pre2[i & 1].as<float>(), h->C(h->coef_c[i]), nullptr, out,
-                               h->g.n_own, st);
+                               nullptr, nullptr, h->g.n_own, st);
             TGNN_CUDA(cudaStreamSynchronize(st));
         } else {
             throw Error("tgnn_debug_read: unknown tensor " + n);

@@ -1,0 +1,258 @@
+// Adjacency branch on PRE-SPLIT fp16 operands ("H" kernel): typed NNConv(mean) + root + bias + LeakyReLU and the
+// BatchNorm partial sums (graph_networks/layers/edge_conv.py:24-27 of the reference; PyG NNConv semantics).
+//
+// Same edge-chunk formulation as k_conv_adj (kernels.cu): a warp owns 64 destination rows and walks chunks of 16
+// same-type edges.  What changes is the arithmetic of the 16x32 . 32x32 products:
+//   * every producer of b1 (k_init<2>, k_combine, k_halo_unpack) also writes a SPLIT copy of the row,
+//       x = hi + lo * 2^-11,   hi = fp16(x),  lo = fp16((x - hi) * 2^11)          (22 significant bits)
+//     laid out so that one LDG.128 of a gathered row IS the lane's A fragments of a k16 step (hi and lo);
+//   * the per-type weights are split the same way into fp16 fragment tables (4 KB per type);
+//   * x.W ~= hi.Whi + (hi.Wlo + lo.Whi) * 2^-11  on  mma.sync.m16n8k16.f16 (fp32 accumulate): 24 MMAs per chunk
+//     instead of the 48 of 3xTF32, and no conversion instructions in the consumer at all.  The dropped lo.lo term
+//     is 2^-22 relative -- the same as 3xTF32 (measured: 1.0e-7 vs 1.2e-7 of sum|x||w|).
+// fp16 has a narrow exponent range, so the producers raise a per-tensor flag when |x| > 60000 (or NaN); this kernel
+// then exits at once and k_conv_adj (3xTF32 on the fp32 rows, launched right behind with the opposite test) does the
+// layer instead.  Values below 2^-14 keep an absolute accuracy of 2^-35, far under fp32 rounding of the O(1) sums.
+#include <cuda_fp16.h>
+
+#include "tgnn_internal.h"
+
+namespace tgnn {
+namespace {
+
+constexpr int XS = 36;          // padded shared-memory row stride (floats)
+constexpr int WARPS = 8;
+constexpr int TPB = WARPS * 32;
+constexpr float LO_SCALE = 2048.f, LO_INV = 1.0f / 2048.f;
+
+__device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
+
+__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Fragment table of a [32 in][32 out] matrix, fp16 hi|lo: 2048 halves = 1024 words.
+//   k -> k16 step ks = k>>4, thread-in-group tt = (k&15)>>2, register (k&3)>>1, half k&1   (matches the row layout of xh)
+//   n -> n-tile nt = (n&7)>>1, group g = 2(n>>3) + (n&1)   (a lane ends up with 8 contiguous output channels 8t..8t+7)
+//   uint4 index ((ks*2 + hl)*2 + j)*32 + lane, lane = 4g + tt, j = nt>>1; component 2(nt&1) + register
+__host__ __device__ __forceinline__ int hfrag_half_index(int k, int n, int hl) {
+    const int ks = k >> 4, r = k & 15, tt = r >> 2, reg = (r & 3) >> 1, e = r & 1;
+    const int rn = n & 7, nt = rn >> 1, g = 2 * (n >> 3) + (rn & 1);
+    const int lane = g * 4 + tt, j = nt >> 1, comp = 2 * (nt & 1) + reg;
+    return (((((ks * 2 + hl) * 2 + j) * 32 + lane) * 4 + comp) * 2) + e;
+}
+__device__ __forceinline__ void hfrag_store(__half* tab, int k, int n, float w, int* flag) {
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn((w - __half2float(hi)) * LO_SCALE);
+    tab[hfrag_half_index(k, n, 0)] = hi;
+    tab[hfrag_half_index(k, n, 1)] = lo;
+    if (flag && !(fabsf(w) <= TG_H_LIMIT)) *flag = 1;
+}
+
+struct BFragH { uint4 h[2][2], l[2][2]; };
+
+__device__ __forceinline__ void load_bfrag_h(BFragH& b, const uint32_t* __restrict__ tab, int lane) {
+    const uint4* p = reinterpret_cast<const uint4*>(tab) + lane;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            b.h[ks][j] = __ldg(p + ((ks * 2 + 0) * 2 + j) * 32);
+            b.l[ks][j] = __ldg(p + ((ks * 2 + 1) * 2 + j) * 32);
+        }
+}
+
+// rows[ks] = uint4 (4ks' + t) of row g, rows[2 + ks] = of row g+8:  {hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)}
+// Tensor cores accumulate with truncation; the main term of each k16 step gets its own zeroed accumulator and the
+// steps are combined with IEEE FADDs (same reasoning as mma3 in kernels.cu); the two small terms share one.
+__device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH& b, float (&m)[4][4]) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        float sm[2][4] = {}, mn[2][2][4] = {};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const uint4 ra = rows[ks], rb = rows[2 + ks];
+            const uint4 bh = b.h[ks][j], bl = b.l[ks][j];
+            mma_f16(sm[0], ra.z, rb.z, ra.w, rb.w, bh.x, bh.y);          // lo . Whi
+            mma_f16(sm[1], ra.z, rb.z, ra.w, rb.w, bh.z, bh.w);
+            mma_f16(sm[0], ra.x, rb.x, ra.y, rb.y, bl.x, bl.y);          // hi . Wlo
+            mma_f16(sm[1], ra.x, rb.x, ra.y, rb.y, bl.z, bl.w);
+            mma_f16(mn[ks][0], ra.x, rb.x, ra.y, rb.y, bh.x, bh.y);      // hi . Whi
+            mma_f16(mn[ks][1], ra.x, rb.x, ra.y, rb.y, bh.z, bh.w);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[2 * j + u][i] = fmaf(sm[u][i], LO_INV, mn[0][u][i] + mn[1][u][i]);
+    }
+}
+
+__device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int half) {
+    float4* p = reinterpret_cast<float4*>(row);
+    float4 v0 = p[0], v1 = p[1];
+    v0.x += c[0][2 * half]; v0.y += c[0][2 * half + 1]; v0.z += c[1][2 * half]; v0.w += c[1][2 * half + 1];
+    v1.x += c[2][2 * half]; v1.y += c[2][2 * half + 1]; v1.z += c[3][2 * half]; v1.w += c[3][2 * half + 1];
+    p[0] = v0; p[1] = v1;
+}
+
+__device__ __forceinline__ uint4 ld_rowh(const uint4* __restrict__ xh, int row, int q) { return __ldg(xh + (size_t)row * 8 + q); }
+
+__global__ void __launch_bounds__(TPB, 2)
+k_conv_h(ConvArgs A) {
+    if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) return;      // out of fp16 range: k_conv_adj takes the layer
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* acc = smem + warp * (WN * XS);
+    const int g = lane >> 2, t = lane & 3;
+    const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
+    double s1 = 0.0, s2 = 0.0;
+    const float bias_c = __ldg(A.bias + lane);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* __restrict__ xh = A.xh;
+    BFragH bf;
+    int cur_type = -1;
+
+    for (int tile = gwarp; tile < A.n_tiles; tile += nwarp) {
+        for (int i = lane; i < WN * XS; i += 32) acc[i] = 0.f;
+        const int c0 = __ldg(A.cptr + tile), c1 = __ldg(A.cptr + tile + 1);
+        uint4 pre[4] = {zero4, zero4, zero4, zero4};
+        int psrc = -1, pdst = 0, ptype = 0;
+        if (c0 < c1) {
+            psrc = __ldg(A.csrc + (size_t)c0 * CH + (lane & 15));
+            pdst = __ldg(A.cdst + (size_t)c0 * CH + (lane & 15));
+            ptype = __ldg(A.ctype + c0);
+            const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
+            if (sa >= 0) { pre[0] = ld_rowh(xh, sa, t); pre[1] = ld_rowh(xh, sa, 4 + t); }
+            if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
+        }
+        __syncwarp();
+        for (int c = c0; c < c1; ++c) {
+            const uint4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
+            const int csrc = psrc, cdst = pdst, type = ptype;
+            if (c + 1 < c1) {
+                psrc = __ldg(A.csrc + (size_t)(c + 1) * CH + (lane & 15));
+                pdst = __ldg(A.cdst + (size_t)(c + 1) * CH + (lane & 15));
+                ptype = __ldg(A.ctype + c + 1);
+                const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
+                pre[0] = pre[1] = pre[2] = pre[3] = zero4;
+                if (sa >= 0) { pre[0] = ld_rowh(xh, sa, t); pre[1] = ld_rowh(xh, sa, 4 + t); }
+                if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
+            }
+            if (type != cur_type) { load_bfrag_h(bf, A.tabH + (size_t)type * TG_HFRAG32, lane); cur_type = type; }
+            if (ptype != type && c + 1 < c1)       // next type's 4 KB table towards L1 (32 lines of 128 B)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(A.tabH + (size_t)ptype * TG_HFRAG32) + lane * 128));
+            float m[4][4];
+            chunk_mma_h(cur, bf, m);
+            // rows 0..7 (group 0), then rows 8..15 (group 1): destinations are distinct inside a group
+            {
+                const int s = __shfl_sync(0xffffffffu, csrc, g), d = __shfl_sync(0xffffffffu, cdst, g);
+                if (s >= 0) acc_add8(acc + d * XS + 8 * t, m, 0);
+            }
+            __syncwarp();
+            {
+                const int s = __shfl_sync(0xffffffffu, csrc, g + 8), d = __shfl_sync(0xffffffffu, cdst, g + 8);
+                if (s >= 0) acc_add8(acc + d * XS + 8 * t, m, 1);
+            }
+            __syncwarp();
+        }
+        // mean over in-edges
+        const int node0 = tile * WN;
+        for (int r = 0; r < WN; ++r) {
+            int node = node0 + r;
+            if (node < A.n_own) acc[r * XS + lane] *= __ldg(A.inv_deg + node);
+        }
+        __syncwarp();
+        // root term: x_i @ root as four 16-row chunks of the tile's own rows (table entry n_types)
+        if (cur_type != A.n_types) { load_bfrag_h(bf, A.tabH + (size_t)A.n_types * TG_HFRAG32, lane); cur_type = A.n_types; }
+        for (int rc = 0; rc < WN / CH; ++rc) {
+            const int na = node0 + rc * CH + g, nb = na + 8;
+            uint4 cur[4] = {zero4, zero4, zero4, zero4};
+            if (na < A.n_own) { cur[0] = ld_rowh(xh, na, t); cur[1] = ld_rowh(xh, na, 4 + t); }
+            if (nb < A.n_own) { cur[2] = ld_rowh(xh, nb, t); cur[3] = ld_rowh(xh, nb, 4 + t); }
+            float m[4][4];
+            chunk_mma_h(cur, bf, m);
+            acc_add8(acc + (rc * CH + g) * XS + 8 * t, m, 0);
+            acc_add8(acc + (rc * CH + g + 8) * XS + 8 * t, m, 1);
+        }
+        __syncwarp();
+        // bias, LeakyReLU, store, statistics (lane = channel)
+        for (int r = 0; r < WN; ++r) {
+            int node = node0 + r;
+            if (node < A.n_own) {
+                float v = leaky(acc[r * XS + lane] + bias_c);
+                A.out[(size_t)node * F + lane] = v;
+                s1 += (double)v;
+                s2 += (double)v * (double)v;
+            }
+        }
+        __syncwarp();
+    }
+    if (A.part) {
+        A.part[(size_t)gwarp * 64 + lane] = s1;
+        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
+    }
+}
+
+// per-type edge weights W_t = sigmoid MLP(e_t), evaluated in fp64, rounded once to fp32 (exactly as k_edge_table in
+// kernels.cu), then split into the fp16 fragment table.  grid = K types, block = 256.
+__global__ void k_edge_table_h(const float* __restrict__ rows, int d_e,
+                               const float* __restrict__ a1, const float* __restrict__ c1,
+                               const float* __restrict__ a2, const float* __restrict__ c2,
+                               const float* __restrict__ a3, const float* __restrict__ c3,
+                               uint32_t* __restrict__ tab) {
+    __shared__ double h1[32], h2[64];
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const float* e = rows + (size_t)t * d_e;
+    if (tid < 32) {
+        double s = (double)c1[tid];
+        for (int k = 0; k < d_e; ++k) s += (double)a1[tid * d_e + k] * (double)e[k];
+        h1[tid] = 1.0 / (1.0 + exp(-s));
+    }
+    __syncthreads();
+    if (tid < 64) {
+        double s = (double)c2[tid];
+        for (int k = 0; k < 32; ++k) s += (double)a2[tid * 32 + k] * h1[k];
+        h2[tid] = 1.0 / (1.0 + exp(-s));
+    }
+    __syncthreads();
+    __half* out = reinterpret_cast<__half*>(tab + (size_t)t * TG_HFRAG32);
+    for (int o = tid; o < F * F; o += 256) {
+        double s = (double)c3[o];
+        for (int k = 0; k < 64; ++k) s += (double)a3[(size_t)o * 64 + k] * h2[k];
+        // o = k_in * 32 + k_out  (NNConv: weight.view(-1, in, out)); a sigmoid is always inside the fp16 range
+        hfrag_store(out, o >> 5, o & 31, (float)(1.0 / (1.0 + exp(-s))), nullptr);
+    }
+}
+
+// nnConv.root [in][out] -> fragment table; raises *flag when a weight is outside the fp16 range
+__global__ void k_root_table_h(const float* __restrict__ root, uint32_t* __restrict__ tab, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F * F) hfrag_store(reinterpret_cast<__half*>(tab), i >> 5, i & 31, root[i], flag);
+}
+
+}  // namespace
+
+static size_t conv_h_smem() { return (size_t)WARPS * (WN * XS) * sizeof(float); }
+
+void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_h_smem()));
+        attr = true;
+    }
+    // same grid as k_conv_adj: the BatchNorm partial layout is shared by the two kernels
+    k_conv_h<<<conv_adj_num_parts(a.n_tiles, sm_count) / WARPS, TPB, conv_h_smem(), st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_edge_table_h(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
+                         const float* c2, const float* a3, const float* c3, const float* root, uint32_t* tab, int* flag_w,
+                         cudaStream_t st) {
+    if (n_types > 0) k_edge_table_h<<<n_types, 256, 0, st>>>(type_rows, d_e, a1, c1, a2, c2, a3, c3, tab);
+    k_root_table_h<<<4, 256, 0, st>>>(root, tab + (size_t)n_types * TG_HFRAG32, flag_w);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+}  // namespace tgnn

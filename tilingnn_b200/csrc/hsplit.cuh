@@ -1,0 +1,27 @@
+// fp16 two-term split of fp32 activations for k_conv_h (conv_h.cu):  x = hi + lo * 2^-11.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "tgnn_internal.h"
+
+namespace tgnn {
+
+// hi = fp16(x), lo = fp16((x - hi) * 2^11); the subtraction and the scaling are exact in fp32.
+__device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
+    hi = __float2half_rn(x);
+    lo = __float2half_rn((x - __half2float(hi)) * 2048.f);
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+// four consecutive channels -> {hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)}; `bad` is set when a value is outside
+// the fp16 range (or NaN)
+__device__ __forceinline__ uint4 split_h4(const float4& v, bool& bad) {
+    __half h0, h1, h2, h3, l0, l1, l2, l3;
+    split_h(v.x, h0, l0); split_h(v.y, h1, l1); split_h(v.z, h2, l2); split_h(v.w, h3, l3);
+    bad |= !(fabsf(v.x) <= TG_H_LIMIT) | !(fabsf(v.y) <= TG_H_LIMIT) | !(fabsf(v.z) <= TG_H_LIMIT) | !(fabsf(v.w) <= TG_H_LIMIT);
+    return make_uint4(pack_h2(h0, h1), pack_h2(h2, h3), pack_h2(l0, l1), pack_h2(l2, l3));
+}
+
+}  // namespace tgnn

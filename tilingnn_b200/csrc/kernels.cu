@@ -4,6 +4,7 @@
 // gather of a neighbour is exactly one coalesced line.  See DESIGN.md for the per-kernel byte model.
 #include <algorithm>
 
+#include "hsplit.cuh"
 #include "tgnn_internal.h"
 
 namespace tgnn {
@@ -171,6 +172,8 @@ __device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int
 
 __global__ void __launch_bounds__(TPB, 2)
 k_conv_adj(ConvArgs A) {
+    // paired with k_conv_h (conv_h.cu): when range flags are given, this kernel only takes the layer if one is raised
+    if (A.flag_x && !(*A.flag_x | (A.flag_w ? *A.flag_w : 0))) return;
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* acc = smem + warp * (WN * XS);
@@ -444,8 +447,10 @@ __device__ __forceinline__ float bn_apply(float x, const float* __restrict__ coe
 
 __global__ void k_combine(const float4* __restrict__ pre1, const float* __restrict__ coef1,
                           const float4* __restrict__ pre2, const float* __restrict__ coef2,
-                          const float4* __restrict__ res, float4* __restrict__ out, int64_t n4) {
+                          const float4* __restrict__ res, float4* __restrict__ out, uint4* __restrict__ xh,
+                          int* __restrict__ flag, int64_t n4) {
     __shared__ float c1[128], c2[128];
+    bool bad = false;
     if (threadIdx.x < 128) { c1[threadIdx.x] = coef1[threadIdx.x]; c2[threadIdx.x] = coef2[threadIdx.x]; }
     __syncthreads();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -458,7 +463,9 @@ __global__ void k_combine(const float4* __restrict__ pre1, const float* __restri
         o.w = bn_apply(p.w, c1, c + 3, 32) * bn_apply(g.w, c2, c + 3, 32);
         if (res) { float4 r = __ldg(res + i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
         out[i] = o;
+        if (xh) xh[i] = split_h4(o, bad);        // float4 i of a row IS uint4 i of the split row (conv_h.cu)
     }
+    if (bad) *flag = 1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -498,7 +505,23 @@ k_init(InitArgs A) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) o = fmaf(__shfl_sync(0xffffffffu, y, k), w1t[k * 33 + lane], o);
             v = leaky(o);
-            if (MODE == 2) { A.out[(size_t)node * F + lane] = bn_apply(v, A.coef1, lane, 32); continue; }
+            if (MODE == 2) {
+                const float o2 = bn_apply(v, A.coef1, lane, 32);
+                A.out[(size_t)node * F + lane] = o2;
+                if (A.xh) {
+                    // lane = channel -> word w of the split row: q = w>>2, {hi(4q,4q+1), hi(4q+2,4q+3), lo(..), lo(..)}[w&3]
+                    __half hi, lo;
+                    split_h(o2, hi, lo);
+                    const uint32_t h16 = __half_as_ushort(hi), l16 = __half_as_ushort(lo);
+                    const uint32_t wh = h16 | (__shfl_down_sync(0xffffffffu, h16, 1) << 16);
+                    const uint32_t wl = l16 | (__shfl_down_sync(0xffffffffu, l16, 1) << 16);
+                    const int src = (lane & ~3) + 2 * (lane & 1);
+                    const uint32_t a = __shfl_sync(0xffffffffu, wh, src), b = __shfl_sync(0xffffffffu, wl, src);
+                    A.xh[(size_t)node * F + lane] = (lane & 2) ? b : a;
+                    if (!(fabsf(o2) <= TG_H_LIMIT)) *A.flag = 1;
+                }
+                continue;
+            }
         }
         s1 += (double)v;
         s2 += (double)v * (double)v;
@@ -722,14 +745,21 @@ __global__ void k_halo_pack(const float4* __restrict__ a, const float4* __restri
 }
 
 __global__ void k_halo_unpack(const float4* __restrict__ recv, int world, int rank, int64_t halo_slot, int64_t n_own,
-                              float4* __restrict__ a, float4* __restrict__ b) {
+                              float4* __restrict__ a, float4* __restrict__ b, uint4* __restrict__ xh, int* __restrict__ flag) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t total = (int64_t)world * halo_slot * 16;
     if (i >= total) return;
     int64_t r = i >> 4; int c = (int)(i & 15);
     if (r / halo_slot == rank) return;               // own slot: rows are read in place
     float4 v = __ldg(recv + i);
-    if (c < 8) a[(size_t)(n_own + r) * 8 + c] = v; else if (b) b[(size_t)(n_own + r) * 8 + (c - 8)] = v;
+    if (c < 8) {
+        a[(size_t)(n_own + r) * 8 + c] = v;
+        if (xh) {                                    // mirrored rows feed k_conv_h too
+            bool bad = false;
+            xh[(size_t)(n_own + r) * 8 + c] = split_h4(v, bad);
+            if (bad) *flag = 1;
+        }
+    } else if (b) b[(size_t)(n_own + r) * 8 + (c - 8)] = v;
 }
 
 int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_per_sm) {
@@ -779,13 +809,13 @@ void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st) {
 }
 
 void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
-                    const float* residual, float* out, int64_t n_own, cudaStream_t st) {
+                    const float* residual, float* out, uint4* xh, int* flag, int64_t n_own, cudaStream_t st) {
     int64_t n4 = n_own * (F / 4);
     int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
     if (blocks < 1) blocks = 1;
     k_combine<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(pre1), coef1,
                                       reinterpret_cast<const float4*>(pre2), coef2,
-                                      reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), n4);
+                                      reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), xh, flag, n4);
     TGNN_CUDA(cudaGetLastError());
 }
 
@@ -854,11 +884,11 @@ void launch_halo_pack(const float* a, const float* b, const int* rows, int n_sen
     TGNN_CUDA(cudaGetLastError());
 }
 void launch_halo_unpack(const float* recv, int world, int rank, int64_t halo_slot, int64_t n_own, float* a, float* b,
-                        cudaStream_t st) {
+                        uint4* xh, int* flag, cudaStream_t st) {
     int64_t n = (int64_t)world * halo_slot * 16;
     if (n <= 0) return;
     k_halo_unpack<<<(int)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(recv), world, rank, halo_slot,
-                                                          n_own, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b));
+                                                          n_own, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), xh, flag);
     TGNN_CUDA(cudaGetLastError());
 }
 

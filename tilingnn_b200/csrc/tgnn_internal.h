@@ -126,9 +126,23 @@ struct ConvArgs {
     float* out;              // pre1 [n_own][32]  LeakyReLU(conv), before BatchNorm
     double* part;            // [n_part][64]  per-warp partial sums (sum, sum of squares)
     int n_own, n_tiles;
+    // fp16-split operands of k_conv_h (conv_h.cu) and the range flags that arbitrate between it and k_conv_adj:
+    // k_conv_h runs when both flags are 0, k_conv_adj when flag_x is null (forced) or a flag is raised
+    const uint4* xh;         // [n_rows][8]   split copy of xin: per 4 channels {hi01, hi23, lo01, lo23} fp16 pairs
+    const uint32_t* tabH;    // [K+1][1024]   fp16 hi|lo fragment tables; entry K = nnConv.root
+    const int* flag_x;       // raised by the producer of xin when a value is outside the fp16 range
+    const int* flag_w;       // raised at table build when a root weight is outside the fp16 range
 };
 int conv_adj_num_parts(int n_tiles, int sm_count);
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
+
+// fp16-split edge-chunk kernel (conv_h.cu)
+constexpr float TG_H_LIMIT = 60000.f;    // |x| above this (or NaN) raises the range flag: fp16 max is 65504
+constexpr int TG_HFRAG32 = 1024;         // 32-bit words of one fp16 hi|lo fragment table of a 32x32 matrix
+void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
+void launch_edge_table_h(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
+                         const float* c2, const float* a3, const float* c3, const float* root, uint32_t* tab, int* flag_w,
+                         cudaStream_t st);
 
 // tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
 void launch_edge_table_s(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
@@ -149,8 +163,9 @@ int gin_num_parts(int n_own, int sm_count);
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st);
 
 // b1_new = BN(pre1) * BN(pre2) + residual
+// xh / flag (optional): fp16-split copy of the result for k_conv_h and its range flag
 void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
-                    const float* residual, float* out, int64_t n_own, cudaStream_t st);
+                    const float* residual, float* out, uint4* xh, int* flag, int64_t n_own, cudaStream_t st);
 
 // init MLP: mode 0 = stats of layer 0, 1 = stats of layer 1, 2 = write h0
 struct InitArgs {
@@ -159,6 +174,7 @@ struct InitArgs {
     const float* w1t; const float* b1;   // [32][32] k-major, [32]
     const float* coef0; const float* coef1;
     float* out; double* part; int n_own;
+    uint32_t* xh; int* flag;             // mode 2: fp16-split copy of h0 and its range flag (optional)
 };
 int init_num_parts(int n_own, int sm_count);
 void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st);
@@ -209,6 +225,6 @@ void launch_frag_pack(const float* w_kn, int K, int N, int kmap, int nmap, float
 // halo pack / unpack (sharded mode)
 void launch_halo_pack(const float* a, const float* b, const int* rows, int n_send, float* sendbuf, cudaStream_t st);
 void launch_halo_unpack(const float* recv, int world, int rank, int64_t halo_slot, int64_t n_own,
-                        float* a, float* b, cudaStream_t st);
+                        float* a, float* b, uint4* xh, int* flag, cudaStream_t st);
 
 }  // namespace tgnn
