@@ -1,0 +1,93 @@
+"""The callers of the scoring path on the GPU: ``ML_Solver.solve`` = greedy assembly with every
+round scored by the CUDA network, on the heart crop (config 1's layout) and on the four bunny layouts of config 5
+(30-60-90+equilateral, D_x = 5, D_e = 66, 41 edge types).  Run on the B200 box: python -m pytest tests -m gpu"""
+import os
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tilingnn_oracle as orc
+from _util import GOLDEN, load_ckpt, load_layout
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def make_solver(ckpt, d_x, d_e, graph, dev):
+    from tilingnn_b200 import ML_Solver, TilinGNN
+    net = TilinGNN(d_e, 20, 32, node_features_dim=d_x)
+    net.load_state_dict(ckpt, strict=True)
+    return ML_Solver(None, dev, graph, net.to(dev).train(), 1)        # .train(): ml_solver.py:131
+
+
+def check_valid(sg, solved):
+    sel = np.asarray(solved.predict).astype(bool)
+    ci = sg.collide_edge_index
+    assert not (sel[ci[0]] & sel[ci[1]]).any(), "two selected tiles collide"
+    blocked = np.zeros(len(sel), bool)
+    blocked[ci[1][sel[ci[0]]]] = True
+    assert (sel | blocked).all(), "the selection is not maximal"
+    assert sorted(solved.predict_order) == np.flatnonzero(sel).tolist()
+    assert solved.predict_probs.shape == (len(sel),) and solved.predict_probs.dtype == np.float32
+
+
+class OracleSolver:
+    """The same greedy loop driven by the CPU oracle network (fp64) -- the checker."""
+
+    def __init__(self, params, graph):
+        self.params, self.complete_graph = params, graph
+
+    def predict(self, lay):
+        n = lay.node_feature.shape[0]
+        if np.size(lay.collide_edge_index) == 0 or np.size(lay.align_edge_index) == 0:
+            return np.ones(n, dtype=np.float32)
+        t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+        s = orc.forward(self.params, t(lay.node_feature, torch.float64), t(lay.align_edge_index, torch.long),
+                        t(lay.align_edge_features, torch.float64), t(lay.collide_edge_index, torch.long), depth=20,
+                        bn_mode="train", dtype=torch.float64)
+        return s[:, 0].float().numpy()
+
+
+def test_solve_heart_matches_the_oracle_driven_greedy(dev):
+    from tilingnn_b200 import greedy
+    z = dict(np.load(os.path.join(GOLDEN, "greedy_heart.npz")))
+    sg, graph = load_layout(z)
+    ckpt = load_ckpt()
+    solver = make_solver(ckpt, 3, sg.align_edge_features.shape[1], graph, dev)
+    solved, score = solver.solve(sg, rng=np.random.RandomState(2))
+    check_valid(sg, solved)
+    assert 0.0 < score <= 1.0 + 0.02
+    ref = greedy.solve_by_probablistic_greedy(OracleSolver(ckpt, graph), sg, rng=np.random.RandomState(2))
+    same = np.array_equal(ref.selection, solved.predict)
+    print(f"heart: {int(solved.predict.sum())} tiles in {solved.greedy_rounds} rounds, score {score:.6f}; oracle-driven: "
+          f"{int(ref.selection.sum())} tiles in {ref.rounds} rounds, score {ref.score:.6f}; identical selection: {same}")
+    # the acceptance test compares exp(p - 1) with a uniform draw: a 1e-4 difference in p flips a decision with
+    # probability ~1e-4 per visit, after which the two runs legitimately diverge -- so equality is reported and the
+    # quality is asserted
+    assert same or abs(score - ref.score) < 0.05
+
+
+def test_config5_bunny_layouts(dev):
+    z = dict(np.load(os.path.join(GOLDEN, "c5_bunny.npz")))
+    ckpt = load_ckpt("ckpt_30-60-90+equilateral.npz")
+    rng = np.random.RandomState(2)
+    total = 0.0
+    for i in range(int(z["n_layouts"])):
+        sg, graph = load_layout(z, prefix=f"L{i}_")
+        solver = make_solver(ckpt, int(z["d_x"]), int(z["d_e"]), graph, dev)
+        t0 = time.perf_counter()
+        solved, score = solver.solve(sg, rng=rng)
+        dt = time.perf_counter() - t0
+        total += dt
+        check_valid(sg, solved)
+        assert 0.0 < score <= 1.0 + 0.02
+        print(f"bunny layout {i}: N={sg.node_feature.shape[0]} -> {int(solved.predict.sum())} tiles, {solved.greedy_rounds} rounds, "
+              f"score {score:.4f}, {dt:.3f} s")
+    print(f"config 5 scoring + greedy assembly, 4 layouts: {total:.3f} s")

@@ -4,8 +4,12 @@ Public surface (mirrors the reference's for this path):
     TilinGNN        graph_networks/networks/TilinGNN.py     (forward / state_dict compatible)
     ML_Solver       solver/ml_solver/ml_solver.py           (predict, load_saved_network)
     get_network_prediction   graph_networks/network_utils.py
+    greedy          util/algorithms.py (probabilistic greedy assembly), brick_layout.compute_sub_layout, losses.py
+    tiling_shape    Tiling-Shape.py driver (no plotting)
+    tile_graph_io   shapely-free readers of the complete-graph pickles / silhouettes, layout cropping
 """
 from .network import TilinGNN
 from .ml_solver import ML_Solver, get_network_prediction, to_torch_tensor
+from . import greedy, tile_graph_io
 
 __all__ = ["TilinGNN", "ML_Solver", "get_network_prediction", "to_torch_tensor"]

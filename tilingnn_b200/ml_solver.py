@@ -58,13 +58,32 @@ class ML_Solver:
     def predict(self, brick_layout):
         """ml_solver.py:29-49.  Returns ``np.ndarray[N]`` float32."""
         n = brick_layout.node_feature.shape[0]
-        if len(brick_layout.collide_edge_index) == 0 or len(brick_layout.align_edge_index) == 0:
+        # the reference's empty edge set is ``np.array([])`` (len 0); a [2, 0] array means the same here
+        if np.size(brick_layout.collide_edge_index) == 0 or np.size(brick_layout.align_edge_index) == 0:
             return np.ones(n, dtype=np.float32)                                   # :31-32
         x, ai, af, ci, _ = to_torch_tensor(self.device, brick_layout.node_feature, brick_layout.align_edge_index,
                                            brick_layout.align_edge_features, brick_layout.collide_edge_index)
         predictions, *_ = self.network(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci, col_e_features=None)
         # get_best_prob_map (:46,133-136) is argsort over num_prob_maps = 1 losses: always column 0
         return predictions[:, 0].detach().cpu().numpy()
+
+    def solve(self, brick_layout, rng=None):
+        """ml_solver.py:59-67: greedy assembly, then one more scoring pass of the full layout.  Returns
+        ``(output_layout, score)``; the layout copy carries ``predict``, ``predict_order``, ``predict_probs``."""
+        from . import greedy
+        res = greedy.solve_by_probablistic_greedy(self, brick_layout, rng=rng, complete_graph=self.complete_graph)
+        output_layout = deepcopy(brick_layout)
+        output_layout.predict_order = res.order
+        output_layout.predict = res.selection
+        output_layout.predict_probs = self.predict(brick_layout)
+        output_layout.greedy_rounds = res.rounds
+        return output_layout, res.score
+
+    def get_unsupervised_losses_from_layout(self, brick_layout, probs):
+        """ml_solver.py:51-57."""
+        from . import greedy
+        return greedy.calculate_unsupervised_loss(probs, brick_layout.node_feature, brick_layout.collide_edge_index,
+                                                  brick_layout.align_edge_index, brick_layout.align_edge_features)[2]
 
     def get_predict_probs(self, brick_layout):
         """ml_solver.py:69-81."""
