@@ -47,12 +47,13 @@ def main():
     net.load_state_dict(ckpt, strict=True)
     net = net.to(dev).train()
     calls = {"n": 0, "nodes": 0}
+    solver = ML_Solver(None, dev, None, net, 1)             # one solver for all layouts, as Tiling-Shape.py:37
 
     def run_gpu(seed):
         out = []
         rng = np.random.RandomState(seed)
         for sg, graph in layouts:
-            solver = ML_Solver(None, dev, graph, net, 1)
+            solver.complete_graph = graph
             solved, score = solver.solve(sg, rng=rng)
             calls["n"] += solved.greedy_rounds + 1
             out.append((int(solved.predict.sum()), score))

@@ -91,6 +91,7 @@ struct tgnn_handle {
     std::vector<size_t> coef_a, coef_c;
     DevBuf tab;                                     // [L][K+1][2048] frag tables (entry K = root)
     DevBuf tabS;                                    // [L][K+1][2048] transposed hi|lo tables of the tcgen05 conv kernel
+    DevBuf table_layers;                            // TableLayer[L]: parameter pointers for tables.cu
     DevBuf tabH;                                    // [L][K+1][1024] fp16 hi|lo fragment tables of k_conv_h
     DevBuf hflags;                                  // int [L+1] activation range flags (per forward) | [L] weight range flags
     bool conv_chunk_only = false;                   // TGNN_CONV=chunk forces the 3xTF32 mma.sync edge-chunk kernel
@@ -104,6 +105,7 @@ struct tgnn_handle {
     DevBuf xh;                                      // [n_rows][8] uint4: fp16-split copy of the current layer's b1
     int* rflag(int i) { return hflags.as<int>() + i; }
     int* wflag(int i) { return hflags.as<int>() + cfg.depth + 1 + i; }
+    unsigned* bn_ticket() { return reinterpret_cast<unsigned*>(hflags.as<int>() + 2 * cfg.depth + 1); }   // k_bn_finish
     size_t workspace_bytes = 0;
 
     // sharding
@@ -231,6 +233,18 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
         h->fin_whl.back()->reserve(2 * ne * sizeof(float));
         launch_weight_image(w, h->fin_whl.back()->as<float>(), dims[k + 1], dims[k], st);
     }
+    {
+        std::vector<TableLayer> tl(L);
+        for (int i = 0; i < L; ++i) {
+            const std::string c = "brch_1_graph_conv_layers." + std::to_string(i), p = c + ".mlp.mlp.";
+            tl[i] = TableLayer{h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"), h->P(p + "1.linear.weight"),
+                               h->P(p + "1.linear.bias"), h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"),
+                               h->P(c + ".nnConv.root")};
+        }
+        h->table_layers.reserve(L * sizeof(TableLayer));
+        TGNN_CUDA(cudaMemcpyAsync(h->table_layers.p, tl.data(), L * sizeof(TableLayer), cudaMemcpyHostToDevice, st));
+        TGNN_CUDA(cudaStreamSynchronize(st));
+    }
     const char* dsel = getenv("TGNN_DENSE");
     h->dense_ffma = dsel && std::string(dsel) == "ffma";
     TGNN_CUDA(cudaMemcpyAsync(&h->fin_last_bias, h->P("final_mlp.1.linear.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -265,35 +279,17 @@ void eval_coefs(tgnn_handle* h, cudaStream_t st) {
 void build_tables(tgnn_handle* h, cudaStream_t st) {
     if (!h->tables_dirty) return;
     const int L = h->cfg.depth, K = h->g.n_types;
-    h->tab.reserve((size_t)L * (K + 1) * TG_FRAG32 * sizeof(float));
-    for (int i = 0; i < L; ++i) {
-        const std::string c = "brch_1_graph_conv_layers." + std::to_string(i);
-        const std::string p = c + ".mlp.mlp.";
-        float* base = h->tab.as<float>() + (size_t)i * (K + 1) * TG_FRAG32;
-        launch_edge_table(h->g.type_rows.as<float>(), K, h->cfg.d_e,
-                          h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
-                          h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
-                          h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), base, st);
-        // nnConv.root is [in][out] = k-major already
-        launch_frag_pack(h->P(c + ".nnConv.root"), F, F, TG_KMAP_GATHER, TG_NMAP_CONTIG8, base + (size_t)K * TG_FRAG32, st);
-        if (h->use_h) {
-            h->tabH.reserve((size_t)L * (K + 1) * TG_HFRAG32 * sizeof(uint32_t));
-            if (i == 0) TGNN_CUDA(cudaMemsetAsync(h->wflag(0), 0, (size_t)L * sizeof(int), st));
-            launch_edge_table_h(h->g.type_rows.as<float>(), K, h->cfg.d_e,
-                                h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
-                                h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
-                                h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), h->P(c + ".nnConv.root"),
-                                h->tabH.as<uint32_t>() + (size_t)i * (K + 1) * TG_HFRAG32, h->wflag(i), st);
-        }
-        if (h->g.has_s) {
-            h->tabS.reserve((size_t)L * (K + 1) * TG_FRAG32 * sizeof(float));
-            launch_edge_table_s(h->g.type_rows.as<float>(), K, h->cfg.d_e,
-                                h->P(p + "0.linear.weight"), h->P(p + "0.linear.bias"),
-                                h->P(p + "1.linear.weight"), h->P(p + "1.linear.bias"),
-                                h->P(p + "2.linear.weight"), h->P(p + "2.linear.bias"), h->P(c + ".nnConv.root"),
-                                h->tabS.as<float>() + (size_t)i * (K + 1) * TG_FRAG32, st);
-        }
+    const size_t slots = (size_t)L * (K + 1);
+    // 3xTF32 fragments: always (k_conv_adj is also the wide-range stand-in of k_conv_h)
+    h->tab.reserve(slots * TG_FRAG32 * sizeof(float));
+    if (h->use_h) {
+        h->tabH.reserve(slots * TG_HFRAG32 * sizeof(uint32_t));
+        TGNN_CUDA(cudaMemsetAsync(h->wflag(0), 0, (size_t)L * sizeof(int), st));
     }
+    if (h->use_s) h->tabS.reserve(slots * TG_FRAG32 * sizeof(float));
+    launch_edge_tables(h->g.type_rows.as<float>(), K, h->cfg.d_e, L, h->table_layers.as<TableLayer>(), h->tab.as<float>(),
+                       h->use_s ? h->tabS.as<float>() : nullptr, h->use_h ? h->tabH.as<uint32_t>() : nullptr,
+                       h->use_h ? h->wflag(0) : nullptr, st);
     h->tables_dirty = false;
 }
 
@@ -383,6 +379,14 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     if (h->use_h) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
 
     auto finish_bn = [&](const double* part, int n_part, int c, const std::string& bn, size_t coef_off) {
+        if (h->world == 1) {
+            BnFinishArgs fa{};
+            fa.part[0] = part; fa.n_part[0] = n_part; fa.C = c; fa.count = count;
+            fa.gamma[0] = h->P(bn + ".weight"); fa.beta[0] = h->P(bn + ".bias"); fa.coef[0] = h->C(coef_off);
+            fa.sums = sums; fa.ticket = h->bn_ticket();
+            launch_bn_finish(fa, 1, st);
+            return;
+        }
         launch_bn_reduce(part, n_part, c, sums, st);
         allreduce_sums(h, sums, 2 * c, st);
         launch_bn_coef(sums, count, h->P(bn + ".weight"), h->P(bn + ".bias"), h->C(coef_off), c, st);
@@ -399,9 +403,9 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     const int np_init = init_num_parts(n_own, h->sm_count);
     if (train) {
         lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
-        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.0.batch_norm", h->coef_init[0]); lz.end(2);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.0.batch_norm", h->coef_init[0]); lz.end(h->world == 1 ? 1 : 2);
         lz.begin("init"); launch_init(ia, 1, h->sm_count, st); lz.end(1);
-        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.1.batch_norm", h->coef_init[1]); lz.end(2);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.1.batch_norm", h->coef_init[1]); lz.end(h->world == 1 ? 1 : 2);
     }
     lz.begin("init"); launch_init(ia, 2, h->sm_count, st); lz.end(1);
     halo_exchange(h, h->mid[0]->as<float>(), nullptr, h->rflag(0), st, lz);
@@ -448,12 +452,24 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
 
         if (train) {
             lz.begin("bnfin");
+            if (h->world == 1) {
+                BnFinishArgs fa{};
+                fa.part[0] = h->partA.as<double>(); fa.n_part[0] = h->use_s ? h->g.s_tiles : np_conv;
+                fa.part[1] = h->partB.as<double>(); fa.n_part[1] = np_gin;
+                fa.C = 32; fa.count = count;
+                fa.gamma[0] = h->P(pa + ".batch_norm.weight"); fa.beta[0] = h->P(pa + ".batch_norm.bias"); fa.coef[0] = h->C(h->coef_a[i]);
+                fa.gamma[1] = h->P(pc + ".batch_norm.weight"); fa.beta[1] = h->P(pc + ".batch_norm.bias"); fa.coef[1] = h->C(h->coef_c[i]);
+                fa.sums = sums; fa.ticket = h->bn_ticket();
+                launch_bn_finish(fa, 2, st);
+                lz.end(1);
+            } else {
             launch_bn_reduce(h->partA.as<double>(), h->use_s ? h->g.s_tiles : np_conv, 32, sums, st);
             launch_bn_reduce(h->partB.as<double>(), np_gin, 32, sums + 64, st);
             allreduce_sums(h, sums, 128, st);
             launch_bn_coef(sums, count, h->P(pa + ".batch_norm.weight"), h->P(pa + ".batch_norm.bias"), h->C(h->coef_a[i]), 32, st);
             launch_bn_coef(sums + 64, count, h->P(pc + ".batch_norm.weight"), h->P(pc + ".batch_norm.bias"), h->C(h->coef_c[i]), 32, st);
             lz.end(4);
+            }
         }
         lz.begin("combine");
         launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[i & 1].as<float>(), h->C(h->coef_c[i]),
@@ -486,7 +502,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             if (train) {
                 lz.begin("bnfin");
                 finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], p + ".batch_norm", h->coef_fin[k]);
-                lz.end(2);
+                lz.end(h->world == 1 ? 1 : 2);
             }
         }
         lz.begin("score");
@@ -550,8 +566,8 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->conv_chunk_only = csel && std::string(csel) == "chunk";
         h->conv_s_only = csel && std::string(csel) == "s";
         h->conv_h_only = csel && std::string(csel) == "h";
-        h->hflags.reserve((size_t)(2 * cfg->depth + 1) * sizeof(int));
-        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 1) * sizeof(int)));
+        h->hflags.reserve((size_t)(2 * cfg->depth + 2) * sizeof(int));
+        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 2) * sizeof(int)));
         h->dev_error.reserve(sizeof(int));
         TGNN_CUDA(cudaMemset(h->dev_error.p, 0, sizeof(int)));
         declare_params(h.get());

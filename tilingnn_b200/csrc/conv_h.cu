@@ -23,7 +23,7 @@ namespace {
 constexpr int XS = 36;          // padded shared-memory row stride (floats)
 constexpr int WARPS = 8;
 constexpr int TPB = WARPS * 32;
-constexpr float LO_SCALE = 2048.f, LO_INV = 1.0f / 2048.f;
+constexpr float LO_INV = 1.0f / 2048.f;
 
 __device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
 
@@ -31,24 +31,6 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-// Fragment table of a [32 in][32 out] matrix, fp16 hi|lo: 2048 halves = 1024 words.
-//   k -> k16 step ks = k>>4, thread-in-group tt = (k&15)>>2, register (k&3)>>1, half k&1   (matches the row layout of xh)
-//   n -> n-tile nt = (n&7)>>1, group g = 2(n>>3) + (n&1)   (a lane ends up with 8 contiguous output channels 8t..8t+7)
-//   uint4 index ((ks*2 + hl)*2 + j)*32 + lane, lane = 4g + tt, j = nt>>1; component 2(nt&1) + register
-__host__ __device__ __forceinline__ int hfrag_half_index(int k, int n, int hl) {
-    const int ks = k >> 4, r = k & 15, tt = r >> 2, reg = (r & 3) >> 1, e = r & 1;
-    const int rn = n & 7, nt = rn >> 1, g = 2 * (n >> 3) + (rn & 1);
-    const int lane = g * 4 + tt, j = nt >> 1, comp = 2 * (nt & 1) + reg;
-    return (((((ks * 2 + hl) * 2 + j) * 32 + lane) * 4 + comp) * 2) + e;
-}
-__device__ __forceinline__ void hfrag_store(__half* tab, int k, int n, float w, int* flag) {
-    const __half hi = __float2half_rn(w);
-    const __half lo = __float2half_rn((w - __half2float(hi)) * LO_SCALE);
-    tab[hfrag_half_index(k, n, 0)] = hi;
-    tab[hfrag_half_index(k, n, 1)] = lo;
-    if (flag && !(fabsf(w) <= TG_H_LIMIT)) *flag = 1;
 }
 
 struct BFragH { uint4 h[2][2], l[2][2]; };
@@ -99,6 +81,10 @@ __device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int
 
 __device__ __forceinline__ uint4 ld_rowh(const uint4* __restrict__ xh, int row, int q) { return __ldg(xh + (size_t)row * 8 + q); }
 
+// SPLIT = false: persistent, one warp per 64-row tile (large graphs).  SPLIT = true: one CTA per tile, its 8 warps take
+// every 8th chunk into private partial tiles that are summed in a fixed order -- the real layouts have ~10 tiles
+// (N ~ 600), where one warp walking ~60 latency-bound chunks per tile would leave the GPU idle.
+template <bool SPLIT>
 __global__ void __launch_bounds__(TPB, 2)
 k_conv_h(ConvArgs A) {
     if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) return;      // out of fp16 range: k_conv_adj takes the layer
@@ -113,10 +99,12 @@ k_conv_h(ConvArgs A) {
     const uint4* __restrict__ xh = A.xh;
     BFragH bf;
     int cur_type = -1;
+    const int tile_first = SPLIT ? blockIdx.x : gwarp, tile_step = SPLIT ? gridDim.x : nwarp;
+    const int cstep = SPLIT ? WARPS : 1;
 
-    for (int tile = gwarp; tile < A.n_tiles; tile += nwarp) {
+    for (int tile = tile_first; tile < A.n_tiles; tile += tile_step) {
         for (int i = lane; i < WN * XS; i += 32) acc[i] = 0.f;
-        const int c0 = __ldg(A.cptr + tile), c1 = __ldg(A.cptr + tile + 1);
+        const int c0 = __ldg(A.cptr + tile) + (SPLIT ? warp : 0), c1 = __ldg(A.cptr + tile + 1);
         uint4 pre[4] = {zero4, zero4, zero4, zero4};
         int psrc = -1, pdst = 0, ptype = 0;
         if (c0 < c1) {
@@ -128,20 +116,21 @@ k_conv_h(ConvArgs A) {
             if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
         }
         __syncwarp();
-        for (int c = c0; c < c1; ++c) {
+        for (int c = c0; c < c1; c += cstep) {
             const uint4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
             const int csrc = psrc, cdst = pdst, type = ptype;
-            if (c + 1 < c1) {
-                psrc = __ldg(A.csrc + (size_t)(c + 1) * CH + (lane & 15));
-                pdst = __ldg(A.cdst + (size_t)(c + 1) * CH + (lane & 15));
-                ptype = __ldg(A.ctype + c + 1);
+            const int cn = c + cstep;
+            if (cn < c1) {
+                psrc = __ldg(A.csrc + (size_t)cn * CH + (lane & 15));
+                pdst = __ldg(A.cdst + (size_t)cn * CH + (lane & 15));
+                ptype = __ldg(A.ctype + cn);
                 const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
                 pre[0] = pre[1] = pre[2] = pre[3] = zero4;
                 if (sa >= 0) { pre[0] = ld_rowh(xh, sa, t); pre[1] = ld_rowh(xh, sa, 4 + t); }
                 if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
             }
             if (type != cur_type) { load_bfrag_h(bf, A.tabH + (size_t)type * TG_HFRAG32, lane); cur_type = type; }
-            if (ptype != type && c + 1 < c1)       // next type's 4 KB table towards L1 (32 lines of 128 B)
+            if (ptype != type && cn < c1)          // next type's 4 KB table towards L1 (32 lines of 128 B)
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(A.tabH + (size_t)ptype * TG_HFRAG32) + lane * 128));
             float m[4][4];
             chunk_mma_h(cur, bf, m);
@@ -157,79 +146,57 @@ k_conv_h(ConvArgs A) {
             }
             __syncwarp();
         }
-        // mean over in-edges
         const int node0 = tile * WN;
-        for (int r = 0; r < WN; ++r) {
+        float* tile_acc = acc;
+        int r0 = 0, r1 = WN;                                      // rows this warp finishes
+        if (SPLIT) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < WN * XS; i += TPB) {    // fixed-order sum of the 8 partial tiles
+                float v = smem[i];
+#pragma unroll
+                for (int w = 1; w < WARPS; ++w) v += smem[w * (WN * XS) + i];
+                smem[i] = v;
+            }
+            __syncthreads();
+            tile_acc = smem; r0 = warp * (WN / WARPS); r1 = r0 + WN / WARPS;
+        }
+        // mean over in-edges
+        for (int r = r0; r < r1; ++r) {
             int node = node0 + r;
-            if (node < A.n_own) acc[r * XS + lane] *= __ldg(A.inv_deg + node);
+            if (node < A.n_own) tile_acc[r * XS + lane] *= __ldg(A.inv_deg + node);
         }
-        __syncwarp();
+        if (SPLIT) __syncthreads(); else __syncwarp();
         // root term: x_i @ root as four 16-row chunks of the tile's own rows (table entry n_types)
-        if (cur_type != A.n_types) { load_bfrag_h(bf, A.tabH + (size_t)A.n_types * TG_HFRAG32, lane); cur_type = A.n_types; }
-        for (int rc = 0; rc < WN / CH; ++rc) {
-            const int na = node0 + rc * CH + g, nb = na + 8;
-            uint4 cur[4] = {zero4, zero4, zero4, zero4};
-            if (na < A.n_own) { cur[0] = ld_rowh(xh, na, t); cur[1] = ld_rowh(xh, na, 4 + t); }
-            if (nb < A.n_own) { cur[2] = ld_rowh(xh, nb, t); cur[3] = ld_rowh(xh, nb, 4 + t); }
-            float m[4][4];
-            chunk_mma_h(cur, bf, m);
-            acc_add8(acc + (rc * CH + g) * XS + 8 * t, m, 0);
-            acc_add8(acc + (rc * CH + g + 8) * XS + 8 * t, m, 1);
+        if (!SPLIT || warp < WN / CH) {
+            if (cur_type != A.n_types) { load_bfrag_h(bf, A.tabH + (size_t)A.n_types * TG_HFRAG32, lane); cur_type = A.n_types; }
+            for (int rc = SPLIT ? warp : 0; rc < (SPLIT ? warp + 1 : WN / CH); ++rc) {
+                const int na = node0 + rc * CH + g, nb = na + 8;
+                uint4 cur[4] = {zero4, zero4, zero4, zero4};
+                if (na < A.n_own) { cur[0] = ld_rowh(xh, na, t); cur[1] = ld_rowh(xh, na, 4 + t); }
+                if (nb < A.n_own) { cur[2] = ld_rowh(xh, nb, t); cur[3] = ld_rowh(xh, nb, 4 + t); }
+                float m[4][4];
+                chunk_mma_h(cur, bf, m);
+                acc_add8(tile_acc + (rc * CH + g) * XS + 8 * t, m, 0);
+                acc_add8(tile_acc + (rc * CH + g + 8) * XS + 8 * t, m, 1);
+            }
         }
-        __syncwarp();
+        if (SPLIT) __syncthreads(); else __syncwarp();
         // bias, LeakyReLU, store, statistics (lane = channel)
-        for (int r = 0; r < WN; ++r) {
+        for (int r = r0; r < r1; ++r) {
             int node = node0 + r;
             if (node < A.n_own) {
-                float v = leaky(acc[r * XS + lane] + bias_c);
+                float v = leaky(tile_acc[r * XS + lane] + bias_c);
                 A.out[(size_t)node * F + lane] = v;
                 s1 += (double)v;
                 s2 += (double)v * (double)v;
             }
         }
-        __syncwarp();
+        if (SPLIT) __syncthreads(); else __syncwarp();
     }
     if (A.part) {
         A.part[(size_t)gwarp * 64 + lane] = s1;
         A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
     }
-}
-
-// per-type edge weights W_t = sigmoid MLP(e_t), evaluated in fp64, rounded once to fp32 (exactly as k_edge_table in
-// kernels.cu), then split into the fp16 fragment table.  grid = K types, block = 256.
-__global__ void k_edge_table_h(const float* __restrict__ rows, int d_e,
-                               const float* __restrict__ a1, const float* __restrict__ c1,
-                               const float* __restrict__ a2, const float* __restrict__ c2,
-                               const float* __restrict__ a3, const float* __restrict__ c3,
-                               uint32_t* __restrict__ tab) {
-    __shared__ double h1[32], h2[64];
-    const int t = blockIdx.x, tid = threadIdx.x;
-    const float* e = rows + (size_t)t * d_e;
-    if (tid < 32) {
-        double s = (double)c1[tid];
-        for (int k = 0; k < d_e; ++k) s += (double)a1[tid * d_e + k] * (double)e[k];
-        h1[tid] = 1.0 / (1.0 + exp(-s));
-    }
-    __syncthreads();
-    if (tid < 64) {
-        double s = (double)c2[tid];
-        for (int k = 0; k < 32; ++k) s += (double)a2[tid * 32 + k] * h1[k];
-        h2[tid] = 1.0 / (1.0 + exp(-s));
-    }
-    __syncthreads();
-    __half* out = reinterpret_cast<__half*>(tab + (size_t)t * TG_HFRAG32);
-    for (int o = tid; o < F * F; o += 256) {
-        double s = (double)c3[o];
-        for (int k = 0; k < 64; ++k) s += (double)a3[(size_t)o * 64 + k] * h2[k];
-        // o = k_in * 32 + k_out  (NNConv: weight.view(-1, in, out)); a sigmoid is always inside the fp16 range
-        hfrag_store(out, o >> 5, o & 31, (float)(1.0 / (1.0 + exp(-s))), nullptr);
-    }
-}
-
-// nnConv.root [in][out] -> fragment table; raises *flag when a weight is outside the fp16 range
-__global__ void k_root_table_h(const float* __restrict__ root, uint32_t* __restrict__ tab, int* __restrict__ flag) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < F * F) hfrag_store(reinterpret_cast<__half*>(tab), i >> 5, i & 31, root[i], flag);
 }
 
 }  // namespace
@@ -239,19 +206,14 @@ static size_t conv_h_smem() { return (size_t)WARPS * (WN * XS) * sizeof(float); 
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_h_smem()));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_h_smem()));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_h_smem()));
         attr = true;
     }
     // same grid as k_conv_adj: the BatchNorm partial layout is shared by the two kernels
-    k_conv_h<<<conv_adj_num_parts(a.n_tiles, sm_count) / WARPS, TPB, conv_h_smem(), st>>>(a);
-    TGNN_CUDA(cudaGetLastError());
-}
-
-void launch_edge_table_h(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
-                         const float* c2, const float* a3, const float* c3, const float* root, uint32_t* tab, int* flag_w,
-                         cudaStream_t st) {
-    if (n_types > 0) k_edge_table_h<<<n_types, 256, 0, st>>>(type_rows, d_e, a1, c1, a2, c2, a3, c3, tab);
-    k_root_table_h<<<4, 256, 0, st>>>(root, tab + (size_t)n_types * TG_HFRAG32, flag_w);
+    const int blocks = conv_adj_num_parts(a.n_tiles, sm_count) / WARPS;
+    if (conv_split_tiles(a.n_tiles, sm_count)) k_conv_h<true><<<blocks, TPB, conv_h_smem(), st>>>(a);
+    else k_conv_h<false><<<blocks, TPB, conv_h_smem(), st>>>(a);
     TGNN_CUDA(cudaGetLastError());
 }
 

@@ -24,6 +24,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "layouts.cuh"
 #include "tc_common.cuh"
 #include "tgnn_internal.h"
 
@@ -418,63 +419,7 @@ k_conv_s(ConvSArgs A) {
     }
 }
 
-// float index of element (row n, column k) inside the SWIZZLE_128B shared-memory IMAGE of a [32 x 32] tf32 tile:
-// the tables are stored in global memory pre-swizzled so that one bulk copy drops a ready-to-use operand tile.
-__host__ __device__ __forceinline__ int tile_pos(int n, int k) { return n * 32 + ((((k >> 2) ^ (n & 7)) << 2) | (k & 3)); }
-
-// per-type edge weights for the S kernel: tabS[t][hi|lo] = swizzled image of W_t^T (row n = out, col k = in), TF32
-// split of W_t evaluated in fp64
-__global__ void k_edge_table_s(const float* __restrict__ rows, int d_e, const float* __restrict__ a1, const float* __restrict__ c1,
-                               const float* __restrict__ a2, const float* __restrict__ c2, const float* __restrict__ a3,
-                               const float* __restrict__ c3, float* __restrict__ tab) {
-    __shared__ double h1[32], h2[64];
-    const int t = blockIdx.x, tid = threadIdx.x;
-    const float* e = rows + (size_t)t * d_e;
-    if (tid < 32) {
-        double s = (double)c1[tid];
-        for (int k = 0; k < d_e; ++k) s += (double)a1[tid * d_e + k] * (double)e[k];
-        h1[tid] = 1.0 / (1.0 + exp(-s));
-    }
-    __syncthreads();
-    if (tid < 64) {
-        double s = (double)c2[tid];
-        for (int k = 0; k < 32; ++k) s += (double)a2[tid * 32 + k] * h1[k];
-        h2[tid] = 1.0 / (1.0 + exp(-s));
-    }
-    __syncthreads();
-    float* out = tab + (size_t)t * 2048;
-    for (int o = tid; o < F * F; o += 256) {
-        double s = (double)c3[o];
-        for (int k = 0; k < 64; ++k) s += (double)a3[(size_t)o * 64 + k] * h2[k];
-        const double w = 1.0 / (1.0 + exp(-s));
-        const int kin = o >> 5, n = o & 31;                   // NNConv: weight.view(-1, in, out)
-        const uint32_t hi = tf32_rna((float)w);
-        const uint32_t lo = tf32_rna((float)(w - (double)__uint_as_float(hi)));
-        const int pos = tile_pos(n, kin);
-        out[pos] = __uint_as_float(hi);
-        out[1024 + pos] = __uint_as_float(lo);
-    }
-}
-// root [in][out] -> [hi|lo][n = out][k = in]
-__global__ void k_root_table_s(const float* __restrict__ root, float* __restrict__ out) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= F * F) return;
-    const int kin = o >> 5, n = o & 31;
-    const float w = root[o];
-    const uint32_t hi = tf32_rna(w);
-    const int pos = tile_pos(n, kin);
-    out[pos] = __uint_as_float(hi);
-    out[1024 + pos] = __uint_as_float(tf32_rna(w - __uint_as_float(hi)));
-}
-
 }  // namespace
-
-void launch_edge_table_s(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
-                         const float* c2, const float* a3, const float* c3, const float* root, float* tab, cudaStream_t st) {
-    if (n_types > 0) k_edge_table_s<<<n_types, 256, 0, st>>>(type_rows, d_e, a1, c1, a2, c2, a3, c3, tab);
-    k_root_table_s<<<4, 256, 0, st>>>(root, tab + (size_t)n_types * 2048);
-    TGNN_CUDA(cudaGetLastError());
-}
 
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st) {
     static bool attr = false;

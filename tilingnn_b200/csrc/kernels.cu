@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "hsplit.cuh"
+#include "layouts.cuh"
 #include "tgnn_internal.h"
 
 namespace tgnn {
@@ -60,34 +61,6 @@ __device__ __forceinline__ void mma3(float (&c0)[4], float (&c1)[4], const uint3
     mma_tf32(t1, ahi, __float_as_uint(bh.z), __float_as_uint(bh.w));
 #pragma unroll
     for (int i = 0; i < 4; ++i) { c0[i] += t0[i]; c1[i] += t1[i]; }
-}
-
-// K / N index maps of the frag tables.
-//  KMAP_GATHER : A comes from two float4 loads per row (cols 4t.., 16+4t..): k-step ks, slot kk=tt+4e  <-> col 16(ks>>1)+4tt+2(ks&1)+e
-//  KMAP_NATURAL: A comes from shared memory, col = 8ks + kk
-//  KMAP_CHAIN  : A is the previous layer's C fragment: k-step ks = previous n-tile, slot kk=tt+4e <-> unit 8ks + 2tt + e
-//  NMAP_NATURAL: unit = 8nt + g          NMAP_CONTIG8: channel = 8(g>>1) + 2nt + (g&1)   (N = 32 only)
-enum { KMAP_GATHER = 0, KMAP_NATURAL = 1, KMAP_CHAIN = 2, NMAP_NATURAL = 0, NMAP_CONTIG8 = 1 };
-
-__host__ __device__ __forceinline__ void frag_coords(int k, int n, int kmap, int nmap, int& ks, int& tt, int& e, int& nt, int& g) {
-    if (kmap == KMAP_GATHER) { int r = k & 15; ks = 2 * (k >> 4) + ((r >> 1) & 1); tt = r >> 2; e = r & 1; }
-    else if (kmap == KMAP_NATURAL) { ks = k >> 3; int kk = k & 7; tt = kk & 3; e = kk >> 2; }
-    else { ks = k >> 3; int r = k & 7; tt = r >> 1; e = r & 1; }
-    if (nmap == NMAP_NATURAL) { nt = n >> 3; g = n & 7; }
-    else { int r = n & 7; nt = r >> 1; g = 2 * (n >> 3) + (r & 1); }
-}
-// float index of element (k, n), hi (hl=0) or lo (hl=1) part, in a frag table of an [K x N] matrix
-__host__ __device__ __forceinline__ size_t frag_index(int k, int n, int N, int kmap, int nmap, int hl) {
-    int ks, tt, e, nt, g;
-    frag_coords(k, n, kmap, nmap, ks, tt, e, nt, g);
-    const int lane = g * 4 + tt, j = nt >> 1, comp = 2 * (nt & 1) + e;
-    return ((((size_t)ks * 2 + hl) * (N / 16) + j) * 32 + lane) * 4 + comp;
-}
-__device__ __forceinline__ void frag_store(float* tab, int k, int n, int N, int kmap, int nmap, double w) {
-    const uint32_t hi = tf32_rna((float)w);
-    const uint32_t lo = tf32_rna((float)(w - (double)__uint_as_float(hi)));
-    tab[frag_index(k, n, N, kmap, nmap, 0)] = __uint_as_float(hi);
-    tab[frag_index(k, n, N, kmap, nmap, 1)] = __uint_as_float(lo);
 }
 
 __device__ __forceinline__ float4 ld_row4(const float* base, int row, int q) {
@@ -674,6 +647,50 @@ __global__ void k_bn_coef(const double* __restrict__ sums, double count, const f
     coef[3 * C + c] = beta[c];
 }
 
+// Single-GPU train mode: reduce the partials of one or two BatchNorms AND turn them into coefficients in one launch.
+// One block per column (fixed reduction order, as k_bn_reduce); the last block to finish (ticket) computes the
+// coefficients from the published sums, so a layer's two BatchNorms cost one launch instead of four.
+__global__ void k_bn_finish(BnFinishArgs A) {
+    __shared__ double sh[256];
+    __shared__ bool last;
+    const int C2 = 2 * A.C;
+    const int which = blockIdx.x / C2, j = blockIdx.x - which * C2;
+    const double* part = A.part[which];
+    const int n_part = A.n_part[which];
+    double s = 0.0;
+    for (int p = threadIdx.x; p < n_part; p += 256) s += part[(size_t)p * C2 + j];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        A.sums[blockIdx.x] = sh[0];
+        __threadfence();
+        last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int nb = gridDim.x / C2;
+    for (int i = threadIdx.x; i < nb * A.C; i += 256) {
+        const int w = i / A.C, c = i - w * A.C;
+        const volatile double* sums = A.sums + (size_t)w * C2;
+        const double mean = sums[c] / A.count;
+        double var = sums[A.C + c] / A.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double rstd = 1.0 / sqrt(var + BN_EPS);
+        const float mh = (float)mean;
+        float* coef = A.coef[w];
+        coef[c] = mh;
+        coef[A.C + c] = (float)(mean - (double)mh);
+        coef[2 * A.C + c] = (float)((double)A.gamma[w][c] * rstd);
+        coef[3 * A.C + c] = A.beta[w][c];
+    }
+    if (threadIdx.x == 0) *A.ticket = 0u;
+}
+
 __global__ void k_bn_coef_eval(const float* __restrict__ rmean, const float* __restrict__ rvar,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* __restrict__ coef, int C) {
@@ -683,39 +700,6 @@ __global__ void k_bn_coef_eval(const float* __restrict__ rmean, const float* __r
     coef[C + c] = 0.f;
     coef[2 * C + c] = (float)((double)gamma[c] / sqrt((double)rvar[c] + BN_EPS));
     coef[3 * C + c] = beta[c];
-}
-
-// ------------------------------------------------------------------------------------------------
-// per-type edge weights: W_t = sigmoid(A3 sigmoid(A2 sigmoid(A1 e_t + a1) + a2) + a3), evaluated in
-// fp64 and rounded once to fp32  (graph_networks/layers/edge_conv.py:17; util.py:10-17).
-// grid = K types, block = 256.
-// ------------------------------------------------------------------------------------------------
-__global__ void k_edge_table(const float* __restrict__ rows, int d_e,
-                             const float* __restrict__ a1, const float* __restrict__ c1,
-                             const float* __restrict__ a2, const float* __restrict__ c2,
-                             const float* __restrict__ a3, const float* __restrict__ c3,
-                             float* __restrict__ tab) {
-    __shared__ double h1[32], h2[64];
-    const int t = blockIdx.x, tid = threadIdx.x;
-    const float* e = rows + (size_t)t * d_e;
-    if (tid < 32) {
-        double s = (double)c1[tid];
-        for (int k = 0; k < d_e; ++k) s += (double)a1[tid * d_e + k] * (double)e[k];
-        h1[tid] = 1.0 / (1.0 + exp(-s));
-    }
-    __syncthreads();
-    if (tid < 64) {
-        double s = (double)c2[tid];
-        for (int k = 0; k < 32; ++k) s += (double)a2[tid * 32 + k] * h1[k];
-        h2[tid] = 1.0 / (1.0 + exp(-s));
-    }
-    __syncthreads();
-    for (int o = tid; o < F * F; o += 256) {
-        double s = (double)c3[o];
-        for (int k = 0; k < 64; ++k) s += (double)a3[(size_t)o * 64 + k] * h2[k];
-        // o = k_in * 32 + k_out  (NNConv: weight.view(-1, in, out))
-        frag_store(tab + (size_t)t * FRAG32, o >> 5, o & 31, 32, KMAP_GATHER, NMAP_CONTIG8, 1.0 / (1.0 + exp(-s)));
-    }
 }
 
 __global__ void k_transpose(const float* __restrict__ in, float* __restrict__ out, int rows, int cols) {
@@ -776,7 +760,12 @@ int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_pe
 static size_t conv_smem() { return (size_t)WARPS * (WN * XS) * sizeof(float); }
 static size_t gin_smem() { return (size_t)(GIN_WFLOATS + WARPS * GIN_WARP_FLOATS) * sizeof(float); }
 
-static int conv_blocks(int n_tiles, int sm_count) { return persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2); }
+// few tiles (small graphs): one CTA per tile so that k_conv_h can split a tile's chunks over its 8 warps
+bool conv_split_tiles(int n_tiles, int sm_count) { return n_tiles <= 2 * sm_count; }
+static int conv_blocks(int n_tiles, int sm_count) {
+    if (conv_split_tiles(n_tiles, sm_count)) return n_tiles < 1 ? 1 : n_tiles;
+    return persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2);
+}
 static int gin_blocks(int n_own, int sm_count) {
     int chunks = (n_own + CH - 1) / CH;
     return persistent_blocks((chunks + WARPS - 1) / WARPS, sm_count, 2);
@@ -852,16 +841,13 @@ void launch_bn_coef(const double* sums, double count, const float* gamma, const 
     k_bn_coef<<<(C + 63) / 64, 64, 0, st>>>(sums, count, gamma, beta, coef_out, C);
     TGNN_CUDA(cudaGetLastError());
 }
+void launch_bn_finish(const BnFinishArgs& a, int n_bn, cudaStream_t st) {
+    k_bn_finish<<<n_bn * 2 * a.C, 256, 0, st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
 void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gamma, const float* beta, float* coef_out,
                          int C, cudaStream_t st) {
     k_bn_coef_eval<<<(C + 63) / 64, 64, 0, st>>>(rmean, rvar, gamma, beta, coef_out, C);
-    TGNN_CUDA(cudaGetLastError());
-}
-
-void launch_edge_table(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
-                       const float* c2, const float* a3, const float* c3, float* tab, cudaStream_t st) {
-    if (n_types <= 0) return;
-    k_edge_table<<<n_types, 256, 0, st>>>(type_rows, d_e, a1, c1, a2, c2, a3, c3, tab);
     TGNN_CUDA(cudaGetLastError());
 }
 

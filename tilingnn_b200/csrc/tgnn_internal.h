@@ -134,19 +134,14 @@ struct ConvArgs {
     const int* flag_w;       // raised at table build when a root weight is outside the fp16 range
 };
 int conv_adj_num_parts(int n_tiles, int sm_count);
+bool conv_split_tiles(int n_tiles, int sm_count);   // small graphs: grid = one CTA per tile (k_conv_h splits the chunks)
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
 
 // fp16-split edge-chunk kernel (conv_h.cu)
 constexpr float TG_H_LIMIT = 60000.f;    // |x| above this (or NaN) raises the range flag: fp16 max is 65504
 constexpr int TG_HFRAG32 = 1024;         // 32-bit words of one fp16 hi|lo fragment table of a 32x32 matrix
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
-void launch_edge_table_h(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
-                         const float* c2, const float* a3, const float* c3, const float* root, uint32_t* tab, int* flag_w,
-                         cudaStream_t st);
-
 // tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
-void launch_edge_table_s(const float* type_rows, int n_types, int d_e, const float* a1, const float* c1, const float* a2,
-                         const float* c2, const float* a3, const float* c3, const float* root, float* tab, cudaStream_t st);
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st);
 
 struct GinArgs {
@@ -206,14 +201,21 @@ void launch_score(const float* a3, const float* coef, const float* w, float b, f
 void launch_bn_reduce(const double* part, int n_part, int C, double* sums_out, cudaStream_t st);
 void launch_bn_coef(const double* sums, double count, const float* gamma, const float* beta,
                     float* coef_out, int C, cudaStream_t st);
+// both steps in one launch for one or two BatchNorms of equal width (single-GPU train mode); sums: [n_bn][2*C]
+struct BnFinishArgs {
+    const double* part[2]; int n_part[2]; int C; double count;
+    const float* gamma[2]; const float* beta[2]; float* coef[2];
+    double* sums; unsigned* ticket;
+};
+void launch_bn_finish(const BnFinishArgs& a, int n_bn, cudaStream_t st);
 // eval mode: coefficients from running statistics
 void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gamma, const float* beta,
                          float* coef_out, int C, cudaStream_t st);
 
-// per-type edge weight table: tab[t] = sigmoid MLP(type_rows[t]) in fp64, rounded to fp32
-void launch_edge_table(const float* type_rows, int n_types, int d_e,
-                       const float* a1, const float* c1, const float* a2, const float* c2,
-                       const float* a3, const float* c3, float* tab, cudaStream_t st);
+// per-type edge weight tables of all layers in one launch (tables.cu); null table pointers are skipped
+struct TableLayer { const float *a1, *c1, *a2, *c2, *a3, *c3, *root; };   // edge MLP (weight, bias) x 3 and nnConv.root
+void launch_edge_tables(const float* type_rows, int n_types, int d_e, int n_layers, const TableLayer* layers_dev,
+                        float* tabF, float* tabS, uint32_t* tabH, int* wflags, cudaStream_t st);
 
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);  // out[c][r] = in[r][c]
 // frag table (tensor-core B fragments, hi|lo TF32 split) of a k-major [K][N] matrix; maps: see kernels.cu
