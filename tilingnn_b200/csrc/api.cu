@@ -442,12 +442,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         }
 
         GinArgs ga{};
-        ga.xin = i == 0 ? h->mid[0]->as<float>() : h->pre2[(i - 1) & 1].as<float>();
-        ga.in_coef = i == 0 ? nullptr : h->C(h->coef_c[i - 1]);
+        // pre2[0] = LeakyReLU(gin) before BatchNorm of this layer, pre2[1] = g2 = BN(pre2) written by k_combine
+        ga.xin = i == 0 ? h->mid[0]->as<float>() : h->pre2[1].as<float>();
         ga.col_ptr = h->g.col_ptr.as<int>(); ga.col_src = h->g.col_src.as<int>();
         ga.wfrag = h->gin_wt[i]->as<float>();
         ga.eps = h->gin_eps[i];
-        ga.out = h->pre2[i & 1].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
+        ga.out = h->pre2[0].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
         lz.begin("gin"); launch_gin(ga, h->sm_count, st); lz.end(1);
 
         if (train) {
@@ -472,11 +472,11 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             }
         }
         lz.begin("combine");
-        launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[i & 1].as<float>(), h->C(h->coef_c[i]),
+        launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[0].as<float>(), h->C(h->coef_c[i]),
                        i >= 2 ? h->mid[i - 2]->as<float>() : nullptr, h->mid[i + 1]->as<float>(),
-                       h->use_h ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), n_own, st);
+                       h->use_h ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), h->pre2[1].as<float>(), n_own, st);
         lz.end(1);
-        if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[i & 1].as<float>(), h->rflag(i + 1), st, lz);
+        if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[1].as<float>(), h->rflag(i + 1), st, lz);
         h->last_layer_run = i;
     }
 
@@ -754,7 +754,7 @@ int tgnn_debug_read(tgnn_handle* h, const char* name, float* out, void* stream) 
             TGNN_CUDA(cudaMemcpyAsync(out, h->pre1.p, bytes, cudaMemcpyDeviceToDevice, st));
         } else if (n == "pre2") {
             TGNN_CHECK(i >= 0, "tgnn_debug_read: no layer has run");
-            TGNN_CUDA(cudaMemcpyAsync(out, h->pre2[i & 1].p, bytes, cudaMemcpyDeviceToDevice, st));
+            TGNN_CUDA(cudaMemcpyAsync(out, h->pre2[0].p, bytes, cudaMemcpyDeviceToDevice, st));
         } else if (n == "g1" || n == "g2") {
             // BN(pre) of the last layer that ran: combine with the other factor's BN replaced by identity
             TGNN_CHECK(i >= 0, "tgnn_debug_read: no layer has run");
@@ -764,11 +764,11 @@ int tgnn_debug_read(tgnn_handle* h, const char* name, float* out, void* stream) 
             for (int c = 0; c < 32; ++c) idc[64 + c] = 0.f, idc[96 + c] = 1.f;     // scale 0, beta 1 -> factor 1
             TGNN_CUDA(cudaMemcpyAsync(ident.p, idc.data(), 128 * sizeof(float), cudaMemcpyHostToDevice, st));
             if (n == "g1")
-                launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[i & 1].as<float>(), ident.as<float>(), nullptr, out,
-                               nullptr, nullptr, h->g.n_own, st);
+                launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[0].as<float>(), ident.as<float>(), nullptr, out,
+                               nullptr, nullptr, nullptr, h->g.n_own, st);
             else
-                launch_combine(h->pre1.as<float>(), ident.as<float>(), h->pre2[i & 1].as<float>(), h->C(h->coef_c[i]), nullptr, out,
-                               nullptr, nullptr, h->g.n_own, st);
+                launch_combine(h->pre1.as<float>(), ident.as<float>(), h->pre2[0].as<float>(), h->C(h->coef_c[i]), nullptr, out,
+                               nullptr, nullptr, nullptr, h->g.n_own, st);
             TGNN_CUDA(cudaStreamSynchronize(st));
         } else {
             throw Error("tgnn_debug_read: unknown tensor " + n);

@@ -17,6 +17,14 @@ constexpr int TPB = WARPS * 32;
 
 __device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
 __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + expf(-v)); }
+// same to within 1 ulp, without the IEEE division's slow-path branch: reciprocal estimate + one Newton step.
+// (the clamp keeps 1 + e finite: sigmoid(-80) = 1.8e-35 is below every tolerance here)
+__device__ __forceinline__ float sigmoidf_nr(float v) {
+    const float x = 1.0f + expf(-fmaxf(v, -80.f));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
 
 
 // ------------------------------------------------------------------------------------------------
@@ -257,10 +265,6 @@ constexpr int GIN_WFLOATS = GIN_W1 + GIN_W2 + GIN_W3 + 128;                // + 
 constexpr int GIN_IDX_CAP = 1024;                                         // staged neighbour indices per 16-node chunk
 constexpr int GIN_WARP_FLOATS = CH * XS + GIN_IDX_CAP;
 
-__device__ __forceinline__ float4 center4(float4 v, const float4& mh, const float4& ml) {
-    v.x = (v.x - mh.x) - ml.x; v.y = (v.y - mh.y) - ml.y; v.z = (v.z - mh.z) - ml.z; v.w = (v.w - mh.w) - ml.w;
-    return v;
-}
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
 __global__ void __launch_bounds__(TPB, 2)
@@ -282,13 +286,6 @@ k_gin(GinArgs A) {
     const int g = lane >> 2, t = lane & 3;       // mma roles
     const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
     const int n_chunks = (A.n_own + CH - 1) / CH;
-    float4 mh = make_float4(0.f, 0.f, 0.f, 0.f), ml = mh, sc = make_float4(1.f, 1.f, 1.f, 1.f), be = mh;
-    if (A.in_coef) {
-        mh = __ldg(reinterpret_cast<const float4*>(A.in_coef) + q);
-        ml = __ldg(reinterpret_cast<const float4*>(A.in_coef + 32) + q);
-        sc = __ldg(reinterpret_cast<const float4*>(A.in_coef + 64) + q);
-        be = __ldg(reinterpret_cast<const float4*>(A.in_coef + 96) + q);
-    }
     const float self_w = 1.0f + A.eps;
     double s1[8], s2[8];
 #pragma unroll
@@ -297,7 +294,8 @@ k_gin(GinArgs A) {
     for (int chunk = gwarp; chunk < n_chunks; chunk += nwarp) {
         const int node0 = chunk * CH;
         // ---- gather + sum: each 8-lane group owns nodes 4i+a of the chunk and keeps 8 neighbour rows in flight;
-        // ---- the chunk's neighbour indices are staged in shared memory first (no dependent global load) -----
+        // ---- the chunk's neighbour indices are staged in shared memory first (no dependent global load).  The rows
+        // ---- are final values (h0 or the previous CollConv output written by k_combine): a plain fp32 sum --------
         int p = 0;
         if (lane <= CH) p = __ldg(A.col_ptr + min(node0 + lane, A.n_own));
         const int e_lo = __shfl_sync(0xffffffffu, p, 0), e_hi = __shfl_sync(0xffffffffu, p, CH);
@@ -308,27 +306,38 @@ k_gin(GinArgs A) {
         for (int i = 0; i < CH / 4; ++i) {
             const int r = 4 * i + a, node = node0 + r;
             const int e0 = __shfl_sync(0xffffffffu, p, r), e1 = __shfl_sync(0xffffffffu, p, r + 1);
-            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool live = node < A.n_own;
+            const int n_mine = live ? e1 - e0 : 0;
+            int n_max = max(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 8));       // warp-uniform trip count
+            n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, 16));
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live) {
-                float4 c = center4(ld_row4(A.xin, node, q), mh, ml);
+                const float4 c = ld_row4(A.xin, node, q);
                 sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
             }
-            for (int e = live ? e0 : e1; e < e1; e += 8) {
+            // indices first (clamped, branch-free: shared memory when staged, else global), then up to 8 predicated
+            // row loads in flight, then the adds
+            const int last = max(n_mine - 1, 0);
+            for (int o = 0; o < n_max; o += 8) {
                 int idx[8];
+                if (staged) {
+                    const int* ip = sidx + (e0 - e_lo);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) idx[k] = ip[min(o + k, last)];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) idx[k] = n_mine > 0 ? __ldg(A.col_src + e0 + min(o + k, last)) : 0;
+                }
                 float4 v[8];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) idx[k] = e + k < e1 ? (staged ? sidx[e + k - e_lo] : __ldg(A.col_src + e + k)) : -1;
+                for (int k = 0; k < 8; ++k) {
+                    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (o + k < n_mine) v[k] = ld_row4(A.xin, idx[k], q);
+                }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = idx[k] >= 0 ? ld_row4(A.xin, idx[k], q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) if (idx[k] >= 0) add4(sum, center4(v[k], mh, ml));
+                for (int k = 0; k < 8; ++k) add4(sum, v[k]);
             }
-            const float nt = live ? self_w + (float)(e1 - e0) : 0.f;
-            float4 h;
-            h.x = fmaf(sc.x, sum.x, nt * be.x); h.y = fmaf(sc.y, sum.y, nt * be.y);
-            h.z = fmaf(sc.z, sum.z, nt * be.z); h.w = fmaf(sc.w, sum.w, nt * be.w);
-            *reinterpret_cast<float4*>(xs + r * XS + 4 * q) = h;
+            *reinterpret_cast<float4*>(xs + r * XS + 4 * q) = sum;
         }
         __syncwarp();
         // ---- layer 1: 32 -> 32, A from shared memory (natural K order) -------------------------------
@@ -350,8 +359,8 @@ k_gin(GinArgs A) {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
             const float bA = b1[8 * ks + 2 * t], bB = b1[8 * ks + 2 * t + 1];
-            float av[4] = {sigmoidf_acc(c1[ks][0] + bA), sigmoidf_acc(c1[ks][2] + bA),
-                           sigmoidf_acc(c1[ks][1] + bB), sigmoidf_acc(c1[ks][3] + bB)};
+            float av[4] = {sigmoidf_nr(c1[ks][0] + bA), sigmoidf_nr(c1[ks][2] + bA),
+                           sigmoidf_nr(c1[ks][1] + bB), sigmoidf_nr(c1[ks][3] + bB)};
             uint32_t ah[4], al[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
@@ -364,8 +373,8 @@ k_gin(GinArgs A) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             const float bA = b2[8 * ks + 2 * t], bB = b2[8 * ks + 2 * t + 1];
-            float av[4] = {sigmoidf_acc(c2[ks][0] + bA), sigmoidf_acc(c2[ks][2] + bA),
-                           sigmoidf_acc(c2[ks][1] + bB), sigmoidf_acc(c2[ks][3] + bB)};
+            float av[4] = {sigmoidf_nr(c2[ks][0] + bA), sigmoidf_nr(c2[ks][2] + bA),
+                           sigmoidf_nr(c2[ks][1] + bB), sigmoidf_nr(c2[ks][3] + bB)};
             uint32_t ah[4], al[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);
@@ -382,7 +391,7 @@ k_gin(GinArgs A) {
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
-                    o[2 * nt + e] = leaky(sigmoidf_acc(c3[nt][2 * half + e] + b3[8 * t + 2 * nt + e]));
+                    o[2 * nt + e] = leaky(sigmoidf_nr(c3[nt][2 * half + e] + b3[8 * t + 2 * nt + e]));
             if (node < A.n_own) {
                 float4* dst = reinterpret_cast<float4*>(A.out + (size_t)node * F + 8 * t);
                 dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -421,7 +430,7 @@ __device__ __forceinline__ float bn_apply(float x, const float* __restrict__ coe
 __global__ void k_combine(const float4* __restrict__ pre1, const float* __restrict__ coef1,
                           const float4* __restrict__ pre2, const float* __restrict__ coef2,
                           const float4* __restrict__ res, float4* __restrict__ out, uint4* __restrict__ xh,
-                          int* __restrict__ flag, int64_t n4) {
+                          int* __restrict__ flag, float4* __restrict__ g2out, int64_t n4) {
     __shared__ float c1[128], c2[128];
     bool bad = false;
     if (threadIdx.x < 128) { c1[threadIdx.x] = coef1[threadIdx.x]; c2[threadIdx.x] = coef2[threadIdx.x]; }
@@ -429,11 +438,14 @@ __global__ void k_combine(const float4* __restrict__ pre1, const float* __restri
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(i & 7) * 4;
         float4 p = __ldg(pre1 + i), g = __ldg(pre2 + i);
-        float4 o;
-        o.x = bn_apply(p.x, c1, c + 0, 32) * bn_apply(g.x, c2, c + 0, 32);
-        o.y = bn_apply(p.y, c1, c + 1, 32) * bn_apply(g.y, c2, c + 1, 32);
-        o.z = bn_apply(p.z, c1, c + 2, 32) * bn_apply(g.z, c2, c + 2, 32);
-        o.w = bn_apply(p.w, c1, c + 3, 32) * bn_apply(g.w, c2, c + 3, 32);
+        float4 o, g2;
+        g2.x = bn_apply(g.x, c2, c + 0, 32); g2.y = bn_apply(g.y, c2, c + 1, 32);
+        g2.z = bn_apply(g.z, c2, c + 2, 32); g2.w = bn_apply(g.w, c2, c + 3, 32);
+        if (g2out) g2out[i] = g2;                 // CollConv output: the next layer's k_gin gathers it as is
+        o.x = bn_apply(p.x, c1, c + 0, 32) * g2.x;
+        o.y = bn_apply(p.y, c1, c + 1, 32) * g2.y;
+        o.z = bn_apply(p.z, c1, c + 2, 32) * g2.z;
+        o.w = bn_apply(p.w, c1, c + 3, 32) * g2.w;
         if (res) { float4 r = __ldg(res + i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
         out[i] = o;
         if (xh) xh[i] = split_h4(o, bad);        // float4 i of a row IS uint4 i of the split row (conv_h.cu)
@@ -798,13 +810,14 @@ void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st) {
 }
 
 void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
-                    const float* residual, float* out, uint4* xh, int* flag, int64_t n_own, cudaStream_t st) {
+                    const float* residual, float* out, uint4* xh, int* flag, float* g2out, int64_t n_own, cudaStream_t st) {
     int64_t n4 = n_own * (F / 4);
     int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
     if (blocks < 1) blocks = 1;
     k_combine<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(pre1), coef1,
                                       reinterpret_cast<const float4*>(pre2), coef2,
-                                      reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), xh, flag, n4);
+                                      reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), xh, flag,
+                                      reinterpret_cast<float4*>(g2out), n4);
     TGNN_CUDA(cudaGetLastError());
 }
 

@@ -145,8 +145,7 @@ void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st);
 
 struct GinArgs {
-    const float* xin;        // [n_rows][32]  pre-BN activations of the previous collision layer (or h0)
-    const float* in_coef;    // [4][32] BN coefficients to apply lazily to xin; nullptr = identity
+    const float* xin;        // [n_rows][32]  output of the previous CollConv (written by k_combine), or h0
     const int* col_ptr; const int* col_src;
     const float* wfrag;      // frag tables W1[2048] W2[4096] W3[4096] then b1[32] b2[64] b3[32]
     float eps;
@@ -158,9 +157,9 @@ int gin_num_parts(int n_own, int sm_count);
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st);
 
 // b1_new = BN(pre1) * BN(pre2) + residual
-// xh / flag (optional): fp16-split copy of the result for k_conv_h and its range flag
+// xh / flag (optional): fp16-split copy of the result for k_conv_h and its range flag; g2out (optional): BN(pre2)
 void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
-                    const float* residual, float* out, uint4* xh, int* flag, int64_t n_own, cudaStream_t st);
+                    const float* residual, float* out, uint4* xh, int* flag, float* g2out, int64_t n_own, cudaStream_t st);
 
 // init MLP: mode 0 = stats of layer 0, 1 = stats of layer 1, 2 = write h0
 struct InitArgs {
