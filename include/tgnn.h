@@ -71,7 +71,9 @@ int tgnn_set_bn_mode(tgnn_handle* h, int32_t bn_mode);
  * source_to_target order, int64, as util/data_util.py:110-117 produces them;
  * adj_feat = adj_e_features [E_a, d_e] fp32 row-major.  Device pointers.
  * Builds the device-side structures (edge-type ids, typed adjacency tiles, collision CSR,
- * per-layer edge-weight tables).  Collision self loops are dropped (PyG GINConv). */
+ * per-layer edge-weight tables).  Collision self loops are dropped (PyG GINConv).
+ * Edge types = distinct adj_feat rows (bitwise, -0 == +0); any number up to 2^22 is accepted -- with
+ * many types (continuous features) the weight tables are built one layer at a time. */
 int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes,
                    int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
                    int64_t e_col, const int64_t* col_src, const int64_t* col_dst,

@@ -209,6 +209,20 @@ def test_random_graph_and_many_edge_types(dev):
     assert net.info()["n_edge_types"] > 1000
 
 
+def test_more_than_65535_edge_types_streams_the_weight_tables(dev):
+    """continuous edge features on ~158k edges (79k distinct rows: the generator is symmetric); the per-type weight tables (12 KB each)
+    are then built one layer at a time instead of for all layers at once."""
+    from tilingnn_b200 import synthetic as syn
+    p = orc.make_params(3, 19, 3, seed=1)
+    x, ai, af, ci = syn.lattice_graph(20000, 8, 8, seed=6, continuous_features=True)
+    gold = orc.forward(p, x, ai, af, ci, depth=3, dtype=torch.float64)[:, 0].numpy()
+    net = make_net(p, 3, 19, 3, dev)
+    err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
+    k = net.info()["n_edge_types"]
+    print(f"{k} edge types: max err {err:.2e}")
+    assert k > 65535 and err <= TOL
+
+
 def test_degenerate_inputs(dev):
     """no adjacency edges / no collision edges / a single node; bad indices raise."""
     from tilingnn_b200 import synthetic as syn

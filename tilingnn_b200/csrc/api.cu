@@ -98,6 +98,7 @@ struct tgnn_handle {
     bool conv_s_only = false;                       // TGNN_CONV=s forces the tcgen05 S kernel whenever its format exists
     bool conv_h_only = false;                       // TGNN_CONV=h forces the fp16-split edge-chunk kernel (never S)
     bool use_s = false, use_h = false;              // decided per graph in set_graph
+    bool tables_streamed = false;                   // many edge types: one layer's weight tables at a time
 
     // workspace
     std::vector<std::unique_ptr<DevBuf>> mid;
@@ -276,21 +277,30 @@ void eval_coefs(tgnn_handle* h, cudaStream_t st) {
     for (int k = 0; k < 4; ++k) one("final_mlp.0.mlp." + std::to_string(k) + ".batch_norm", h->coef_fin[k], FIN_DIMS[k + 1]);
 }
 
-void build_tables(tgnn_handle* h, cudaStream_t st) {
-    if (!h->tables_dirty) return;
+// Few edge types (the shipped tile sets: 20-41; the synthetic configs: <= 51): the tables of all layers are built once
+// per graph.  Many types (continuous edge features -> up to one type per edge): one layer's tables at a time, built
+// right before that layer runs ("streamed"), so memory stays at 12 KB per type instead of 12 KB x depth.
+constexpr size_t TABLES_RESIDENT_BYTES = size_t(1) << 30;
+
+void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
     const int L = h->cfg.depth, K = h->g.n_types;
-    const size_t slots = (size_t)L * (K + 1);
+    const size_t per_layer = (size_t)(K + 1);
+    h->tables_streamed = per_layer * L * (TG_FRAG32 * sizeof(float) + TG_HFRAG32 * sizeof(uint32_t)) > TABLES_RESIDENT_BYTES;
+    if (layer < 0 && (h->tables_streamed || !h->tables_dirty)) return;
+    if (layer >= 0 && !h->tables_streamed) return;
+    const int nl = layer < 0 ? L : 1, l0 = layer < 0 ? 0 : layer;
+    const size_t slots = per_layer * nl;
     // 3xTF32 fragments: always (k_conv_adj is also the wide-range stand-in of k_conv_h)
     h->tab.reserve(slots * TG_FRAG32 * sizeof(float));
     if (h->use_h) {
         h->tabH.reserve(slots * TG_HFRAG32 * sizeof(uint32_t));
-        TGNN_CUDA(cudaMemsetAsync(h->wflag(0), 0, (size_t)L * sizeof(int), st));
+        TGNN_CUDA(cudaMemsetAsync(h->wflag(l0), 0, (size_t)nl * sizeof(int), st));
     }
     if (h->use_s) h->tabS.reserve(slots * TG_FRAG32 * sizeof(float));
-    launch_edge_tables(h->g.type_rows.as<float>(), K, h->cfg.d_e, L, h->table_layers.as<TableLayer>(), h->tab.as<float>(),
+    launch_edge_tables(h->g.type_rows.as<float>(), K, h->cfg.d_e, nl, h->table_layers.as<TableLayer>() + l0, h->tab.as<float>(),
                        h->use_s ? h->tabS.as<float>() : nullptr, h->use_h ? h->tabH.as<uint32_t>() : nullptr,
-                       h->use_h ? h->wflag(0) : nullptr, st);
-    h->tables_dirty = false;
+                       h->use_h ? h->wflag(l0) : nullptr, st);
+    if (layer < 0) h->tables_dirty = false;
 }
 
 // Cost model from B200 measurements (1M nodes, deg 32, 51 types): the edge-chunk mma.sync kernel costs ~72 ps per
@@ -416,9 +426,11 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     for (int i = 0; i < n_layers; ++i) {
         std::string pa = "brch_1_graph_conv_layers." + std::to_string(i);
         std::string pc = "brch_2_coll_conv_layers." + std::to_string(i);
+        if (h->tables_streamed) { lz.begin("conv"); build_tables(h, st, i); lz.end(1); }
+        const size_t tslot = h->tables_streamed ? 0 : (size_t)i * (h->g.n_types + 1);
         ConvArgs ca{};
         ca.xin = h->mid[i]->as<float>();
-        ca.tabF = h->tab.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32;
+        ca.tabF = h->tab.as<float>() + tslot * TG_FRAG32;
         ca.n_types = h->g.n_types; ca.bias = h->P(pa + ".nnConv.bias");
         ca.cptr = h->g.cptr.as<int>(); ca.ctype = h->g.ctype.as<int>(); ca.csrc = h->g.csrc.as<int>();
         ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->g.inv_deg.as<float>();
@@ -426,12 +438,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles;
         lz.begin("conv");
         if (h->use_s) {
-            launch_conv_s(ca, h->g, h->tabS.as<float>() + (size_t)i * (h->g.n_types + 1) * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
+            launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
             lz.end(1);
         } else if (h->use_h) {
             // fp16-split kernel; k_conv_adj right behind it takes the layer only if a range flag is raised
             ca.xh = h->xh.as<uint4>();
-            ca.tabH = h->tabH.as<uint32_t>() + (size_t)i * (h->g.n_types + 1) * TG_HFRAG32;
+            ca.tabH = h->tabH.as<uint32_t>() + tslot * TG_HFRAG32;
             ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
             launch_conv_h(ca, h->sm_count, st);
             launch_conv_adj(ca, h->sm_count, st);

@@ -96,16 +96,16 @@ __global__ void k_gather_type_rows(const float* __restrict__ feat, int d_e, cons
     rows[i] = feat[(int64_t)rep_edge[t] * d_e + k];
 }
 
-// key = (warp tile << 22) | (type << 6) | local destination
+// key = (warp tile << (6 + tb)) | (type << 6) | local destination;  tb = bits of the largest type id
 __global__ void k_adj_keys(const int64_t* __restrict__ dst, const int* __restrict__ type_of_edge, int64_t e,
-                           int64_t n_own, unsigned long long* __restrict__ key, int* __restrict__ eid, int* __restrict__ deg) {
+                           int64_t n_own, int tb, unsigned long long* __restrict__ key, int* __restrict__ eid, int* __restrict__ deg) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= e) return;
     long long d = dst[i];
     if (d < 0 || d >= n_own) d = 0;                     // flagged by k_validate; keep the access in range
     unsigned long long tile = (unsigned long long)(d / WN);
     unsigned long long dl = (unsigned long long)(d % WN);
-    key[i] = (tile << 22) | ((unsigned long long)type_of_edge[i] << 6) | dl;
+    key[i] = (tile << (6 + tb)) | ((unsigned long long)type_of_edge[i] << 6) | dl;
     eid[i] = (int)i;
     atomicAdd(&deg[d], 1);
 }
@@ -149,15 +149,15 @@ __global__ void k_run_chunks(const int* __restrict__ run_pos, const int* __restr
 // per run: chunk types, and the end of the tile's chunk range if this is the tile's last run
 __global__ void k_run_fill(const unsigned long long* __restrict__ key, const int* __restrict__ run_pos,
                            const int* __restrict__ run_chunks, const int* __restrict__ chunk_base,
-                           int n_runs, int* __restrict__ ctype, int* __restrict__ tile_end) {
+                           int n_runs, int tb, int* __restrict__ ctype, int* __restrict__ tile_end) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
     unsigned long long k = key[run_pos[r]];
-    int type = (int)((k >> 6) & 0xFFFFull);
-    long long tile = (long long)(k >> 22);
+    int type = (int)((k >> 6) & ((1ull << tb) - 1ull));
+    long long tile = (long long)(k >> (6 + tb));
     int base = chunk_base[r], nc = run_chunks[r];
     for (int c = 0; c < nc; ++c) ctype[base + c] = type;
-    bool last = (r + 1 == n_runs) || ((long long)(key[run_pos[r + 1]] >> 22) != tile);
+    bool last = (r + 1 == n_runs) || ((long long)(key[run_pos[r + 1]] >> (6 + tb)) != tile);
     if (last) tile_end[tile] = base + nc;
 }
 
@@ -324,8 +324,8 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         int n_types = read_int(scan + (e_adj - 1), st);
         TGNN_CHECK(read_int(err, st) == 0, "tgnn_set_graph: adjacency edge index out of range");
         TGNN_CHECK(n_types <= MAX_TYPES,
-                   "tgnn_set_graph: more than 65535 distinct adjacency edge-feature rows; the dense "
-                   "per-edge weight path for non-repeating edge features is not implemented");
+                   "tgnn_set_graph: more than 4194304 distinct adjacency edge-feature rows (one 12 KB weight table each "
+                   "per layer would not fit the GPU)");
         g.n_types = n_types;
         int* type_of_edge = sc.get<int>(e_adj);
         int* rep_edge = sc.get<int>(n_types);
@@ -338,8 +338,10 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         // ---------------- adjacency: typed tiles ---------------------------------------------------
         unsigned long long* k0 = h0;      // reuse
         unsigned long long* k1 = h1;
-        k_adj_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, k0, id0, deg);
-        int end_bit = 22 + bits_for((unsigned long long)g.n_tiles);
+        const int tb = bits_for((unsigned long long)(n_types > 0 ? n_types - 1 : 0));
+        k_adj_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, tb, k0, id0, deg);
+        int end_bit = 6 + tb + bits_for((unsigned long long)g.n_tiles);
+        TGNN_CHECK(end_bit <= 64, "tgnn_set_graph: sort key overflow (tiles x edge types)");
         sort_pairs(sc, k0, k1, id0, id1, e_adj, end_bit, st);
         int* run_head = head;
         int* run_seed = sc.get<int>(e_adj);
@@ -370,7 +372,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         TGNN_CUDA(cudaMemsetAsync(g.cdst.p, 0, (size_t)n_chunks * CH, st));
         int* tile_end = sc.get<int>(g.n_tiles);
         TGNN_CUDA(cudaMemsetAsync(tile_end, 0, (size_t)g.n_tiles * sizeof(int), st));
-        k_run_fill<<<nblk(n_runs), TPB, 0, st>>>(k1, run_pos, run_chunks, chunk_base, n_runs,
+        k_run_fill<<<nblk(n_runs), TPB, 0, st>>>(k1, run_pos, run_chunks, chunk_base, n_runs, tb,
                                                   g.ctype.as<int>(), tile_end);
         k_cptr_first<<<1, 32, 0, st>>>(g.cptr.as<int>());
         incl_max(sc, tile_end, g.cptr.as<int>() + 1, g.n_tiles, st);

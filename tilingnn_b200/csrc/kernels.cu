@@ -454,35 +454,124 @@ __global__ void k_combine(const float4* __restrict__ pre1, const float* __restri
 }
 
 // ------------------------------------------------------------------------------------------------
-// init MLP (TilinGNN.py:31,54): two Linear -> LeakyReLU -> BN stages, recomputed from x per pass.
-// lane = channel, one warp per node (d_x is tiny).
+// init MLP (TilinGNN.py:31,54): two Linear -> LeakyReLU -> BN stages, recomputed from x per pass
+// (MODE 0: statistics of stage 0, 1: statistics of stage 1, 2: write h0 and its fp16-split copy).
+// One THREAD per node does both small matrix products out of registers (weights are shared-memory broadcasts:
+// 8 LDS.128 feed 32 FFMA); the 32 nodes x 32 channels block of a warp is then transposed through shared memory
+// so that lane = channel for the fp64 statistics (fixed order) and the coalesced row stores.
 // ------------------------------------------------------------------------------------------------
+constexpr int INIT_MAX_DX = 64;       // wider node features take k_init_wide (one warp per node)
+
 template <int MODE>
 __global__ void __launch_bounds__(TPB)
 k_init(InitArgs A) {
+    __shared__ __align__(16) float w0t[INIT_MAX_DX * 32];      // [d][c]
+    __shared__ __align__(16) float w1t[32 * 32];               // [k][c]
+    __shared__ float cf[2][128];
+    __shared__ float tile[WARPS][32 * 33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < A.d_x * 32; i += TPB) w0t[i] = __ldg(A.w0 + (i & 31) * A.d_x + (i >> 5));
+    if (MODE >= 1) {
+        for (int i = threadIdx.x; i < 32 * 32; i += TPB) w1t[i] = __ldg(A.w1t + i);
+        if (threadIdx.x < 128) cf[0][threadIdx.x] = A.coef0[threadIdx.x];
+    }
+    if (MODE == 2 && threadIdx.x < 128) cf[1][threadIdx.x] = A.coef1[threadIdx.x];
+    __syncthreads();
+    const float b0 = __ldg(A.b0 + lane), b1 = MODE >= 1 ? __ldg(A.b1 + lane) : 0.f;
+    const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
+    float* tl = tile[warp];
+    double s1 = 0.0, s2 = 0.0;
+    bool bad = false;
+    for (int base = gwarp * 32; base < A.n_own; base += nwarp * 32) {
+        const int node = base + lane;
+        float v[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = __shfl_sync(0xffffffffu, b0, c);
+        if (node < A.n_own) {
+            for (int d = 0; d < A.d_x; ++d) {
+                const float xd = __ldg(A.x + (size_t)node * A.d_x + d);
+                const float4* w = reinterpret_cast<const float4*>(w0t + d * 32);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 wv = w[c4];
+                    v[4 * c4 + 0] = fmaf(xd, wv.x, v[4 * c4 + 0]); v[4 * c4 + 1] = fmaf(xd, wv.y, v[4 * c4 + 1]);
+                    v[4 * c4 + 2] = fmaf(xd, wv.z, v[4 * c4 + 2]); v[4 * c4 + 3] = fmaf(xd, wv.w, v[4 * c4 + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) v[c] = leaky(v[c]);
+        if (MODE >= 1) {
+            float o[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __shfl_sync(0xffffffffu, b1, c);
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+                const float y = fmaf((v[k] - cf[0][k]) - cf[0][32 + k], cf[0][64 + k], cf[0][96 + k]);
+                const float4* w = reinterpret_cast<const float4*>(w1t + k * 32);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 wv = w[c4];
+                    o[4 * c4 + 0] = fmaf(y, wv.x, o[4 * c4 + 0]); o[4 * c4 + 1] = fmaf(y, wv.y, o[4 * c4 + 1]);
+                    o[4 * c4 + 2] = fmaf(y, wv.z, o[4 * c4 + 2]); o[4 * c4 + 3] = fmaf(y, wv.w, o[4 * c4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = leaky(o[c]);
+        }
+        // transpose: thread (node) major -> lane = channel
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) tl[lane * 33 + c] = v[c];
+        __syncwarp();
+        const int n_here = min(32, A.n_own - base);
+        for (int j = 0; j < n_here; ++j) {
+            const float val = tl[j * 33 + lane];
+            if (MODE == 2) {
+                const float o2 = fmaf((val - cf[1][lane]) - cf[1][32 + lane], cf[1][64 + lane], cf[1][96 + lane]);
+                A.out[(size_t)(base + j) * F + lane] = o2;
+                if (A.xh) {
+                    // lane = channel -> word w of the split row: q = w>>2, {hi(4q,4q+1), hi(4q+2,4q+3), lo(..), lo(..)}[w&3]
+                    __half hi, lo;
+                    split_h(o2, hi, lo);
+                    const uint32_t h16 = __half_as_ushort(hi), l16 = __half_as_ushort(lo);
+                    const uint32_t wh = h16 | (__shfl_down_sync(0xffffffffu, h16, 1) << 16);
+                    const uint32_t wl = l16 | (__shfl_down_sync(0xffffffffu, l16, 1) << 16);
+                    const int src = (lane & ~3) + 2 * (lane & 1);
+                    const uint32_t a = __shfl_sync(0xffffffffu, wh, src), b = __shfl_sync(0xffffffffu, wl, src);
+                    A.xh[(size_t)(base + j) * F + lane] = (lane & 2) ? b : a;
+                    bad |= !(fabsf(o2) <= TG_H_LIMIT);
+                }
+            } else {
+                s1 += (double)val;
+                s2 += (double)val * (double)val;
+            }
+        }
+    }
+    if (MODE == 2 && bad) *A.flag = 1;
+    if (MODE < 2 && A.part) {
+        A.part[(size_t)gwarp * 64 + lane] = s1;
+        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
+    }
+}
+
+// the same for d_x > 64: lane = channel, one warp per node
+template <int MODE>
+__global__ void __launch_bounds__(TPB)
+k_init_wide(InitArgs A) {
     __shared__ float w1t[32 * 33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (MODE >= 1) {
         for (int i = threadIdx.x; i < 32 * 32; i += TPB) w1t[(i >> 5) * 33 + (i & 31)] = __ldg(A.w1t + i);
         __syncthreads();
     }
-    float w0[8];
-#pragma unroll
-    for (int d = 0; d < 8; ++d) w0[d] = d < A.d_x ? __ldg(A.w0 + lane * A.d_x + d) : 0.f;
     const float b0 = __ldg(A.b0 + lane);
     const float b1 = MODE >= 1 ? __ldg(A.b1 + lane) : 0.f;
     const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
     double s1 = 0.0, s2 = 0.0;
     for (int node = gwarp; node < A.n_own; node += nwarp) {
         float v = b0;
-        for (int d0 = 0; d0 < A.d_x; d0 += 8) {
-#pragma unroll
-            for (int d = 0; d < 8; ++d)
-                if (d0 + d < A.d_x) {
-                    float wv = d0 == 0 ? w0[d] : __ldg(A.w0 + lane * A.d_x + d0 + d);
-                    v = fmaf(__ldg(A.x + (size_t)node * A.d_x + d0 + d), wv, v);
-                }
-        }
+        for (int d = 0; d < A.d_x; ++d) v = fmaf(__ldg(A.x + (size_t)node * A.d_x + d), __ldg(A.w0 + lane * A.d_x + d), v);
         v = leaky(v);
         if (MODE >= 1) {
             float y = bn_apply(v, A.coef0, lane, 32);
@@ -494,7 +583,6 @@ k_init(InitArgs A) {
                 const float o2 = bn_apply(v, A.coef1, lane, 32);
                 A.out[(size_t)node * F + lane] = o2;
                 if (A.xh) {
-                    // lane = channel -> word w of the split row: q = w>>2, {hi(4q,4q+1), hi(4q+2,4q+3), lo(..), lo(..)}[w&3]
                     __half hi, lo;
                     split_h(o2, hi, lo);
                     const uint32_t h16 = __half_as_ushort(hi), l16 = __half_as_ushort(lo);
@@ -782,7 +870,7 @@ static int gin_blocks(int n_own, int sm_count) {
     int chunks = (n_own + CH - 1) / CH;
     return persistent_blocks((chunks + WARPS - 1) / WARPS, sm_count, 2);
 }
-static int init_blocks(int n_own, int sm_count) { return persistent_blocks((n_own + WARPS * 8 - 1) / (WARPS * 8), sm_count, 4); }
+static int init_blocks(int n_own, int sm_count) { return persistent_blocks((n_own + WARPS * 32 - 1) / (WARPS * 32), sm_count, 4); }
 
 int conv_adj_num_parts(int n_tiles, int sm_count) { return conv_blocks(n_tiles, sm_count) * WARPS; }
 int gin_num_parts(int n_own, int sm_count) { return gin_blocks(n_own, sm_count) * WARPS; }
@@ -823,9 +911,15 @@ void launch_combine(const float* pre1, const float* coef1, const float* pre2, co
 
 void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st) {
     int blocks = init_blocks(a.n_own, sm_count);
-    if (mode == 0) k_init<0><<<blocks, TPB, 0, st>>>(a);
-    else if (mode == 1) k_init<1><<<blocks, TPB, 0, st>>>(a);
-    else k_init<2><<<blocks, TPB, 0, st>>>(a);
+    if (a.d_x <= INIT_MAX_DX) {
+        if (mode == 0) k_init<0><<<blocks, TPB, 0, st>>>(a);
+        else if (mode == 1) k_init<1><<<blocks, TPB, 0, st>>>(a);
+        else k_init<2><<<blocks, TPB, 0, st>>>(a);
+    } else {
+        if (mode == 0) k_init_wide<0><<<blocks, TPB, 0, st>>>(a);
+        else if (mode == 1) k_init_wide<1><<<blocks, TPB, 0, st>>>(a);
+        else k_init_wide<2><<<blocks, TPB, 0, st>>>(a);
+    }
     TGNN_CUDA(cudaGetLastError());
 }
 

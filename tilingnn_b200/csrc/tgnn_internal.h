@@ -19,7 +19,7 @@ constexpr int F = 32;            // network_width (inputs/config.py:38 of the re
 constexpr int WN = 64;           // destination rows owned by one warp tile of the typed adjacency format
 constexpr int CH = 16;           // edge slots per chunk (all of one edge type)
 constexpr int GRP = 8;           // slots per group; destinations are distinct inside a group
-constexpr int MAX_TYPES = 65535; // edge-type ids are 16 bit inside the sort key
+constexpr int MAX_TYPES = 1 << 22; // distinct adjacency feature rows; each costs a 12 KB weight table per resident layer
 constexpr float LEAKY = 0.01f;
 constexpr double BN_EPS = 1e-5;
 
