@@ -201,6 +201,9 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    # NCCL writes its banner to stdout when NCCL_DEBUG=VERSION/INFO is set in the environment; stdout must carry
+    # exactly one JSON line.  TGNN_NCCL_DEBUG passes a level through explicitly (output then goes to stderr's file).
+    os.environ["NCCL_DEBUG"] = os.environ.get("TGNN_NCCL_DEBUG", "WARN")
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
@@ -343,8 +346,8 @@ def main():
                        "nodes_per_gpu": args.nodes, "deg": args.deg, "depth": args.depth, "bn": args.bn,
                        "parallelism": f"node-range shards x{world}" if world > 1 else "single GPU",
                        "l2_policy": f"no flush needed: per-step working set {info['workspace_bytes'] / 1e9:.1f} GB >> 126 MB L2"},
-            "roofline": {"bound": "hbm", "kernel": {"conv": "k_conv_adj", "gin": "k_gin", "final": "k_dense",
-                                                    "combine": "k_combine"}.get(dom, dom),
+            "roofline": {"bound": "hbm", "kernel": {"conv": {0: "k_conv_adj", 1: "k_conv_s", 2: "k_conv_h"}[int(info["conv_kernel"])],
+                                                    "gin": "k_gin", "final": "k_dense_tc", "combine": "k_combine"}.get(dom, dom),
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kb, "ms_per_launch": per_launch_ms,

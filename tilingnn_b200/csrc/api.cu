@@ -346,11 +346,12 @@ struct Launcher {
         cudaEventRecord(e.a, st);
         h->prof.push_back(e);
     }
-    void end(int n_launch) {
+    // n_work: launches that do the family's work (k_conv_h's stand-by twin k_conv_adj exits at once and is not one)
+    void end(int n_launch, int n_work = -1) {
         h->launches += n_launch;
         if (!h->profiling) return;
         cudaEventRecord(h->prof.back().b, st);
-        h->prof_result[h->prof.back().fam].second += n_launch;
+        h->prof_result[h->prof.back().fam].second += n_work < 0 ? n_launch : n_work;
     }
 };
 
@@ -447,7 +448,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
             launch_conv_h(ca, h->sm_count, st);
             launch_conv_adj(ca, h->sm_count, st);
-            lz.end(2);
+            lz.end(2, 1);
         } else {
             launch_conv_adj(ca, h->sm_count, st);
             lz.end(1);
