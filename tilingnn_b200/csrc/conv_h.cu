@@ -103,14 +103,22 @@ k_conv_h(ConvArgs A) {
     const int cstep = SPLIT ? WARPS : 1;
 
     for (int tile = tile_first; tile < A.n_tiles; tile += tile_step) {
-        for (int i = lane; i < WN * XS; i += 32) acc[i] = 0.f;
+        for (int i = lane; i < WN * XS / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int c0 = __ldg(A.cptr + tile) + (SPLIT ? warp : 0), c1 = __ldg(A.cptr + tile + 1);
+        // software pipeline: slot indices run TWO chunks ahead of the MMAs, gathered rows ONE chunk ahead, so neither
+        // the index load nor the dependent row loads are waited for in the iteration that issues them
         uint4 pre[4] = {zero4, zero4, zero4, zero4};
-        int psrc = -1, pdst = 0, ptype = 0;
+        int psrc = -1, pdst = 0, ptype = 0;            // chunk c
+        int nsrc = -1, ndst = 0, ntype = 0;            // chunk c + cstep
         if (c0 < c1) {
             psrc = __ldg(A.csrc + (size_t)c0 * CH + (lane & 15));
             pdst = __ldg(A.cdst + (size_t)c0 * CH + (lane & 15));
             ptype = __ldg(A.ctype + c0);
+            if (c0 + cstep < c1) {
+                nsrc = __ldg(A.csrc + (size_t)(c0 + cstep) * CH + (lane & 15));
+                ndst = __ldg(A.cdst + (size_t)(c0 + cstep) * CH + (lane & 15));
+                ntype = __ldg(A.ctype + c0 + cstep);
+            }
             const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
             if (sa >= 0) { pre[0] = ld_rowh(xh, sa, t); pre[1] = ld_rowh(xh, sa, 4 + t); }
             if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
@@ -119,15 +127,18 @@ k_conv_h(ConvArgs A) {
         for (int c = c0; c < c1; c += cstep) {
             const uint4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
             const int csrc = psrc, cdst = pdst, type = ptype;
-            const int cn = c + cstep;
-            if (cn < c1) {
-                psrc = __ldg(A.csrc + (size_t)cn * CH + (lane & 15));
-                pdst = __ldg(A.cdst + (size_t)cn * CH + (lane & 15));
-                ptype = __ldg(A.ctype + cn);
-                const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
+            const int cn = c + cstep, cn2 = c + 2 * cstep;
+            if (cn < c1) {                                 // rows of the next chunk (its indices arrived an iteration ago)
+                const int sa = __shfl_sync(0xffffffffu, nsrc, g), sb = __shfl_sync(0xffffffffu, nsrc, g + 8);
                 pre[0] = pre[1] = pre[2] = pre[3] = zero4;
                 if (sa >= 0) { pre[0] = ld_rowh(xh, sa, t); pre[1] = ld_rowh(xh, sa, 4 + t); }
                 if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
+            }
+            psrc = nsrc; pdst = ndst; ptype = ntype;
+            if (cn2 < c1) {                                // indices of the chunk after that
+                nsrc = __ldg(A.csrc + (size_t)cn2 * CH + (lane & 15));
+                ndst = __ldg(A.cdst + (size_t)cn2 * CH + (lane & 15));
+                ntype = __ldg(A.ctype + cn2);
             }
             if (type != cur_type) { load_bfrag_h(bf, A.tabH + (size_t)type * TG_HFRAG32, lane); cur_type = type; }
             if (ptype != type && cn < c1)          // next type's 4 KB table towards L1 (32 lines of 128 B)
