@@ -321,18 +321,20 @@ k_gin(GinArgs A) {
             for (int o = 0; o < n_max; o += 8) {
                 int idx[8];
                 if (staged) {
+                    // the four lane groups walk a batch in rotated order (k + 2a): with equal degrees of 32 their lists
+                    // are 32 words apart and the same position would be four words of ONE bank
                     const int* ip = sidx + (e0 - e_lo);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) idx[k] = ip[min(o + k, last)];
+                    for (int k = 0; k < 8; ++k) idx[k] = ip[min(o + ((k + 2 * a) & 7), last)];
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) idx[k] = n_mine > 0 ? __ldg(A.col_src + e0 + min(o + k, last)) : 0;
+                    for (int k = 0; k < 8; ++k) idx[k] = n_mine > 0 ? __ldg(A.col_src + e0 + min(o + ((k + 2 * a) & 7), last)) : 0;
                 }
                 float4 v[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (o + k < n_mine) v[k] = ld_row4(A.xin, idx[k], q);
+                    if (o + ((k + 2 * a) & 7) < n_mine) v[k] = ld_row4(A.xin, idx[k], q);
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k) add4(sum, v[k]);
