@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGNN_ABI_VERSION 2
+#define TGNN_ABI_VERSION 3
 
 #define TGNN_BN_TRAIN 0   /* batch statistics over the rows of THIS call -- the reference's
                              behaviour: solver/ml_solver/ml_solver.py:129-131 ends in network.train() */
@@ -110,6 +110,7 @@ typedef struct tgnn_info {
     int64_t collectives_per_forward;
     int64_t conv_kernel;           /* adjacency kernel chosen for this graph: 0 = 3xTF32 edge-chunk (mma.sync),
                                       1 = tcgen05 S formulation, 2 = fp16-split edge-chunk (mma.sync.f16)      */
+    int64_t tile_rows;             /* destination rows per warp tile of the typed adjacency format (64 or 128)  */
     int64_t range_fallback_layers; /* layers of the LAST forward that kernel 2 handed to kernel 0 because an
                                       activation or root weight was outside the fp16 range (synchronises)      */
 } tgnn_info;
@@ -123,7 +124,7 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out);
  *   "g1" / "g2"      GraphConv / CollConv output (after BatchNorm) of the last layer that ran
  * tgnn_debug_graph copies the built graph structures out (sizes: tgnn_get_info; null = skip):
  *   cptr[n_tiles+1] ctype[n_chunks] csrc[adj_slots] cdst[adj_slots] inv_deg[n_own]
- *   col_ptr[n_own+1] col_src[e_col] type_rows[n_edge_types*d_e];  n_tiles = ceil(n_own/64), n_chunks = adj_slots/16. */
+ *   col_ptr[n_own+1] col_src[e_col] type_rows[n_edge_types*d_e];  n_tiles = ceil(n_own/tile_rows), n_chunks = adj_slots/16. */
 int tgnn_debug_set_stop_layer(tgnn_handle* h, int32_t layer);
 int tgnn_debug_read(tgnn_handle* h, const char* name, float* out, void* stream);
 int tgnn_debug_graph(tgnn_handle* h, int32_t* cptr, int32_t* ctype, int32_t* csrc, uint8_t* cdst, float* inv_deg,

@@ -70,7 +70,7 @@ def test_graph_structures_are_a_faithful_reencoding(dev):
                 d = cdst[sl][live]
                 assert len(set(d.tolist())) == len(d), "duplicate destination inside a group"
                 for s_, d_ in zip(csrc[sl][live], d):
-                    got.append((int(s_), t * 64 + int(d_), tuple(rows[ctype[c]])))
+                    got.append((int(s_), t * info["tile_rows"] + int(d_), tuple(rows[ctype[c]])))
     want = [(int(a), int(b), tuple(f)) for (a, b), f in zip(ai.t().tolist(), af.numpy())]
     assert sorted(got) == sorted(want)
     deg = np.bincount(ai[1].numpy(), minlength=n)

@@ -98,6 +98,7 @@ struct tgnn_handle {
     bool conv_s_only = false;                       // TGNN_CONV=s forces the tcgen05 S kernel whenever its format exists
     bool conv_h_only = false;                       // TGNN_CONV=h forces the fp16-split edge-chunk kernel (never S)
     bool use_s = false, use_h = false;              // decided per graph in set_graph
+    int tile_rows_forced = 0;                       // TGNN_TILE=64|128 (A/B runs)
     bool tables_streamed = false;                   // many edge types: one layer's weight tables at a time
 
     // workspace
@@ -311,6 +312,11 @@ void choose_conv_kernel(tgnn_handle* h) {
     h->use_h = !h->use_s && !h->conv_chunk_only;
 }
 
+// 128-row warp tiles give longer same-type runs (half the weight-table reloads, ~10 % fewer padded slots) but only 12
+// resident warps per SM instead of 16; measured on B200 at 1M nodes x deg 32 the two cancel (7.5 vs 7.3 ms per forward),
+// so 64 stays the default and TGNN_TILE=128 is kept for A/B runs.
+int tile_rows_for(tgnn_handle* h, int64_t) { return h->tile_rows_forced ? h->tile_rows_forced : WN_SMALL; }
+
 void alloc_workspace(tgnn_handle* h) {
     const int L = h->cfg.depth;
     const size_t rows = (size_t)h->g.n_rows, own = (size_t)h->g.n_own;
@@ -323,7 +329,7 @@ void alloc_workspace(tgnn_handle* h) {
     res(h->pre2[0], rows * F * sizeof(float));
     res(h->pre2[1], rows * F * sizeof(float));
     for (int k = 0; k < 4; ++k) res(h->fa[k], own * FIN_DIMS[k + 1] * sizeof(float));
-    size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->sm_count), (size_t)h->g.s_tiles, (size_t)gin_num_parts((int)own, h->sm_count),
+    size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count), (size_t)h->g.s_tiles, (size_t)gin_num_parts((int)own, h->sm_count),
                           (size_t)init_num_parts((int)own, h->sm_count)});
     size_t part_bytes = std::max(np * 64, (size_t)dense_row_blocks((int)own) * 2 * 256) * sizeof(double);
     res(h->partA, part_bytes);
@@ -423,7 +429,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
 
     // ---- message-passing layers ----------------------------------------------------------------
     const int n_layers = h->stop_layer >= 0 ? std::min(L, h->stop_layer + 1) : L;
-    const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->sm_count), np_gin = gin_num_parts(n_own, h->sm_count);
+    const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count), np_gin = gin_num_parts(n_own, h->sm_count);
     for (int i = 0; i < n_layers; ++i) {
         std::string pa = "brch_1_graph_conv_layers." + std::to_string(i);
         std::string pc = "brch_2_coll_conv_layers." + std::to_string(i);
@@ -436,7 +442,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.cptr = h->g.cptr.as<int>(); ca.ctype = h->g.ctype.as<int>(); ca.csrc = h->g.csrc.as<int>();
         ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->g.inv_deg.as<float>();
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
-        ca.n_own = n_own; ca.n_tiles = h->g.n_tiles;
+        ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn;
         lz.begin("conv");
         if (h->use_s) {
             launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
@@ -579,6 +585,8 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->conv_chunk_only = csel && std::string(csel) == "chunk";
         h->conv_s_only = csel && std::string(csel) == "s";
         h->conv_h_only = csel && std::string(csel) == "h";
+        const char* tsel = getenv("TGNN_TILE");
+        if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
         h->hflags.reserve((size_t)(2 * cfg->depth + 2) * sizeof(int));
         TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 2) * sizeof(int)));
         h->dev_error.reserve(sizeof(int));
@@ -653,7 +661,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         cudaStream_t st = (cudaStream_t)stream;
         h->graph_set = false;
         build_graph(h->g, h->scratch, h->cfg.d_e, n_nodes, n_nodes, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src,
-                    col_dst, !h->conv_chunk_only, st);
+                    col_dst, !h->conv_chunk_only, tile_rows_for(h, n_nodes), st);
         h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
         choose_conv_kernel(h);
         alloc_workspace(h);
@@ -703,7 +711,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
         h->graph_set = false;
         const int64_t n_rows = n_own + (h->world > 1 ? (int64_t)h->world * halo_slot : 0);
         build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst,
-                    !h->conv_chunk_only, st);
+                    !h->conv_chunk_only, tile_rows_for(h, n_own), st);
         h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
         choose_conv_kernel(h);
         if (n_send > 0) {
@@ -735,6 +743,7 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         out->workspace_bytes = (int64_t)h->workspace_bytes;
         out->collectives_per_forward = h->collectives;
         out->conv_kernel = h->use_s ? 1 : (h->use_h ? 2 : 0);
+        out->tile_rows = h->g.wn;
         out->range_fallback_layers = 0;
         if (h->use_h && h->graph_set) {
             DeviceGuard dg(h->cfg.device);

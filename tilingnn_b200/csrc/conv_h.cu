@@ -15,14 +15,13 @@
 // layer instead.  Values below 2^-14 keep an absolute accuracy of 2^-35, far under fp32 rounding of the O(1) sums.
 #include <cuda_fp16.h>
 
+#include "hsplit.cuh"
 #include "tgnn_internal.h"
 
 namespace tgnn {
 namespace {
 
 constexpr int XS = 36;          // padded shared-memory row stride (floats)
-constexpr int WARPS = 8;
-constexpr int TPB = WARPS * 32;
 constexpr float LO_INV = 1.0f / 2048.f;
 
 __device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
@@ -79,14 +78,21 @@ __device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int
     p[0] = v0; p[1] = v1;
 }
 
-__device__ __forceinline__ uint4 ld_rowh(const uint4* __restrict__ xh, int row, int q) { return __ldg(xh + (size_t)row * 8 + q); }
+// lane t's 32 bytes of a split row (both k16 steps) with one 256-bit load: a whole 128-byte line per 4 lanes, so the
+// L1 data stage spends one wavefront per gathered row instead of two
+__device__ __forceinline__ void ld_rowh2(const uint4* __restrict__ xh, int row, int t, uint4& k0, uint4& k1) {
+    const uint4* p = xh + (size_t)row * 8 + 2 * t;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(k0.x), "=r"(k0.y), "=r"(k0.z), "=r"(k0.w), "=r"(k1.x), "=r"(k1.y), "=r"(k1.z), "=r"(k1.w) : "l"(p));
+}
 
 // SPLIT = false: persistent, one warp per 64-row tile (large graphs).  SPLIT = true: one CTA per tile, its 8 warps take
 // every 8th chunk into private partial tiles that are summed in a fixed order -- the real layouts have ~10 tiles
 // (N ~ 600), where one warp walking ~60 latency-bound chunks per tile would leave the GPU idle.
-template <bool SPLIT>
-__global__ void __launch_bounds__(TPB, 2)
+template <int WN, int WARPS, bool SPLIT>
+__global__ void __launch_bounds__(WARPS * 32, WN == WN_BIG ? 1 : 2)
 k_conv_h(ConvArgs A) {
+    constexpr int TPB = WARPS * 32;
     if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) return;      // out of fp16 range: k_conv_adj takes the layer
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,8 +126,8 @@ k_conv_h(ConvArgs A) {
                 ntype = __ldg(A.ctype + c0 + cstep);
             }
             const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
-            if (sa >= 0) { pre[0] = ld_rowh(xh, sa, t); pre[1] = ld_rowh(xh, sa, 4 + t); }
-            if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
+            if (sa >= 0) ld_rowh2(xh, sa, t, pre[0], pre[1]);
+            if (sb >= 0) ld_rowh2(xh, sb, t, pre[2], pre[3]);
         }
         __syncwarp();
         for (int c = c0; c < c1; c += cstep) {
@@ -131,8 +137,8 @@ k_conv_h(ConvArgs A) {
             if (cn < c1) {                                 // rows of the next chunk (its indices arrived an iteration ago)
                 const int sa = __shfl_sync(0xffffffffu, nsrc, g), sb = __shfl_sync(0xffffffffu, nsrc, g + 8);
                 pre[0] = pre[1] = pre[2] = pre[3] = zero4;
-                if (sa >= 0) { pre[0] = ld_rowh(xh, sa, t); pre[1] = ld_rowh(xh, sa, 4 + t); }
-                if (sb >= 0) { pre[2] = ld_rowh(xh, sb, t); pre[3] = ld_rowh(xh, sb, 4 + t); }
+                if (sa >= 0) ld_rowh2(xh, sa, t, pre[0], pre[1]);
+                if (sb >= 0) ld_rowh2(xh, sb, t, pre[2], pre[3]);
             }
             psrc = nsrc; pdst = ndst; ptype = ntype;
             if (cn2 < c1) {                                // indices of the chunk after that
@@ -183,8 +189,8 @@ k_conv_h(ConvArgs A) {
             for (int rc = SPLIT ? warp : 0; rc < (SPLIT ? warp + 1 : WN / CH); ++rc) {
                 const int na = node0 + rc * CH + g, nb = na + 8;
                 uint4 cur[4] = {zero4, zero4, zero4, zero4};
-                if (na < A.n_own) { cur[0] = ld_rowh(xh, na, t); cur[1] = ld_rowh(xh, na, 4 + t); }
-                if (nb < A.n_own) { cur[2] = ld_rowh(xh, nb, t); cur[3] = ld_rowh(xh, nb, 4 + t); }
+                if (na < A.n_own) ld_rowh2(xh, na, t, cur[0], cur[1]);
+                if (nb < A.n_own) ld_rowh2(xh, nb, t, cur[2], cur[3]);
                 float m[4][4];
                 chunk_mma_h(cur, bf, m);
                 acc_add8(tile_acc + (rc * CH + g) * XS + 8 * t, m, 0);
@@ -212,19 +218,20 @@ k_conv_h(ConvArgs A) {
 
 }  // namespace
 
-static size_t conv_h_smem() { return (size_t)WARPS * (WN * XS) * sizeof(float); }
-
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool attr = false;
+    const size_t smem_small = (size_t)8 * WN_SMALL * XS * sizeof(float), smem_big = (size_t)12 * WN_BIG * XS * sizeof(float);
     if (!attr) {
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_h_smem()));
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_h_smem()));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_BIG, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
         attr = true;
     }
     // same grid as k_conv_adj: the BatchNorm partial layout is shared by the two kernels
-    const int blocks = conv_adj_num_parts(a.n_tiles, sm_count) / WARPS;
-    if (conv_split_tiles(a.n_tiles, sm_count)) k_conv_h<true><<<blocks, TPB, conv_h_smem(), st>>>(a);
-    else k_conv_h<false><<<blocks, TPB, conv_h_smem(), st>>>(a);
+    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
+    if (a.wn == WN_BIG) k_conv_h<WN_BIG, 12, false><<<g.blocks, 12 * 32, smem_big, st>>>(a);
+    else if (g.split) k_conv_h<WN_SMALL, 8, true><<<g.blocks, 256, smem_small, st>>>(a);
+    else k_conv_h<WN_SMALL, 8, false><<<g.blocks, 256, smem_small, st>>>(a);
     TGNN_CUDA(cudaGetLastError());
 }
 

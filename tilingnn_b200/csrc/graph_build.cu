@@ -96,26 +96,26 @@ __global__ void k_gather_type_rows(const float* __restrict__ feat, int d_e, cons
     rows[i] = feat[(int64_t)rep_edge[t] * d_e + k];
 }
 
-// key = (warp tile << (6 + tb)) | (type << 6) | local destination;  tb = bits of the largest type id
+// key = (warp tile << (db + tb)) | (type << db) | local destination;  tb = bits of the largest type id, db = log2(wn)
 __global__ void k_adj_keys(const int64_t* __restrict__ dst, const int* __restrict__ type_of_edge, int64_t e,
-                           int64_t n_own, int tb, unsigned long long* __restrict__ key, int* __restrict__ eid, int* __restrict__ deg) {
+                           int64_t n_own, int tb, int db, unsigned long long* __restrict__ key, int* __restrict__ eid, int* __restrict__ deg) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= e) return;
     long long d = dst[i];
     if (d < 0 || d >= n_own) d = 0;                     // flagged by k_validate; keep the access in range
-    unsigned long long tile = (unsigned long long)(d / WN);
-    unsigned long long dl = (unsigned long long)(d % WN);
-    key[i] = (tile << (6 + tb)) | ((unsigned long long)type_of_edge[i] << 6) | dl;
+    unsigned long long tile = (unsigned long long)(d >> db);
+    unsigned long long dl = (unsigned long long)(d & ((1ll << db) - 1));
+    key[i] = (tile << (db + tb)) | ((unsigned long long)type_of_edge[i] << db) | dl;
     eid[i] = (int)i;
     atomicAdd(&deg[d], 1);
 }
 
-__global__ void k_adj_flags(const unsigned long long* __restrict__ key, int64_t e,
+__global__ void k_adj_flags(const unsigned long long* __restrict__ key, int64_t e, int db,
                             int* __restrict__ run_head, int* __restrict__ run_start_seed,
                             int* __restrict__ grp_start_seed) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= e) return;
-    bool rh = (i == 0) || ((key[i] >> 6) != (key[i - 1] >> 6));
+    bool rh = (i == 0) || ((key[i] >> db) != (key[i - 1] >> db));
     bool gh = (i == 0) || (key[i] != key[i - 1]);
     run_head[i] = rh ? 1 : 0;
     run_start_seed[i] = rh ? (int)i : 0;
@@ -149,22 +149,22 @@ __global__ void k_run_chunks(const int* __restrict__ run_pos, const int* __restr
 // per run: chunk types, and the end of the tile's chunk range if this is the tile's last run
 __global__ void k_run_fill(const unsigned long long* __restrict__ key, const int* __restrict__ run_pos,
                            const int* __restrict__ run_chunks, const int* __restrict__ chunk_base,
-                           int n_runs, int tb, int* __restrict__ ctype, int* __restrict__ tile_end) {
+                           int n_runs, int tb, int db, int* __restrict__ ctype, int* __restrict__ tile_end) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_runs) return;
     unsigned long long k = key[run_pos[r]];
-    int type = (int)((k >> 6) & ((1ull << tb) - 1ull));
-    long long tile = (long long)(k >> (6 + tb));
+    int type = (int)((k >> db) & ((1ull << tb) - 1ull));
+    long long tile = (long long)(k >> (db + tb));
     int base = chunk_base[r], nc = run_chunks[r];
     for (int c = 0; c < nc; ++c) ctype[base + c] = type;
-    bool last = (r + 1 == n_runs) || ((long long)(key[run_pos[r + 1]] >> (6 + tb)) != tile);
+    bool last = (r + 1 == n_runs) || ((long long)(key[run_pos[r + 1]] >> (db + tb)) != tile);
     if (last) tile_end[tile] = base + nc;
 }
 
 __global__ void k_adj_scatter(const unsigned long long* __restrict__ key, const int* __restrict__ eid_sorted,
                               const int64_t* __restrict__ src, int64_t e,
                               const int* __restrict__ run_idx_incl, const int* __restrict__ run_pos,
-                              const int* __restrict__ run_chunks, const int* __restrict__ chunk_base,
+                              const int* __restrict__ run_chunks, const int* __restrict__ chunk_base, int db,
                               int* __restrict__ csrc, uint8_t* __restrict__ cdst) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= e) return;
@@ -173,7 +173,7 @@ __global__ void k_adj_scatter(const unsigned long long* __restrict__ key, const 
     int g = 2 * run_chunks[r];
     int64_t slot = (int64_t)chunk_base[r] * CH + (int64_t)(p % g) * GRP + p / g;
     csrc[slot] = (int)src[eid_sorted[i]];
-    cdst[slot] = (uint8_t)(key[i] & 63ull);
+    cdst[slot] = (uint8_t)(key[i] & ((1ull << db) - 1ull));
 }
 
 __global__ void k_fill_int(int* __restrict__ p, int64_t n, int v) {
@@ -292,14 +292,17 @@ int read_int(const int* dptr, cudaStream_t st) {
 
 void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
-                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, cudaStream_t st) {
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, int wn, cudaStream_t st) {
+    TGNN_CHECK(wn == WN_SMALL || wn == WN_BIG, "internal: bad warp-tile height");
+    const int db = wn == WN_BIG ? 7 : 6;
+    g.wn = wn;
     TGNN_CHECK(n_own > 0 && n_rows >= n_own, "tgnn_set_graph: need n_nodes > 0");
     TGNN_CHECK(n_rows < (1ll << 31) - 64, "tgnn_set_graph: more than 2^31 rows per GPU is not supported");
     TGNN_CHECK(e_adj >= 0 && e_adj < (1ll << 31) - 64 && e_col >= 0 && e_col < (1ll << 31) - 64,
                "tgnn_set_graph: edge count per GPU must be below 2^31");
     sc.reset();
     g.n_own = n_own; g.n_rows = n_rows;
-    g.n_tiles = (int)((n_own + WN - 1) / WN);
+    g.n_tiles = (int)((n_own + wn - 1) / wn);
     int* err = sc.get<int>(1);
     TGNN_CUDA(cudaMemsetAsync(err, 0, sizeof(int), st));
 
@@ -339,14 +342,14 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         unsigned long long* k0 = h0;      // reuse
         unsigned long long* k1 = h1;
         const int tb = bits_for((unsigned long long)(n_types > 0 ? n_types - 1 : 0));
-        k_adj_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, tb, k0, id0, deg);
-        int end_bit = 6 + tb + bits_for((unsigned long long)g.n_tiles);
+        k_adj_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, tb, db, k0, id0, deg);
+        int end_bit = db + tb + bits_for((unsigned long long)g.n_tiles);
         TGNN_CHECK(end_bit <= 64, "tgnn_set_graph: sort key overflow (tiles x edge types)");
         sort_pairs(sc, k0, k1, id0, id1, e_adj, end_bit, st);
         int* run_head = head;
         int* run_seed = sc.get<int>(e_adj);
         int* grp_seed = sc.get<int>(e_adj);
-        k_adj_flags<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, run_head, run_seed, grp_seed);
+        k_adj_flags<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, db, run_head, run_seed, grp_seed);
         int* run_idx = scan;
         incl_sum(sc, run_head, run_idx, e_adj, st);
         int* grp_start = sc.get<int>(e_adj);
@@ -372,12 +375,12 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         TGNN_CUDA(cudaMemsetAsync(g.cdst.p, 0, (size_t)n_chunks * CH, st));
         int* tile_end = sc.get<int>(g.n_tiles);
         TGNN_CUDA(cudaMemsetAsync(tile_end, 0, (size_t)g.n_tiles * sizeof(int), st));
-        k_run_fill<<<nblk(n_runs), TPB, 0, st>>>(k1, run_pos, run_chunks, chunk_base, n_runs, tb,
+        k_run_fill<<<nblk(n_runs), TPB, 0, st>>>(k1, run_pos, run_chunks, chunk_base, n_runs, tb, db,
                                                   g.ctype.as<int>(), tile_end);
         k_cptr_first<<<1, 32, 0, st>>>(g.cptr.as<int>());
         incl_max(sc, tile_end, g.cptr.as<int>() + 1, g.n_tiles, st);
         k_adj_scatter<<<nblk(e_adj), TPB, 0, st>>>(k1, id1, adj_src, e_adj, run_idx, run_pos, run_chunks,
-                                                    chunk_base, g.csrc.as<int>(), g.cdst.as<uint8_t>());
+                                                    chunk_base, db, g.csrc.as<int>(), g.cdst.as<uint8_t>());
         // ---------------- adjacency: S format (tcgen05 kernel) -----------------------------------------
         g.has_s = false;
         if (want_s && n_types <= S_MAX_TYPES) {

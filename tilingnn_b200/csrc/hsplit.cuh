@@ -15,6 +15,10 @@ __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
+// Position of the uint4 holding channels 4q..4q+3 inside a split row: lane t of k_conv_h needs the pieces q = t (k16
+// step 0) and q = 4 + t (step 1), so they are stored next to each other and come in with ONE 256-bit load.
+__host__ __device__ __forceinline__ int xh_pos(int q) { return 2 * (q & 3) + (q >> 2); }
+
 // four consecutive channels -> {hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)}; `bad` is set when a value is outside
 // the fp16 range (or NaN)
 __device__ __forceinline__ uint4 split_h4(const float4& v, bool& bad) {

@@ -151,7 +151,8 @@ __device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int
     p[0] = v0; p[1] = v1;
 }
 
-__global__ void __launch_bounds__(TPB, 2)
+template <int WN, int NW>
+__global__ void __launch_bounds__(NW * 32, WN == WN_BIG ? 1 : 2)
 k_conv_adj(ConvArgs A) {
     // paired with k_conv_h (conv_h.cu): when range flags are given, this kernel only takes the layer if one is raised
     if (A.flag_x && !(*A.flag_x | (A.flag_w ? *A.flag_w : 0))) return;
@@ -159,7 +160,7 @@ k_conv_adj(ConvArgs A) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* acc = smem + warp * (WN * XS);
     const int g = lane >> 2, t = lane & 3;
-    const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
+    const int gwarp = blockIdx.x * NW + warp, nwarp = gridDim.x * NW;
     double s1 = 0.0, s2 = 0.0;
     const float bias_c = __ldg(A.bias + lane);
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -450,7 +451,7 @@ __global__ void k_combine(const float4* __restrict__ pre1, const float* __restri
         o.w = bn_apply(p.w, c1, c + 3, 32) * g2.w;
         if (res) { float4 r = __ldg(res + i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
         out[i] = o;
-        if (xh) xh[i] = split_h4(o, bad);        // float4 i of a row IS uint4 i of the split row (conv_h.cu)
+        if (xh) xh[(i & ~(int64_t)7) + xh_pos((int)(i & 7))] = split_h4(o, bad);     // float4 q of a row -> uint4 xh_pos(q)
     }
     if (bad) *flag = 1;
 }
@@ -541,7 +542,7 @@ k_init(InitArgs A) {
                     const uint32_t wl = l16 | (__shfl_down_sync(0xffffffffu, l16, 1) << 16);
                     const int src = (lane & ~3) + 2 * (lane & 1);
                     const uint32_t a = __shfl_sync(0xffffffffu, wh, src), b = __shfl_sync(0xffffffffu, wl, src);
-                    A.xh[(size_t)(base + j) * F + lane] = (lane & 2) ? b : a;
+                    A.xh[(size_t)(base + j) * F + 4 * xh_pos(lane >> 2) + (lane & 3)] = (lane & 2) ? b : a;
                     bad |= !(fabsf(o2) <= TG_H_LIMIT);
                 }
             } else {
@@ -592,7 +593,7 @@ k_init_wide(InitArgs A) {
                     const uint32_t wl = l16 | (__shfl_down_sync(0xffffffffu, l16, 1) << 16);
                     const int src = (lane & ~3) + 2 * (lane & 1);
                     const uint32_t a = __shfl_sync(0xffffffffu, wh, src), b = __shfl_sync(0xffffffffu, wl, src);
-                    A.xh[(size_t)node * F + lane] = (lane & 2) ? b : a;
+                    A.xh[(size_t)node * F + 4 * xh_pos(lane >> 2) + (lane & 3)] = (lane & 2) ? b : a;
                     if (!(fabsf(o2) <= TG_H_LIMIT)) *A.flag = 1;
                 }
                 continue;
@@ -842,7 +843,7 @@ __global__ void k_halo_unpack(const float4* __restrict__ recv, int world, int ra
         a[(size_t)(n_own + r) * 8 + c] = v;
         if (xh) {                                    // mirrored rows feed k_conv_h too
             bool bad = false;
-            xh[(size_t)(n_own + r) * 8 + c] = split_h4(v, bad);
+            xh[(size_t)(n_own + r) * 8 + xh_pos(c)] = split_h4(v, bad);
             if (bad) *flag = 1;
         }
     } else if (b) b[(size_t)(n_own + r) * 8 + (c - 8)] = v;
@@ -859,14 +860,19 @@ int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_pe
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static size_t conv_smem() { return (size_t)WARPS * (WN * XS) * sizeof(float); }
 static size_t gin_smem() { return (size_t)(GIN_WFLOATS + WARPS * GIN_WARP_FLOATS) * sizeof(float); }
 
-// few tiles (small graphs): one CTA per tile so that k_conv_h can split a tile's chunks over its 8 warps
-bool conv_split_tiles(int n_tiles, int sm_count) { return n_tiles <= 2 * sm_count; }
-static int conv_blocks(int n_tiles, int sm_count) {
-    if (conv_split_tiles(n_tiles, sm_count)) return n_tiles < 1 ? 1 : n_tiles;
-    return persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2);
+ConvGeom conv_geom(int n_tiles, int wn, int sm_count) {
+    ConvGeom g{};
+    if (wn == WN_BIG) {
+        g.warps = 12; g.split = false;
+        g.blocks = persistent_blocks((n_tiles + 11) / 12, sm_count, 1);
+    } else {
+        g.warps = WARPS;
+        g.split = n_tiles <= 2 * sm_count;          // few tiles (small graphs): one CTA per tile, chunks split over its warps
+        g.blocks = g.split ? (n_tiles < 1 ? 1 : n_tiles) : persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2);
+    }
+    return g;
 }
 static int gin_blocks(int n_own, int sm_count) {
     int chunks = (n_own + CH - 1) / CH;
@@ -874,18 +880,21 @@ static int gin_blocks(int n_own, int sm_count) {
 }
 static int init_blocks(int n_own, int sm_count) { return persistent_blocks((n_own + WARPS * 32 - 1) / (WARPS * 32), sm_count, 4); }
 
-int conv_adj_num_parts(int n_tiles, int sm_count) { return conv_blocks(n_tiles, sm_count) * WARPS; }
 int gin_num_parts(int n_own, int sm_count) { return gin_blocks(n_own, sm_count) * WARPS; }
 int init_num_parts(int n_own, int sm_count) { return init_blocks(n_own, sm_count) * WARPS; }
 int dense_row_blocks(int n) { return (n + DM - 1) / DM; }
 
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st) {
     static bool attr = false;
+    const size_t smem_small = (size_t)WARPS * WN_SMALL * XS * sizeof(float), smem_big = (size_t)12 * WN_BIG * XS * sizeof(float);
     if (!attr) {
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem()));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj<WN_SMALL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj<WN_BIG, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
         attr = true;
     }
-    k_conv_adj<<<conv_blocks(a.n_tiles, sm_count), TPB, conv_smem(), st>>>(a);
+    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
+    if (a.wn == WN_BIG) k_conv_adj<WN_BIG, 12><<<g.blocks, 12 * 32, smem_big, st>>>(a);
+    else k_conv_adj<WN_SMALL, WARPS><<<g.blocks, TPB, smem_small, st>>>(a);
     TGNN_CUDA(cudaGetLastError());
 }
 

@@ -16,7 +16,8 @@
 namespace tgnn {
 
 constexpr int F = 32;            // network_width (inputs/config.py:38 of the reference)
-constexpr int WN = 64;           // destination rows owned by one warp tile of the typed adjacency format
+constexpr int WN_SMALL = 64;     // destination rows owned by one warp tile of the typed adjacency format ...
+constexpr int WN_BIG = 128;      // ... and for large graphs: longer same-type runs (fewer weight-table reloads, less padding)
 constexpr int CH = 16;           // edge slots per chunk (all of one edge type)
 constexpr int GRP = 8;           // slots per group; destinations are distinct inside a group
 constexpr int MAX_TYPES = 1 << 22; // distinct adjacency feature rows; each costs a 12 KB weight table per resident layer
@@ -69,7 +70,8 @@ struct Graph {
     int64_t n_own = 0, n_rows = 0, n_global = 0;
     int64_t e_adj = 0, e_col = 0;
     int n_types = 0;
-    int n_tiles = 0;          // ceil(n_own / WN)
+    int wn = WN_SMALL;        // rows per warp tile (WN_SMALL or WN_BIG)
+    int n_tiles = 0;          // ceil(n_own / wn)
     int n_chunks = 0;
     // typed adjacency tiles
     DevBuf cptr;              // int32 [n_tiles + 1]   chunk range per warp tile
@@ -110,7 +112,7 @@ struct Scratch {
 // graph_build.cu
 void build_graph(Graph& g, Scratch& scratch, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
-                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, cudaStream_t st);
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, int wn, cudaStream_t st);
 constexpr int S_BM = 128;         // destination rows per tile of the S format
 constexpr int S_OFF_STRIDE = 136; // uint16 per pass (129 used; 272 B keeps 16-byte alignment)
 constexpr int S_MAX_TYPES = 120;  // the S path is chosen only when K + 1 (root) passes fit its per-tile tables
@@ -126,6 +128,7 @@ struct ConvArgs {
     float* out;              // pre1 [n_own][32]  LeakyReLU(conv), before BatchNorm
     double* part;            // [n_part][64]  per-warp partial sums (sum, sum of squares)
     int n_own, n_tiles;
+    int wn;                  // rows per warp tile: WN_SMALL or WN_BIG
     // fp16-split operands of k_conv_h (conv_h.cu) and the range flags that arbitrate between it and k_conv_adj:
     // k_conv_h runs when both flags are 0, k_conv_adj when flag_x is null (forced) or a flag is raised
     const uint4* xh;         // [n_rows][8]   split copy of xin: per 4 channels {hi01, hi23, lo01, lo23} fp16 pairs
@@ -133,8 +136,12 @@ struct ConvArgs {
     const int* flag_x;       // raised by the producer of xin when a value is outside the fp16 range
     const int* flag_w;       // raised at table build when a root weight is outside the fp16 range
 };
-int conv_adj_num_parts(int n_tiles, int sm_count);
-bool conv_split_tiles(int n_tiles, int sm_count);   // small graphs: grid = one CTA per tile (k_conv_h splits the chunks)
+// launch geometry shared by k_conv_adj and k_conv_h (same grid => same BatchNorm partial layout):
+//   wn = 64 : 8 warps per CTA, 2 CTAs per SM; few tiles (small graphs) => one CTA per tile, k_conv_h splits its chunks
+//   wn = 128: 12 warps per CTA (216 KB of accumulator tiles), 1 CTA per SM
+struct ConvGeom { int blocks, warps; bool split; };
+ConvGeom conv_geom(int n_tiles, int wn, int sm_count);
+inline int conv_adj_num_parts(int n_tiles, int wn, int sm_count) { ConvGeom g = conv_geom(n_tiles, wn, sm_count); return g.blocks * g.warps; }
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
 
 // fp16-split edge-chunk kernel (conv_h.cu)

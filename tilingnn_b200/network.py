@@ -353,7 +353,7 @@ class TilinGNN(nn.Module):
         """Built graph structures as CPU tensors (tests)."""
         nat = self._ensure_handle()
         inf = self.info()
-        n_tiles = (inf["n_own"] + 63) // 64
+        n_tiles = (inf["n_own"] + inf["tile_rows"] - 1) // inf["tile_rows"]
         n_chunks = inf["adj_slots"] // 16
         t = dict(cptr=torch.zeros(n_tiles + 1, dtype=torch.int32), ctype=torch.zeros(n_chunks, dtype=torch.int32),
                  csrc=torch.zeros(n_chunks * 16, dtype=torch.int32), cdst=torch.zeros(n_chunks * 16, dtype=torch.uint8),
