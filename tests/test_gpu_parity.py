@@ -177,6 +177,19 @@ def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2}[kernel] and info["range_fallback_layers"] == 0
 
 
+def test_gin_mlp_on_3xtf32(dev, monkeypatch):
+    """the GIN MLP's layers 2-3 run on fp16-split operands by default; TGNN_GIN=tf32 keeps all three on 3xTF32 (the
+    variant used when a GIN weight is outside the fp16 range)."""
+    monkeypatch.setenv("TGNN_GIN", "tf32")
+    from tilingnn_b200 import synthetic as syn
+    x, ai, af, ci = syn.lattice_graph(6000, 32, 32, seed=3)
+    p = orc.make_params(3, 19, 4, seed=3)
+    gold = orc.forward(p, x, ai, af, ci, depth=4, dtype=torch.float64)[:, 0].numpy()
+    err = np.abs(run(make_net(p, 3, 19, 4, dev), x, ai, af, ci, dev) - gold).max()
+    print(f"TGNN_GIN=tf32: max err {err:.2e}")
+    assert err <= TOL
+
+
 def test_fp16_range_guard_hands_layers_to_the_tf32_kernel(dev, monkeypatch):
     """k_conv_h works on fp16-split operands; activations beyond +-60000 (here: a BatchNorm gain of 1e6 in layer 0)
     and root weights beyond it (layer 2) must raise the range flags so the 3xTF32 kernel takes those layers."""

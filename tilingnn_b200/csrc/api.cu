@@ -85,6 +85,8 @@ struct tgnn_handle {
     DevBuf dev_error;                               // int: device-side error flag (pipeline timeouts)
     bool dense_ffma = false;                        // TGNN_DENSE=ffma selects the CUDA-core dense stage (debug A/B)
     std::vector<float> gin_eps;
+    std::vector<int> gin_hmlp;                      // per layer: GIN MLP layers 2, 3 may use the fp16 tables
+    bool gin_tf32_only = getenv("TGNN_GIN") && std::string(getenv("TGNN_GIN")) == "tf32";   // A/B runs
     float fin_last_bias = 0.f;
     DevBuf coef;                                    // all BatchNorm coefficient blocks
     size_t coef_init[2]{}, coef_fin[4]{};
@@ -200,7 +202,7 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
     const int L = h->cfg.depth;
     h->init_w1t.reserve(32 * 32 * sizeof(float));
     launch_transpose(h->P("init_node_feature_trans.mlp.1.linear.weight"), h->init_w1t.as<float>(), 32, 32, st);
-    h->gin_wt.clear(); h->gin_eps.assign(L, 0.f);
+    h->gin_wt.clear(); h->gin_eps.assign(L, 0.f); h->gin_hmlp.assign(L, 0);
     DevBuf tmp_t;
     for (int i = 0; i < L; ++i) {
         std::string p = "brch_2_coll_conv_layers." + std::to_string(i);
@@ -217,11 +219,19 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
             tmp_t.reserve((size_t)dims[k] * dims[k + 1] * sizeof(float));
             launch_transpose(h->P(lin + ".weight"), tmp_t.as<float>(), dims[k + 1], dims[k], st);       // -> [K][N]
             launch_frag_pack(tmp_t.as<float>(), dims[k], dims[k + 1], kmap[k], nmap[k], wf + off[k], st);
+            if (k >= 1)          // fp16 tables of layers 2, 3 behind the 3xTF32 block; range flag in the scratch int
+                launch_frag_pack_h16(tmp_t.as<float>(), dims[k], dims[k + 1], nmap[k], wf + 2048 + 4096 + 4096 + 128 + (k - 1) * 2048,
+                                     h->dev_error.as<int>() + 1, st);
             TGNN_CUDA(cudaMemcpyAsync(boff, h->P(lin + ".bias"), dims[k + 1] * sizeof(float), cudaMemcpyDeviceToDevice, st));
             boff += dims[k + 1];
             TGNN_CUDA(cudaStreamSynchronize(st));                                                        // tmp_t is reused
         }
         TGNN_CUDA(cudaMemcpyAsync(&h->gin_eps[i], h->P(p + ".ginConv.eps"), sizeof(float), cudaMemcpyDeviceToHost, st));
+        int out_of_range = 0;
+        TGNN_CUDA(cudaMemcpyAsync(&out_of_range, h->dev_error.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TGNN_CUDA(cudaStreamSynchronize(st));
+        h->gin_hmlp[i] = out_of_range == 0 && !h->gin_tf32_only;
+        TGNN_CUDA(cudaMemsetAsync(h->dev_error.as<int>() + 1, 0, sizeof(int), st));
     }
     h->fin_wt.clear(); h->fin_whl.clear();
     int dims[5] = {F * (L + 1), 256, 128, 64, F};
@@ -465,7 +475,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ga.xin = i == 0 ? h->mid[0]->as<float>() : h->pre2[1].as<float>();
         ga.col_ptr = h->g.col_ptr.as<int>(); ga.col_src = h->g.col_src.as<int>();
         ga.wfrag = h->gin_wt[i]->as<float>();
-        ga.eps = h->gin_eps[i];
+        ga.eps = h->gin_eps[i]; ga.hmlp = h->gin_hmlp[i];
         ga.out = h->pre2[0].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
         lz.begin("gin"); launch_gin(ga, h->sm_count, st); lz.end(1);
 
@@ -589,8 +599,8 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
         h->hflags.reserve((size_t)(2 * cfg->depth + 2) * sizeof(int));
         TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 2) * sizeof(int)));
-        h->dev_error.reserve(sizeof(int));
-        TGNN_CUDA(cudaMemset(h->dev_error.p, 0, sizeof(int)));
+        h->dev_error.reserve(2 * sizeof(int));                         // [0] pipeline timeout flag, [1] scratch flag of pack_params
+        TGNN_CUDA(cudaMemset(h->dev_error.p, 0, 2 * sizeof(int)));
         declare_params(h.get());
         *out = h.release();
     });

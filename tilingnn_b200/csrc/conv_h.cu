@@ -26,12 +26,6 @@ constexpr float LO_INV = 1.0f / 2048.f;
 
 __device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
 
-__device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
 struct BFragH { uint4 h[2][2], l[2][2]; };
 
 __device__ __forceinline__ void load_bfrag_h(BFragH& b, const uint32_t* __restrict__ tab, int lane) {

@@ -263,25 +263,42 @@ k_conv_adj(ConvArgs A) {
 // ------------------------------------------------------------------------------------------------
 constexpr int GIN_W1 = 2048, GIN_W2 = 4096, GIN_W3 = 4096;                 // floats (hi + lo)
 constexpr int GIN_WFLOATS = GIN_W1 + GIN_W2 + GIN_W3 + 128;                // + b1[32] b2[64] b3[32]
+constexpr int GIN_W2H = 2048, GIN_W3H = 2048;                              // fp16 hi|lo tables of layers 2, 3 (float-sized words)
+constexpr int GIN_WFLOATS_H = GIN_W1 + GIN_W2H + GIN_W3H + 128;
+static_assert(TG_GIN_WFLOATS == GIN_WFLOATS + GIN_W2H + GIN_W3H, "gin weight buffer layout");
 constexpr int GIN_IDX_CAP = 1024;                                         // staged neighbour indices per 16-node chunk
 constexpr int GIN_WARP_FLOATS = CH * XS + GIN_IDX_CAP;
 
 __device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
 
+// HMLP: layers 2 and 3 of the MLP on fp16-split operands (mma.sync m16n8k16: half the MMAs and half the weight-table
+// reads of 3xTF32).  Their inputs are sigmoid outputs in (0, 1), always inside the fp16 range; layer 1 sees unbounded
+// neighbour sums and stays on 3xTF32.  The host picks HMLP only when the layer's weights are inside the range too.
+// weight buffer (global): [W1 | W2 | W3 | biases] (3xTF32 tables) then [W2h | W3h] (fp16 hi|lo tables).
+template <bool HMLP>
 __global__ void __launch_bounds__(TPB, 2)
 k_gin(GinArgs A) {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < GIN_WFLOATS / 4; i += TPB)
-        reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(A.wfrag) + i);
+    constexpr int WF = HMLP ? GIN_WFLOATS_H : GIN_WFLOATS;
+    if (HMLP) {
+        const float4* src = reinterpret_cast<const float4*>(A.wfrag);
+        float4* dst = reinterpret_cast<float4*>(smem);
+        for (int i = threadIdx.x; i < GIN_W1 / 4; i += TPB) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < (GIN_W2H + GIN_W3H) / 4; i += TPB) dst[GIN_W1 / 4 + i] = __ldg(src + GIN_WFLOATS / 4 + i);
+        for (int i = threadIdx.x; i < 128 / 4; i += TPB) dst[(GIN_W1 + GIN_W2H + GIN_W3H) / 4 + i] = __ldg(src + (GIN_W1 + GIN_W2 + GIN_W3) / 4 + i);
+    } else {
+        for (int i = threadIdx.x; i < GIN_WFLOATS / 4; i += TPB)
+            reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(A.wfrag) + i);
+    }
     __syncthreads();
     const float4* W1 = reinterpret_cast<const float4*>(smem);
     const float4* W2 = reinterpret_cast<const float4*>(smem + GIN_W1);
-    const float4* W3 = reinterpret_cast<const float4*>(smem + GIN_W1 + GIN_W2);
-    const float* b1 = smem + GIN_W1 + GIN_W2 + GIN_W3;
+    const float4* W3 = reinterpret_cast<const float4*>(smem + GIN_W1 + (HMLP ? GIN_W2H : GIN_W2));
+    const float* b1 = smem + WF - 128;
     const float* b2 = b1 + 32;
     const float* b3 = b2 + 64;
-    float* xs = smem + GIN_WFLOATS + warp * GIN_WARP_FLOATS;
+    float* xs = smem + WF + warp * GIN_WARP_FLOATS;
     int* sidx = reinterpret_cast<int*>(xs + CH * XS);
     const int a = lane >> 3, q = lane & 7;       // gather roles
     const int g = lane >> 2, t = lane & 3;       // mma roles
@@ -357,6 +374,75 @@ k_gin(GinArgs A) {
                 mma3(c1[2 * j], c1[2 * j + 1], ah, al, W1[((ks * 2 + 0) * 2 + j) * 32 + lane], W1[((ks * 2 + 1) * 2 + j) * 32 + lane]);
         }
         __syncwarp();
+        float c3[4][4];
+        if (HMLP) {
+            const uint4* W2h = reinterpret_cast<const uint4*>(W2);
+            const uint4* W3h = reinterpret_cast<const uint4*>(W3);
+            // ---- layer 2: 32 -> 64; A fragments = fp16 split of sigmoid(c1 + b1): n-tiles 2ks, 2ks+1 -> k16 step ks
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int nt = 2 * ks + hh;
+                    const float bA = b1[8 * nt + 2 * t], bB = b1[8 * nt + 2 * t + 1];
+                    split_h2(sigmoidf_nr(c1[nt][0] + bA), sigmoidf_nr(c1[nt][1] + bB), ah[ks][2 * hh], al[ks][2 * hh]);
+                    split_h2(sigmoidf_nr(c1[nt][2] + bA), sigmoidf_nr(c1[nt][3] + bB), ah[ks][2 * hh + 1], al[ks][2 * hh + 1]);
+                }
+            float c2[8][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float sm[2][4] = {}, mn[2][2][4] = {};
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint4 bh = W2h[((ks * 2 + 0) * 4 + j) * 32 + lane], bl = W2h[((ks * 2 + 1) * 4 + j) * 32 + lane];
+                    mma_f16(sm[0], al[ks][0], al[ks][1], al[ks][2], al[ks][3], bh.x, bh.y);
+                    mma_f16(sm[1], al[ks][0], al[ks][1], al[ks][2], al[ks][3], bh.z, bh.w);
+                    mma_f16(sm[0], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bl.x, bl.y);
+                    mma_f16(sm[1], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bl.z, bl.w);
+                    mma_f16(mn[ks][0], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bh.x, bh.y);
+                    mma_f16(mn[ks][1], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bh.z, bh.w);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c2[2 * j + u][i] = fmaf(sm[u][i], 1.0f / 2048.f, mn[0][u][i] + mn[1][u][i]);
+            }
+            // ---- layer 3: 64 -> 32 (output channels 8t..8t+7 per lane); A = fp16 split of sigmoid(c2 + b2) ----------
+            uint32_t a3h[4][4], a3l[4][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int nt = 2 * ks + hh;
+                    const float bA = b2[8 * nt + 2 * t], bB = b2[8 * nt + 2 * t + 1];
+                    split_h2(sigmoidf_nr(c2[nt][0] + bA), sigmoidf_nr(c2[nt][1] + bB), a3h[ks][2 * hh], a3l[ks][2 * hh]);
+                    split_h2(sigmoidf_nr(c2[nt][2] + bA), sigmoidf_nr(c2[nt][3] + bB), a3h[ks][2 * hh + 1], a3l[ks][2 * hh + 1]);
+                }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float sm[2][4] = {}, acc[2][4] = {};
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint4 bh = W3h[((ks * 2 + 0) * 2 + j) * 32 + lane], bl = W3h[((ks * 2 + 1) * 2 + j) * 32 + lane];
+                    float mn[2][4] = {};
+                    mma_f16(sm[0], a3l[ks][0], a3l[ks][1], a3l[ks][2], a3l[ks][3], bh.x, bh.y);
+                    mma_f16(sm[1], a3l[ks][0], a3l[ks][1], a3l[ks][2], a3l[ks][3], bh.z, bh.w);
+                    mma_f16(sm[0], a3h[ks][0], a3h[ks][1], a3h[ks][2], a3h[ks][3], bl.x, bl.y);
+                    mma_f16(sm[1], a3h[ks][0], a3h[ks][1], a3h[ks][2], a3h[ks][3], bl.z, bl.w);
+                    mma_f16(mn[0], a3h[ks][0], a3h[ks][1], a3h[ks][2], a3h[ks][3], bh.x, bh.y);
+                    mma_f16(mn[1], a3h[ks][0], a3h[ks][1], a3h[ks][2], a3h[ks][3], bh.z, bh.w);
+#pragma unroll
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[u][i] += mn[u][i];           // IEEE adds between the k16 steps
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) c3[2 * j + u][i] = fmaf(sm[u][i], 1.0f / 2048.f, acc[u][i]);
+            }
+        } else {
         // ---- layer 2: 32 -> 64, A = sigmoid(c1 + b1) straight from the C fragments ------------------
         float c2[8][4] = {};
 #pragma unroll
@@ -372,7 +458,10 @@ k_gin(GinArgs A) {
                 mma3(c2[2 * j], c2[2 * j + 1], ah, al, W2[((ks * 2 + 0) * 4 + j) * 32 + lane], W2[((ks * 2 + 1) * 4 + j) * 32 + lane]);
         }
         // ---- layer 3: 64 -> 32 (output channels 8t..8t+7 per lane) ----------------------------------
-        float c3[4][4] = {};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c3[nt][i] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
             const float bA = b2[8 * ks + 2 * t], bB = b2[8 * ks + 2 * t + 1];
@@ -384,6 +473,7 @@ k_gin(GinArgs A) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
                 mma3(c3[2 * j], c3[2 * j + 1], ah, al, W3[((ks * 2 + 0) * 2 + j) * 32 + lane], W3[((ks * 2 + 1) * 2 + j) * 32 + lane]);
+        }
         }
         // ---- sigmoid, LeakyReLU, store, statistics ------------------------------------------------
 #pragma unroll
@@ -819,6 +909,18 @@ __global__ void k_frag_pack(const float* __restrict__ w, int K, int N, int kmap,
     frag_store(out, i / N, i % N, N, kmap, nmap, (double)w[i]);
 }
 
+// fp16 hi|lo fragment table (natural k order) of a k-major [K][N] matrix; raises *flag outside the fp16 range
+__global__ void k_frag_pack_h16(const float* __restrict__ w, int K, int N, int nmap, __half* __restrict__ out, int* __restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * N) return;
+    const float v = w[i];
+    __half hi, lo;
+    split_h(v, hi, lo);
+    out[hfrag_nat_half_index(i / N, i % N, N, nmap, 0)] = hi;
+    out[hfrag_nat_half_index(i / N, i % N, N, nmap, 1)] = lo;
+    if (!(fabsf(v) <= TG_H_LIMIT)) *flag = 1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // halo pack / unpack: rows of two [*, 32] tensors <-> [slot rows][64] exchange buffer
 // ------------------------------------------------------------------------------------------------
@@ -860,7 +962,7 @@ int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_pe
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-static size_t gin_smem() { return (size_t)(GIN_WFLOATS + WARPS * GIN_WARP_FLOATS) * sizeof(float); }
+static size_t gin_smem(bool hmlp) { return (size_t)((hmlp ? GIN_WFLOATS_H : GIN_WFLOATS) + WARPS * GIN_WARP_FLOATS) * sizeof(float); }
 
 ConvGeom conv_geom(int n_tiles, int wn, int sm_count) {
     ConvGeom g{};
@@ -901,10 +1003,17 @@ void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st) {
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        TGNN_CUDA(cudaFuncSetAttribute(k_gin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem()));
+        TGNN_CUDA(cudaFuncSetAttribute(k_gin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem(false)));
+        TGNN_CUDA(cudaFuncSetAttribute(k_gin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem(true)));
         attr = true;
     }
-    k_gin<<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(), st>>>(a);
+    if (a.hmlp) k_gin<true><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(true), st>>>(a);
+    else k_gin<false><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(false), st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_frag_pack_h16(const float* w_kn, int K, int N, int nmap, float* out, int* flag, cudaStream_t st) {
+    k_frag_pack_h16<<<(K * N + 255) / 256, 256, 0, st>>>(w_kn, K, N, nmap, reinterpret_cast<__half*>(out), flag);
     TGNN_CUDA(cudaGetLastError());
 }
 

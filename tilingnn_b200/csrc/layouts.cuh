@@ -63,4 +63,16 @@ __device__ __forceinline__ void hfrag_store(__half* tab, int k, int n, float w, 
     if (flag && !(fabsf(w) <= limit)) *flag = 1;
 }
 
+// ---- fp16 hi|lo fragment table of a k-major [K][N] matrix in NATURAL k order (k = 16 ks + 8 reg + 2 tt + e), for
+// the chained GIN layers whose A fragments are the previous layer's C fragments (k_gin<true>; kernels.cu) ----------
+//   uint4 index ((ks*2 + hl) * (N/16) + j)*32 + lane ; component 2(nt&1) + reg ; half e
+__host__ __device__ __forceinline__ size_t hfrag_nat_half_index(int k, int n, int N, int nmap, int hl) {
+    const int ks = k >> 4, r = k & 15, reg = r >> 3, tt = (r & 7) >> 1, e = r & 1;
+    int nt, g;
+    if (nmap == NMAP_NATURAL) { nt = n >> 3; g = n & 7; }
+    else { const int r8 = n & 7; nt = r8 >> 1; g = 2 * (n >> 3) + (r8 & 1); }
+    const int lane = g * 4 + tt, j = nt >> 1, comp = 2 * (nt & 1) + reg;
+    return ((((((size_t)ks * 2 + hl) * (N / 16) + j) * 32 + lane) * 4 + comp) * 2) + e;
+}
+
 }  // namespace tgnn

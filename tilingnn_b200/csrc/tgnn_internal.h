@@ -154,7 +154,8 @@ void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* er
 struct GinArgs {
     const float* xin;        // [n_rows][32]  output of the previous CollConv (written by k_combine), or h0
     const int* col_ptr; const int* col_src;
-    const float* wfrag;      // frag tables W1[2048] W2[4096] W3[4096] then b1[32] b2[64] b3[32]
+    const float* wfrag;      // 3xTF32 frag tables W1[2048] W2[4096] W3[4096], b1[32] b2[64] b3[32], then fp16 tables W2h[2048] W3h[2048]
+    int hmlp;                // layers 2, 3 of the MLP on the fp16 tables (their weights are inside the fp16 range)
     float eps;
     float* out;              // pre2 [n_own][32]
     double* part;            // [n_part][64]
@@ -227,8 +228,10 @@ void launch_transpose(const float* in, float* out, int rows, int cols, cudaStrea
 // frag table (tensor-core B fragments, hi|lo TF32 split) of a k-major [K][N] matrix; maps: see kernels.cu
 enum { TG_KMAP_GATHER = 0, TG_KMAP_NATURAL = 1, TG_KMAP_CHAIN = 2, TG_NMAP_NATURAL = 0, TG_NMAP_CONTIG8 = 1 };
 constexpr int TG_FRAG32 = 2048;          // floats of a 32x32 frag table
-constexpr int TG_GIN_WFLOATS = 2048 + 4096 + 4096 + 128;
+constexpr int TG_GIN_WFLOATS = 2048 + 4096 + 4096 + 128 + 2048 + 2048;
 void launch_frag_pack(const float* w_kn, int K, int N, int kmap, int nmap, float* out, cudaStream_t st);
+// fp16 hi|lo table in natural k order (GIN layers 2, 3); *flag is raised when a weight is outside the fp16 range
+void launch_frag_pack_h16(const float* w_kn, int K, int N, int nmap, float* out, int* flag, cudaStream_t st);
 
 // halo pack / unpack (sharded mode)
 void launch_halo_pack(const float* a, const float* b, const int* rows, int n_send, float* sendbuf, cudaStream_t st);
