@@ -318,13 +318,14 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
 // adjacency edge, the tcgen05 S kernel ~5.9 ns per (128-row tile, edge type) pass -> S pays off when the tiles see
 // few types relative to their edge count (the shipped tile graphs: 20-41 types), chunk when types are many.
 void choose_conv_kernel(tgnn_handle* h) {
-    h->use_s = h->g.has_s && !h->conv_h_only && (h->conv_s_only || (double)h->g.s_passes * 164.0 < (double)h->g.e_adj);
+    h->use_s = h->g.has_s && !h->conv_h_only && (h->conv_s_only || (double)h->g.s_passes * S_EDGES_PER_PASS_BREAK_EVEN < (double)h->g.e_adj);
     h->use_h = !h->use_s && !h->conv_chunk_only;
 }
 
 // 128-row warp tiles give longer same-type runs (half the weight-table reloads, ~10 % fewer padded slots) but only 12
 // resident warps per SM instead of 16; measured on B200 at 1M nodes x deg 32 the two cancel (7.5 vs 7.3 ms per forward),
 // so 64 stays the default and TGNN_TILE=128 is kept for A/B runs.
+int want_s_mode(tgnn_handle* h) { return h->conv_s_only ? 2 : ((h->conv_chunk_only || h->conv_h_only) ? 0 : 1); }
 int tile_rows_for(tgnn_handle* h, int64_t) { return h->tile_rows_forced ? h->tile_rows_forced : WN_SMALL; }
 
 void alloc_workspace(tgnn_handle* h) {
@@ -671,7 +672,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         cudaStream_t st = (cudaStream_t)stream;
         h->graph_set = false;
         build_graph(h->g, h->scratch, h->cfg.d_e, n_nodes, n_nodes, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src,
-                    col_dst, !h->conv_chunk_only, tile_rows_for(h, n_nodes), st);
+                    col_dst, want_s_mode(h), tile_rows_for(h, n_nodes), st);
         h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
         choose_conv_kernel(h);
         alloc_workspace(h);
@@ -721,7 +722,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
         h->graph_set = false;
         const int64_t n_rows = n_own + (h->world > 1 ? (int64_t)h->world * halo_slot : 0);
         build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst,
-                    !h->conv_chunk_only, tile_rows_for(h, n_own), st);
+                    want_s_mode(h), tile_rows_for(h, n_own), st);
         h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
         choose_conv_kernel(h);
         if (n_send > 0) {

@@ -292,7 +292,7 @@ int read_int(const int* dptr, cudaStream_t st) {
 
 void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
-                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, int wn, cudaStream_t st) {
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, int want_s, int wn, cudaStream_t st) {
     TGNN_CHECK(wn == WN_SMALL || wn == WN_BIG, "internal: bad warp-tile height");
     const int db = wn == WN_BIG ? 7 : 6;
     g.wn = wn;
@@ -383,7 +383,12 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
                                                     chunk_base, db, g.csrc.as<int>(), g.cdst.as<uint8_t>());
         // ---------------- adjacency: S format (tcgen05 kernel) -----------------------------------------
         g.has_s = false;
-        if (want_s && n_types <= S_MAX_TYPES) {
+        // the S format costs a 64-bit sort; in "auto" mode (want_s == 1) it is only built when the tcgen05 kernel could be
+        // chosen at all: it needs ~164 edges per (128-row tile, type) pass to beat the fp16 edge-chunk kernel
+        const double passes_est = 0.8 * (double)((n_own + S_BM - 1) / S_BM) *
+                                  std::min<double>((double)n_types, (double)e_adj * S_BM / (double)n_own);
+        const bool s_may_win = want_s >= 2 || passes_est * S_EDGES_PER_PASS_BREAK_EVEN < (double)e_adj;
+        if (want_s && s_may_win && n_types <= S_MAX_TYPES) {
             g.s_tiles = (int)((n_own + S_BM - 1) / S_BM);
             k_s_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, k0, id0);
             sort_pairs(sc, k0, k1, id0, id1, e_adj, 23 + bits_for((unsigned long long)g.s_tiles), st);

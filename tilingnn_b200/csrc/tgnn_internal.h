@@ -112,9 +112,11 @@ struct Scratch {
 // graph_build.cu
 void build_graph(Graph& g, Scratch& scratch, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
-                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, bool want_s, int wn, cudaStream_t st);
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, int want_s /* 0 no, 1 auto, 2 force */,
+                 int wn, cudaStream_t st);
 constexpr int S_BM = 128;         // destination rows per tile of the S format
 constexpr int S_OFF_STRIDE = 136; // uint16 per pass (129 used; 272 B keeps 16-byte alignment)
+constexpr double S_EDGES_PER_PASS_BREAK_EVEN = 164.0;   // measured: S pass ~5.9 ns, fp16 edge-chunk kernel ~36 ps per edge
 constexpr int S_MAX_TYPES = 120;  // the S path is chosen only when K + 1 (root) passes fit its per-tile tables
 
 // ----- kernels.cu launchers --------------------------------------------------------------------

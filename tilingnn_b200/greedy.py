@@ -103,13 +103,18 @@ def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_gr
         previous_prob = saved[keep]
         prob_per_node = np.power(np.power(previous_prob, round_cnt - 1) * prob, 1 / round_cnt)
         saved[keep] = prob_per_node
-        for idx in np.argsort(-prob_per_node):
-            origin_idx = node_re_index[idx]
+        # the visiting loop runs on plain Python scalars (a numpy scalar operation costs ~10x a float one); the
+        # acceptance threshold exp(p - 1) is evaluated by numpy for the whole round at once, elementwise as the reference
+        accept_at = np.exp((prob_per_node - 1) * 1.0).tolist()
+        origin_of = node_re_index.tolist()
+        uniform = rng.uniform
+        for idx in np.argsort(-prob_per_node).tolist():
+            origin_idx = origin_of[idx]
             if label[origin_idx] >= 0:                                    # collision handling: stop this round
                 break
-            if np.exp((prob_per_node[idx] - 1) * 1.0) > rng.uniform():
+            if accept_at[idx] > uniform():
                 label[origin_idx] = 1
-                order.append(int(origin_idx))
+                order.append(origin_idx)
                 adj = nbr[ptr[origin_idx]:ptr[origin_idx + 1]]            # label_collision_neighbor (:196-207)
                 label[adj[label[adj] < 0]] = 0
         round_cnt += 1
