@@ -98,8 +98,18 @@ def config5():
     out = {"n_layouts": len(layouts), "d_e": g.total_feature_dim, "d_x": g.tile_type_count + 1}
     for i, sg in enumerate(layouts):
         out.update(pack_layout(g, sg, prefix=f"L{i}_"))
-    np.savez_compressed(os.path.join(HERE, "c5_bunny.npz"), **out)
     sd = torch.load(os.path.join(REF, f"pre-trained_models/{env}.pth"), map_location="cpu", weights_only=True)
+    # scores of the reference's own graph_networks code (oracle/ref_harness.py) on layout 0: a second tile set
+    # (D_x = 5, D_e = 66, 41 edge types) for the network parity tests
+    from oracle import ref_harness as rh
+    sg = layouts[0]
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+    for mode in ("train", "eval"):
+        for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+            sc = rh.run_reference(sd, t(sg.node_feature, dt), t(sg.align_edge_index, torch.long), t(sg.align_edge_features, dt),
+                                  t(sg.collide_edge_index, torch.long), depth=20, bn_mode=mode, dtype=dt)
+            out[f"L0_ref_{mode}_{name}"] = sc[:, 0].double().numpy()
+    np.savez_compressed(os.path.join(HERE, "c5_bunny.npz"), **out)
     np.savez_compressed(os.path.join(HERE, f"ckpt_{env}.npz"),
                         **{k: v.float().numpy() for k, v in sd.items()
                            if ".nnConv.nn.mlp." not in k and not k.endswith("num_batches_tracked")})

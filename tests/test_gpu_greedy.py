@@ -74,6 +74,27 @@ def test_solve_heart_matches_the_oracle_driven_greedy(dev):
     assert same or abs(score - ref.score) < 0.05
 
 
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_second_tile_set_network_parity(dev, mode):
+    """30-60-90+equilateral (D_x = 5, D_e = 66, 41 edge types), bunny layout 0, shipped checkpoint: scores vs the
+    reference's own graph_networks code in fp64 (tests/golden/make_greedy_golden.py), same tiers as config 1."""
+    from tilingnn_b200 import TilinGNN
+    z = dict(np.load(os.path.join(GOLDEN, "c5_bunny.npz")))
+    sg, _ = load_layout(z, prefix="L0_")
+    net = TilinGNN(int(z["d_e"]), 20, 32, node_features_dim=int(z["d_x"]))
+    net.load_state_dict(load_ckpt("ckpt_30-60-90+equilateral.npz"), strict=True)
+    net = net.to(dev)
+    net = net.train() if mode == "train" else net.eval()
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    s, _ = net(x=t(sg.node_feature, torch.float32), adj_e_index=t(sg.align_edge_index, torch.long),
+               adj_e_features=t(sg.align_edge_features, torch.float32), col_e_idx=t(sg.collide_edge_index, torch.long))
+    s = s[:, 0].double().cpu().numpy()
+    gold, ref32 = z[f"L0_ref_{mode}_f64"], z[f"L0_ref_{mode}_f32"]
+    ours, theirs = np.abs(s - gold).max(), np.abs(ref32 - gold).max()
+    print(f"bunny/equilateral {mode}-BN: ours {ours:.2e}  reference-fp32 {theirs:.2e}  types {net.info()['n_edge_types']}")
+    assert ours <= max(1e-4, 1.5 * theirs)
+
+
 def test_config5_bunny_layouts(dev):
     z = dict(np.load(os.path.join(GOLDEN, "c5_bunny.npz")))
     ckpt = load_ckpt("ckpt_30-60-90+equilateral.npz")

@@ -84,6 +84,13 @@ struct tgnn_handle {
     std::vector<std::unique_ptr<DevBuf>> fin_whl;   // 4: pre-swizzled hi|lo slab images of the weights (tcgen05 path)
     DevBuf dev_error;                               // int: device-side error flag (pipeline timeouts)
     bool dense_ffma = false;                        // TGNN_DENSE=ffma selects the CUDA-core dense stage (debug A/B)
+    // parameter pointers resolved once per pack_params (no string building / map lookups per launch in the forward)
+    struct LayerP { const float *conv_bias, *bn_a_w, *bn_a_b, *bn_c_w, *bn_c_b; };
+    struct BnP { const float *w, *b; };
+    std::vector<LayerP> lp;
+    BnP init_bn[2]{}, fin_bn[4]{};
+    const float *init_w0 = nullptr, *init_b0 = nullptr, *init_b1 = nullptr, *fin_bias[4]{}, *score_w = nullptr;
+    bool eval_coefs_valid = false;                  // eval-mode coefficients depend on the parameters only
     std::vector<float> gin_eps;
     std::vector<int> gin_hmlp;                      // per layer: GIN MLP layers 2, 3 may use the fp16 tables
     bool gin_tf32_only = getenv("TGNN_GIN") && std::string(getenv("TGNN_GIN")) == "tf32";   // A/B runs
@@ -257,6 +264,24 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
         TGNN_CUDA(cudaMemcpyAsync(h->table_layers.p, tl.data(), L * sizeof(TableLayer), cudaMemcpyHostToDevice, st));
         TGNN_CUDA(cudaStreamSynchronize(st));
     }
+    h->lp.resize(L);
+    for (int i = 0; i < L; ++i) {
+        const std::string a = "brch_1_graph_conv_layers." + std::to_string(i), c = "brch_2_coll_conv_layers." + std::to_string(i);
+        h->lp[i] = {h->P(a + ".nnConv.bias"), h->P(a + ".batch_norm.weight"), h->P(a + ".batch_norm.bias"),
+                    h->P(c + ".batch_norm.weight"), h->P(c + ".batch_norm.bias")};
+    }
+    for (int k = 0; k < 2; ++k) {
+        const std::string b = "init_node_feature_trans.mlp." + std::to_string(k) + ".batch_norm";
+        h->init_bn[k] = {h->P(b + ".weight"), h->P(b + ".bias")};
+    }
+    for (int k = 0; k < 4; ++k) {
+        const std::string b = "final_mlp.0.mlp." + std::to_string(k);
+        h->fin_bn[k] = {h->P(b + ".batch_norm.weight"), h->P(b + ".batch_norm.bias")};
+        h->fin_bias[k] = h->P(b + ".linear.bias");
+    }
+    h->init_w0 = h->P("init_node_feature_trans.mlp.0.linear.weight"); h->init_b0 = h->P("init_node_feature_trans.mlp.0.linear.bias");
+    h->init_b1 = h->P("init_node_feature_trans.mlp.1.linear.bias"); h->score_w = h->P("final_mlp.1.linear.weight");
+    h->eval_coefs_valid = false;
     const char* dsel = getenv("TGNN_DENSE");
     h->dense_ffma = dsel && std::string(dsel) == "ffma";
     TGNN_CUDA(cudaMemcpyAsync(&h->fin_last_bias, h->P("final_mlp.1.linear.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -403,37 +428,38 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     h->prof.clear(); h->prof_result.clear();
     Launcher lz{h, st};
     double* sums = h->sums.as<double>();
-    if (!train) { lz.begin("bnfin"); eval_coefs(h, st); lz.end(2 + 2 * L + 4); }
+    if (!train && !h->eval_coefs_valid) { lz.begin("bnfin"); eval_coefs(h, st); lz.end(2 + 2 * L + 4); h->eval_coefs_valid = true; }
+    if (train) h->eval_coefs_valid = false;          // train-mode forwards overwrite the coefficient blocks
     if (h->use_h) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
 
-    auto finish_bn = [&](const double* part, int n_part, int c, const std::string& bn, size_t coef_off) {
+    auto finish_bn = [&](const double* part, int n_part, int c, const tgnn_handle::BnP& bn, size_t coef_off) {
         if (h->world == 1) {
             BnFinishArgs fa{};
             fa.part[0] = part; fa.n_part[0] = n_part; fa.C = c; fa.count = count;
-            fa.gamma[0] = h->P(bn + ".weight"); fa.beta[0] = h->P(bn + ".bias"); fa.coef[0] = h->C(coef_off);
+            fa.gamma[0] = bn.w; fa.beta[0] = bn.b; fa.coef[0] = h->C(coef_off);
             fa.sums = sums; fa.ticket = h->bn_ticket();
             launch_bn_finish(fa, 1, st);
             return;
         }
         launch_bn_reduce(part, n_part, c, sums, st);
         allreduce_sums(h, sums, 2 * c, st);
-        launch_bn_coef(sums, count, h->P(bn + ".weight"), h->P(bn + ".bias"), h->C(coef_off), c, st);
+        launch_bn_coef(sums, count, bn.w, bn.b, h->C(coef_off), c, st);
     };
 
     // ---- init MLP ------------------------------------------------------------------------------
     InitArgs ia{};
     ia.x = x; ia.d_x = h->cfg.d_x;
-    ia.w0 = h->P("init_node_feature_trans.mlp.0.linear.weight"); ia.b0 = h->P("init_node_feature_trans.mlp.0.linear.bias");
-    ia.w1t = h->init_w1t.as<float>(); ia.b1 = h->P("init_node_feature_trans.mlp.1.linear.bias");
+    ia.w0 = h->init_w0; ia.b0 = h->init_b0;
+    ia.w1t = h->init_w1t.as<float>(); ia.b1 = h->init_b1;
     ia.coef0 = h->C(h->coef_init[0]); ia.coef1 = h->C(h->coef_init[1]);
     ia.out = h->mid[0]->as<float>(); ia.part = h->partA.as<double>(); ia.n_own = n_own;
     ia.xh = h->use_h ? h->xh.as<uint32_t>() : nullptr; ia.flag = h->use_h ? h->rflag(0) : nullptr;
     const int np_init = init_num_parts(n_own, h->sm_count);
     if (train) {
         lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
-        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.0.batch_norm", h->coef_init[0]); lz.end(h->world == 1 ? 1 : 2);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[0], h->coef_init[0]); lz.end(h->world == 1 ? 1 : 2);
         lz.begin("init"); launch_init(ia, 1, h->sm_count, st); lz.end(1);
-        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, "init_node_feature_trans.mlp.1.batch_norm", h->coef_init[1]); lz.end(h->world == 1 ? 1 : 2);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[1], h->coef_init[1]); lz.end(h->world == 1 ? 1 : 2);
     }
     lz.begin("init"); launch_init(ia, 2, h->sm_count, st); lz.end(1);
     halo_exchange(h, h->mid[0]->as<float>(), nullptr, h->rflag(0), st, lz);
@@ -442,14 +468,13 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     const int n_layers = h->stop_layer >= 0 ? std::min(L, h->stop_layer + 1) : L;
     const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count), np_gin = gin_num_parts(n_own, h->sm_count);
     for (int i = 0; i < n_layers; ++i) {
-        std::string pa = "brch_1_graph_conv_layers." + std::to_string(i);
-        std::string pc = "brch_2_coll_conv_layers." + std::to_string(i);
+        const tgnn_handle::LayerP& P = h->lp[i];
         if (h->tables_streamed) { lz.begin("conv"); build_tables(h, st, i); lz.end(1); }
         const size_t tslot = h->tables_streamed ? 0 : (size_t)i * (h->g.n_types + 1);
         ConvArgs ca{};
         ca.xin = h->mid[i]->as<float>();
         ca.tabF = h->tab.as<float>() + tslot * TG_FRAG32;
-        ca.n_types = h->g.n_types; ca.bias = h->P(pa + ".nnConv.bias");
+        ca.n_types = h->g.n_types; ca.bias = P.conv_bias;
         ca.cptr = h->g.cptr.as<int>(); ca.ctype = h->g.ctype.as<int>(); ca.csrc = h->g.csrc.as<int>();
         ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->g.inv_deg.as<float>();
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
@@ -487,8 +512,8 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
                 fa.part[0] = h->partA.as<double>(); fa.n_part[0] = h->use_s ? h->g.s_tiles : np_conv;
                 fa.part[1] = h->partB.as<double>(); fa.n_part[1] = np_gin;
                 fa.C = 32; fa.count = count;
-                fa.gamma[0] = h->P(pa + ".batch_norm.weight"); fa.beta[0] = h->P(pa + ".batch_norm.bias"); fa.coef[0] = h->C(h->coef_a[i]);
-                fa.gamma[1] = h->P(pc + ".batch_norm.weight"); fa.beta[1] = h->P(pc + ".batch_norm.bias"); fa.coef[1] = h->C(h->coef_c[i]);
+                fa.gamma[0] = P.bn_a_w; fa.beta[0] = P.bn_a_b; fa.coef[0] = h->C(h->coef_a[i]);
+                fa.gamma[1] = P.bn_c_w; fa.beta[1] = P.bn_c_b; fa.coef[1] = h->C(h->coef_c[i]);
                 fa.sums = sums; fa.ticket = h->bn_ticket();
                 launch_bn_finish(fa, 2, st);
                 lz.end(1);
@@ -496,8 +521,8 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             launch_bn_reduce(h->partA.as<double>(), h->use_s ? h->g.s_tiles : np_conv, 32, sums, st);
             launch_bn_reduce(h->partB.as<double>(), np_gin, 32, sums + 64, st);
             allreduce_sums(h, sums, 128, st);
-            launch_bn_coef(sums, count, h->P(pa + ".batch_norm.weight"), h->P(pa + ".batch_norm.bias"), h->C(h->coef_a[i]), 32, st);
-            launch_bn_coef(sums + 64, count, h->P(pc + ".batch_norm.weight"), h->P(pc + ".batch_norm.bias"), h->C(h->coef_c[i]), 32, st);
+            launch_bn_coef(sums, count, P.bn_a_w, P.bn_a_b, h->C(h->coef_a[i]), 32, st);
+            launch_bn_coef(sums + 64, count, P.bn_c_w, P.bn_c_b, h->C(h->coef_c[i]), 32, st);
             lz.end(4);
             }
         }
@@ -514,13 +539,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     if (h->stop_layer < 0) {
         int dims[5] = {F * (L + 1), 256, 128, 64, F};
         for (int k = 0; k < 4; ++k) {
-            std::string p = "final_mlp.0.mlp." + std::to_string(k);
             DenseArgs da{};
             da.slabs = k == 0 ? h->slab_ptrs.as<const float*>() : nullptr;
             da.a = k == 0 ? nullptr : h->fa[k - 1].as<float>();
             da.virtual_concat = k == 0;
             da.in_coef = k == 0 ? nullptr : h->C(h->coef_fin[k - 1]);
-            da.wt = h->fin_wt[k]->as<float>(); da.bias = h->P(p + ".linear.bias");
+            da.wt = h->fin_wt[k]->as<float>(); da.bias = h->fin_bias[k];
             da.out = h->fa[k].as<float>(); da.part = train ? h->partA.as<double>() : nullptr;
             da.n = n_own; da.K = dims[k]; da.n_out = dims[k + 1];
             lz.begin("final");
@@ -531,12 +555,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             lz.end(1);
             if (train) {
                 lz.begin("bnfin");
-                finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], p + ".batch_norm", h->coef_fin[k]);
+                finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], h->fin_bn[k], h->coef_fin[k]);
                 lz.end(h->world == 1 ? 1 : 2);
             }
         }
         lz.begin("score");
-        launch_score(h->fa[3].as<float>(), h->C(h->coef_fin[3]), h->P("final_mlp.1.linear.weight"), h->fin_last_bias, scores,
+        launch_score(h->fa[3].as<float>(), h->C(h->coef_fin[3]), h->score_w, h->fin_last_bias, scores,
                      n_own, st);
         lz.end(1);
     }
