@@ -484,13 +484,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
             lz.end(1);
         } else if (h->use_h) {
-            // fp16-split kernel; k_conv_adj right behind it takes the layer only if a range flag is raised
+            // fp16-split kernel; falls through to the 3xTF32 arithmetic itself when a range flag is raised
             ca.xh = h->xh.as<uint4>();
             ca.tabH = h->tabH.as<uint32_t>() + tslot * TG_HFRAG32;
             ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
             launch_conv_h(ca, h->sm_count, st);
-            launch_conv_adj(ca, h->sm_count, st);
-            lz.end(2, 1);
+            lz.end(1);
         } else {
             launch_conv_adj(ca, h->sm_count, st);
             lz.end(1);
@@ -505,7 +504,17 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ga.out = h->pre2[0].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
         lz.begin("gin"); launch_gin(ga, h->sm_count, st); lz.end(1);
 
-        if (train) {
+        const int np_a = h->use_s ? h->g.s_tiles : np_conv;
+        // small graphs: k_combine finishes the two BatchNorms in its prologue (one launch less per layer)
+        const bool fin_in_combine = train && h->world == 1 && np_a + np_gin <= 1024;
+        CombineFin cf{};
+        if (fin_in_combine) {
+            cf.part[0] = h->partA.as<double>(); cf.n_part[0] = np_a; cf.part[1] = h->partB.as<double>(); cf.n_part[1] = np_gin;
+            cf.count = count;
+            cf.gamma[0] = P.bn_a_w; cf.beta[0] = P.bn_a_b; cf.gamma[1] = P.bn_c_w; cf.beta[1] = P.bn_c_b;
+            cf.coef_out[0] = h->C(h->coef_a[i]); cf.coef_out[1] = h->C(h->coef_c[i]);
+        }
+        if (train && !fin_in_combine) {
             lz.begin("bnfin");
             if (h->world == 1) {
                 BnFinishArgs fa{};
@@ -529,7 +538,8 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         lz.begin("combine");
         launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[0].as<float>(), h->C(h->coef_c[i]),
                        i >= 2 ? h->mid[i - 2]->as<float>() : nullptr, h->mid[i + 1]->as<float>(),
-                       h->use_h ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), h->pre2[1].as<float>(), n_own, st);
+                       h->use_h ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), h->pre2[1].as<float>(), n_own, st,
+                       fin_in_combine ? &cf : nullptr);
         lz.end(1);
         if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[1].as<float>(), h->rflag(i + 1), st, lz);
         h->last_layer_run = i;

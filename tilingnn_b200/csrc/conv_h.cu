@@ -11,20 +11,21 @@
 //     instead of the 48 of 3xTF32, and no conversion instructions in the consumer at all.  The dropped lo.lo term
 //     is 2^-22 relative -- the same as 3xTF32 (measured: 1.0e-7 vs 1.2e-7 of sum|x||w|).
 // fp16 has a narrow exponent range, so the producers raise a per-tensor flag when |x| > 60000 (or NaN); this kernel
-// then exits at once and k_conv_adj (3xTF32 on the fp32 rows, launched right behind with the opposite test) does the
-// layer instead.  Values below 2^-14 keep an absolute accuracy of 2^-35, far under fp32 rounding of the O(1) sums.
+// then runs the layer with the 3xTF32 arithmetic of k_conv_adj on the fp32 rows instead (conv_adj_body.cuh).  Values below 2^-14 keep an absolute accuracy of 2^-35, far under fp32 rounding of the O(1) sums.
 #include <cuda_fp16.h>
 
+#include "conv_adj_body.cuh"
 #include "hsplit.cuh"
 #include "tgnn_internal.h"
 
 namespace tgnn {
 namespace {
 
-constexpr int XS = 36;          // padded shared-memory row stride (floats)
+using tfx::XS;                  // padded shared-memory row stride (floats)
 constexpr float LO_INV = 1.0f / 2048.f;
 
-__device__ __forceinline__ float leaky(float v) { return v >= 0.f ? v : v * LEAKY; }
+using tfx::leaky;
+using tfx::acc_add8;
 
 struct BFragH { uint4 h[2][2], l[2][2]; };
 
@@ -64,14 +65,6 @@ __device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH
     }
 }
 
-__device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int half) {
-    float4* p = reinterpret_cast<float4*>(row);
-    float4 v0 = p[0], v1 = p[1];
-    v0.x += c[0][2 * half]; v0.y += c[0][2 * half + 1]; v0.z += c[1][2 * half]; v0.w += c[1][2 * half + 1];
-    v1.x += c[2][2 * half]; v1.y += c[2][2 * half + 1]; v1.z += c[3][2 * half]; v1.w += c[3][2 * half + 1];
-    p[0] = v0; p[1] = v1;
-}
-
 // lane t's 32 bytes of a split row (both k16 steps) with one 256-bit load: a whole 128-byte line per 4 lanes, so the
 // L1 data stage spends one wavefront per gathered row instead of two
 __device__ __forceinline__ void ld_rowh2(const uint4* __restrict__ xh, int row, int t, uint4& k0, uint4& k1) {
@@ -80,6 +73,11 @@ __device__ __forceinline__ void ld_rowh2(const uint4* __restrict__ xh, int row, 
                  : "=r"(k0.x), "=r"(k0.y), "=r"(k0.z), "=r"(k0.w), "=r"(k1.x), "=r"(k1.y), "=r"(k1.z), "=r"(k1.w) : "l"(p));
 }
 
+// Out of line on purpose: the 3xTF32 body needs 64 registers of weight fragments; inlined, its allocation would spill
+// into k_conv_h's hot loop.
+template <int WN, int WARPS>
+__device__ __noinline__ void conv_adj_fallback(const ConvArgs& A, float* smem) { tfx::conv_adj_body<WN, WARPS>(A, smem); }
+
 // SPLIT = false: persistent, one warp per 64-row tile (large graphs).  SPLIT = true: one CTA per tile, its 8 warps take
 // every 8th chunk into private partial tiles that are summed in a fixed order -- the real layouts have ~10 tiles
 // (N ~ 600), where one warp walking ~60 latency-bound chunks per tile would leave the GPU idle.
@@ -87,8 +85,11 @@ template <int WN, int WARPS, bool SPLIT>
 __global__ void __launch_bounds__(WARPS * 32, WN == WN_BIG ? 1 : 2)
 k_conv_h(ConvArgs A) {
     constexpr int TPB = WARPS * 32;
-    if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) return;      // out of fp16 range: k_conv_adj takes the layer
     extern __shared__ __align__(16) float smem[];
+    if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) {            // out of the fp16 range: 3xTF32 on the fp32 rows
+        conv_adj_fallback<WN, WARPS>(A, smem);                           // (same grid, same BatchNorm partial layout)
+        return;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* acc = smem + warp * (WN * XS);
     const int g = lane >> 2, t = lane & 3;

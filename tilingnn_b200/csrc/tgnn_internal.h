@@ -131,8 +131,8 @@ struct ConvArgs {
     double* part;            // [n_part][64]  per-warp partial sums (sum, sum of squares)
     int n_own, n_tiles;
     int wn;                  // rows per warp tile: WN_SMALL or WN_BIG
-    // fp16-split operands of k_conv_h (conv_h.cu) and the range flags that arbitrate between it and k_conv_adj:
-    // k_conv_h runs when both flags are 0, k_conv_adj when flag_x is null (forced) or a flag is raised
+    // fp16-split operands of k_conv_h (conv_h.cu) and the range flags: k_conv_h uses them when both flags are 0 and the
+    // 3xTF32 arithmetic on xin (conv_adj_body.cuh) when one is raised
     const uint4* xh;         // [n_rows][8]   split copy of xin: per 4 channels {hi01, hi23, lo01, lo23} fp16 pairs
     const uint32_t* tabH;    // [K+1][1024]   fp16 hi|lo fragment tables; entry K = nnConv.root
     const int* flag_x;       // raised by the producer of xin when a value is outside the fp16 range
@@ -167,9 +167,16 @@ int gin_num_parts(int n_own, int sm_count);
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st);
 
 // b1_new = BN(pre1) * BN(pre2) + residual
-// xh / flag (optional): fp16-split copy of the result for k_conv_h and its range flag; g2out (optional): BN(pre2)
+// xh / flag (optional): fp16-split copy of the result for k_conv_h and its range flag; g2out (optional): BN(pre2).
+// fin (optional, small graphs): BatchNorm partials of the two branches -- the kernel then computes the coefficients in
+// its prologue (and block 0 stores them to coef_out) instead of reading coef1 / coef2.
+struct CombineFin {
+    const double* part[2] = {nullptr, nullptr}; int n_part[2] = {0, 0}; double count = 1.0;
+    const float* gamma[2] = {nullptr, nullptr}; const float* beta[2] = {nullptr, nullptr}; float* coef_out[2] = {nullptr, nullptr};
+};
 void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
-                    const float* residual, float* out, uint4* xh, int* flag, float* g2out, int64_t n_own, cudaStream_t st);
+                    const float* residual, float* out, uint4* xh, int* flag, float* g2out, int64_t n_own, cudaStream_t st,
+                    const CombineFin* fin = nullptr);
 
 // init MLP: mode 0 = stats of layer 0, 1 = stats of layer 1, 2 = write h0
 struct InitArgs {
