@@ -79,3 +79,26 @@ def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, mode, mo
     err = np.abs(out - gold).max()
     print(f"2-GPU sharded N={n} deg={deg} {mode}: max err vs fp64 oracle {err:.2e}")
     assert err <= 1e-4
+
+
+def test_two_devices_in_one_process():
+    """kernel attributes (opt-in shared memory sizes) are per device: two handles on two GPUs of the same process must
+    both work and agree bit for bit."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    import __graft_entry__ as ge
+    ge.build()
+    from oracle import tilingnn_oracle as orc
+    from tilingnn_b200 import TilinGNN, synthetic as syn
+    x, ai, af, ci = syn.lattice_graph(5000, 8, 8, seed=1)
+    p = orc.make_params(3, 19, 3, seed=1)
+    outs = []
+    for d in (1, 0):                                   # the second device first
+        dev = torch.device("cuda", d)
+        net = TilinGNN(19, 3, 32, node_features_dim=3)
+        net.load_state_dict(p)
+        net = net.to(dev).train()
+        s, _ = net(x=x.to(dev), adj_e_index=ai.to(dev), adj_e_features=af.to(dev), col_e_idx=ci.to(dev))
+        torch.cuda.synchronize(dev)
+        outs.append(s.cpu())
+    assert torch.equal(outs[0], outs[1])

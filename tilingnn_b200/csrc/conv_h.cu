@@ -214,14 +214,13 @@ k_conv_h(ConvArgs A) {
 }  // namespace
 
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
-    static bool attr = false;
+    static PerDeviceOnce once;
     const size_t smem_small = (size_t)8 * WN_SMALL * XS * sizeof(float), smem_big = (size_t)12 * WN_BIG * XS * sizeof(float);
-    if (!attr) {
+    once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_BIG, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
-        attr = true;
-    }
+    });
     // same grid as k_conv_adj: the BatchNorm partial layout is shared by the two kernels
     const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
     if (a.wn == WN_BIG) k_conv_h<WN_BIG, 12, false><<<g.blocks, 12 * 32, smem_big, st>>>(a);

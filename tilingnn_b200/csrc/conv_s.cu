@@ -422,11 +422,10 @@ k_conv_s(ConvSArgs A) {
 }  // namespace
 
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_s, cudaFuncAttributeMaxDynamicSharedMemorySize, CS_SMEM));
-        attr = true;
-    }
+    });
     ConvSArgs a{};
     a.xin = c.xin; a.tabS = tabS; a.n_types = g.n_types;
     a.pptr = g.s_pptr.as<int>(); a.ptype = g.s_ptype.as<int>(); a.pbase = g.s_pbase.as<int>();

@@ -329,11 +329,10 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
 template <int NOUT>
 void launch_one(const DenseTcArgs& a, int sm_count, cudaStream_t st) {
     constexpr size_t smem = DenseCfg<NOUT>::SMEM;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_dense_tc<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    });
     const int n_tiles = (a.n + BM - 1) / BM;
     static long long* dbg = nullptr;
     static const bool want_dbg = getenv("TGNN_DENSE_DBG") != nullptr;

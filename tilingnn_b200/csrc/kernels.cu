@@ -830,13 +830,12 @@ int init_num_parts(int n_own, int sm_count) { return init_blocks(n_own, sm_count
 int dense_row_blocks(int n) { return (n + DM - 1) / DM; }
 
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st) {
-    static bool attr = false;
+    static PerDeviceOnce once;
     const size_t smem_small = (size_t)WARPS * WN_SMALL * XS * sizeof(float), smem_big = (size_t)12 * WN_BIG * XS * sizeof(float);
-    if (!attr) {
+    once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj<WN_SMALL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj<WN_BIG, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
-        attr = true;
-    }
+    });
     const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
     if (a.wn == WN_BIG) k_conv_adj<WN_BIG, 12><<<g.blocks, 12 * 32, smem_big, st>>>(a);
     else k_conv_adj<WN_SMALL, WARPS><<<g.blocks, TPB, smem_small, st>>>(a);
@@ -844,12 +843,11 @@ void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st) {
 }
 
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce once;
+    once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_gin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem(false)));
         TGNN_CUDA(cudaFuncSetAttribute(k_gin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem(true)));
-        attr = true;
-    }
+    });
     if (a.hmlp) k_gin<true><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(true), st>>>(a);
     else k_gin<false><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(false), st>>>(a);
     TGNN_CUDA(cudaGetLastError());

@@ -7,6 +7,7 @@
 
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -40,6 +41,21 @@ struct Error : std::runtime_error {
     do {                                                                                      \
         if (!(cond)) throw ::tgnn::Error(std::string(msg));                                   \
     } while (0)
+
+// cudaFuncSetAttribute is per DEVICE: a launcher keeps one of these (static) and prepares each device once,
+// also when handles on several devices / threads share the process.
+struct PerDeviceOnce {
+    std::mutex m;
+    uint64_t done = 0;                 // bit per device ordinal
+    template <class Fn> void run(Fn&& fn) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lk(m);
+        if (dev < 64 && ((done >> dev) & 1ull)) return;
+        fn();
+        if (dev < 64) done |= 1ull << dev;
+    }
+};
 
 // Owning device buffer (grow-only reuse keeps cudaMalloc out of repeated set_graph calls).
 struct DevBuf {
