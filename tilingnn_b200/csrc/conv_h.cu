@@ -69,7 +69,11 @@ __device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH
 // L1 data stage spends one wavefront per gathered row instead of two
 __device__ __forceinline__ void ld_rowh2(const uint4* __restrict__ xh, int row, int t, uint4& k0, uint4& k1) {
     const uint4* p = xh + (size_t)row * 8 + 2 * t;
+#ifdef TGNN_CONV_NOALLOC
+    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
                  : "=r"(k0.x), "=r"(k0.y), "=r"(k0.z), "=r"(k0.w), "=r"(k1.x), "=r"(k1.y), "=r"(k1.z), "=r"(k1.w) : "l"(p));
 }
 

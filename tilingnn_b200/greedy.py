@@ -48,20 +48,23 @@ def _rows(feat, n_edges, like=None):
 # ------------------------------------------------------------------------------------------------ #
 # f2: sub-layout                                                                                    #
 # ------------------------------------------------------------------------------------------------ #
-def compute_sub_layout(layout, keep):
+def compute_sub_layout(layout, keep, collide_features=True):
     """Induced sub-graph on the nodes ``keep`` (ascending original indices).  Returns ``(sub_layout, keep)``;
-    ``keep[i]`` is the reference's ``node_inverse_index[i]`` (brick_layout.py:248-286)."""
+    ``keep[i]`` is the reference's ``node_inverse_index[i]`` (brick_layout.py:248-286).
+    ``collide_features=False`` leaves the collision edge FEATURES out (an ``[E_c', 0]`` array): the network never
+    reads them (TilinGNN.py:51,63) and gathering them is the dominant host cost of a greedy round."""
     keep = np.asarray(keep, dtype=np.int64)
     n = layout.node_feature.shape[0]
     new = -np.ones(n, dtype=np.int64)
     new[keep] = np.arange(len(keep))
 
-    def sub(index, feat):
+    def sub(index, feat, with_feat=True):
         e = _edges(index)
-        m = (new[e[0]] >= 0) & (new[e[1]] >= 0)
-        f = _rows(feat, e.shape[1], feat)
-        return new[e[:, m]], f[m]
-    ci, cf = sub(layout.collide_edge_index, layout.collide_edge_features)
+        keep_e = np.flatnonzero((new[e[0]] >= 0) & (new[e[1]] >= 0))
+        if not with_feat:
+            return new[e[:, keep_e]], np.zeros((len(keep_e), 0))
+        return new[e[:, keep_e]], np.take(_rows(feat, e.shape[1], feat), keep_e, axis=0)
+    ci, cf = sub(layout.collide_edge_index, layout.collide_edge_features, collide_features)
     ai, af = sub(layout.align_edge_index, layout.align_edge_features)
     out = replace(layout, node_feature=layout.node_feature[keep], collide_edge_index=ci, collide_edge_features=cf,
                   align_edge_index=ai, align_edge_features=af, tiles=np.asarray(layout.tiles)[keep])
@@ -98,7 +101,7 @@ def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_gr
         if max_rounds is not None and round_cnt > max_rounds:
             raise RuntimeError(f"greedy assembly did not finish in {max_rounds} rounds")
         keep = np.flatnonzero(label < 0)
-        temp_layout, node_re_index = compute_sub_layout(origin_layout, keep)
+        temp_layout, node_re_index = compute_sub_layout(origin_layout, keep, collide_features=False)
         prob = np.asarray(ml_solver.predict(temp_layout))
         previous_prob = saved[keep]
         prob_per_node = np.power(np.power(previous_prob, round_cnt - 1) * prob, 1 / round_cnt)
@@ -156,9 +159,8 @@ def calculate_unsupervised_loss(probs, node_feature, collide_edge_index, adj_edg
 
 def ring_perimeter(ring):
     r = np.asarray(ring, dtype=np.float64)
-    if not np.allclose(r[0], r[-1]):
-        r = np.vstack([r, r[:1]])
-    return float(np.linalg.norm(np.diff(r, axis=0), axis=1).sum())
+    d = r - np.roll(r, 1, axis=0)               # closed rings contribute a zero-length segment for the repeated vertex
+    return float(np.sqrt((d * d).sum(axis=1)).sum())
 
 
 def union_area(rings, tol=1e-9):
@@ -247,7 +249,14 @@ def solution_score(predict, brick_layout, complete_graph):
     if adj.shape[1] > 0:
         lengths = np.asarray(brick_layout.align_edge_features, dtype=np.float64)[:, 1] * g.max_align_length
         loss_align_length = float((predict[adj[0]] * predict[adj[1]]).dot(lengths))
-    all_edge_length = sum(ring_perimeter(g.tile_rings[tiles[i]]) for i in np.flatnonzero(predict == 1))
+    perim = getattr(brick_layout, "_tile_perimeters", None)
+    if perim is None:
+        perim = np.asarray([ring_perimeter(g.tile_rings[t]) for t in tiles])
+        try:
+            object.__setattr__(brick_layout, "_tile_perimeters", perim)
+        except Exception:
+            pass
+    all_edge_length = float(perim[predict == 1].sum())
     if all_edge_length == 0:
         return float("nan")
     ratio = loss_align_length / all_edge_length

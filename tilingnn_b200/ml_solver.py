@@ -11,7 +11,7 @@ A "layout" is anything with the five numpy attributes of the reference's ``Brick
 from __future__ import annotations
 
 import traceback
-from copy import deepcopy
+from copy import copy, deepcopy
 
 import numpy as np
 import torch
@@ -72,7 +72,7 @@ class ML_Solver:
         ``(output_layout, score)``; the layout copy carries ``predict``, ``predict_order``, ``predict_probs``."""
         from . import greedy
         res = greedy.solve_by_probablistic_greedy(self, brick_layout, rng=rng, complete_graph=self.complete_graph)
-        output_layout = deepcopy(brick_layout)
+        output_layout = copy(brick_layout)          # the reference deep-copies; nothing mutates the arrays afterwards
         output_layout.predict_order = res.order
         output_layout.predict = res.selection
         output_layout.predict_probs = self.predict(brick_layout)
