@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGNN_ABI_VERSION 3
+#define TGNN_ABI_VERSION 4
 
 #define TGNN_BN_TRAIN 0   /* batch statistics over the rows of THIS call -- the reference's
                              behaviour: solver/ml_solver/ml_solver.py:129-131 ends in network.train() */
@@ -83,7 +83,11 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes,
  * x: [n_nodes, d_x] fp32 device; scores_out: [n_nodes] fp32 device (the [N,1] column). */
 int tgnn_forward(tgnn_handle* h, const float* x, float* scores_out, void* stream);
 
-/* ---- multi-GPU: node-range shards (new work; the reference is single-device) ------------ */
+/* ---- multi-GPU: node-range shards (new work; the reference is single-device) ------------
+ * Per layer one exchange of boundary rows and one of BatchNorm sums.  By default both are peer-memory
+ * exchanges: tgnn_set_graph_shard maps every peer's exchange buffer with CUDA IPC (handles travel through
+ * a 64-byte NCCL all-gather) and the producing kernels store straight into the peers' buffers over NVLink;
+ * if the mapping fails on any rank, or with TGNN_P2P=0, ncclAllGather / ncclAllReduce are used instead. */
 /* 128-byte NCCL unique id; rank 0 creates it, the host side broadcasts it. */
 int tgnn_nccl_unique_id(void* out128);
 /* Join the communicator.  Must be called before tgnn_set_graph_shard. */
@@ -111,6 +115,8 @@ typedef struct tgnn_info {
     int64_t conv_kernel;           /* adjacency kernel chosen for this graph: 0 = 3xTF32 edge-chunk (mma.sync),
                                       1 = tcgen05 S formulation, 2 = fp16-split edge-chunk (mma.sync.f16)      */
     int64_t tile_rows;             /* destination rows per warp tile of the typed adjacency format (64 or 128)  */
+    int64_t peer_exchange;         /* sharded mode: 1 = boundary rows and BatchNorm sums travel as direct NVLink stores into
+                                      the peers' CUDA-IPC-mapped buffers (flags, no NCCL call); 0 = NCCL collectives     */
     int64_t range_fallback_layers; /* layers of the LAST forward that kernel 2 handed to kernel 0 because an
                                       activation or root weight was outside the fp16 range (synchronises)      */
 } tgnn_info;

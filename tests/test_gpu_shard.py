@@ -40,18 +40,21 @@ def _worker(rank, world, port, n, deg, depth, mode, q):
         s2 = net.score(x).clone()          # second pass: halo buffers are reused
         torch.cuda.synchronize()
         info = net.info()
-        q.put((rank, "ok", lo, hi, s1.cpu().numpy(), bool(torch.equal(s1, s2)), info["collectives_per_forward"], plan.halo_slot))
+        q.put((rank, "ok", lo, hi, s1.cpu().numpy(), bool(torch.equal(s1, s2)), info["collectives_per_forward"], plan.halo_slot,
+               info["peer_exchange"]))
         dist.barrier()
         dist.destroy_process_group()
     except Exception:  # pragma: no cover
         import traceback
-        q.put((rank, "fail: " + traceback.format_exc(), 0, 0, None, False, 0, 0))
+        q.put((rank, "fail: " + traceback.format_exc(), 0, 0, None, False, 0, 0, 0))
 
 
 @pytest.mark.parametrize("mode", ["train"])
-@pytest.mark.parametrize("n,deg,conv", [(20000, 8, "chunk"), (6000, 32, "s"), (6000, 32, "chunk")])
-def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, mode, monkeypatch):
+@pytest.mark.parametrize("n,deg,conv,p2p", [(20000, 8, "h", 1), (6000, 32, "s", 1), (6000, 32, "chunk", 0), (20000, 8, "h", 0)])
+def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, p2p, mode, monkeypatch):
+    """both exchange paths: peer-memory stores over NVLink (CUDA IPC, default) and NCCL collectives (TGNN_P2P=0)"""
     monkeypatch.setenv("TGNN_CONV", conv)          # inherited by the spawned ranks
+    monkeypatch.setenv("TGNN_P2P", str(p2p))
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from oracle import tilingnn_oracle as orc
@@ -71,13 +74,14 @@ def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, mode, mo
         pr.join(timeout=120)
     assert all(r[1] == "ok" for r in res), [r[1] for r in res]
     out = np.zeros(n)
-    for rank, _, lo, hi, s, same, ncoll, slot in res:
+    for rank, _, lo, hi, s, same, ncoll, slot, peer in res:
         out[lo:hi] = s
+        assert peer == p2p, "exchange path: peer-memory mapping must succeed on an NVLink box (and stay off with TGNN_P2P=0)"
         assert same, "sharded forward must be run-to-run deterministic"
         assert ncoll == (2 + depth + 4) + depth, ncoll        # BN all-reduces + halo all-gathers (train mode)
         assert 0 < slot < n // 4
     err = np.abs(out - gold).max()
-    print(f"2-GPU sharded N={n} deg={deg} {mode}: max err vs fp64 oracle {err:.2e}")
+    print(f"2-GPU sharded N={n} deg={deg} {mode} conv={conv} p2p={p2p}: max err vs fp64 oracle {err:.2e}")
     assert err <= 1e-4
 
 

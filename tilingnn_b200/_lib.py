@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libtgnn.so")
 
 TGNN_BN_TRAIN, TGNN_BN_EVAL = 0, 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class tgnn_cfg(C.Structure):
@@ -26,7 +26,7 @@ class tgnn_info(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("n_own", "n_rows", "n_global", "e_adj", "e_col", "n_edge_types", "adj_slots",
                  "launches_per_forward", "workspace_bytes", "collectives_per_forward", "conv_kernel",
-                 "tile_rows", "range_fallback_layers")]
+                 "tile_rows", "peer_exchange", "range_fallback_layers")]
 
 
 _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32

@@ -116,12 +116,23 @@ struct tgnn_handle {
     DevBuf xh;                                      // [n_rows][8] uint4: fp16-split copy of the current layer's b1
     int* rflag(int i) { return hflags.as<int>() + i; }
     int* wflag(int i) { return hflags.as<int>() + cfg.depth + 1 + i; }
-    unsigned* bn_ticket() { return reinterpret_cast<unsigned*>(hflags.as<int>() + 2 * cfg.depth + 1); }   // k_bn_finish
+    unsigned* bn_ticket() { return reinterpret_cast<unsigned*>(hflags.as<int>() + 2 * cfg.depth + 1); }   // k_bn_finish; +1: k_halo_push
     size_t workspace_bytes = 0;
 
     // sharding
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
+
+    // peer-memory exchange (CUDA IPC over NVLink); falls back to NCCL collectives when it cannot be set up
+    struct PeerX {
+        DevBuf buf;                                  // this rank's exchange buffer (tgnn_internal.h: PX_* layout)
+        DevBuf staging;                              // handle all-gather staging
+        void* peer[PX_MAX_WORLD] = {};               // mapped peer buffers (own slot = buf.p)
+        char handles[PX_MAX_WORLD][64] = {};         // the IPC handles currently mapped
+        bool ok = false, disabled = getenv("TGNN_P2P") && std::string(getenv("TGNN_P2P")) == "0";
+        unsigned epoch_halo = 0, epoch_bn = 0;
+        int64_t halo_slot = -1;
+    } px;
 
     // bookkeeping
     int64_t launches = 0, collectives = 0;
@@ -375,7 +386,11 @@ void alloc_workspace(tgnn_handle* h) {
     std::vector<const float*> slabs(L + 1);
     for (int i = 0; i <= L; ++i) slabs[i] = h->mid[i]->as<float>();
     TGNN_CUDA(cudaMemcpy(h->slab_ptrs.p, slabs.data(), slabs.size() * sizeof(float*), cudaMemcpyHostToDevice));
-    if (h->world > 1) res(h->halo, (size_t)h->world * h->g.halo_slot * 64 * sizeof(float));
+    if (h->world > 1) {
+        const void* before = h->halo.p;
+        res(h->halo, (size_t)h->world * h->g.halo_slot * 64 * sizeof(float));
+        if (h->halo.p != before) TGNN_CUDA(cudaMemset(h->halo.p, 0, h->halo.cap));       // padding rows are never written
+    }
     h->workspace_bytes = total;
 }
 
@@ -397,6 +412,69 @@ struct Launcher {
     }
 };
 
+PeerPtrs peer_ptrs(tgnn_handle* h) {
+    PeerPtrs p{};
+    for (int q = 0; q < h->world; ++q) p.base[q] = static_cast<char*>(h->px.peer[q]);
+    p.world = h->world; p.rank = h->rank;
+    return p;
+}
+
+void peer_close(tgnn_handle* h) {
+    for (int q = 0; q < PX_MAX_WORLD; ++q) {
+        if (h->px.peer[q] && q != h->rank) cudaIpcCloseMemHandle(h->px.peer[q]);
+        h->px.peer[q] = nullptr;
+        memset(h->px.handles[q], 0, 64);
+    }
+    h->px.ok = false;
+}
+
+// Collective (every rank calls it from tgnn_set_graph_shard): size this rank's exchange buffer for the graph, publish
+// its IPC handle through a 64-byte NCCL all-gather, map the peers' buffers.  Any failure on any rank -> all ranks keep
+// the NCCL collectives (agreed through an all-reduce).
+void peer_setup(tgnn_handle* h, cudaStream_t st) {
+    tgnn_handle::PeerX& x = h->px;
+    if (h->world <= 1 || h->world > PX_MAX_WORLD || x.disabled) { x.ok = false; return; }
+    const size_t need = PX_HALO_OFF + 2 * (size_t)h->world * (size_t)h->g.halo_slot * 64 * sizeof(float);
+    const void* before = x.buf.p;
+    x.buf.reserve(need);
+    if (x.buf.p != before || x.halo_slot != h->g.halo_slot) {
+        TGNN_CUDA(cudaMemsetAsync(x.buf.p, 0, x.buf.cap, st));        // flags, and no garbage in padding rows
+        x.epoch_halo = 0; x.epoch_bn = 0;
+    }
+    x.halo_slot = h->g.halo_slot;
+    x.staging.reserve((size_t)(h->world + 1) * 64 + 2 * sizeof(float));
+    cudaIpcMemHandle_t mine;
+    float good = cudaIpcGetMemHandle(&mine, x.buf.p) == cudaSuccess ? 1.f : 0.f;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char* stg = x.staging.as<char>();
+    TGNN_CUDA(cudaMemcpyAsync(stg, &mine, 64, cudaMemcpyHostToDevice, st));
+    nccl_check(nccl().AllGather(stg, stg + 64, 16, ncclFloat32, h->comm, st), "IPC handle all-gather");
+    std::vector<char> all((size_t)h->world * 64);
+    TGNN_CUDA(cudaMemcpyAsync(all.data(), stg + 64, all.size(), cudaMemcpyDeviceToHost, st));
+    TGNN_CUDA(cudaStreamSynchronize(st));                             // (also orders every rank's memset before any push)
+    for (int q = 0; q < h->world && good > 0.f; ++q) {
+        if (q == h->rank) { x.peer[q] = x.buf.p; continue; }
+        if (x.peer[q] && memcmp(x.handles[q], all.data() + (size_t)q * 64, 64) == 0) continue;     // still mapped
+        if (x.peer[q]) { cudaIpcCloseMemHandle(x.peer[q]); x.peer[q] = nullptr; }
+        cudaIpcMemHandle_t hq;
+        memcpy(&hq, all.data() + (size_t)q * 64, 64);
+        if (cudaIpcOpenMemHandle(&x.peer[q], hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            x.peer[q] = nullptr; good = 0.f;
+        } else {
+            memcpy(x.handles[q], &hq, 64);
+        }
+    }
+    float* flagp = reinterpret_cast<float*>(stg + (size_t)(h->world + 1) * 64);
+    TGNN_CUDA(cudaMemcpyAsync(flagp, &good, sizeof(float), cudaMemcpyHostToDevice, st));
+    nccl_check(nccl().AllReduce(flagp, flagp + 1, 1, ncclFloat32, ncclSum, h->comm, st), "peer setup agreement");
+    float total = 0.f;
+    TGNN_CUDA(cudaMemcpyAsync(&total, flagp + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+    TGNN_CUDA(cudaStreamSynchronize(st));
+    x.ok = total > (float)h->world - 0.5f;
+    if (!x.ok) peer_close(h);
+}
+
 void allreduce_sums(tgnn_handle* h, double* sums, int n, cudaStream_t st) {
     if (h->world <= 1) return;
     nccl_check(nccl().AllReduce(sums, sums, (size_t)n, ncclFloat64, ncclSum, h->comm, st), "BatchNorm all-reduce");
@@ -406,6 +484,16 @@ void allreduce_sums(tgnn_handle* h, double* sums, int n, cudaStream_t st) {
 void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t st, Launcher& lz) {
     if (h->world <= 1) return;
     lz.begin("halo");
+    if (h->px.ok) {
+        // boundary rows go straight into the peers' buffers (NVLink stores), flags follow; the unpack waits for the flags
+        const unsigned epoch = ++h->px.epoch_halo;
+        const PeerPtrs pp = peer_ptrs(h);
+        launch_halo_push(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, h->g.halo_slot, pp, epoch, h->bn_ticket() + 1, st);
+        launch_halo_unpack_x(pp, epoch, h->g.halo_slot, h->g.n_own, a, b, h->use_h ? h->xh.as<uint4>() : nullptr, flag, st);
+        h->collectives += 1;
+        lz.end(2);
+        return;
+    }
     float* slot = h->halo.as<float>() + (size_t)h->rank * h->g.halo_slot * 64;
     launch_halo_pack(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, slot, st);
     nccl_check(nccl().AllGather(slot, h->halo.p, (size_t)h->g.halo_slot * 64, ncclFloat32, h->comm, st), "halo all-gather");
@@ -433,12 +521,13 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     if (h->use_h) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
 
     auto finish_bn = [&](const double* part, int n_part, int c, const tgnn_handle::BnP& bn, size_t coef_off) {
-        if (h->world == 1) {
+        if (h->world == 1 || h->px.ok) {
             BnFinishArgs fa{};
             fa.part[0] = part; fa.n_part[0] = n_part; fa.C = c; fa.count = count;
             fa.gamma[0] = bn.w; fa.beta[0] = bn.b; fa.coef[0] = h->C(coef_off);
             fa.sums = sums; fa.ticket = h->bn_ticket();
-            launch_bn_finish(fa, 1, st);
+            if (h->world == 1) launch_bn_finish(fa, 1, st);
+            else { launch_bn_finish_x(fa, 1, peer_ptrs(h), ++h->px.epoch_bn, st); h->collectives += 1; }
             return;
         }
         launch_bn_reduce(part, n_part, c, sums, st);
@@ -457,9 +546,9 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     const int np_init = init_num_parts(n_own, h->sm_count);
     if (train) {
         lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
-        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[0], h->coef_init[0]); lz.end(h->world == 1 ? 1 : 2);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[0], h->coef_init[0]); lz.end(h->world == 1 || h->px.ok ? 1 : 2);
         lz.begin("init"); launch_init(ia, 1, h->sm_count, st); lz.end(1);
-        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[1], h->coef_init[1]); lz.end(h->world == 1 ? 1 : 2);
+        lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[1], h->coef_init[1]); lz.end(h->world == 1 || h->px.ok ? 1 : 2);
     }
     lz.begin("init"); launch_init(ia, 2, h->sm_count, st); lz.end(1);
     halo_exchange(h, h->mid[0]->as<float>(), nullptr, h->rflag(0), st, lz);
@@ -516,7 +605,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         }
         if (train && !fin_in_combine) {
             lz.begin("bnfin");
-            if (h->world == 1) {
+            if (h->world == 1 || h->px.ok) {
                 BnFinishArgs fa{};
                 fa.part[0] = h->partA.as<double>(); fa.n_part[0] = h->use_s ? h->g.s_tiles : np_conv;
                 fa.part[1] = h->partB.as<double>(); fa.n_part[1] = np_gin;
@@ -524,7 +613,8 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
                 fa.gamma[0] = P.bn_a_w; fa.beta[0] = P.bn_a_b; fa.coef[0] = h->C(h->coef_a[i]);
                 fa.gamma[1] = P.bn_c_w; fa.beta[1] = P.bn_c_b; fa.coef[1] = h->C(h->coef_c[i]);
                 fa.sums = sums; fa.ticket = h->bn_ticket();
-                launch_bn_finish(fa, 2, st);
+                if (h->world == 1) launch_bn_finish(fa, 2, st);
+                else { launch_bn_finish_x(fa, 2, peer_ptrs(h), ++h->px.epoch_bn, st); h->collectives += 1; }
                 lz.end(1);
             } else {
             launch_bn_reduce(h->partA.as<double>(), h->use_s ? h->g.s_tiles : np_conv, 32, sums, st);
@@ -566,7 +656,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             if (train) {
                 lz.begin("bnfin");
                 finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], h->fin_bn[k], h->coef_fin[k]);
-                lz.end(h->world == 1 ? 1 : 2);
+                lz.end(h->world == 1 || h->px.ok ? 1 : 2);
             }
         }
         lz.begin("score");
@@ -632,8 +722,8 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->conv_h_only = csel && std::string(csel) == "h";
         const char* tsel = getenv("TGNN_TILE");
         if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
-        h->hflags.reserve((size_t)(2 * cfg->depth + 2) * sizeof(int));
-        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 2) * sizeof(int)));
+        h->hflags.reserve((size_t)(2 * cfg->depth + 3) * sizeof(int));
+        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 3) * sizeof(int)));
         h->dev_error.reserve(2 * sizeof(int));                         // [0] pipeline timeout flag, [1] scratch flag of pack_params
         TGNN_CUDA(cudaMemset(h->dev_error.p, 0, 2 * sizeof(int)));
         declare_params(h.get());
@@ -646,6 +736,7 @@ int tgnn_destroy(tgnn_handle* h) {
     {
         DeviceGuard dg(h->cfg.device);
         for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        peer_close(h);
         if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
         delete h;
     }
@@ -773,6 +864,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
             TGNN_CUDA(cudaStreamSynchronize(st));
         }
         alloc_workspace(h);
+        peer_setup(h, st);
         h->tables_dirty = true;
         h->graph_set = true;
     });
@@ -789,6 +881,7 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         out->collectives_per_forward = h->collectives;
         out->conv_kernel = h->use_s ? 1 : (h->use_h ? 2 : 0);
         out->tile_rows = h->g.wn;
+        out->peer_exchange = h->px.ok ? 1 : 0;
         out->range_fallback_layers = 0;
         if (h->use_h && h->graph_set) {
             DeviceGuard dg(h->cfg.device);

@@ -727,6 +727,143 @@ __global__ void k_bn_finish(BnFinishArgs A) {
     if (threadIdx.x == 0) *A.ticket = 0u;
 }
 
+// ---- peer-memory variants (sharded mode) ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until flags[q] >= epoch for every peer q (bounded: ~2 s, then the error flag is raised by the caller's check)
+__device__ __forceinline__ bool wait_peers(const unsigned* flags, int world, int rank, unsigned epoch) {
+    for (int q = 0; q < world; ++q) {
+        if (q == rank) continue;
+        long long t0 = clock64();
+        while ((int)(ld_acquire_sys(flags + q) - epoch) < 0) {
+            __nanosleep(64);
+            if (clock64() - t0 > 4000000000ll) return false;
+        }
+    }
+    return true;
+}
+
+__global__ void k_bn_finish_x(BnFinishArgs A, PeerPtrs P, unsigned epoch) {
+    __shared__ double sh[256];
+    __shared__ bool last;
+    const int C2 = 2 * A.C;
+    const int which = blockIdx.x / C2, j = blockIdx.x - which * C2;
+    const double* part = A.part[which];
+    const int n_part = A.n_part[which];
+    double s = 0.0;
+    for (int p = threadIdx.x; p < n_part; p += 256) s += part[(size_t)p * C2 + j];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        A.sums[blockIdx.x] = sh[0];
+        __threadfence();
+        last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const int n = gridDim.x, par = epoch & 1u;                 // n = n_bn * 2C local sums
+    const size_t slot = (size_t)(par * PX_MAX_WORLD + P.rank) * PX_BN_SLOT;
+    const volatile double* loc = A.sums;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const double v = loc[i];
+        for (int q = 0; q < P.world; ++q)                      // own copy too: the sum below reads one buffer only
+            reinterpret_cast<double*>(P.base[q] + PX_FLAG_BYTES)[slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < P.world && threadIdx.x != P.rank)
+        st_release_sys(reinterpret_cast<unsigned*>(P.base[threadIdx.x] + 256) + par * PX_MAX_WORLD + P.rank, epoch);
+    __shared__ bool ok;
+    if (threadIdx.x == 0) ok = wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank] + 256) + par * PX_MAX_WORLD, P.world, P.rank, epoch);
+    __syncthreads();
+    __threadfence_system();
+    const double* mine = reinterpret_cast<const double*>(P.base[P.rank] + PX_FLAG_BYTES) + (size_t)par * PX_MAX_WORLD * PX_BN_SLOT;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        double t = 0.0;
+        for (int q = 0; q < P.world; ++q) t += __ldcg(mine + (size_t)q * PX_BN_SLOT + i);      // fixed rank order
+        A.sums[i] = ok ? t : __longlong_as_double(0x7ff8000000000000ll);                       // timeout -> NaN scores, loudly
+    }
+    __syncthreads();
+    __threadfence();
+    const int nb = n / C2;
+    for (int i = threadIdx.x; i < nb * A.C; i += 256) {
+        const int w = i / A.C, c = i - w * A.C;
+        const volatile double* sums = A.sums + (size_t)w * C2;
+        const double mean = sums[c] / A.count;
+        double var = sums[A.C + c] / A.count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const double rstd = 1.0 / sqrt(var + BN_EPS);
+        const float mh = (float)mean;
+        float* coef = w == 0 ? A.coef[0] : A.coef[1];
+        coef[c] = mh;
+        coef[A.C + c] = (float)(mean - (double)mh);
+        coef[2 * A.C + c] = (float)((double)(w == 0 ? A.gamma[0] : A.gamma[1])[c] * rstd);
+        coef[3 * A.C + c] = (w == 0 ? A.beta[0] : A.beta[1])[c];
+    }
+    if (threadIdx.x == 0) *A.ticket = 0u;
+}
+
+__global__ void k_halo_push(const float4* __restrict__ a, const float4* __restrict__ b, const int* __restrict__ rows, int n_send,
+                            int64_t halo_slot, PeerPtrs P, unsigned epoch, unsigned* __restrict__ ticket) {
+    const int par = epoch & 1u;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < (int64_t)n_send * 16) {
+        const int r = (int)(i >> 4), c = (int)(i & 15);
+        const int row = rows[r];
+        const float4 v = c < 8 ? __ldg(a + (size_t)row * 8 + c) : (b ? __ldg(b + (size_t)row * 8 + (c - 8)) : make_float4(0.f, 0.f, 0.f, 0.f));
+        const size_t off = ((size_t)par * P.world * halo_slot + (size_t)P.rank * halo_slot) * 16 + (size_t)i;     // float4 units
+        for (int q = 0; q < P.world; ++q)
+            if (q != P.rank) reinterpret_cast<float4*>(P.base[q] + PX_HALO_OFF)[off] = v;
+    }
+    // last block: everything this rank wrote is visible system-wide before the flags go up
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence_system();
+    if (threadIdx.x < P.world && threadIdx.x != P.rank)
+        st_release_sys(reinterpret_cast<unsigned*>(P.base[threadIdx.x]) + par * PX_MAX_WORLD + P.rank, epoch);
+    if (threadIdx.x == 0) *ticket = 0u;
+}
+
+__global__ void k_halo_unpack_x(PeerPtrs P, unsigned epoch, int64_t halo_slot, int64_t n_own,
+                                float4* __restrict__ a, float4* __restrict__ b, uint4* __restrict__ xh, int* __restrict__ flag) {
+    const int par = epoch & 1u;
+    __shared__ bool ok;
+    if (threadIdx.x == 0) ok = wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank]) + par * PX_MAX_WORLD, P.world, P.rank, epoch);
+    __syncthreads();
+    __threadfence_system();
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)P.world * halo_slot * 16;
+    if (i >= total) return;
+    const int64_t r = i >> 4; const int c = (int)(i & 15);
+    if (r / halo_slot == P.rank) return;               // own slot: rows are read in place
+    const float4* recv = reinterpret_cast<const float4*>(P.base[P.rank] + PX_HALO_OFF) + (size_t)par * total;
+    float4 v = __ldcg(recv + i);                       // written by a peer over NVLink: L2 is the coherence point
+    if (!ok) v = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    if (c < 8) {
+        a[(size_t)(n_own + r) * 8 + c] = v;
+        if (xh) {
+            bool bad = false;
+            xh[(size_t)(n_own + r) * 8 + xh_pos(c)] = split_h4(v, bad);
+            if (bad) *flag = 1;
+        }
+    } else if (b) b[(size_t)(n_own + r) * 8 + (c - 8)] = v;
+}
+
 __global__ void k_bn_coef_eval(const float* __restrict__ rmean, const float* __restrict__ rvar,
                                const float* __restrict__ gamma, const float* __restrict__ beta,
                                float* __restrict__ coef, int C) {
@@ -913,6 +1050,26 @@ void launch_bn_coef(const double* sums, double count, const float* gamma, const 
 }
 void launch_bn_finish(const BnFinishArgs& a, int n_bn, cudaStream_t st) {
     k_bn_finish<<<n_bn * 2 * a.C, 256, 0, st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+void launch_bn_finish_x(const BnFinishArgs& a, int n_bn, const PeerPtrs& p, unsigned epoch, cudaStream_t st) {
+    TGNN_CHECK((size_t)n_bn * 2 * a.C <= PX_BN_SLOT, "internal: BatchNorm exchange slot too small");
+    k_bn_finish_x<<<n_bn * 2 * a.C, 256, 0, st>>>(a, p, epoch);
+    TGNN_CUDA(cudaGetLastError());
+}
+void launch_halo_push(const float* a, const float* b, const int* rows, int n_send, int64_t halo_slot, const PeerPtrs& p,
+                      unsigned epoch, unsigned* ticket, cudaStream_t st) {
+    const int64_t n = (int64_t)n_send * 16;
+    const int blocks = (int)std::max<int64_t>(1, (n + 255) / 256);           // at least one block: the flags must go up
+    k_halo_push<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), rows, n_send,
+                                        halo_slot, p, epoch, ticket);
+    TGNN_CUDA(cudaGetLastError());
+}
+void launch_halo_unpack_x(const PeerPtrs& p, unsigned epoch, int64_t halo_slot, int64_t n_own, float* a, float* b,
+                          uint4* xh, int* flag, cudaStream_t st) {
+    const int64_t n = (int64_t)p.world * halo_slot * 16;
+    const int blocks = (int)std::max<int64_t>(1, (n + 255) / 256);
+    k_halo_unpack_x<<<blocks, 256, 0, st>>>(p, epoch, halo_slot, n_own, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), xh, flag);
     TGNN_CUDA(cudaGetLastError());
 }
 void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gamma, const float* beta, float* coef_out,

@@ -258,6 +258,26 @@ void launch_frag_pack(const float* w_kn, int K, int N, int kmap, int nmap, float
 // fp16 hi|lo table in natural k order (GIN layers 2, 3); *flag is raised when a weight is outside the fp16 range
 void launch_frag_pack_h16(const float* w_kn, int K, int N, int nmap, float* out, int* flag, cudaStream_t st);
 
+// ---- peer-memory exchange (sharded mode, one process per GPU): every rank maps every peer's exchange buffer with
+// CUDA IPC; boundary rows and BatchNorm sums are then WRITTEN straight into the peers' buffers over NVLink by the
+// producing kernel and signalled with epoch flags -- no NCCL call, no extra launch, rank-ordered (deterministic) sums.
+// Buffer layout (per rank): [flags 4 KB][BN sums 2 x 8 x 512 doubles][halo rows 2 x world x halo_slot x 64 floats];
+// everything is double buffered by epoch parity (a rank can run at most one exchange ahead of a peer).
+constexpr int PX_MAX_WORLD = 8;
+constexpr size_t PX_FLAG_BYTES = 4096;                          // uint32 halo_flag[2][8] at 0, bn_flag[2][8] at 256
+constexpr size_t PX_BN_SLOT = 512;                              // doubles per (parity, rank)
+constexpr size_t PX_BN_BYTES = 2 * PX_MAX_WORLD * PX_BN_SLOT * sizeof(double);
+constexpr size_t PX_HALO_OFF = PX_FLAG_BYTES + PX_BN_BYTES;
+struct PeerPtrs { char* base[PX_MAX_WORLD]; int world, rank; };
+// k_bn_finish with the cross-rank sum inside: the last block pushes the local sums to all peers, waits for theirs
+void launch_bn_finish_x(const BnFinishArgs& a, int n_bn, const PeerPtrs& p, unsigned epoch, cudaStream_t st);
+// boundary rows (a | b) -> slot `rank` of every peer's halo buffer, then the epoch flags (last block)
+void launch_halo_push(const float* a, const float* b, const int* rows, int n_send, int64_t halo_slot, const PeerPtrs& p,
+                      unsigned epoch, unsigned* ticket, cudaStream_t st);
+// waits for the peers' flags of `epoch`, then unpacks this rank's halo buffer (as launch_halo_unpack)
+void launch_halo_unpack_x(const PeerPtrs& p, unsigned epoch, int64_t halo_slot, int64_t n_own, float* a, float* b,
+                          uint4* xh, int* flag, cudaStream_t st);
+
 // halo pack / unpack (sharded mode)
 void launch_halo_pack(const float* a, const float* b, const int* rows, int n_send, float* sendbuf, cudaStream_t st);
 void launch_halo_unpack(const float* recv, int world, int rank, int64_t halo_slot, int64_t n_own,
