@@ -133,3 +133,39 @@ def test_readers_reproduce_the_golden_crop():
     assert sizes == z["crop_sizes"].tolist()
     assert np.array_equal(crops[0].tiles, z["tiles"])
     assert np.allclose(crops[0].node_feature, z["x"])
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference data only exists in the build container")
+def test_tiling_shape_driver_on_the_reference_files(tmp_path):
+    """Tiling-Shape.py end to end on the reference's own files (pickle, checkpoint, silhouette) with the fp32 oracle network
+    standing in for the CUDA one: four bunny layouts, valid maximal selections, result pickles written."""
+    import pickle
+    from oracle import tilingnn_oracle as orc
+    from tilingnn_b200 import ML_Solver, tiling_shape
+
+    class OracleSolver(ML_Solver):
+        def __init__(self, g, state):
+            self.complete_graph, self.params = g, state
+
+        def predict(self, lay):
+            n = lay.node_feature.shape[0]
+            if np.size(lay.collide_edge_index) == 0 or np.size(lay.align_edge_index) == 0:
+                return np.ones(n, dtype=np.float32)
+            t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+            s = orc.forward(self.params, t(lay.node_feature, torch.float32), t(lay.align_edge_index, torch.long),
+                            t(lay.align_edge_features, torch.float32), t(lay.collide_edge_index, torch.long), depth=20,
+                            bn_mode="train", dtype=torch.float32)
+            return s[:, 0].numpy()
+    ref = "/root/reference"
+    sols = tiling_shape.tiling_a_region(f"{ref}/data/30-60-90+equilateral/complete_graph_ring9.pkl",
+                                        f"{ref}/pre-trained_models/30-60-90+equilateral.pth", f"{ref}/silhouette/bunny.txt",
+                                        out_dir=str(tmp_path), verbose=False, solver_factory=OracleSolver)
+    assert [s.node_feature.shape[0] for s, _ in sols] == [604, 562, 591, 565]
+    for lay, score in sols:
+        sel = lay.predict.astype(bool)
+        ci = lay.collide_edge_index
+        assert not (sel[ci[0]] & sel[ci[1]]).any() and 0 < score <= 1.02
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 4
+    d = pickle.load(open(os.path.join(tmp_path, files[0]), "rb"))
+    assert set(d) == {"tiles", "predict", "predict_order", "predict_probs", "score"}

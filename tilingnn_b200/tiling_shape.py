@@ -22,20 +22,25 @@ from .network import TilinGNN
 
 def tiling_a_region(complete_graph_path, network_path, silhouette_path, device="cuda", network_depth=20,
                     network_width=32, tile_type_count=None, start_angle=0, end_angle=30, num_of_angle=1,
-                    movement_delta_ratio=(0, 0.5), margin_padding_ratios=(0.5,), seed=2, out_dir=None, verbose=True):
+                    movement_delta_ratio=(0, 0.5), margin_padding_ratios=(0.5,), seed=2, out_dir=None, verbose=True,
+                    solver_factory=None):
     """Defaults are the reference's (Tiling-Shape.py:52-54, inputs/config.py:38-45).  Returns a list of
-    ``(solved_layout, score)``; ``solved_layout.predict`` is the 0/1 selection, ``.predict_order`` the order."""
-    device = torch.device(device)
+    ``(solved_layout, score)``; ``solved_layout.predict`` is the 0/1 selection, ``.predict_order`` the order.
+    ``solver_factory(complete_graph, state_dict)`` (tests) replaces the CUDA network + ``ML_Solver`` construction."""
     state = torch.load(network_path, map_location="cpu", weights_only=True)
     d_x = state["init_node_feature_trans.mlp.0.linear.weight"].shape[1]
     # environment.tile_count counts mirrored prototypes too (inputs/env.py:26-36), which the pickle alone cannot tell
     g = tio.load_complete_graph(complete_graph_path, d_x - 1 if tile_type_count is None else tile_type_count)
     if d_x != g.tile_type_count + 1:
         raise ValueError(f"checkpoint expects {d_x} node features, the complete graph gives {g.tile_type_count + 1}")
-    network = TilinGNN(adj_edge_features_dim=g.total_feature_dim, network_depth=network_depth,
-                       network_width=network_width, node_features_dim=d_x).to(device)
-    solver = ML_Solver(None, device, g, network, num_prob_maps=1)
-    solver.load_saved_network(network_path)
+    if solver_factory is not None:
+        solver = solver_factory(g, state)
+    else:
+        device = torch.device(device)
+        network = TilinGNN(adj_edge_features_dim=g.total_feature_dim, network_depth=network_depth,
+                           network_width=network_width, node_features_dim=d_x).to(device)
+        solver = ML_Solver(None, device, g, network, num_prob_maps=1)
+        solver.load_saved_network(network_path)
     exterior, interiors = tio.load_polygons(silhouette_path)
     layouts = tio.crop_multiple_layouts_from_contour(exterior, interiors, g, start_angle=start_angle, end_angle=end_angle,
                                                      num_of_angle=num_of_angle, movement_delta_ratio=movement_delta_ratio,
