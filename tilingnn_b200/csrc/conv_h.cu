@@ -65,6 +65,17 @@ __device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH
     }
 }
 
+// row = row * scale + the lane's 8 message channels of C-fragment half `half`
+__device__ __forceinline__ void acc_fma8(float* row, const float (&c)[4][4], int half, float scale) {
+    float4* p = reinterpret_cast<float4*>(row);
+    float4 v0 = p[0], v1 = p[1];
+    v0.x = fmaf(v0.x, scale, c[0][2 * half]); v0.y = fmaf(v0.y, scale, c[0][2 * half + 1]);
+    v0.z = fmaf(v0.z, scale, c[1][2 * half]); v0.w = fmaf(v0.w, scale, c[1][2 * half + 1]);
+    v1.x = fmaf(v1.x, scale, c[2][2 * half]); v1.y = fmaf(v1.y, scale, c[2][2 * half + 1]);
+    v1.z = fmaf(v1.z, scale, c[3][2 * half]); v1.w = fmaf(v1.w, scale, c[3][2 * half + 1]);
+    p[0] = v0; p[1] = v1;
+}
+
 // lane t's 32 bytes of a split row (both k16 steps) with one 256-bit load: a whole 128-byte line per 4 lanes, so the
 // L1 data stage spends one wavefront per gathered row instead of two
 __device__ __forceinline__ void ld_rowh2(const uint4* __restrict__ xh, int row, int t, uint4& k0, uint4& k1) {
@@ -176,24 +187,22 @@ k_conv_h(ConvArgs A) {
             __syncthreads();
             tile_acc = smem; r0 = warp * (WN / WARPS); r1 = r0 + WN / WARPS;
         }
-        // mean over in-edges
-        for (int r = r0; r < r1; ++r) {
-            int node = node0 + r;
-            if (node < A.n_own) tile_acc[r * XS + lane] *= __ldg(A.inv_deg + node);
-        }
-        if (SPLIT) __syncthreads(); else __syncwarp();
-        // root term: x_i @ root as four 16-row chunks of the tile's own rows (table entry n_types)
+        // mean over in-edges and root term in ONE read-modify-write of the tile: the root pass visits every row exactly
+        // once (four 16-row chunks of the tile's own rows against table entry n_types), so
+        //   acc[row] = fma(acc[row], inv_deg[row], x_row @ root)
+        // replaces a separate scaling pass: 128 shared-memory wavefronts less per tile (and one rounding less)
         if (!SPLIT || warp < WN / CH) {
             if (cur_type != A.n_types) { load_bfrag_h(bf, A.tabH + (size_t)A.n_types * TG_HFRAG32, lane); cur_type = A.n_types; }
             for (int rc = SPLIT ? warp : 0; rc < (SPLIT ? warp + 1 : WN / CH); ++rc) {
                 const int na = node0 + rc * CH + g, nb = na + 8;
                 uint4 cur[4] = {zero4, zero4, zero4, zero4};
-                if (na < A.n_own) ld_rowh2(xh, na, t, cur[0], cur[1]);
-                if (nb < A.n_own) ld_rowh2(xh, nb, t, cur[2], cur[3]);
+                float ia = 0.f, ib = 0.f;
+                if (na < A.n_own) { ld_rowh2(xh, na, t, cur[0], cur[1]); ia = __ldg(A.inv_deg + na); }
+                if (nb < A.n_own) { ld_rowh2(xh, nb, t, cur[2], cur[3]); ib = __ldg(A.inv_deg + nb); }
                 float m[4][4];
                 chunk_mma_h(cur, bf, m);
-                acc_add8(tile_acc + (rc * CH + g) * XS + 8 * t, m, 0);
-                acc_add8(tile_acc + (rc * CH + g + 8) * XS + 8 * t, m, 1);
+                acc_fma8(tile_acc + (rc * CH + g) * XS + 8 * t, m, 0, ia);
+                acc_fma8(tile_acc + (rc * CH + g + 8) * XS + 8 * t, m, 1, ib);
             }
         }
         if (SPLIT) __syncthreads(); else __syncwarp();

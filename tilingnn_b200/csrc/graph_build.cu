@@ -176,6 +176,58 @@ __global__ void k_adj_scatter(const unsigned long long* __restrict__ key, const 
     cdst[slot] = (uint8_t)(key[i] & ((1ull << db) - 1ull));
 }
 
+// Inside every 8-slot group, put destinations of opposite parity next to each other (slots 2i, 2i+1) and lone
+// leftovers next to an empty slot.  The two rows a quarter-warp of the adjacency kernels accumulates into (lanes
+// g = 2q, 2q+1; row stride 36 floats) then fall on disjoint shared-memory bank groups; rows of equal parity are a 2-way
+// conflict on every LDS.128 / STS.128 of the accumulate (ncu: 14 of 98 L1 wavefronts per chunk before this pass).
+__global__ void k_pair_parity(int* __restrict__ csrc, uint8_t* __restrict__ cdst, int64_t n_groups) {
+    const int64_t gi = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;
+    int* ps = csrc + gi * GRP;
+    uint8_t* pd = cdst + gi * GRP;
+    int s[GRP], d[GRP];
+#pragma unroll
+    for (int i = 0; i < GRP; ++i) { s[i] = ps[i]; d[i] = pd[i]; }
+    int os[GRP], od[GRP];
+#pragma unroll
+    for (int i = 0; i < GRP; ++i) { os[i] = -1; od[i] = 0; }
+    // pass 1: mixed (even, odd) pairs
+    int p = 0;
+    unsigned used = 0;
+    for (;;) {
+        int e = -1, o = -1;
+#pragma unroll
+        for (int i = 0; i < GRP; ++i)
+            if (s[i] >= 0 && !((used >> i) & 1u)) {
+                if ((d[i] & 1) == 0) { if (e < 0) e = i; }
+                else if (o < 0) o = i;
+            }
+        if (e < 0 || o < 0) break;
+        used |= (1u << e) | (1u << o);
+#pragma unroll
+        for (int i = 0; i < GRP; ++i) {
+            if (i == e) { os[p] = s[i]; od[p] = d[i]; }
+            if (i == o) { os[p + 1] = s[i]; od[p + 1] = d[i]; }
+        }
+        p += 2;
+    }
+    // pass 2: leftovers (all of one parity): first one per remaining pair (its partner stays empty), then the partners
+    for (int round = 0; round < 2; ++round)
+        for (int q = p + round; q < GRP; q += 2) {
+            int pick = -1;
+#pragma unroll
+            for (int i = 0; i < GRP; ++i)
+                if (pick < 0 && s[i] >= 0 && !((used >> i) & 1u)) pick = i;
+            if (pick < 0) break;
+            used |= 1u << pick;
+#pragma unroll
+            for (int i = 0; i < GRP; ++i)
+                if (i == pick) { os[q] = s[i]; od[q] = d[i]; }
+        }
+#pragma unroll
+    for (int i = 0; i < GRP; ++i) { ps[i] = os[i]; pd[i] = (uint8_t)od[i]; }
+}
+
 __global__ void k_fill_int(int* __restrict__ p, int64_t n, int v) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -381,6 +433,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         incl_max(sc, tile_end, g.cptr.as<int>() + 1, g.n_tiles, st);
         k_adj_scatter<<<nblk(e_adj), TPB, 0, st>>>(k1, id1, adj_src, e_adj, run_idx, run_pos, run_chunks,
                                                     chunk_base, db, g.csrc.as<int>(), g.cdst.as<uint8_t>());
+        k_pair_parity<<<nblk(n_chunks * (CH / GRP)), TPB, 0, st>>>(g.csrc.as<int>(), g.cdst.as<uint8_t>(), n_chunks * (CH / GRP));
         // ---------------- adjacency: S format (tcgen05 kernel) -----------------------------------------
         g.has_s = false;
         // the S format costs a 64-bit sort; in "auto" mode (want_s == 1) it is only built when the tcgen05 kernel could be
