@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-nodes", type=int, default=0, help="0 = calibrate to ~15 s")
+    ap.add_argument("--config5", action="store_true",
+                    help="BASELINE.json config 5 instead: 30-60-90+equilateral, bunny.txt, 4 layouts, scoring + greedy "
+                         "assembly wall-clock (fixtures under tests/golden/), CPU port beside it")
     return ap.parse_args()
 
 
@@ -197,8 +200,93 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_config5(args):
+    """BASELINE.json config 5: the four bunny layouts of Tiling-Shape.py:52-54 (30-60-90+equilateral, shipped
+    checkpoint, depth 20, train-mode BatchNorm) solved by ``ML_Solver.solve`` = greedy assembly with every round
+    scored by the CUDA network; beside it the CPU port (oracle network, fp32, all host threads) driving the SAME
+    greedy loop -- the cpu_baseline leg, the only place this file touches oracle/.  Prints ONE JSON line."""
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _util import GOLDEN, load_ckpt, load_layout
+    from tilingnn_b200 import ML_Solver, TilinGNN, greedy
+    ge.build()
+    z = dict(np.load(os.path.join(GOLDEN, "c5_bunny.npz")))
+    ckpt = load_ckpt("ckpt_30-60-90+equilateral.npz")
+    layouts = [load_layout(z, prefix=f"L{i}_") for i in range(int(z["n_layouts"]))]
+    dev = torch.device("cuda:0")
+    net = TilinGNN(int(z["d_e"]), 20, 32, node_features_dim=int(z["d_x"]))
+    net.load_state_dict(ckpt, strict=True)
+    net = net.to(dev).train()
+    solver = ML_Solver(None, dev, None, net, 1)             # one solver for all layouts, as Tiling-Shape.py:37
+    calls = {"n": 0}
+
+    def run_gpu(seed):
+        out, rng = [], np.random.RandomState(seed)
+        for sg, graph in layouts:
+            solver.complete_graph = graph
+            solved, score = solver.solve(sg, rng=rng)
+            calls["n"] += solved.greedy_rounds + 1
+            out.append((int(solved.predict.sum()), score))
+        return out
+    for _ in range(max(1, args.warmup // 3)):
+        run_gpu(0)                                          # library load, parameter upload, cached contour areas
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(max(1, args.steps // 4)):
+        calls["n"] = 0
+        t0 = time.perf_counter()
+        res = run_gpu(2)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    gpu_s = float(np.median(times))
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import tilingnn_oracle as orc           # cpu_baseline leg
+
+        class OracleSolver:
+            def __init__(self, graph):
+                self.complete_graph, self.calls = graph, 0
+
+            def predict(self, lay):
+                n = lay.node_feature.shape[0]
+                if np.size(lay.collide_edge_index) == 0 or np.size(lay.align_edge_index) == 0:
+                    return np.ones(n, dtype=np.float32)
+                self.calls += 1
+                t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+                s = orc.forward(ckpt, t(lay.node_feature, torch.float32), t(lay.align_edge_index, torch.long),
+                                t(lay.align_edge_features, torch.float32), t(lay.collide_edge_index, torch.long), depth=20,
+                                bn_mode="train", dtype=torch.float32)
+                return s[:, 0].float().numpy()
+        torch.set_num_threads(os.cpu_count())
+        t0 = time.perf_counter()
+        rng, cpu_res, cpu_calls = np.random.RandomState(2), [], 0
+        for sg, graph in layouts:
+            s = OracleSolver(graph)
+            r = greedy.solve_by_probablistic_greedy(s, sg, rng=rng)
+            s.predict(sg)                                   # ML_Solver.solve's final scoring pass (ml_solver.py:65)
+            cpu_calls += s.calls
+            cpu_res.append((int(r.selection.sum()), r.score))
+        cpu_s = time.perf_counter() - t0
+        cpu = {"value": cpu_s, "unit": "s", "cores": os.cpu_count(), "kind": "port", "network_calls": cpu_calls,
+               "sample": "the same 4 layouts, oracle network fp32 driving the same greedy loop (one run)",
+               "layouts": [{"tiles_placed": a, "score": b} for a, b in cpu_res]}
+    print(json.dumps({
+        "metric": "Tiling-Shape scoring + greedy assembly wall-clock (config 5)", "unit": "s", "higher_is_better": False,
+        "value": gpu_s, "times": times, "network_calls": calls["n"], "n_gpus": 1, "dtype": "f32",
+        "data": "tests/golden/c5_bunny.npz + shipped 30-60-90+equilateral checkpoint",
+        "layouts": [{"nodes": int(sg.node_feature.shape[0]), "tiles_placed": a, "score": b} for (sg, _), (a, b) in zip(layouts, res)],
+        "cpu_baseline": cpu, "speedup_vs_cpu_port": (cpu["value"] / gpu_s) if cpu else None,
+        "config": {"workload": "30-60-90+equilateral, bunny.txt, 4 layouts (604/562/591/565 candidate tiles), depth 20, "
+                               "train-mode BatchNorm, shipped checkpoint"}}))
+
+
 def main():
     args = parse()
+    if args.config5:
+        return run_config5(args)
     if args.impl == "reference":
         return run_reference(args)
     # NCCL writes its banner to stdout when NCCL_DEBUG=VERSION/INFO is set in the environment; stdout must carry

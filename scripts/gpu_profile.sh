@@ -14,7 +14,7 @@ python bench.py --steps 10 --warmup 3 --bn eval --no-cpu-baseline --no-e2e > $OU
 TGNN_CONV=s python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_${TAG}_convs.json 2>> $OUT/bench_${TAG}.err
 TGNN_CONV=chunk python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > $OUT/bench_${TAG}_convtf32.json 2>> $OUT/bench_${TAG}.err
 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/bench_${TAG}_reference.json 2>> $OUT/bench_${TAG}.err
-python scripts/bench_config5.py 5 > $OUT/bench_${TAG}_config5.json 2>> $OUT/bench_${TAG}.err
+python bench.py --config5 --steps 20 --warmup 3 > $OUT/bench_${TAG}_config5.json 2>> $OUT/bench_${TAG}.err
 # every launch of this library's kernels with its device time (cold cache, serialised: compare SHARES)
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_' -c 300 --csv --log-file $OUT/launches_${TAG}.csv \
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_launch_${TAG}.log 2>&1
