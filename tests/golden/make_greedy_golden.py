@@ -116,7 +116,37 @@ def config5():
     print(f"c5_bunny.npz: {[l.node_feature.shape[0] for l in layouts]} nodes, d_x={out['d_x']} d_e={out['d_e']}")
 
 
+def third_tile_set():
+    """45-45-90+rectangle (symmetry_tiles = False: D_x = 3, D_e = 22), heart.txt layout 0, shipped checkpoint: scores of the
+    reference's own graph_networks code -- with the 30-60-90 and 30-60-90+equilateral files this covers all three shipped
+    checkpoints."""
+    from oracle import ref_harness as rh
+    env = "45-45-90+rectangle"
+    sd = torch.load(os.path.join(REF, f"pre-trained_models/{env}.pth"), map_location="cpu", weights_only=True)
+    d_x = sd["init_node_feature_trans.mlp.0.linear.weight"].shape[1]
+    g = tio.load_complete_graph(os.path.join(REF, f"data/{env}/complete_graph_ring9.pkl"), tile_type_count=d_x - 1)
+    ext, ints = tio.load_polygons(os.path.join(REF, "silhouette/heart.txt"))
+    sg = tio.crop_multiple_layouts_from_contour(ext, ints, g, start_angle=0, end_angle=30, num_of_angle=1,
+                                                movement_delta_ratio=[0, 0.5], margin_padding_ratios=[0.5])[0]
+    out = {"d_x": d_x, "d_e": g.total_feature_dim}
+    out.update(pack_layout(g, sg))
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt)
+    for mode in ("train", "eval"):
+        for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+            sc = rh.run_reference(sd, t(sg.node_feature, dt), t(sg.align_edge_index, torch.long), t(sg.align_edge_features, dt),
+                                  t(sg.collide_edge_index, torch.long), depth=20, bn_mode=mode, dtype=dt)
+            out[f"ref_{mode}_{name}"] = sc[:, 0].double().numpy()
+    np.savez_compressed(os.path.join(HERE, "c1_rect_heart.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, f"ckpt_{env}.npz"),
+                        **{k: v.float().numpy() for k, v in sd.items()
+                           if ".nnConv.nn.mlp." not in k and not k.endswith("num_batches_tracked")})
+    print(f"c1_rect_heart.npz: N={sg.node_feature.shape[0]} d_x={d_x} d_e={g.total_feature_dim} "
+          f"fp32-vs-fp64 train {np.abs(out['ref_train_f32'] - out['ref_train_f64']).max():.2e} "
+          f"eval {np.abs(out['ref_eval_f32'] - out['ref_eval_f64']).max():.2e}")
+
+
 def main():
+    third_tile_set()
     config5()
     g = tio.load_complete_graph(os.path.join(REF, "data/30-60-90/complete_graph_ring9.pkl"))
     ext, ints = tio.load_polygons(os.path.join(REF, "silhouette/heart.txt"))

@@ -95,6 +95,26 @@ def test_second_tile_set_network_parity(dev, mode):
     assert ours <= max(1e-4, 1.5 * theirs)
 
 
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_third_tile_set_network_parity(dev, mode):
+    """45-45-90+rectangle (D_x = 3, D_e = 22), heart layout 0, shipped checkpoint -- the third and last shipped model."""
+    from tilingnn_b200 import TilinGNN
+    z = dict(np.load(os.path.join(GOLDEN, "c1_rect_heart.npz")))
+    sg, _ = load_layout(z)
+    net = TilinGNN(int(z["d_e"]), 20, 32, node_features_dim=int(z["d_x"]))
+    net.load_state_dict(load_ckpt("ckpt_45-45-90+rectangle.npz"), strict=True)
+    net = net.to(dev)
+    net = net.train() if mode == "train" else net.eval()
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    s, _ = net(x=t(sg.node_feature, torch.float32), adj_e_index=t(sg.align_edge_index, torch.long),
+               adj_e_features=t(sg.align_edge_features, torch.float32), col_e_idx=t(sg.collide_edge_index, torch.long))
+    s = s[:, 0].double().cpu().numpy()
+    gold, ref32 = z[f"ref_{mode}_f64"], z[f"ref_{mode}_f32"]
+    ours, theirs = np.abs(s - gold).max(), np.abs(ref32 - gold).max()
+    print(f"heart/45-45-90+rectangle {mode}-BN: ours {ours:.2e}  reference-fp32 {theirs:.2e}  types {net.info()['n_edge_types']}")
+    assert ours <= max(1e-4, 1.5 * theirs)
+
+
 def test_config5_bunny_layouts(dev):
     z = dict(np.load(os.path.join(GOLDEN, "c5_bunny.npz")))
     ckpt = load_ckpt("ckpt_30-60-90+equilateral.npz")
