@@ -169,3 +169,19 @@ def test_tiling_shape_driver_on_the_reference_files(tmp_path):
     assert len(files) == 4
     d = pickle.load(open(os.path.join(tmp_path, files[0]), "rb"))
     assert set(d) == {"tiles", "predict", "predict_order", "predict_probs", "score"}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference data only exists in the build container")
+def test_batched_clip_equals_per_tile_clip():
+    """the vectorised Sutherland-Hodgman of crop_from_contour against the per-tile implementation (areas and kept tiles)"""
+    from tilingnn_b200 import tile_graph_io as tio
+    g = tio.load_complete_graph("/root/reference/data/45-45-90+rectangle/complete_graph_ring9.pkl", tile_type_count=2)
+    for name, margin, ang, dx in (("heart.txt", 0.5, 0.0, 0.0), ("bunny.txt", 0.7, 15.0, 0.3)):
+        ext, ints = tio.load_polygons(f"/root/reference/silhouette/{name}")
+        _, e2, i2 = tio.shape_transform(g, ext, ints, margin, ang, dx, dx)
+        idx = list(range(0, g.num_nodes, 7))
+        rings = [g.tile_rings[i] for i in idx]
+        batch = tio.intersection_areas_with_convex(e2, i2, rings)
+        single = np.asarray([tio.intersection_area_with_convex(e2, i2, r) for r in rings])
+        assert np.allclose(batch, single, rtol=0, atol=1e-12)
+        assert (np.abs(batch - g.tile_areas[idx]) < 1e-6).any() and (batch == 0).any()      # contained and disjoint tiles both occur

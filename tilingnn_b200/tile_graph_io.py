@@ -190,6 +190,76 @@ def intersection_area_with_convex(exterior, interiors, tile_ring):
     return a
 
 
+def _clip_area_batch(subject, tiles):
+    """Area of ``subject`` (open ring [n,2], any orientation) clipped by each CONVEX tile of ``tiles`` [B,m,2] (open
+    rings): Sutherland-Hodgman for all tiles at once on padded arrays -- the same arithmetic as ``_clip_by_convex`` +
+    ``shoelace_area`` per tile, without the Python loop over tiles and vertices."""
+    tiles = np.asarray(tiles, dtype=np.float64)
+    B, m = tiles.shape[:2]
+    x, y = tiles[:, :, 0], tiles[:, :, 1]
+    signed = 0.5 * (x * np.roll(y, -1, axis=1) - np.roll(x, -1, axis=1) * y).sum(axis=1)
+    tiles = np.where((signed < 0)[:, None, None], tiles[:, ::-1], tiles)                 # counter-clockwise clip rings
+    n = len(subject)
+    pts = np.broadcast_to(np.asarray(subject, dtype=np.float64), (B, n, 2)).copy()
+    cnt = np.full(B, n, dtype=np.int64)
+    rows = np.arange(B)[:, None]
+    for i in range(m):
+        L = pts.shape[1]
+        if L == 0:
+            break
+        p, q = tiles[:, i], tiles[:, (i + 1) % m]
+        ex, ey = (q[:, 0] - p[:, 0])[:, None], (q[:, 1] - p[:, 1])[:, None]
+        ar = np.arange(L)[None, :]
+        valid = ar < cnt[:, None]
+        d = ex * (pts[:, :, 1] - p[:, 1, None]) - ey * (pts[:, :, 0] - p[:, 0, None])     # >= 0: inside
+        nxt_i = (ar + 1) % np.maximum(cnt, 1)[:, None]
+        nxt = pts[rows, nxt_i]
+        dn = d[rows, nxt_i]
+        s_in, e_in = d >= 0, dn >= 0
+        emit1 = s_in & valid
+        emit2 = (s_in != e_in) & valid
+        with np.errstate(divide="ignore", invalid="ignore"):
+            t = d / (d - dn)
+            inter = pts + t[:, :, None] * (nxt - pts)                                     # only read where emit2
+        c = emit1.astype(np.int64) + emit2.astype(np.int64)
+        pos = np.cumsum(c, axis=1) - c
+        new_cnt = c.sum(axis=1)
+        out = np.zeros((B, max(int(new_cnt.max()), 1), 2))
+        bb = np.broadcast_to(rows, (B, L))
+        out[bb[emit1], pos[emit1]] = pts[emit1]
+        pos2 = pos + emit1
+        out[bb[emit2], pos2[emit2]] = inter[emit2]
+        pts, cnt = out, new_cnt
+    L = pts.shape[1]
+    if L == 0:
+        return np.zeros(B)
+    ar = np.arange(L)[None, :]
+    valid = ar < cnt[:, None]
+    nxt_i = (ar + 1) % np.maximum(cnt, 1)[:, None]
+    nx = pts[rows, nxt_i]
+    cross = np.where(valid, pts[:, :, 0] * nx[:, :, 1] - nx[:, :, 0] * pts[:, :, 1], 0.0)
+    area = 0.5 * np.abs(cross.sum(axis=1))
+    return np.where(cnt >= 3, area, 0.0)
+
+
+def intersection_areas_with_convex(exterior, interiors, tile_rings):
+    """``intersection_area_with_convex`` for many tiles (rings grouped by vertex count and clipped in batches)."""
+    open_rings = [_open_ring(r) for r in tile_rings]
+    out = np.zeros(len(open_rings))
+    ext = _open_ring(exterior)
+    holes = [_open_ring(h) for h in interiors]
+    by_m = {}
+    for i, r in enumerate(open_rings):
+        by_m.setdefault(len(r), []).append(i)
+    for m, idx in by_m.items():
+        tiles = np.stack([open_rings[i] for i in idx])
+        a = _clip_area_batch(ext, tiles)
+        for h in holes:
+            a = a - _clip_area_batch(h, tiles)
+        out[idx] = a
+    return out
+
+
 def graph_bound(g: CompleteGraph):
     allpts = np.concatenate(g.tile_rings, axis=0)
     return allpts[:, 0].min(), allpts[:, 0].max(), allpts[:, 1].min(), allpts[:, 1].max()
@@ -254,14 +324,16 @@ def crop_from_contour(g, exterior, interiors, margin_padding_ratio=0.5, rotate_a
     _, ext, ints = shape_transform(g, exterior, interiors, margin_padding_ratio,
                                    rotate_angle, x_delta, y_delta)
     lo, hi = ext.min(axis=0), ext.max(axis=0)
-    keep = []
-    for i, ring in enumerate(g.tile_rings):
-        rl, rh = ring.min(axis=0), ring.max(axis=0)
-        if rl[0] < lo[0] - 1e-9 or rl[1] < lo[1] - 1e-9 or rh[0] > hi[0] + 1e-9 or rh[1] > hi[1] + 1e-9:
-            continue                                                    # bbox reject: cannot be contained
-        a = intersection_area_with_convex(ext, ints, ring)
-        if abs(a - g.tile_areas[i]) < 1e-6:                             # algo_util.py:143-144
-            keep.append(i)
+    bb = g._edge_pos.get("tile_bbox")                                   # per-graph cache: [N,4] xmin, ymin, xmax, ymax
+    if bb is None:
+        bb = np.asarray([[*r.min(axis=0), *r.max(axis=0)] for r in g.tile_rings])
+        g._edge_pos["tile_bbox"] = bb
+    inside = (bb[:, 0] >= lo[0] - 1e-9) & (bb[:, 1] >= lo[1] - 1e-9) & (bb[:, 2] <= hi[0] + 1e-9) & (bb[:, 3] <= hi[1] + 1e-9)
+    cand = np.flatnonzero(inside).tolist()                              # bbox reject: the others cannot be contained
+    if not cand:
+        return super_graph_from_tiles(g, [])
+    areas = intersection_areas_with_convex(ext, ints, [g.tile_rings[i] for i in cand])
+    keep = [i for i, a in zip(cand, areas) if abs(a - g.tile_areas[i]) < 1e-6]      # algo_util.py:143-144
     return super_graph_from_tiles(g, keep)
 
 
