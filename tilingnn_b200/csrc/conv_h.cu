@@ -51,12 +51,14 @@ __device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH
         for (int ks = 0; ks < 2; ++ks) {
             const uint4 ra = rows[ks], rb = rows[2 + ks];
             const uint4 bh = b.h[ks][j], bl = b.l[ks][j];
+            // issue order: the two updates of sm[u] are four instructions apart (an HMMA's result is ready after ~4
+            // issue slots of the tensor pipe), the independent main products sit between them
             mma_f16(sm[0], ra.z, rb.z, ra.w, rb.w, bh.x, bh.y);          // lo . Whi
             mma_f16(sm[1], ra.z, rb.z, ra.w, rb.w, bh.z, bh.w);
-            mma_f16(sm[0], ra.x, rb.x, ra.y, rb.y, bl.x, bl.y);          // hi . Wlo
-            mma_f16(sm[1], ra.x, rb.x, ra.y, rb.y, bl.z, bl.w);
             mma_f16(mn[ks][0], ra.x, rb.x, ra.y, rb.y, bh.x, bh.y);      // hi . Whi
             mma_f16(mn[ks][1], ra.x, rb.x, ra.y, rb.y, bh.z, bh.w);
+            mma_f16(sm[0], ra.x, rb.x, ra.y, rb.y, bl.x, bl.y);          // hi . Wlo
+            mma_f16(sm[1], ra.x, rb.x, ra.y, rb.y, bl.z, bl.w);
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u)
