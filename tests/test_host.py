@@ -96,6 +96,10 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
                 assert "/root/reference" not in src.replace("/root/reference/", "REFDOC/") or f.endswith(".py")
+    # outside the package only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may touch oracle/
+    for f in os.listdir(os.path.join(ROOT, "scripts")):
+        if f.endswith((".py", ".sh")):
+            assert not re.search(r"^\s*(from|import)\s+oracle", open(os.path.join(ROOT, "scripts", f)).read(), flags=re.M), f
 
 
 def test_synthetic_generator_properties():
