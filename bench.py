@@ -36,7 +36,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="tilingnn", choices=["tilingnn", "reference"])
-    ap.add_argument("--nodes", type=int, default=1_000_000, help="nodes per GPU")
+    ap.add_argument("--nodes", type=int, default=1_000_000, help="nodes per GPU (weak scaling) / in total (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank owns --nodes nodes of an N x larger graph; strong: ONE --nodes graph is cut into "
+                         "N node-range shards (BASELINE.json config 4)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded-vs-oracle parity check of multi-GPU runs")
     ap.add_argument("--deg", type=int, default=32, help="adjacency and collision stencil size")
     ap.add_argument("--depth", type=int, default=6)
     ap.add_argument("--bn", default="train", choices=["train", "eval"])
@@ -76,14 +80,57 @@ def kernel_bytes_model(fam, n, e_adj, e_col, L):
     return 0
 
 
+def kernel_flops_model(fam, n, e_adj, e_col, L):
+    """ALGORITHMIC tensor-core FLOPs of ONE launch of a kernel family, times the THREE
+    half-precision products a split-precision fp32-accurate contraction costs (hi.hi + hi.lo + lo.hi)."""
+    if fam == "conv":      # per adjacency edge a [1x32].[32x32] product, per node the root term
+        return 3 * 2.0 * 1024 * (e_adj + n)
+    if fam == "gin":       # node MLP 32 -> 32 -> 64 -> 32
+        return 3 * 2.0 * 5120 * n
+    if fam == "final":     # averaged over the four dense stages
+        return 3 * 2.0 * (32 * (L + 1) * 256 + 256 * 128 + 128 * 64 + 64 * 32) * n / 4
+    return 0.0
+
+
 def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s, source)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), float(j.get("bf16_tflops", 1640.9)), "measured (MEASURED_PEAKS.json, burst figures)"
         except Exception:
             pass
-    return 6650.0, "fallback (B200_PROFILING.md)"
+    return 6650.0, 1640.9, "fallback (B200_PROFILING.md)"
+
+
+def sharded_parity(net_factory, dev, rank, world, group=None):
+    """Driver-visible multi-GPU parity: two small lattices scored through the SHARDED path (same exchange kernels as
+    the benchmark) and compared on rank 0 with the fp64 oracle of the UNSHARDED graph.  Returns the max abs error."""
+    import torch
+    import torch.distributed as dist
+    from tilingnn_b200 import shard as shard_mod, synthetic as syn
+    worst = 0.0
+    for n, deg in ((20000, 8), (6000, 32)):
+        bounds = shard_mod.even_bounds(n, world)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        x, ai, af, ci = syn.lattice_graph(n, deg, deg, D_X, D_E, seed=1, device=dev, lo=lo, hi=hi)
+        net, params = net_factory()
+        plan = shard_mod.make_plan(n, bounds, ai, ci)
+        net.set_graph_shard(plan, af)
+        s = net.score(x)
+        net.check_errors()
+        parts = [torch.zeros(bounds[q + 1] - bounds[q], dtype=torch.float32, device=dev) for q in range(world)]
+        dist.all_gather(parts, s.contiguous())
+        if rank == 0:
+            from oracle import tilingnn_oracle as orc          # the checker (fp64, unsharded), never the thing measured
+            xg, aig, afg, cig = syn.lattice_graph(n, deg, deg, D_X, D_E, seed=1)
+            gold = orc.forward(params, xg, aig, afg, cig, depth=net.network_depth, bn_mode="train", dtype=torch.float64)[:, 0]
+            worst = max(worst, float((torch.cat(parts).double().cpu() - gold).abs().max()))
+        del net
+    t = torch.tensor([worst], device=dev)
+    dist.broadcast(t, src=0)
+    return float(t.item())
 
 
 class ClockSampler:
@@ -291,7 +338,9 @@ def main():
         return run_reference(args)
     # NCCL writes its banner to stdout when NCCL_DEBUG=VERSION/INFO is set in the environment; stdout must carry
     # exactly one JSON line.  TGNN_NCCL_DEBUG passes a level through explicitly (output then goes to stderr's file).
-    os.environ["NCCL_DEBUG"] = os.environ.get("TGNN_NCCL_DEBUG", "WARN")
+    # NCCL writes its log to stdout by default; stdout must carry exactly one JSON line, so the log goes to stderr --
+    # at whatever level the caller asked for (NCCL_DEBUG is left alone: the driver reads the communicator sizes from it).
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import __graft_entry__ as ge
@@ -311,12 +360,26 @@ def main():
     from tilingnn_b200 import shard as shard_mod
     warmup = max(3, args.warmup)
 
-    n_global = args.nodes * world
+    n_global = args.nodes * world if args.scaling == "weak" else args.nodes
     bounds = shard_mod.even_bounds(n_global, world)
     lo, hi = bounds[rank], bounds[rank + 1]
     net, sd = seeded_state_dict(args.depth)
     net = net.to(dev)
     net.train() if args.bn == "train" else net.eval()
+    parity_err = None
+    if world > 1 and not args.no_parity:
+        def small_net():
+            from oracle import tilingnn_oracle as orc
+            from tilingnn_b200 import TilinGNN
+            p = orc.make_params(D_X, D_E, args.depth, seed=1)          # conditioned weights, identical on every rank
+            m = TilinGNN(D_E, args.depth, 32, node_features_dim=D_X)
+            m.load_state_dict(p, strict=True)
+            m = m.to(dev).train()
+            m.shard_init()
+            return m, p
+        parity_err = sharded_parity(small_net, dev, rank, world)
+        if not (parity_err <= 1e-4):
+            raise SystemExit(f"sharded parity check failed: max |sharded CUDA - unsharded fp64 oracle| = {parity_err:.3e} > 1e-4")
     x, ai, af, ci = make_graph(args, n_global, lo, hi, dev)
     e_adj, e_col, n_own = ai.shape[1], ci.shape[1], hi - lo
     plan = None
@@ -370,17 +433,24 @@ def main():
             a[0] += ms / reps; a[1] = nl
     net.set_profiling(False)
     torch.cuda.synchronize()
-    peak, peak_src = measured_peaks()
+    peak, peak_tc, peak_src = measured_peaks()
     dom = max(fam_ms, key=lambda f: fam_ms[f][0])
     dom_ms, dom_launches = fam_ms[dom]
     per_launch_ms = dom_ms / max(1, dom_launches)
     kb = kernel_bytes_model(dom, n_own, e_adj, e_col, args.depth)
+    kf = kernel_flops_model(dom, n_own, e_adj, e_col, args.depth)
     achieved = kb / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-    traffic = None
+    achieved_tf = kf / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+    t_hbm_ms, t_tc_ms = kb / (peak * 1e9) * 1e3, kf / (peak_tc * 1e12) * 1e3
+    bound = "tensor" if t_tc_ms > t_hbm_ms else "hbm"
+    traffic, traffic_src = None, None
     prof_json = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(prof_json):
         try:
-            traffic = json.load(open(prof_json)).get("traffic_bytes_per_launch", {}).get(dom)
+            pj = json.load(open(prof_json))
+            traffic = pj.get("traffic_bytes_per_launch", {}).get(dom)
+            traffic_src = (f"profiles/ncu_summary.json: dram__bytes_read+write of ONE ncu --set full capture "
+                           f"({pj.get('captured_on', 'single GPU, headline workload')}); not re-measured in this run")
         except Exception:
             traffic = None
     bpn = bytes_per_node_model(args.depth, e_adj / n_own, e_col / n_own, args.bn)
@@ -426,18 +496,26 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"synthetic {args.graph} super-graph, {args.nodes} nodes per GPU ({n_global} total), "
+            "config": {"workload": f"synthetic {args.graph} super-graph, {n_own} nodes per GPU ({n_global} total, {args.scaling} scaling), "
                                    f"avg-deg {e_adj / n_own:.1f} adj + {e_col / n_own:.1f} col, {args.depth} layers, width 32, "
                                    f"{args.bn}-mode BatchNorm (reference behaviour), {info['n_edge_types']} edge types",
-                       "nodes_per_gpu": args.nodes, "deg": args.deg, "depth": args.depth, "bn": args.bn,
+                       "nodes_per_gpu": n_own, "deg": args.deg, "depth": args.depth, "bn": args.bn,
                        "parallelism": f"node-range shards x{world}" if world > 1 else "single GPU",
                        "l2_policy": f"no flush needed: per-step working set {info['workspace_bytes'] / 1e9:.1f} GB >> 126 MB L2"},
-            "roofline": {"bound": "hbm", "kernel": {"conv": {0: "k_conv_adj", 1: "k_conv_s", 2: "k_conv_h"}[int(info["conv_kernel"])],
+            "roofline": {"bound": bound, "kernel": {"conv": {0: "k_conv_adj", 1: "k_conv_s", 2: "k_conv_h"}[int(info["conv_kernel"])],
                                                     "gin": "k_gin", "final": "k_dense_tc", "combine": "k_combine"}.get(dom, dom),
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
+                         "achieved": achieved_tf if bound == "tensor" else achieved,
+                         "peak": peak_tc if bound == "tensor" else peak,
+                         "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                         "frac": (achieved_tf / peak_tc) if bound == "tensor" else (achieved / peak),
+                         "t_hbm_ms": t_hbm_ms, "t_tc_ms": t_tc_ms,
+                         "hbm": {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak},
+                         "tensor": {"achieved": achieved_tf, "peak": peak_tc, "unit": "TFLOP/s", "frac": achieved_tf / peak_tc,
+                                    "algorithmic_flops_per_launch": kf,
+                                    "note": "3 half-precision products per fp32-accurate contraction (split precision)"},
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": kb, "ms_per_launch": per_launch_ms,
                          "share_of_step": dom_ms / max(1e-9, sum(v[0] for v in fam_ms.values())),
                          "forward": {"algorithmic_bytes_per_node": bpn, "achieved": fwd_gbs, "frac": fwd_gbs / peak}},
@@ -446,6 +524,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": int(info["launches_per_forward"]) * args.steps,
             "collectives_per_step": int(info["collectives_per_forward"]),
+            "parity_max_err": parity_err,
             "clocks": clocks,
         }
         print(json.dumps(line))

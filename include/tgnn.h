@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TGNN_ABI_VERSION 4
+#define TGNN_ABI_VERSION 5
 
 #define TGNN_BN_TRAIN 0   /* batch statistics over the rows of THIS call -- the reference's
                              behaviour: solver/ml_solver/ml_solver.py:129-131 ends in network.train() */
@@ -82,6 +82,15 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes,
 /* TilinGNN.forward(x, ...) -> scores  (graph_networks/networks/TilinGNN.py:51-78).
  * x: [n_nodes, d_x] fp32 device; scores_out: [n_nodes] fp32 device (the [N,1] column). */
 int tgnn_forward(tgnn_handle* h, const float* x, float* scores_out, void* stream);
+
+/* Device-side failures (a tcgen05 pipeline timeout, a peer-exchange wait that timed out) are recorded by
+ * the kernels in a word of mapped host memory.  They are always surfaced: by tgnn_forward itself when the
+ * graph is small (it then synchronises `stream`, the callers read the scores back at once anyway), otherwise
+ * at the start of the next API call on the handle -- or here.  synchronize != 0: wait for `stream` first (what
+ * a caller does before trusting scores of a large graph); 0: host read only.  Non-zero return = an error was
+ * pending (tgnn_last_error has the text; the word is cleared).  Keeps the reference's contract that a failed
+ * forward surfaces as a Python exception (graph_networks/network_utils.py:10-19). */
+int tgnn_check_error(tgnn_handle* h, void* stream, int32_t synchronize);
 
 /* ---- multi-GPU: node-range shards (new work; the reference is single-device) ------------
  * Per layer one exchange of boundary rows and one of BatchNorm sums.  By default both are peer-memory

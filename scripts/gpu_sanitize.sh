@@ -1,0 +1,26 @@
+#!/bin/bash
+# compute-sanitizer passes over the scoring path: memcheck + racecheck + synccheck on the 10k x deg 8
+# configuration (every kernel family runs, incl. the tcgen05 dense stages) and on a small real-layout-sized graph
+# (split-tile conv, BatchNorm finish inside k_combine); with 2+ GPUs also memcheck of a sharded forward through the
+# peer-memory exchange (epoch flags: st.release.sys / ld.acquire.sys, double buffering by epoch parity).
+# Run on the B200 box:  bash scripts/gpu_sanitize.sh [tag]      logs -> gpurun_out/sanitize_<tag>_*.log
+set -u
+OUT=gpurun_out; mkdir -p $OUT
+TAG=${1:-r2}
+CS=/usr/local/cuda/bin/compute-sanitizer
+DRV='python scripts/sanitize_driver.py'
+for tool in memcheck racecheck synccheck; do
+  timeout 900 $CS --tool $tool --print-limit 20 --error-exitcode 3 $DRV --nodes 10000 --deg 8 --depth 6 \
+      > $OUT/sanitize_${TAG}_${tool}_10k.log 2>&1
+  echo "$tool 10k: exit $?"; tail -3 $OUT/sanitize_${TAG}_${tool}_10k.log
+done
+timeout 900 $CS --tool racecheck --print-limit 20 --error-exitcode 3 $DRV --nodes 600 --deg 16 --depth 20 \
+    > $OUT/sanitize_${TAG}_racecheck_600.log 2>&1
+echo "racecheck 600: exit $?"; tail -3 $OUT/sanitize_${TAG}_racecheck_600.log
+NG=$(nvidia-smi -L | wc -l)
+if [ "$NG" -ge 2 ]; then
+  timeout 1200 $CS --tool memcheck --print-limit 20 --error-exitcode 3 --target-processes all \
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29577 \
+      scripts/sanitize_driver.py --nodes 20000 --deg 8 --depth 6 > $OUT/sanitize_${TAG}_memcheck_2gpu.log 2>&1
+  echo "memcheck 2gpu: exit $?"; tail -3 $OUT/sanitize_${TAG}_memcheck_2gpu.log
+fi

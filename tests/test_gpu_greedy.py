@@ -64,14 +64,31 @@ def test_solve_heart_matches_the_oracle_driven_greedy(dev):
     solved, score = solver.solve(sg, rng=np.random.RandomState(2))
     check_valid(sg, solved)
     assert 0.0 < score <= 1.0 + 0.02
-    ref = greedy.solve_by_probablistic_greedy(OracleSolver(ckpt, graph), sg, rng=np.random.RandomState(2))
+    tr_ours, tr_ref = [], []
+    ours = greedy.solve_by_probablistic_greedy(solver, sg, rng=np.random.RandomState(2), trace=tr_ours)
+    assert np.array_equal(ours.selection, solved.predict)                # solve() = this loop + one more scoring pass
+    ref = greedy.solve_by_probablistic_greedy(OracleSolver(ckpt, graph), sg, rng=np.random.RandomState(2), trace=tr_ref)
     same = np.array_equal(ref.selection, solved.predict)
     print(f"heart: {int(solved.predict.sum())} tiles in {solved.greedy_rounds} rounds, score {score:.6f}; oracle-driven: "
           f"{int(ref.selection.sum())} tiles in {ref.rounds} rounds, score {ref.score:.6f}; identical selection: {same}")
-    # the acceptance test compares exp(p - 1) with a uniform draw: a 1e-4 difference in p flips a decision with
-    # probability ~1e-4 per visit, after which the two runs legitimately diverge -- so equality is reported and the
-    # quality is asserted
-    assert same or abs(score - ref.score) < 0.05
+    # Same seed, same loop, scores from two sources (CUDA fp32 vs fp64 oracle).  Either every decision is identical, or
+    # the FIRST decision at which the two runs part ways must be a numerical tie: the acceptance test exp(p - 1) > u
+    # within MARGIN of its threshold, or two candidates whose thresholds are within MARGIN swapping places in the
+    # visiting order.  Anything else is a real scoring difference and fails.
+    MARGIN = 1e-3          # tier-3 scores on this graph differ from fp64 by 2e-4 (test_gpu_parity), blended over rounds
+    if not same:
+        k = next((i for i, (a, b) in enumerate(zip(tr_ours, tr_ref)) if a[1] != b[1] or a[4] != b[4]), None)
+        assert k is not None, "selections differ but the visited decisions do not"
+        a, b = tr_ours[k], tr_ref[k]
+        print(f"first diverging decision #{k}: ours {a}  oracle-driven {b}")
+        if a[1] == b[1]:
+            assert abs(a[2] - a[3]) < MARGIN and abs(b[2] - b[3]) < MARGIN, "acceptance flipped far from its threshold"
+        else:
+            assert abs(a[2] - b[2]) < MARGIN, "visiting order differs between candidates that are not a numerical tie"
+    for a, b in zip(tr_ours, tr_ref):                                      # up to the divergence the thresholds agree closely
+        if a[1] != b[1] or a[4] != b[4]:
+            break
+        assert abs(a[2] - b[2]) < MARGIN
 
 
 @pytest.mark.parametrize("mode", ["train", "eval"])
@@ -92,7 +109,7 @@ def test_second_tile_set_network_parity(dev, mode):
     gold, ref32 = z[f"L0_ref_{mode}_f64"], z[f"L0_ref_{mode}_f32"]
     ours, theirs = np.abs(s - gold).max(), np.abs(ref32 - gold).max()
     print(f"bunny/equilateral {mode}-BN: ours {ours:.2e}  reference-fp32 {theirs:.2e}  types {net.info()['n_edge_types']}")
-    assert ours <= max(1e-4, 1.5 * theirs)
+    assert ours <= max(1e-4, theirs)
 
 
 @pytest.mark.parametrize("mode", ["train", "eval"])
@@ -112,7 +129,7 @@ def test_third_tile_set_network_parity(dev, mode):
     gold, ref32 = z[f"ref_{mode}_f64"], z[f"ref_{mode}_f32"]
     ours, theirs = np.abs(s - gold).max(), np.abs(ref32 - gold).max()
     print(f"heart/45-45-90+rectangle {mode}-BN: ours {ours:.2e}  reference-fp32 {theirs:.2e}  types {net.info()['n_edge_types']}")
-    assert ours <= max(1e-4, 1.5 * theirs)
+    assert ours <= max(1e-4, theirs)
 
 
 def test_config5_bunny_layouts(dev):

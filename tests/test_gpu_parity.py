@@ -6,8 +6,9 @@ Tolerances (fp32 arithmetic):
   tier 2  end-to-end, well-conditioned nets (eval-BN on the shipped checkpoint; synthetic
           conditioned weights in train-BN): <= 1e-4 absolute on the [0,1] scores
   tier 3  end-to-end train-BN on the shipped checkpoint (ill-conditioned: the reference's own fp32
-          run is 1e-3..7e-2 away from fp64): ours must be no further from fp64 than the reference's
-          fp32 run is (x1.5 slack), and rank the nodes the same way.
+          run is 1e-3..7e-2 away from fp64): ours must be within 1e-3 absolute of fp64 (measured
+          2.0e-4 / 4.1e-4) AND no further from it than the reference's fp32 run is, and rank the nodes
+          the same way (top-100 overlap >= 98; measured 100 / 99).
 """
 import numpy as np
 import pytest
@@ -118,7 +119,9 @@ def test_config1_eval_bn_end_to_end(dev, graph):
     ours = np.abs(s - z["ref_eval_f64"]).max()
     ref32 = np.abs(z["ref_eval_f32"] - z["ref_eval_f64"]).max()
     print(f"{graph} eval-BN: ours {ours:.2e}  reference-fp32 {ref32:.2e}")
-    assert ours <= max(TOL, 1.5 * ref32)
+    # the reference's own fp32 run is 2.7e-4 from fp64 here (collapsed running_var in the collision branch: gains of
+    # ~316 on fp32 rounding); ours must not be worse than it, with a hard cap of 3e-4
+    assert ours <= max(TOL, ref32) and ours <= 3e-4
 
 
 @pytest.mark.parametrize("graph", ["c1_heart.npz", "c1_complete.npz"])
@@ -133,8 +136,8 @@ def test_config1_train_bn_end_to_end(dev, graph):
     overlap, ref_overlap = len(top(s) & top(gold)), len(top(z["ref_train_f32"]) & top(gold))
     print(f"{graph} train-BN: ours max {ours:.2e} mean {np.abs(s - gold).mean():.2e} | reference-fp32 max {ref32:.2e} "
           f"mean {np.abs(z['ref_train_f32'] - gold).mean():.2e} | top-100 overlap ours {overlap} ref {ref_overlap}")
-    assert ours <= max(TOL, 1.5 * ref32)
-    assert overlap >= min(ref_overlap, 95) - 3
+    assert ours <= 1e-3 and ours <= max(TOL, ref32)
+    assert overlap >= 98
 
 
 @pytest.mark.parametrize("n,deg", [(10000, 8), (4000, 32)])
@@ -165,7 +168,7 @@ def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     net = make_net(load_ckpt(), 3, 19, 20, dev, "train")
     s = run(net, x, ai, af, ci, dev)
     gold = z["ref_train_f64"]
-    assert np.abs(s - gold).max() <= max(TOL, 1.5 * np.abs(z["ref_train_f32"] - gold).max())
+    assert np.abs(s - gold).max() <= 1e-3          # tier 3 (reference fp32: 6.6e-2)
     x, ai, af, ci = syn.lattice_graph(6000, 32, 32, seed=3)
     p = orc.make_params(3, 19, 4, seed=3)
     gold = orc.forward(p, x, ai, af, ci, depth=4, dtype=torch.float64)[:, 0].numpy()
@@ -307,4 +310,37 @@ def test_ml_solver_predict_matches_oracle(dev):
     solver = ML_Solver(None, dev, None, net, 1)
     out = solver.predict(Layout())
     assert out.dtype == np.float32 and out.shape == (x.shape[0],)
-    assert np.abs(out - z["ref_eval_f64"]).max() <= max(TOL, 1.5 * np.abs(z["ref_eval_f32"] - z["ref_eval_f64"]).max())
+    assert np.abs(out - z["ref_eval_f64"]).max() <= 3e-4           # tier 2 cap (reference fp32: 2.8e-4)
+
+
+def test_get_network_prediction_and_get_predict_probs(dev, capsys):
+    """a7: ``get_network_prediction`` (graph_networks/network_utils.py:4-21) returns ``probs`` only, keyword-calls the
+    network, prints the traceback and re-raises on failure; ``ML_Solver.get_predict_probs`` (ml_solver.py:69-81) is the
+    same call from a layout.  Both must give exactly what ``network.forward`` gives."""
+    from tilingnn_b200 import ML_Solver
+    from tilingnn_b200.ml_solver import get_network_prediction
+    z, x, ai, af, ci = load_graph("c1_heart.npz")
+    net = make_net(load_ckpt(), 3, 19, 20, dev, "train")
+    xd, aid, afd, cid = x.to(dev), ai.to(dev), af.to(dev), ci.to(dev)
+    direct, feats = net(x=xd, adj_e_index=aid, adj_e_features=afd, col_e_idx=cid)
+    direct = direct.clone()
+    probs = get_network_prediction(net, xd, aid, afd, cid, None)
+    assert isinstance(probs, torch.Tensor) and probs.shape == (x.shape[0], 1) and probs.device.type == "cuda"
+    assert torch.equal(probs, direct)
+    gold = z["ref_train_f64"]
+    assert np.abs(probs[:, 0].double().cpu().numpy() - gold).max() <= 1e-3
+
+    class Layout:
+        node_feature = x.double().numpy()
+        align_edge_index = ai.numpy()
+        align_edge_features = af.double().numpy()
+        collide_edge_index = ci.numpy()
+        collide_edge_features = np.zeros((ci.shape[1], 19))
+    solver = ML_Solver(None, dev, None, net, 1)
+    p2 = solver.get_predict_probs(Layout())
+    assert p2.shape == (x.shape[0], 1) and torch.equal(p2, direct)
+    assert np.array_equal(solver.predict(Layout()), direct[:, 0].cpu().numpy())
+    # failure contract: traceback printed, exception re-raised (network_utils.py:16-19)
+    with pytest.raises(RuntimeError):
+        get_network_prediction(net, xd.cpu(), aid, afd, cid)
+    assert "Traceback" in capsys.readouterr().out

@@ -189,3 +189,25 @@ def test_batched_clip_equals_per_tile_clip():
         single = np.asarray([tio.intersection_area_with_convex(e2, i2, r) for r in rings])
         assert np.allclose(batch, single, rtol=0, atol=1e-12)
         assert (np.abs(batch - g.tile_areas[idx]) < 1e-6).any() and (batch == 0).any()      # contained and disjoint tiles both occur
+
+
+def test_graph_unpickler_rejects_globals_outside_the_allow_list():
+    """complete_graph_ring*.pkl are external data files: the stub unpickler must not import arbitrary callables."""
+    import io
+    import pickle
+    from tilingnn_b200 import tile_graph_io as tio
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+    with pytest.raises(pickle.UnpicklingError, match="allow-list"):
+        tio._GraphUnpickler(io.BytesIO(pickle.dumps({"tiles": [Evil()]}))).load()
+    ok = tio._GraphUnpickler(io.BytesIO(pickle.dumps({"a": np.arange(3), "b": [1.0, (2, 3)]}))).load()
+    assert ok["a"].tolist() == [0, 1, 2]
+
+
+def test_even_bounds_rejects_empty_ranges_on_every_rank():
+    from tilingnn_b200 import shard
+    assert shard.even_bounds(1000, 4) == [0, 256, 512, 768, 1000]
+    with pytest.raises(ValueError, match="non-empty"):
+        shard.even_bounds(128, 4)          # 64-aligned ranges would leave ranks 2 and 3 empty

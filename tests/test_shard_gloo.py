@@ -74,8 +74,11 @@ def test_shard_plan_gloo(world, n, deg):
 
 def test_even_bounds():
     from tilingnn_b200 import shard
-    for n, w in ((1000000, 8), (10000, 2), (100, 4), (63, 2)):
+    for n, w in ((1000000, 8), (10000, 2), (200, 4), (65, 2)):
         b = shard.even_bounds(n, w)
         assert b[0] == 0 and b[-1] == n and len(b) == w + 1
-        assert all(b[i] <= b[i + 1] for i in range(w))
+        assert all(b[i] < b[i + 1] for i in range(w))                    # no rank is left without nodes
         assert all(x % 64 == 0 or x == n for x in b[:-1])
+    for n, w in ((100, 4), (63, 2)):                                     # would leave trailing ranks empty: rejected everywhere
+        with pytest.raises(ValueError):
+            shard.even_bounds(n, w)

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_C", "libtgnn.so")
 
 TGNN_BN_TRAIN, TGNN_BN_EVAL = 0, 1
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class tgnn_cfg(C.Structure):
@@ -41,6 +41,7 @@ SIGNATURES = {
     "tgnn_set_bn_mode": (C.c_int, [_vp, _i32]),
     "tgnn_set_graph": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "tgnn_forward": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "tgnn_check_error": (C.c_int, [_vp, _vp, _i32]),
     "tgnn_nccl_unique_id": (C.c_int, [_vp]),
     "tgnn_shard_init": (C.c_int, [_vp, _vp, _i32, _i32]),
     "tgnn_set_graph_shard": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),

@@ -82,7 +82,12 @@ struct tgnn_handle {
     std::vector<std::unique_ptr<DevBuf>> gin_wt;    // per layer: frag tables W1|W2|W3 and biases b1|b2|b3
     std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4: k-major transposes (CUDA-core path)
     std::vector<std::unique_ptr<DevBuf>> fin_whl;   // 4: pre-swizzled hi|lo slab images of the weights (tcgen05 path)
-    DevBuf dev_error;                               // int: device-side error flag (pipeline timeouts)
+    DevBuf dev_error;                               // int[2]: [1] = scratch range flag of pack_params ([0] unused)
+    // Device-side error word in MAPPED PINNED HOST memory: kernels store a code there (1 = tcgen05 pipeline timeout,
+    // 2 = peer-exchange wait timeout) and the host reads it without a CUDA call -- at the start of every API call, after
+    // the synchronous checks, and from tgnn_check_error.  It stays readable even after a kernel trap killed the context.
+    int* err_host = nullptr;
+    int* err_dev = nullptr;
     bool dense_ffma = false;                        // TGNN_DENSE=ffma selects the CUDA-core dense stage (debug A/B)
     // parameter pointers resolved once per pack_params (no string building / map lookups per launch in the forward)
     struct LayerP { const float *conv_bias, *bn_a_w, *bn_a_b, *bn_c_w, *bn_c_b; };
@@ -394,6 +399,8 @@ void alloc_workspace(tgnn_handle* h) {
     h->workspace_bytes = total;
 }
 
+constexpr int64_t SYNC_CHECK_MAX_NODES = 16384;
+
 struct Launcher {
     tgnn_handle* h; cudaStream_t st;
     void begin(const char* fam) {
@@ -412,8 +419,25 @@ struct Launcher {
     }
 };
 
+const char* device_error_text(int code) {
+    switch (code) {
+        case TGNN_DEVERR_PIPELINE: return "device-side pipeline timeout in a tcgen05 kernel (mbarrier wait exceeded its bound); the scores of that forward are invalid";
+        case TGNN_DEVERR_PEER: return "peer-memory exchange timed out waiting for another rank (a rank stalled or died); the kernel was aborted";
+        default: return "unknown device-side error code";
+    }
+}
+// Host read of the mapped error word; throws (and clears the word) when a kernel reported an error.
+void check_device_error(tgnn_handle* h, const char* where) {
+    if (!h->err_host) return;
+    const int e = *reinterpret_cast<volatile int*>(h->err_host);
+    if (e == 0) return;
+    *reinterpret_cast<volatile int*>(h->err_host) = 0;
+    throw Error(std::string(where) + ": " + device_error_text(e));
+}
+
 PeerPtrs peer_ptrs(tgnn_handle* h) {
     PeerPtrs p{};
+    p.err = h->err_dev;
     for (int q = 0; q < h->world; ++q) p.base[q] = static_cast<char*>(h->px.peer[q]);
     p.world = h->world; p.rank = h->rank;
     return p;
@@ -436,6 +460,17 @@ void peer_setup(tgnn_handle* h, cudaStream_t st) {
     if (h->world <= 1 || h->world > PX_MAX_WORLD || x.disabled) { x.ok = false; return; }
     const size_t need = PX_HALO_OFF + 2 * (size_t)h->world * (size_t)h->g.halo_slot * 64 * sizeof(float);
     const void* before = x.buf.p;
+    if (need > x.buf.cap && x.buf.p) {
+        // The buffer is exported through CUDA IPC: freeing it while a peer still has it mapped is undefined behaviour.
+        // halo_slot is the same on every rank (shard.make_plan takes the maximum), so every rank grows in the SAME
+        // call: close the mappings of the peers' buffers first, then a collective barrier, then reallocate.
+        peer_close(h);
+        x.staging.reserve((size_t)(h->world + 1) * 64 + 2 * sizeof(float));
+        float* bar = reinterpret_cast<float*>(x.staging.as<char>());
+        TGNN_CUDA(cudaMemsetAsync(bar, 0, 2 * sizeof(float), st));
+        nccl_check(nccl().AllReduce(bar, bar + 1, 1, ncclFloat32, ncclSum, h->comm, st), "peer buffer regrow barrier");
+        TGNN_CUDA(cudaStreamSynchronize(st));
+    }
     x.buf.reserve(need);
     if (x.buf.p != before || x.halo_slot != h->g.halo_slot) {
         TGNN_CUDA(cudaMemsetAsync(x.buf.p, 0, x.buf.cap, st));        // flags, and no garbage in padding rows
@@ -505,6 +540,7 @@ void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t s
 
 void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st) {
     TGNN_CHECK(h->graph_set, "tgnn_forward: no graph set (call tgnn_set_graph first)");
+    check_device_error(h, "tgnn_forward (reported by an earlier forward)");
     pack_params(h, st);
     build_tables(h, st);
     const int L = h->cfg.depth;
@@ -570,7 +606,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn;
         lz.begin("conv");
         if (h->use_s) {
-            launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->dev_error.as<int>(), h->sm_count, st);
+            launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->err_dev, h->sm_count, st);
             lz.end(1);
         } else if (h->use_h) {
             // fp16-split kernel; falls through to the 3xTF32 arithmetic itself when a range flag is raised
@@ -650,7 +686,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             lz.begin("final");
             if (h->dense_ffma) launch_dense(da, st);
             else {
-                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->dev_error.as<int>(), h->sm_count, st);
+                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->err_dev, h->sm_count, st);
             }
             lz.end(1);
             if (train) {
@@ -664,11 +700,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
                      n_own, st);
         lz.end(1);
     }
-    if (h->profiling || h->check_errors) {
+    // Device-side errors are ALWAYS surfaced: synchronously here when that is cheap or asked for (small graphs: the
+    // callers read the scores back at once anyway), otherwise at the next API call / tgnn_check_error (the error word
+    // lives in mapped host memory, so reading it needs no CUDA call and no stall of the launch queue).
+    if (h->profiling || h->check_errors || h->g.n_own <= SYNC_CHECK_MAX_NODES) {
         TGNN_CUDA(cudaStreamSynchronize(st));
-        int e = 0;
-        TGNN_CUDA(cudaMemcpy(&e, h->dev_error.p, sizeof(int), cudaMemcpyDeviceToHost));
-        TGNN_CHECK(e == 0, "tgnn_forward: device-side pipeline timeout in a tcgen05 kernel (mbarrier wait exceeded its bound)");
+        check_device_error(h, "tgnn_forward");
     }
     if (h->profiling) {
         for (auto& e : h->prof) {
@@ -685,7 +722,14 @@ int guarded(tgnn_handle* h, Fn&& fn) {
         fn();
         return 0;
     } catch (const std::exception& e) {
-        if (h) h->err = e.what(); else g_create_error = e.what();
+        if (h) {
+            h->err = e.what();
+            // a kernel that aborted (trap) makes the next CUDA call fail with a generic message: say why
+            if (h->err_host && *reinterpret_cast<volatile int*>(h->err_host) != 0) {
+                h->err += std::string(" [device reported: ") + device_error_text(*reinterpret_cast<volatile int*>(h->err_host)) + "]";
+                *reinterpret_cast<volatile int*>(h->err_host) = 0;
+            }
+        } else g_create_error = e.what();
         return 1;
     }
 }
@@ -724,8 +768,11 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
         h->hflags.reserve((size_t)(2 * cfg->depth + 3) * sizeof(int));
         TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 3) * sizeof(int)));
-        h->dev_error.reserve(2 * sizeof(int));                         // [0] pipeline timeout flag, [1] scratch flag of pack_params
+        h->dev_error.reserve(2 * sizeof(int));                         // [1] scratch flag of pack_params
         TGNN_CUDA(cudaMemset(h->dev_error.p, 0, 2 * sizeof(int)));
+        TGNN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->err_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+        memset(h->err_host, 0, 64);
+        TGNN_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->err_dev), h->err_host, 0));
         declare_params(h.get());
         *out = h.release();
     });
@@ -738,6 +785,7 @@ int tgnn_destroy(tgnn_handle* h) {
         for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         peer_close(h);
         if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
+        if (h->err_host) cudaFreeHost(h->err_host);
         delete h;
     }
     return 0;
@@ -793,6 +841,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
     return guarded(h, [&] {
         TGNN_CHECK(h, "tgnn_set_graph: null handle");
         TGNN_CHECK(h->world == 1, "tgnn_set_graph: handle is sharded, use tgnn_set_graph_shard");
+        check_device_error(h, "tgnn_set_graph (reported by an earlier forward)");
         DeviceGuard dg(h->cfg.device);
         cudaStream_t st = (cudaStream_t)stream;
         h->graph_set = false;
@@ -842,6 +891,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
     return guarded(h, [&] {
         TGNN_CHECK(h, "tgnn_set_graph_shard: null handle");
         TGNN_CHECK(halo_slot >= 0 && n_send >= 0 && n_send <= halo_slot && n_global >= n_own, "tgnn_set_graph_shard: bad sizes");
+        check_device_error(h, "tgnn_set_graph_shard (reported by an earlier forward)");
         DeviceGuard dg(h->cfg.device);
         cudaStream_t st = (cudaStream_t)stream;
         h->graph_set = false;
@@ -891,6 +941,17 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
             TGNN_CUDA(cudaMemcpy(f.data(), h->hflags.p, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
             for (int i = 0; i < L; ++i) out->range_fallback_layers += (f[i] | f[L + 1 + i]) ? 1 : 0;
         }
+    });
+}
+
+int tgnn_check_error(tgnn_handle* h, void* stream, int32_t synchronize) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h, "tgnn_check_error: null handle");
+        if (synchronize) {
+            DeviceGuard dg(h->cfg.device);
+            TGNN_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        }
+        check_device_error(h, "tgnn_check_error");
     });
 }
 

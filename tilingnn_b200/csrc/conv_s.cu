@@ -411,7 +411,7 @@ k_conv_s(ConvSArgs A) {
     }
     tc_fence_before();
     __syncthreads();
-    if (timeout_flag && tid == 0) atomicExch(A.error_flag, 1);
+    if (timeout_flag && tid == 0) { *reinterpret_cast<volatile int*>(A.error_flag) = TGNN_DEVERR_PIPELINE; __threadfence_system(); }   // mapped host word
     if (warp == W_MMA) {
         __syncwarp();
         tc_fence_after();

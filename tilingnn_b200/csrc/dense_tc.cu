@@ -303,7 +303,7 @@ k_dense_tc(DenseTcArgs A) {
     if (A.dbg && blockIdx.x == 0 && lane == 0) { long long* d = A.dbg + warp * 4; d[0] = clock64() - t_start; d[1] = w0; d[2] = w1; }
     tc_fence_before();
     __syncthreads();
-    if (timeout_flag && tid == 0) atomicExch(A.error_flag, 1);
+    if (timeout_flag && tid == 0) { *reinterpret_cast<volatile int*>(A.error_flag) = TGNN_DEVERR_PIPELINE; __threadfence_system(); }   // mapped host word
     if (warp == MMA_WARP) {
         __syncwarp();
         tc_fence_after();

@@ -736,17 +736,23 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// spin until flags[q] >= epoch for every peer q (bounded: ~2 s, then the error flag is raised by the caller's check)
-__device__ __forceinline__ bool wait_peers(const unsigned* flags, int world, int rank, unsigned epoch) {
+// Spin until flags[q] >= epoch for every peer q.  A peer's host may lag (first-call module load, garbage collection,
+// CPU work between forwards), so the bound is generous (~30 s); past it the exchange cannot be trusted any more
+// (a fast rank running on would break the "at most one exchange ahead" double-buffer invariant), so the kernel stores
+// an error code in the handle's mapped host word and ABORTS: the stream's next operation fails and tgnn_forward /
+// tgnn_check_error report it -- no NaN results, no later epochs.
+__device__ __forceinline__ void wait_peers(const unsigned* flags, int world, int rank, unsigned epoch, int* err) {
     for (int q = 0; q < world; ++q) {
         if (q == rank) continue;
         long long t0 = clock64();
         while ((int)(ld_acquire_sys(flags + q) - epoch) < 0) {
             __nanosleep(64);
-            if (clock64() - t0 > 4000000000ll) return false;
+            if (clock64() - t0 > 60000000000ll) {
+                if (err) { *reinterpret_cast<volatile int*>(err) = TGNN_DEVERR_PEER; __threadfence_system(); }
+                __trap();
+            }
         }
     }
-    return true;
 }
 
 __global__ void k_bn_finish_x(BnFinishArgs A, PeerPtrs P, unsigned epoch) {
@@ -784,15 +790,14 @@ __global__ void k_bn_finish_x(BnFinishArgs A, PeerPtrs P, unsigned epoch) {
     __syncthreads();
     if (threadIdx.x < P.world && threadIdx.x != P.rank)
         st_release_sys(reinterpret_cast<unsigned*>(P.base[threadIdx.x] + 256) + par * PX_MAX_WORLD + P.rank, epoch);
-    __shared__ bool ok;
-    if (threadIdx.x == 0) ok = wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank] + 256) + par * PX_MAX_WORLD, P.world, P.rank, epoch);
+    if (threadIdx.x == 0) wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank] + 256) + par * PX_MAX_WORLD, P.world, P.rank, epoch, P.err);
     __syncthreads();
     __threadfence_system();
     const double* mine = reinterpret_cast<const double*>(P.base[P.rank] + PX_FLAG_BYTES) + (size_t)par * PX_MAX_WORLD * PX_BN_SLOT;
     for (int i = threadIdx.x; i < n; i += 256) {
         double t = 0.0;
         for (int q = 0; q < P.world; ++q) t += __ldcg(mine + (size_t)q * PX_BN_SLOT + i);      // fixed rank order
-        A.sums[i] = ok ? t : __longlong_as_double(0x7ff8000000000000ll);                       // timeout -> NaN scores, loudly
+        A.sums[i] = t;
     }
     __syncthreads();
     __threadfence();
@@ -842,8 +847,7 @@ __global__ void k_halo_push(const float4* __restrict__ a, const float4* __restri
 __global__ void k_halo_unpack_x(PeerPtrs P, unsigned epoch, int64_t halo_slot, int64_t n_own,
                                 float4* __restrict__ a, float4* __restrict__ b, uint4* __restrict__ xh, int* __restrict__ flag) {
     const int par = epoch & 1u;
-    __shared__ bool ok;
-    if (threadIdx.x == 0) ok = wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank]) + par * PX_MAX_WORLD, P.world, P.rank, epoch);
+    if (threadIdx.x == 0) wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank]) + par * PX_MAX_WORLD, P.world, P.rank, epoch, P.err);
     __syncthreads();
     __threadfence_system();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -853,7 +857,6 @@ __global__ void k_halo_unpack_x(PeerPtrs P, unsigned epoch, int64_t halo_slot, i
     if (r / halo_slot == P.rank) return;               // own slot: rows are read in place
     const float4* recv = reinterpret_cast<const float4*>(P.base[P.rank] + PX_HALO_OFF) + (size_t)par * total;
     float4 v = __ldcg(recv + i);                       // written by a peer over NVLink: L2 is the coherence point
-    if (!ok) v = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
     if (c < 8) {
         a[(size_t)(n_own + r) * 8 + c] = v;
         if (xh) {

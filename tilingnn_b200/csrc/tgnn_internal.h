@@ -268,7 +268,8 @@ constexpr size_t PX_FLAG_BYTES = 4096;                          // uint32 halo_f
 constexpr size_t PX_BN_SLOT = 512;                              // doubles per (parity, rank)
 constexpr size_t PX_BN_BYTES = 2 * PX_MAX_WORLD * PX_BN_SLOT * sizeof(double);
 constexpr size_t PX_HALO_OFF = PX_FLAG_BYTES + PX_BN_BYTES;
-struct PeerPtrs { char* base[PX_MAX_WORLD]; int world, rank; };
+struct PeerPtrs { char* base[PX_MAX_WORLD]; int world, rank; int* err; };   // err: mapped host error word
+enum { TGNN_DEVERR_PIPELINE = 1, TGNN_DEVERR_PEER = 2 };
 // k_bn_finish with the cross-rank sum inside: the last block pushes the local sums to all peers, waits for theirs
 void launch_bn_finish_x(const BnFinishArgs& a, int n_bn, const PeerPtrs& p, unsigned epoch, cudaStream_t st);
 // boundary rows (a | b) -> slot `rank` of every peer's halo buffer, then the epoch flags (last block)

@@ -83,8 +83,10 @@ class GreedyResult:
     labels: np.ndarray = field(default=None, repr=False)   # [N] int8: 1 selected, 0 knocked out by a collision
 
 
-def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_graph=None, max_rounds=None):
-    """algorithms.py:18-62.  ``ml_solver.predict(layout) -> np.ndarray[N]`` is the only network access."""
+def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_graph=None, max_rounds=None, trace=None):
+    """algorithms.py:18-62.  ``ml_solver.predict(layout) -> np.ndarray[N]`` is the only network access.
+    ``trace`` (optional list) receives one ``(round, node, accept threshold exp(p-1), uniform draw, accepted)`` tuple per
+    visited node -- the tests use it to locate the first decision at which two score sources part ways."""
     rng = np.random if rng is None else rng
     n = origin_layout.node_feature.shape[0]
     col = _edges(origin_layout.collide_edge_index)
@@ -115,7 +117,10 @@ def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_gr
             origin_idx = origin_of[idx]
             if label[origin_idx] >= 0:                                    # collision handling: stop this round
                 break
-            if accept_at[idx] > uniform():
+            u = uniform()
+            if trace is not None:
+                trace.append((round_cnt, origin_idx, accept_at[idx], u, accept_at[idx] > u))
+            if accept_at[idx] > u:
                 label[origin_idx] = 1
                 order.append(origin_idx)
                 adj = nbr[ptr[origin_idx]:ptr[origin_idx + 1]]            # label_collision_neighbor (:196-207)

@@ -260,6 +260,17 @@ class TilinGNN(nn.Module):
         _lib.check(nat.h, rc, "tgnn_forward")
         return out
 
+    def check_errors(self, synchronize=True):
+        """Raise if a kernel of an earlier forward reported a device-side failure (tcgen05 pipeline or peer-exchange
+        timeout).  ``tgnn_forward`` checks by itself for small graphs and at the next call for large ones; call this
+        after the last forward of a batch of large graphs."""
+        nat = self._ensure_handle()
+        dev = self._device()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            rc = _lib.load().tgnn_check_error(nat.h, C.c_void_p(st), int(bool(synchronize)))
+        _lib.check(nat.h, rc, "tgnn_check_error")
+
     # ---- multi-GPU: node-range shards (SURVEY.md §8e) --------------------------------------------
     def shard_init(self, group=None):
         """Join this module's handle to an NCCL communicator of its own (one process per GPU).

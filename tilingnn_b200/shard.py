@@ -21,7 +21,13 @@ def even_bounds(n_global: int, world: int):
     """Contiguous, 64-aligned (warp-tile aligned) node ranges of near-equal size."""
     per = -(-n_global // world)
     per = -(-per // 64) * 64
-    return [min(n_global, r * per) for r in range(world)] + [n_global]
+    bounds = [min(n_global, r * per) for r in range(world)] + [n_global]
+    if any(b1 <= b0 for b0, b1 in zip(bounds, bounds[1:])):
+        # every rank computes the same bounds, so every rank raises here -- before any collective is entered
+        # (an empty rank would otherwise fail alone in tgnn_set_graph_shard and leave its peers blocked in NCCL)
+        raise ValueError(f"even_bounds: {n_global} nodes cannot be cut into {world} non-empty 64-aligned ranges "
+                         f"(need more than {64 * (world - 1)} nodes)")
+    return bounds
 
 
 @dataclass

@@ -41,11 +41,27 @@ class _Opaque:
         self.state = state
 
 
+# The graph pickles are external data files.  Only the few globals they actually need are resolved; anything else
+# (os.system, builtins.eval, ...) raises instead of being imported -- a crafted file cannot run code through this loader.
+_SAFE_GLOBALS = {
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+    ("numpy", "ndarray"), ("numpy", "dtype"),
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("builtins", "list"), ("builtins", "dict"), ("builtins", "tuple"), ("builtins", "set"), ("builtins", "frozenset"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "complex"), ("builtins", "bool"), ("builtins", "str"),
+    ("builtins", "bytes"), ("builtins", "bytearray"), ("builtins", "slice"), ("builtins", "range"), ("builtins", "object"),
+    ("copyreg", "_reconstructor"),
+}
+
+
 class _GraphUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.split(".")[0] in ("shapely", "tiling"):
             return type(name, (_Opaque,), {})
-        return super().find_class(module, name)
+        if (module, name) in _SAFE_GLOBALS:
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"graph pickle references {module}.{name}, which is not on the allow-list")
 
 
 def _wkb_polygon_exterior(buf: bytes) -> np.ndarray:
