@@ -126,6 +126,10 @@ typedef struct tgnn_info {
     int64_t tile_rows;             /* destination rows per warp tile of the typed adjacency format (64 or 128)  */
     int64_t peer_exchange;         /* sharded mode: 1 = boundary rows and BatchNorm sums travel as direct NVLink stores into
                                       the peers' CUDA-IPC-mapped buffers (flags, no NCCL call); 0 = NCCL collectives     */
+    int64_t gin_kernel;            /* collision kernel chosen for this graph: 0 = per-lane global gathers (k_gin),
+                                      1 = neighbour rows staged in shared-memory windows by TMA bulk copies (k_gin_w)  */
+    int64_t gin_window_tiles;      /* 64-row tiles that got a window / that are gathered from global ("direct")        */
+    int64_t gin_direct_tiles;
     int64_t range_fallback_layers; /* layers of the LAST forward that kernel 2 handed to kernel 0 because an
                                       activation or root weight was outside the fp16 range (synchronises)      */
 } tgnn_info;

@@ -50,11 +50,14 @@ def _worker(rank, world, port, n, deg, depth, mode, q):
 
 
 @pytest.mark.parametrize("mode", ["train"])
-@pytest.mark.parametrize("n,deg,conv,p2p", [(20000, 8, "h", 1), (6000, 32, "s", 1), (6000, 32, "chunk", 0), (20000, 8, "h", 0)])
-def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, p2p, mode, monkeypatch):
-    """both exchange paths: peer-memory stores over NVLink (CUDA IPC, default) and NCCL collectives (TGNN_P2P=0)"""
+@pytest.mark.parametrize("n,deg,conv,p2p,ginw", [(20000, 8, "h", 1, 0), (6000, 32, "s", 1, 1), (6000, 32, "chunk", 0, 0),
+                                                 (20000, 8, "h", 0, 1)])
+def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, p2p, ginw, mode, monkeypatch):
+    """both exchange paths: peer-memory stores over NVLink (CUDA IPC, default) and NCCL collectives (TGNN_P2P=0); both
+    collision kernels (ginw = 1: staged windows, whose runs then include mirrored halo rows)"""
     monkeypatch.setenv("TGNN_CONV", conv)          # inherited by the spawned ranks
     monkeypatch.setenv("TGNN_P2P", str(p2p))
+    monkeypatch.setenv("TGNN_GINW", str(ginw))
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from oracle import tilingnn_oracle as orc
@@ -84,7 +87,7 @@ def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, p2p, mod
         assert ncoll == (2 + depth + 4) + depth, ncoll        # BN all-reduces + halo all-gathers (train mode)
         assert 0 < slot < n // 4
     err = np.abs(out - gold).max()
-    print(f"2-GPU sharded N={n} deg={deg} {mode} conv={conv} p2p={p2p}: max err vs fp64 oracle {err:.2e}")
+    print(f"2-GPU sharded N={n} deg={deg} {mode} conv={conv} p2p={p2p} ginw={ginw}: max err vs fp64 oracle {err:.2e}")
     assert err <= 1e-4
 
 

@@ -26,7 +26,8 @@ class tgnn_info(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("n_own", "n_rows", "n_global", "e_adj", "e_col", "n_edge_types", "adj_slots",
                  "launches_per_forward", "workspace_bytes", "collectives_per_forward", "conv_kernel",
-                 "tile_rows", "peer_exchange", "range_fallback_layers")]
+                 "tile_rows", "peer_exchange", "gin_kernel", "gin_window_tiles", "gin_direct_tiles",
+                 "range_fallback_layers")]
 
 
 _vp, _i64, _i32 = C.c_void_p, C.c_int64, C.c_int32

@@ -114,6 +114,8 @@ struct tgnn_handle {
     bool use_s = false, use_h = false;              // decided per graph in set_graph
     int tile_rows_forced = 0;                       // TGNN_TILE=64|128 (A/B runs)
     bool tables_streamed = false;                   // many edge types: one layer's weight tables at a time
+    int ginw_mode = getenv("TGNN_GINW") ? atoi(getenv("TGNN_GINW")) : -1;   // -1 auto, 0 never, 1 whenever the windows exist (A/B, tests)
+    bool use_gw = false;                            // k_gin_w (staged neighbour windows) for this graph
 
     // workspace
     std::vector<std::unique_ptr<DevBuf>> mid;
@@ -363,6 +365,18 @@ void choose_conv_kernel(tgnn_handle* h) {
     h->use_h = !h->use_s && !h->conv_chunk_only;
 }
 
+// Staged-window collision kernel (gin_w.cu): worth it when the graph is large enough to fill the SMs with 64-row tiles
+// and local enough that most tiles get a window; otherwise k_gin's per-lane gathers stay.
+constexpr int64_t GINW_MIN_NODES = 32768;
+void choose_gin_kernel(tgnn_handle* h, cudaStream_t st) {
+    h->use_gw = false; h->g.has_gw = false; h->g.gw_direct = 0;
+    if (h->ginw_mode == 0 || h->g.e_col <= 0) return;
+    if (h->ginw_mode < 0 && h->g.n_own < GINW_MIN_NODES) return;
+    h->g.gw_direct = build_gin_windows(h->g, h->scratch, st);
+    h->g.has_gw = true;
+    h->use_gw = h->ginw_mode == 1 || 4 * (int64_t)h->g.gw_direct <= (int64_t)h->g.gw_tiles;
+}
+
 // 128-row warp tiles give longer same-type runs (half the weight-table reloads, ~10 % fewer padded slots) but only 12
 // resident warps per SM instead of 16; measured on B200 at 1M nodes x deg 32 the two cancel (7.5 vs 7.3 ms per forward),
 // so 64 stays the default and TGNN_TILE=128 is kept for A/B runs.
@@ -382,6 +396,7 @@ void alloc_workspace(tgnn_handle* h) {
     res(h->pre2[1], rows * F * sizeof(float));
     for (int k = 0; k < 4; ++k) res(h->fa[k], own * FIN_DIMS[k + 1] * sizeof(float));
     size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count), (size_t)h->g.s_tiles, (size_t)gin_num_parts((int)own, h->sm_count),
+                          (size_t)gin_w_num_parts(h->g.gw_tiles, h->sm_count),
                           (size_t)init_num_parts((int)own, h->sm_count)});
     size_t part_bytes = std::max(np * 64, (size_t)dense_row_blocks((int)own) * 2 * 256) * sizeof(double);
     res(h->partA, part_bytes);
@@ -591,7 +606,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
 
     // ---- message-passing layers ----------------------------------------------------------------
     const int n_layers = h->stop_layer >= 0 ? std::min(L, h->stop_layer + 1) : L;
-    const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count), np_gin = gin_num_parts(n_own, h->sm_count);
+    const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count);
     for (int i = 0; i < n_layers; ++i) {
         const tgnn_handle::LayerP& P = h->lp[i];
         if (h->tables_streamed) { lz.begin("conv"); build_tables(h, st, i); lz.end(1); }
@@ -627,7 +642,15 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ga.wfrag = h->gin_wt[i]->as<float>();
         ga.eps = h->gin_eps[i]; ga.hmlp = h->gin_hmlp[i];
         ga.out = h->pre2[0].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
-        lz.begin("gin"); launch_gin(ga, h->sm_count, st); lz.end(1);
+        const bool gw = h->use_gw && ga.hmlp;        // layers whose GIN weights are outside the fp16 range stay on k_gin
+        const int np_gin = gw ? gin_w_num_parts(h->g.gw_tiles, h->sm_count) : gin_num_parts(n_own, h->sm_count);
+        lz.begin("gin");
+        if (gw) {
+            ga.gw_meta = h->g.gw_meta.as<int>(); ga.gw_seg = h->g.gw_seg.as<int>(); ga.gw_loc = h->g.gw_loc.as<uint16_t>();
+            ga.gw_tiles = h->g.gw_tiles; ga.err = h->err_dev;
+            launch_gin_w(ga, h->sm_count, st);
+        } else launch_gin(ga, h->sm_count, st);
+        lz.end(1);
 
         const int np_a = h->use_s ? h->g.s_tiles : np_conv;
         // small graphs: k_combine finishes the two BatchNorms in its prologue (one launch less per layer)
@@ -849,6 +872,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
                     col_dst, want_s_mode(h), tile_rows_for(h, n_nodes), st);
         h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
         choose_conv_kernel(h);
+        choose_gin_kernel(h, st);
         alloc_workspace(h);
         h->tables_dirty = true;
         h->graph_set = true;
@@ -900,6 +924,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
                     want_s_mode(h), tile_rows_for(h, n_own), st);
         h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
         choose_conv_kernel(h);
+        choose_gin_kernel(h, st);
         if (n_send > 0) {
             std::vector<int64_t> rows64(n_send);
             TGNN_CUDA(cudaMemcpyAsync(rows64.data(), send_rows, n_send * sizeof(int64_t), cudaMemcpyDefault, st));
@@ -932,6 +957,9 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         out->conv_kernel = h->use_s ? 1 : (h->use_h ? 2 : 0);
         out->tile_rows = h->g.wn;
         out->peer_exchange = h->px.ok ? 1 : 0;
+        out->gin_kernel = h->use_gw ? 1 : 0;
+        out->gin_window_tiles = h->g.has_gw ? h->g.gw_tiles - h->g.gw_direct : 0;
+        out->gin_direct_tiles = h->g.has_gw ? h->g.gw_direct : 0;
         out->range_fallback_layers = 0;
         if (h->use_h && h->graph_set) {
             DeviceGuard dg(h->cfg.device);

@@ -473,7 +473,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
     k_inv_deg<<<nblk(n_own), TPB, 0, st>>>(deg, n_own, g.inv_deg.as<float>());
 
     // ---------------- collision CSR -----------------------------------------------------------------
-    g.col_ptr.reserve((size_t)(n_own + 1) * sizeof(int));
+    g.col_ptr.reserve((size_t)(n_own + 1 + 72) * sizeof(int));     // + padding: k_gin_w copies 68 pointers per 64-row tile
     g.e_col = 0;
     if (e_col > 0) {
         k_validate<<<nblk(e_col), TPB, 0, st>>>(col_src, col_dst, e_col, n_rows, n_own, err);

@@ -108,6 +108,12 @@ struct Graph {
     // collision CSR by destination (self loops removed)
     DevBuf col_ptr;           // int32 [n_own + 1]
     DevBuf col_src;           // int32 [e_col]
+    // collision windows of k_gin_w (gin_w.cu): per 64-row tile the distinct source rows as contiguous runs
+    bool has_gw = false;
+    int gw_tiles = 0, gw_direct = 0;   // gw_direct: tiles without a window (sources not local), gathered from global
+    DevBuf gw_meta;           // int32  [gw_tiles][8]             {runs (0 = direct), window rows, offset into gw_loc, window row of the tile's first node, edges, -, -, -}
+    DevBuf gw_seg;            // int32  [gw_tiles][GW_MAXSEG][2]  {first source row, first window row} per run
+    DevBuf gw_loc;            // uint16 [e_col + padding]         window row of every collision edge's source, CSR order, tile blocks 16-byte aligned
     // halo (sharded mode)
     int64_t halo_slot = 0, n_send = 0;
     DevBuf send_rows;         // int32 [n_send]
@@ -169,9 +175,18 @@ void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
 // tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st);
 
+constexpr int GW_T = 64;          // destination rows per window tile
+constexpr int GW_MAXSEG = 32;     // contiguous runs per window (one bulk copy each, one producer lane each)
+constexpr int GW_WMAX = 656;      // window rows (82 KB; two buffers per SM)
+constexpr int GW_CAP = 4096;      // sorted items per tile in the builder = edges + own rows
+constexpr int GW_GAP = 2;         // runs closer than this many rows are merged (the gap rows are loaded)
+int build_gin_windows(Graph& g, Scratch& sc, cudaStream_t st);
+
 struct GinArgs {
     const float* xin;        // [n_rows][32]  output of the previous CollConv (written by k_combine), or h0
     const int* col_ptr; const int* col_src;
+    // k_gin_w only (null / 0 -> k_gin): windows built by build_gin_windows, and the mapped error word for timeouts
+    const int* gw_meta = nullptr; const int* gw_seg = nullptr; const uint16_t* gw_loc = nullptr; int gw_tiles = 0; int* err = nullptr;
     const float* wfrag;      // 3xTF32 frag tables W1[2048] W2[4096] W3[4096], b1[32] b2[64] b3[32], then fp16 tables W2h[2048] W3h[2048]
     int hmlp;                // layers 2, 3 of the MLP on the fp16 tables (their weights are inside the fp16 range)
     float eps;
@@ -181,6 +196,9 @@ struct GinArgs {
 };
 int gin_num_parts(int n_own, int sm_count);
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st);
+int gin_w_blocks(int gw_tiles, int sm_count);
+inline int gin_w_num_parts(int gw_tiles, int sm_count) { return gin_w_blocks(gw_tiles, sm_count) * 4; }
+void launch_gin_w(const GinArgs& a, int sm_count, cudaStream_t st);
 
 // b1_new = BN(pre1) * BN(pre2) + residual
 // xh / flag (optional): fp16-split copy of the result for k_conv_h and its range flag; g2out (optional): BN(pre2).
