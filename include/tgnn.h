@@ -122,10 +122,13 @@ typedef struct tgnn_info {
     int64_t workspace_bytes;
     int64_t collectives_per_forward;
     int64_t conv_kernel;           /* adjacency kernel chosen for this graph: 0 = 3xTF32 edge-chunk (mma.sync),
-                                      1 = tcgen05 S formulation, 2 = fp16-split edge-chunk (mma.sync.f16)      */
+                                      1 = tcgen05 S formulation, 2 = fp16-split edge-chunk (mma.sync.f16),
+                                      3 = tcgen05 edge-block kernel (128-edge blocks, TMEM accumulators)       */
     int64_t tile_rows;             /* destination rows per warp tile of the typed adjacency format (64 or 128)  */
     int64_t peer_exchange;         /* sharded mode: 1 = boundary rows and BatchNorm sums travel as direct NVLink stores into
                                       the peers' CUDA-IPC-mapped buffers (flags, no NCCL call); 0 = NCCL collectives     */
+    int64_t t_rows, t_blocks;      /* edge-block format of kernel 3 (0 when not built): destination rows per super-tile,
+                                      blocks of 128 same-type slots (incl. t_rows / 128 root blocks per super-tile)         */
     int64_t gin_kernel;            /* collision kernel chosen for this graph: 0 = per-lane global gathers (k_gin),
                                       1 = neighbour rows staged in shared-memory windows by TMA bulk copies (k_gin_w)  */
     int64_t gin_window_tiles;      /* 64-row tiles that got a window / that are gathered from global ("direct")        */
@@ -148,6 +151,8 @@ int tgnn_debug_set_stop_layer(tgnn_handle* h, int32_t layer);
 int tgnn_debug_read(tgnn_handle* h, const char* name, float* out, void* stream);
 int tgnn_debug_graph(tgnn_handle* h, int32_t* cptr, int32_t* ctype, int32_t* csrc, uint8_t* cdst, float* inv_deg,
                      int32_t* col_ptr, int32_t* col_src, float* type_rows, void* stream);
+/* the edge-block format of kernel 3: bptr[ceil(n_own/t_rows)+1] btype[t_blocks] tsrc[t_blocks*128] tdst[t_blocks*128] */
+int tgnn_debug_graph_t(tgnn_handle* h, int32_t* bptr, int32_t* btype, int32_t* tsrc, uint16_t* tdst, void* stream);
 
 /* Per-kernel-family device time of the last forward (ms), measured with CUDA events on `stream`
  * when enabled.  names: "init","conv","gin","bnfin","combine","final","score","halo". */

@@ -158,10 +158,11 @@ def test_synthetic_configs_vs_oracle(dev, n, deg, mode):
     assert err <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["chunk", "s", "h"])
+@pytest.mark.parametrize("kernel", ["chunk", "s", "h", "t"])
 def test_all_adjacency_kernels(dev, kernel, monkeypatch):
-    """The fp16-split edge-chunk kernel, its 3xTF32 twin and the tcgen05 S kernel are selected per graph by a cost
-    model; force each (TGNN_CONV) on the shipped checkpoint (20 edge types) and on a synthetic graph (51 types)."""
+    """The fp16-split edge-chunk kernel, its 3xTF32 twin, the tcgen05 S kernel and the tcgen05 edge-block kernel are
+    selected per graph by size / a cost model; force each (TGNN_CONV) on the shipped checkpoint (20 edge types) and on a
+    synthetic graph (51 types)."""
     monkeypatch.setenv("TGNN_CONV", kernel)
     from tilingnn_b200 import synthetic as syn
     z, x, ai, af, ci = load_graph("c1_complete.npz")
@@ -177,7 +178,7 @@ def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     print(f"TGNN_CONV={kernel}: max err {err:.2e}")
     assert err <= TOL
     info = net.info()
-    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2}[kernel] and info["range_fallback_layers"] == 0
+    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2, "t": 3}[kernel] and info["range_fallback_layers"] == 0
 
 
 def test_gin_mlp_on_3xtf32(dev, monkeypatch):
@@ -193,10 +194,12 @@ def test_gin_mlp_on_3xtf32(dev, monkeypatch):
     assert err <= TOL
 
 
-def test_fp16_range_guard_hands_layers_to_the_tf32_kernel(dev, monkeypatch):
-    """k_conv_h works on fp16-split operands; activations beyond +-60000 (here: a BatchNorm gain of 1e6 in layer 0)
-    and root weights beyond it (layer 2) must raise the range flags so the 3xTF32 kernel takes those layers."""
-    monkeypatch.setenv("TGNN_CONV", "h")
+@pytest.mark.parametrize("kernel", ["h", "t"])
+def test_fp16_range_guard_hands_layers_to_the_tf32_kernel(dev, kernel, monkeypatch):
+    """k_conv_h / k_conv_t work on fp16-split operands; activations beyond +-60000 (here: a BatchNorm gain of 1e6 in
+    layer 0) and root weights beyond it (layer 2) must raise the range flags so the 3xTF32 arithmetic (k_conv_h) / the
+    fp32 stand-by kernel (k_conv_t) takes those layers."""
+    monkeypatch.setenv("TGNN_CONV", kernel)
     from tilingnn_b200 import synthetic as syn
     x, ai, af, ci = syn.lattice_graph(3000, 8, 8, seed=4)
     p = dict(orc.make_params(3, 19, 4, seed=4))
@@ -207,7 +210,7 @@ def test_fp16_range_guard_hands_layers_to_the_tf32_kernel(dev, monkeypatch):
     err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
     info = net.info()
     print(f"range guard: max err {err:.2e}, fallback layers {info['range_fallback_layers']}")
-    assert info["conv_kernel"] == 2 and info["range_fallback_layers"] >= 2
+    assert info["conv_kernel"] == {"h": 2, "t": 3}[kernel] and info["range_fallback_layers"] >= 2
     assert err <= TOL
 
 
@@ -383,3 +386,44 @@ def test_gin_staged_window_kernel(dev, monkeypatch):
     monkeypatch.setenv("TGNN_GINW", "0")
     net = make_net(p, 3, 19, 3, dev)
     assert np.abs(run(net, x, ai, af, ci, dev) - gold).max() <= TOL and net.info()["gin_kernel"] == 0
+
+
+def test_edge_block_format_is_a_faithful_reencoding(dev, monkeypatch):
+    """T format of the tcgen05 edge-block kernel: every adjacency edge sits in exactly one slot of a block of its type;
+    quarter q of a block only holds destinations with dst % 4 == q, no destination twice inside a quarter (that is what
+    lets four epilogue warps accumulate into one shared tile without atomics); every super-tile ends with its root blocks."""
+    monkeypatch.setenv("TGNN_CONV", "t")
+    for name in ("syn_small.npz", "c1_complete.npz"):
+        z, x, ai, af, ci = load_graph(name)
+        if name == "syn_small.npz":
+            p, depth = syn_small_params(z)
+        else:
+            p, depth = load_ckpt(), 20
+        net = make_net(p, x.shape[1], af.shape[1], depth, dev)
+        net.set_graph(x.shape[0], ai.to(dev), af.to(dev), ci.to(dev))
+        info = net.info()
+        g, gt = net.debug_graph(), net.debug_graph_t()
+        rows, n, rt, K = g["type_rows"].numpy(), x.shape[0], info["t_rows"], info["n_edge_types"]
+        bptr, btype, tsrc, tdst = (gt[k].numpy() for k in ("bptr", "btype", "tsrc", "tdst"))
+        assert rt == 256 and bptr[0] == 0 and bptr[-1] == info["t_blocks"] == len(btype)
+        got, roots = [], []
+        for t in range(len(bptr) - 1):
+            assert bptr[t + 1] - bptr[t] >= rt // 128
+            for b in range(bptr[t], bptr[t + 1]):
+                is_root = btype[b] == K
+                assert is_root == (b >= bptr[t + 1] - rt // 128), "root blocks must be the last blocks of a super-tile"
+                for q in range(4):
+                    sl = slice(b * 128 + 32 * q, b * 128 + 32 * q + 32)
+                    live = tsrc[sl] >= 0
+                    d = tdst[sl][live]
+                    assert (tdst[sl][~live] == 0xFFFF).all()
+                    assert (d % 4 == q).all(), "destination class"
+                    assert len(set(d.tolist())) == len(d), "duplicate destination inside a quarter"
+                    for s_, d_ in zip(tsrc[sl][live], d):
+                        if is_root:
+                            roots.append((int(s_), t * rt + int(d_)))
+                        else:
+                            got.append((int(s_), t * rt + int(d_), tuple(rows[btype[b]])))
+        want = [(int(a), int(b), tuple(f)) for (a, b), f in zip(ai.t().tolist(), af.numpy())]
+        assert sorted(got) == sorted(want)
+        assert sorted(roots) == [(i, i) for i in range(n)]

@@ -51,7 +51,7 @@ def _worker(rank, world, port, n, deg, depth, mode, q):
 
 @pytest.mark.parametrize("mode", ["train"])
 @pytest.mark.parametrize("n,deg,conv,p2p,ginw", [(20000, 8, "h", 1, 0), (6000, 32, "s", 1, 1), (6000, 32, "chunk", 0, 0),
-                                                 (20000, 8, "h", 0, 1)])
+                                                 (20000, 8, "h", 0, 1), (6000, 32, "t", 1, 1)])
 def test_two_gpu_shards_match_unsharded_oracle(built_lib, n, deg, conv, p2p, ginw, mode, monkeypatch):
     """both exchange paths: peer-memory stores over NVLink (CUDA IPC, default) and NCCL collectives (TGNN_P2P=0); both
     collision kernels (ginw = 1: staged windows, whose runs then include mirrored halo rows)"""

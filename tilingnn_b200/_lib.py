@@ -26,7 +26,7 @@ class tgnn_info(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
                 ("n_own", "n_rows", "n_global", "e_adj", "e_col", "n_edge_types", "adj_slots",
                  "launches_per_forward", "workspace_bytes", "collectives_per_forward", "conv_kernel",
-                 "tile_rows", "peer_exchange", "gin_kernel", "gin_window_tiles", "gin_direct_tiles",
+                 "tile_rows", "peer_exchange", "t_rows", "t_blocks", "gin_kernel", "gin_window_tiles", "gin_direct_tiles",
                  "range_fallback_layers")]
 
 
@@ -50,6 +50,7 @@ SIGNATURES = {
     "tgnn_debug_set_stop_layer": (C.c_int, [_vp, _i32]),
     "tgnn_debug_read": (C.c_int, [_vp, C.c_char_p, _vp, _vp]),
     "tgnn_debug_graph": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tgnn_debug_graph_t": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "tgnn_set_profiling": (C.c_int, [_vp, _i32]),
     "tgnn_get_profile": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "tgnn_last_error": (C.c_char_p, [_vp]),

@@ -111,7 +111,10 @@ struct tgnn_handle {
     bool conv_chunk_only = false;                   // TGNN_CONV=chunk forces the 3xTF32 mma.sync edge-chunk kernel
     bool conv_s_only = false;                       // TGNN_CONV=s forces the tcgen05 S kernel whenever its format exists
     bool conv_h_only = false;                       // TGNN_CONV=h forces the fp16-split edge-chunk kernel (never S)
-    bool use_s = false, use_h = false;              // decided per graph in set_graph
+    bool conv_t_only = false;                       // TGNN_CONV=t forces the tcgen05 edge-block kernel (any graph size, 256-row super-tiles)
+    bool use_s = false, use_h = false, use_t = false;   // decided per graph in set_graph
+    bool need_xh() const { return use_h || use_t; }  // the fp16-split copy of b1 is an operand of both kernels
+    DevBuf tabT, tab32;                             // [L][K+1] pre-swizzled fp16 weight images / plain fp32 tables of k_conv_t (+ stand-by)
     int tile_rows_forced = 0;                       // TGNN_TILE=64|128 (A/B runs)
     bool tables_streamed = false;                   // many edge types: one layer's weight tables at a time
     int ginw_mode = getenv("TGNN_GINW") ? atoi(getenv("TGNN_GINW")) : -1;   // -1 auto, 0 never, 1 whenever the windows exist (A/B, tests)
@@ -346,14 +349,17 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
     const size_t slots = per_layer * nl;
     // 3xTF32 fragments: always (k_conv_adj is also the wide-range stand-in of k_conv_h)
     h->tab.reserve(slots * TG_FRAG32 * sizeof(float));
-    if (h->use_h) {
-        h->tabH.reserve(slots * TG_HFRAG32 * sizeof(uint32_t));
-        TGNN_CUDA(cudaMemsetAsync(h->wflag(l0), 0, (size_t)nl * sizeof(int), st));
+    if (h->need_xh()) TGNN_CUDA(cudaMemsetAsync(h->wflag(l0), 0, (size_t)nl * sizeof(int), st));
+    if (h->use_h) h->tabH.reserve(slots * TG_HFRAG32 * sizeof(uint32_t));
+    if (h->use_t) {
+        h->tabT.reserve(slots * TG_TIMG32 * sizeof(uint32_t));
+        h->tab32.reserve(slots * F * F * sizeof(float));
     }
     if (h->use_s) h->tabS.reserve(slots * TG_FRAG32 * sizeof(float));
     launch_edge_tables(h->g.type_rows.as<float>(), K, h->cfg.d_e, nl, h->table_layers.as<TableLayer>() + l0, h->tab.as<float>(),
                        h->use_s ? h->tabS.as<float>() : nullptr, h->use_h ? h->tabH.as<uint32_t>() : nullptr,
-                       h->use_h ? h->wflag(l0) : nullptr, st);
+                       h->use_t ? h->tabT.as<uint32_t>() : nullptr, h->use_t ? h->tab32.as<float>() : nullptr,
+                       h->need_xh() ? h->wflag(l0) : nullptr, st);
     if (layer < 0) h->tables_dirty = false;
 }
 
@@ -362,7 +368,20 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
 // few types relative to their edge count (the shipped tile graphs: 20-41 types), chunk when types are many.
 void choose_conv_kernel(tgnn_handle* h) {
     h->use_s = h->g.has_s && !h->conv_h_only && (h->conv_s_only || (double)h->g.s_passes * S_EDGES_PER_PASS_BREAK_EVEN < (double)h->g.e_adj);
-    h->use_h = !h->use_s && !h->conv_chunk_only;
+    h->use_t = h->g.has_t && !h->conv_h_only && !h->conv_s_only && !h->conv_chunk_only;
+    if (h->use_t) h->use_s = false;
+    h->use_h = !h->use_s && !h->use_t && !h->conv_chunk_only;
+}
+
+// The tcgen05 edge-block kernel (conv_t.cu) wants long same-type runs per super-tile (blocks of 128 slots, four
+// destination classes): worth building for large graphs with few edge types.  Rows per super-tile: as many as still
+// give every SM two tiles.  0 = do not build the format.
+int want_t_rows(tgnn_handle* h, int64_t n_own) {
+    if (h->conv_t_only) return 256;
+    if (h->conv_h_only || h->conv_s_only || h->conv_chunk_only) return 0;
+    if (getenv("TGNN_CONV_T_ROWS")) { const int r = atoi(getenv("TGNN_CONV_T_ROWS")); if (r == 256 || r == 512 || r == 1024) return r; }
+    for (int rt : {1024, 512}) if (n_own >= (int64_t)2 * h->sm_count * rt) return rt;
+    return 0;
 }
 
 // Staged-window collision kernel (gin_w.cu): worth it when the graph is large enough to fill the SMs with 64-row tiles
@@ -380,7 +399,7 @@ void choose_gin_kernel(tgnn_handle* h, cudaStream_t st) {
 // 128-row warp tiles give longer same-type runs (half the weight-table reloads, ~10 % fewer padded slots) but only 12
 // resident warps per SM instead of 16; measured on B200 at 1M nodes x deg 32 the two cancel (7.5 vs 7.3 ms per forward),
 // so 64 stays the default and TGNN_TILE=128 is kept for A/B runs.
-int want_s_mode(tgnn_handle* h) { return h->conv_s_only ? 2 : ((h->conv_chunk_only || h->conv_h_only) ? 0 : 1); }
+int want_s_mode(tgnn_handle* h) { return h->conv_s_only ? 2 : ((h->conv_chunk_only || h->conv_h_only || h->conv_t_only) ? 0 : 1); }
 int tile_rows_for(tgnn_handle* h, int64_t) { return h->tile_rows_forced ? h->tile_rows_forced : WN_SMALL; }
 
 void alloc_workspace(tgnn_handle* h) {
@@ -391,11 +410,12 @@ void alloc_workspace(tgnn_handle* h) {
     while ((int)h->mid.size() < L + 1) h->mid.emplace_back(new DevBuf());
     for (int i = 0; i <= L; ++i) res(*h->mid[i], rows * F * sizeof(float));
     res(h->pre1, own * F * sizeof(float));
-    if (h->use_h) res(h->xh, rows * F * sizeof(float));
+    if (h->need_xh()) res(h->xh, rows * F * sizeof(float));
     res(h->pre2[0], rows * F * sizeof(float));
     res(h->pre2[1], rows * F * sizeof(float));
     for (int k = 0; k < 4; ++k) res(h->fa[k], own * FIN_DIMS[k + 1] * sizeof(float));
     size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count), (size_t)h->g.s_tiles, (size_t)gin_num_parts((int)own, h->sm_count),
+                          (size_t)(h->g.has_t ? conv_t_num_parts(h->g.t_tiles, h->sm_count) : 0),
                           (size_t)gin_w_num_parts(h->g.gw_tiles, h->sm_count),
                           (size_t)init_num_parts((int)own, h->sm_count)});
     size_t part_bytes = std::max(np * 64, (size_t)dense_row_blocks((int)own) * 2 * 256) * sizeof(double);
@@ -539,7 +559,7 @@ void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t s
         const unsigned epoch = ++h->px.epoch_halo;
         const PeerPtrs pp = peer_ptrs(h);
         launch_halo_push(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, h->g.halo_slot, pp, epoch, h->bn_ticket() + 1, st);
-        launch_halo_unpack_x(pp, epoch, h->g.halo_slot, h->g.n_own, a, b, h->use_h ? h->xh.as<uint4>() : nullptr, flag, st);
+        launch_halo_unpack_x(pp, epoch, h->g.halo_slot, h->g.n_own, a, b, h->need_xh() ? h->xh.as<uint4>() : nullptr, flag, st);
         h->collectives += 1;
         lz.end(2);
         return;
@@ -548,7 +568,7 @@ void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t s
     launch_halo_pack(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, slot, st);
     nccl_check(nccl().AllGather(slot, h->halo.p, (size_t)h->g.halo_slot * 64, ncclFloat32, h->comm, st), "halo all-gather");
     launch_halo_unpack(h->halo.as<float>(), h->world, h->rank, h->g.halo_slot, h->g.n_own, a, b,
-                       h->use_h ? h->xh.as<uint4>() : nullptr, flag, st);
+                       h->need_xh() ? h->xh.as<uint4>() : nullptr, flag, st);
     h->collectives += 1;
     lz.end(2);
 }
@@ -569,7 +589,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     double* sums = h->sums.as<double>();
     if (!train && !h->eval_coefs_valid) { lz.begin("bnfin"); eval_coefs(h, st); lz.end(2 + 2 * L + 4); h->eval_coefs_valid = true; }
     if (train) h->eval_coefs_valid = false;          // train-mode forwards overwrite the coefficient blocks
-    if (h->use_h) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
+    if (h->need_xh()) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
 
     auto finish_bn = [&](const double* part, int n_part, int c, const tgnn_handle::BnP& bn, size_t coef_off) {
         if (h->world == 1 || h->px.ok) {
@@ -593,7 +613,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     ia.w1t = h->init_w1t.as<float>(); ia.b1 = h->init_b1;
     ia.coef0 = h->C(h->coef_init[0]); ia.coef1 = h->C(h->coef_init[1]);
     ia.out = h->mid[0]->as<float>(); ia.part = h->partA.as<double>(); ia.n_own = n_own;
-    ia.xh = h->use_h ? h->xh.as<uint32_t>() : nullptr; ia.flag = h->use_h ? h->rflag(0) : nullptr;
+    ia.xh = h->need_xh() ? h->xh.as<uint32_t>() : nullptr; ia.flag = h->need_xh() ? h->rflag(0) : nullptr;
     const int np_init = init_num_parts(n_own, h->sm_count);
     if (train) {
         lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
@@ -623,6 +643,13 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         if (h->use_s) {
             launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->err_dev, h->sm_count, st);
             lz.end(1);
+        } else if (h->use_t) {
+            // tcgen05 edge-block kernel + its fp32 stand-by (exits at once unless a range flag is raised)
+            ca.xh = h->xh.as<uint4>();
+            ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
+            launch_conv_t(ca, h->g, h->tabT.as<uint32_t>() + tslot * TG_TIMG32, h->tab32.as<float>() + tslot * F * F, h->err_dev,
+                          h->sm_count, st);
+            lz.end(2, 1);
         } else if (h->use_h) {
             // fp16-split kernel; falls through to the 3xTF32 arithmetic itself when a range flag is raised
             ca.xh = h->xh.as<uint4>();
@@ -652,7 +679,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         } else launch_gin(ga, h->sm_count, st);
         lz.end(1);
 
-        const int np_a = h->use_s ? h->g.s_tiles : np_conv;
+        const int np_a = h->use_s ? h->g.s_tiles : (h->use_t ? conv_t_num_parts(h->g.t_tiles, h->sm_count) : np_conv);
         // small graphs: k_combine finishes the two BatchNorms in its prologue (one launch less per layer)
         const bool fin_in_combine = train && h->world == 1 && np_a + np_gin <= 1024;
         CombineFin cf{};
@@ -666,7 +693,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             lz.begin("bnfin");
             if (h->world == 1 || h->px.ok) {
                 BnFinishArgs fa{};
-                fa.part[0] = h->partA.as<double>(); fa.n_part[0] = h->use_s ? h->g.s_tiles : np_conv;
+                fa.part[0] = h->partA.as<double>(); fa.n_part[0] = np_a;
                 fa.part[1] = h->partB.as<double>(); fa.n_part[1] = np_gin;
                 fa.C = 32; fa.count = count;
                 fa.gamma[0] = P.bn_a_w; fa.beta[0] = P.bn_a_b; fa.coef[0] = h->C(h->coef_a[i]);
@@ -676,7 +703,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
                 else { launch_bn_finish_x(fa, 2, peer_ptrs(h), ++h->px.epoch_bn, st); h->collectives += 1; }
                 lz.end(1);
             } else {
-            launch_bn_reduce(h->partA.as<double>(), h->use_s ? h->g.s_tiles : np_conv, 32, sums, st);
+            launch_bn_reduce(h->partA.as<double>(), np_a, 32, sums, st);
             launch_bn_reduce(h->partB.as<double>(), np_gin, 32, sums + 64, st);
             allreduce_sums(h, sums, 128, st);
             launch_bn_coef(sums, count, P.bn_a_w, P.bn_a_b, h->C(h->coef_a[i]), 32, st);
@@ -687,7 +714,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         lz.begin("combine");
         launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[0].as<float>(), h->C(h->coef_c[i]),
                        i >= 2 ? h->mid[i - 2]->as<float>() : nullptr, h->mid[i + 1]->as<float>(),
-                       h->use_h ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), h->pre2[1].as<float>(), n_own, st,
+                       h->need_xh() ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), h->pre2[1].as<float>(), n_own, st,
                        fin_in_combine ? &cf : nullptr);
         lz.end(1);
         if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[1].as<float>(), h->rflag(i + 1), st, lz);
@@ -787,6 +814,7 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->conv_chunk_only = csel && std::string(csel) == "chunk";
         h->conv_s_only = csel && std::string(csel) == "s";
         h->conv_h_only = csel && std::string(csel) == "h";
+        h->conv_t_only = csel && std::string(csel) == "t";
         const char* tsel = getenv("TGNN_TILE");
         if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
         h->hflags.reserve((size_t)(2 * cfg->depth + 3) * sizeof(int));
@@ -869,7 +897,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         cudaStream_t st = (cudaStream_t)stream;
         h->graph_set = false;
         build_graph(h->g, h->scratch, h->cfg.d_e, n_nodes, n_nodes, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src,
-                    col_dst, want_s_mode(h), tile_rows_for(h, n_nodes), st);
+                    col_dst, want_s_mode(h), tile_rows_for(h, n_nodes), want_t_rows(h, n_nodes), st);
         h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
         choose_conv_kernel(h);
         choose_gin_kernel(h, st);
@@ -921,7 +949,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
         h->graph_set = false;
         const int64_t n_rows = n_own + (h->world > 1 ? (int64_t)h->world * halo_slot : 0);
         build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst,
-                    want_s_mode(h), tile_rows_for(h, n_own), st);
+                    want_s_mode(h), tile_rows_for(h, n_own), want_t_rows(h, n_own), st);
         h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
         choose_conv_kernel(h);
         choose_gin_kernel(h, st);
@@ -954,14 +982,16 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         out->launches_per_forward = h->launches;
         out->workspace_bytes = (int64_t)h->workspace_bytes;
         out->collectives_per_forward = h->collectives;
-        out->conv_kernel = h->use_s ? 1 : (h->use_h ? 2 : 0);
+        out->conv_kernel = h->use_s ? 1 : (h->use_t ? 3 : (h->use_h ? 2 : 0));
         out->tile_rows = h->g.wn;
         out->peer_exchange = h->px.ok ? 1 : 0;
+        out->t_rows = h->g.has_t ? h->g.t_rows : 0;
+        out->t_blocks = h->g.has_t ? h->g.t_blocks : 0;
         out->gin_kernel = h->use_gw ? 1 : 0;
         out->gin_window_tiles = h->g.has_gw ? h->g.gw_tiles - h->g.gw_direct : 0;
         out->gin_direct_tiles = h->g.has_gw ? h->g.gw_direct : 0;
         out->range_fallback_layers = 0;
-        if (h->use_h && h->graph_set) {
+        if (h->need_xh() && h->graph_set) {
             DeviceGuard dg(h->cfg.device);
             const int L = h->cfg.depth;
             std::vector<int> f(2 * L + 1);
@@ -1044,6 +1074,22 @@ int tgnn_debug_graph(tgnn_handle* h, int32_t* cptr, int32_t* ctype, int32_t* csr
         cp(col_ptr, h->g.col_ptr, (size_t)(h->g.n_own + 1) * 4);
         cp(col_src, h->g.col_src, (size_t)h->g.e_col * 4);
         cp(type_rows, h->g.type_rows, (size_t)h->g.n_types * h->cfg.d_e * 4);
+        TGNN_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int tgnn_debug_graph_t(tgnn_handle* h, int32_t* bptr, int32_t* btype, int32_t* tsrc, uint16_t* tdst, void* stream) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && h->graph_set && h->g.has_t, "tgnn_debug_graph_t: no edge-block format on this graph");
+        DeviceGuard dg(h->cfg.device);
+        cudaStream_t st = (cudaStream_t)stream;
+        auto cp = [&](void* dst, const DevBuf& b, size_t bytes) {
+            if (dst && bytes) TGNN_CUDA(cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDefault, st));
+        };
+        cp(bptr, h->g.t_bptr, (size_t)(h->g.t_tiles + 1) * 4);
+        cp(btype, h->g.t_btype, (size_t)h->g.t_blocks * 4);
+        cp(tsrc, h->g.t_src, (size_t)h->g.t_blocks * 128 * 4);
+        cp(tdst, h->g.t_dst, (size_t)h->g.t_blocks * 128 * 2);
         TGNN_CUDA(cudaStreamSynchronize(st));
     });
 }

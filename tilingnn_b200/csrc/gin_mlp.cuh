@@ -59,20 +59,31 @@ __device__ __forceinline__ void gin_load_weights(float* smem, const float* __res
     }
 }
 
-// xs: [16][XS] neighbour sums (+ self term) of nodes node0 .. node0+15 in shared memory.  HMLP: layers 2 and 3 on fp16-split
-// operands (their inputs are sigmoid outputs in (0, 1)); layer 1 sees unbounded sums and stays on 3xTF32.
+// A fragments of layer 1 for a 16-node chunk whose neighbour sums (+ self term) sit in shared memory as xs[16][XS]
+// (natural K order): a1[ks] = {row g, row g+8} x {col 8ks+t, 8ks+t+4}.  Once they are in registers the chunk's
+// shared-memory rows may be overwritten.
+__device__ __forceinline__ void gin_load_a1(const float* xs, int lane, float (&a1)[4][4]) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+        a1[ks][0] = xs[g * XS + 8 * ks + t]; a1[ks][1] = xs[(g + 8) * XS + 8 * ks + t];
+        a1[ks][2] = xs[g * XS + 8 * ks + t + 4]; a1[ks][3] = xs[(g + 8) * XS + 8 * ks + t + 4];
+    }
+}
+
+// HMLP: layers 2 and 3 on fp16-split operands (their inputs are sigmoid outputs in (0, 1)); layer 1 sees unbounded sums
+// and stays on 3xTF32.
 template <bool HMLP>
-__device__ __forceinline__ void gin_mlp_chunk(const float* xs, const GinW<HMLP>& Wt, int node0, int n_own, float* __restrict__ out,
+__device__ __forceinline__ void gin_mlp_chunk(const float (&a1)[4][4], const GinW<HMLP>& Wt, int node0, int n_own, float* __restrict__ out,
                                               double (&s1)[8], double (&s2)[8], int lane) {
     const float4 *W1 = Wt.W1, *W2 = Wt.W2, *W3 = Wt.W3;
     const float *b1 = Wt.b1, *b2 = Wt.b2, *b3 = Wt.b3;
     const int g = lane >> 2, t = lane & 3;
-    // ---- layer 1: 32 -> 32, A from shared memory (natural K order) -------------------------------
+    // ---- layer 1: 32 -> 32 (natural K order) -------------------------------------------------------
     float c1[4][4] = {};
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-        float av[4] = {xs[g * XS + 8 * ks + t], xs[(g + 8) * XS + 8 * ks + t],
-                       xs[g * XS + 8 * ks + t + 4], xs[(g + 8) * XS + 8 * ks + t + 4]};
+        const float (&av)[4] = a1[ks];
         uint32_t ah[4], al[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) split_tf32(av[i], ah[i], al[i]);

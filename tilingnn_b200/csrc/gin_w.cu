@@ -10,10 +10,13 @@
 // copies (cp.async.bulk -> UBLKCP, completion on an mbarrier, double buffered against the previous tile's compute)
 // and the gather warps read neighbour rows with LDS.128 at shared-memory latency:
 //   L2 -> SM traffic / 3.3, no dependent global load in the gather loop, indices 2 B instead of 4 B per edge.
-// Warp roles (13 warps, one CTA per SM, persistent over tiles):
-//   warps 0-3   node MLP on tensor cores (mma.sync; one 16-node chunk each, one warp per SM sub-partition)
-//   warps 4-11  gather-sum from the window (8 lanes per 128-byte row, 8 rows in flight per lane)
-//   warp  12    producer: per tile <= 32 bulk copies (window runs), 1 for the uint16 indices, 1 for the row pointers
+// Warp roles (16 warps = 512 threads x 128 registers, one CTA per SM, persistent over tiles):
+//   warps 0-10  node MLP on tensor cores (mma.sync): the four 16-node chunks of a tile go round-robin over the 11 warps,
+//               so three tiles' MLPs are in flight (one chunk is ~6000 cycles of dependent MMAs and sigmoids; the
+//               gather delivers a tile every ~2600) -- measured: with 4 MLP warps the kernel was MLP-latency-bound
+//   warps 11-14 gather-sum from the window (8 lanes per 128-byte row, 8 rows in flight per lane): shared-memory
+//               bandwidth bound, four warps keep 16 KB of LDS in flight
+//   warp  15    producer: per tile <= 32 bulk copies (window runs), 1 for the uint16 indices, 1 for the row pointers
 // Tiles whose sources are not local (window > 656 rows / > 32 runs / > 4032 edges) are marked "direct" by the
 // builder and gathered from global memory by the same warps; graphs that are mostly direct keep k_gin.
 #include <cub/cub.cuh>
@@ -28,7 +31,7 @@ namespace {
 using namespace ginx;
 using namespace tc;
 
-constexpr int GATHER_WARPS = 8, MLP_WARPS = 4;
+constexpr int GATHER_WARPS = 4, MLP_WARPS = GW_MLP_WARPS, CHUNKS_PER_TILE = GW_T / CH;
 constexpr int W_GATHER0 = MLP_WARPS, W_PROD = MLP_WARPS + GATHER_WARPS;
 constexpr int GW_THREADS = (W_PROD + 1) * 32;
 constexpr int PTR_INTS = 68;                                    // 65 row pointers, padded to a multiple of 16 bytes
@@ -55,7 +58,7 @@ k_gin_w(GinArgs A) {
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_wf + 8 * i, 1); mbar_init(bar_we + 8 * i, GATHER_WARPS);
-            mbar_init(bar_sf + 8 * i, GATHER_WARPS); mbar_init(bar_se + 8 * i, MLP_WARPS);
+            mbar_init(bar_sf + 8 * i, GATHER_WARPS); mbar_init(bar_se + 8 * i, CHUNKS_PER_TILE);
         }
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,20 +170,24 @@ k_gin_w(GinArgs A) {
             if (lane == 0) { mbar_arrive(bar_we + 8 * b); mbar_arrive(bar_sf + 8 * b); }
         }
     } else {
-        // ===================== node MLP: warp m takes rows 16m .. 16m+15 of every tile =====================
+        // ===================== node MLP: chunk c of the CTA's it-th tile goes to warp (4 it + c) % 11 =====================
         const GinW<HMLP> Wt(wsm);
         double s1[8], s2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
-        int it = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        for (int ci = warp;; ci += MLP_WARPS) {
+            const int it = ci / CHUNKS_PER_TILE, c = ci % CHUNKS_PER_TILE;
+            const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+            if (tile >= n_tiles) break;
             const int b = it & 1;
             if (!mbar_wait(bar_sf + 8 * b, (uint32_t)((it >> 1) & 1))) { timeout_flag = 1; break; }
-            const float* S = reinterpret_cast<const float*>(smem + OFF_S + b * (GW_T * XS * 4)) + warp * CH * XS;
-            const int node0 = tile * GW_T + warp * CH;
-            if (node0 < A.n_own) gin_mlp_chunk<HMLP>(S, Wt, node0, A.n_own, A.out, s1, s2, lane);
+            const float* S = reinterpret_cast<const float*>(smem + OFF_S + b * (GW_T * XS * 4)) + c * CH * XS;
+            float a1[4][4];
+            gin_load_a1(S, lane, a1);              // into registers, then the buffer goes back to the gather warps
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_se + 8 * b);
+            const int node0 = (int)tile * GW_T + c * CH;
+            if (node0 < A.n_own) gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane);
         }
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll

@@ -304,6 +304,105 @@ __global__ void k_s_offsets(const unsigned long long* __restrict__ key, const in
     }
 }
 
+// ---- T format (tcgen05 edge-block kernel, conv_t.cu) -----------------------------------------------------------
+// Destinations are cut into super-tiles of RT = 2^db rows.  A super-tile's in-edges are grouped into BLOCKS of 128 slots
+// that all share one edge type (the A operand of one tcgen05.mma M = 128); quarter q of a block (slots 32q .. 32q+31 =
+// TMEM lanes of epilogue warp q) only holds destinations with dst % 4 == q, and inside a quarter all destinations are
+// distinct -- so the four epilogue warps accumulate into ONE shared-memory tile without atomics or races.
+// key = (tile << (db + tb)) | (type << db) | ((dst & 3) << (db - 2)) | (dst_local >> 2)
+__global__ void k_t_keys(const int64_t* __restrict__ dst, const int* __restrict__ type_of_edge, int64_t e, int64_t n_own,
+                         int tb, int db, unsigned long long* __restrict__ key, int* __restrict__ eid) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    long long d = dst[i];
+    if (d < 0 || d >= n_own) d = 0;
+    const unsigned long long tile = (unsigned long long)(d >> db), dl = (unsigned long long)(d & ((1ll << db) - 1));
+    key[i] = (tile << (db + tb)) | ((unsigned long long)type_of_edge[i] << db) | ((dl & 3ull) << (db - 2)) | (dl >> 2);
+    eid[i] = (int)i;
+}
+__global__ void k_t_flags(const unsigned long long* __restrict__ key, int64_t e, int db, int* __restrict__ run_head,
+                          int* __restrict__ pair_head, int* __restrict__ grp_seed) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    run_head[i] = (i == 0 || (key[i] >> (db - 2)) != (key[i - 1] >> (db - 2))) ? 1 : 0;      // (tile, type, class)
+    pair_head[i] = (i == 0 || (key[i] >> db) != (key[i - 1] >> db)) ? 1 : 0;                  // (tile, type)
+    grp_seed[i] = (i == 0 || key[i] != key[i - 1]) ? (int)i : 0;                              // same destination
+}
+__global__ void k_t_runs(int64_t e, const int* __restrict__ run_idx, const int* __restrict__ run_head,
+                         const int* __restrict__ pair_idx, const int* __restrict__ pair_head, const int* __restrict__ grp_start,
+                         int* __restrict__ run_pos, int* __restrict__ run_pair, int* __restrict__ run_maxmult, int* __restrict__ pair_pos) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const int r = run_idx[i] - 1;
+    if (run_head[i]) { run_pos[r] = (int)i; run_pair[r] = pair_idx[i] - 1; }
+    if (pair_head[i]) pair_pos[pair_idx[i] - 1] = (int)i;
+    const int mult = (int)i - grp_start[i] + 1;
+    if (mult > 1) atomicMax(&run_maxmult[r], mult);
+}
+// groups (quarter-blocks of 32 slots) per run; blocks per (tile, type) pair = the most groups any of its classes needs
+__global__ void k_t_groups(const int* __restrict__ run_pos, const int* __restrict__ run_pair, const int* __restrict__ run_maxmult,
+                           int n_runs, int e, int* __restrict__ run_g, int* __restrict__ pair_nb) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_runs) return;
+    const int len = ((r + 1 < n_runs) ? run_pos[r + 1] : e) - run_pos[r];
+    int g = (len + 31) / 32;
+    if (run_maxmult[r] > g) g = run_maxmult[r];
+    run_g[r] = g;
+    atomicMax(&pair_nb[run_pair[r]], g);
+}
+__global__ void k_t_pairs(const unsigned long long* __restrict__ key, const int* __restrict__ pair_pos, const int* __restrict__ pair_nb,
+                          const int* __restrict__ pair_base, int n_pairs, int tb, int db, int* __restrict__ tile_end) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const long long tile = (long long)(key[pair_pos[p]] >> (db + tb));
+    const bool last = (p + 1 == n_pairs) || ((long long)(key[pair_pos[p + 1]] >> (db + tb)) != tile);
+    if (last) tile_end[tile] = pair_base[p] + pair_nb[p];             // edge blocks of all tiles up to and including this one
+}
+__global__ void k_t_bptr(const int* __restrict__ cum, int n_tiles, int rb, int* __restrict__ bptr) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) bptr[0] = 0;
+    if (t < n_tiles) bptr[t + 1] = cum[t] + rb * (t + 1);             // + the root blocks of every tile so far
+}
+__global__ void k_t_btype(const unsigned long long* __restrict__ key, const int* __restrict__ pair_pos, const int* __restrict__ pair_nb,
+                          const int* __restrict__ pair_base, int n_pairs, int tb, int db, int rb, int* __restrict__ btype) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const unsigned long long k = key[pair_pos[p]];
+    const int type = (int)((k >> db) & ((1ull << tb) - 1ull));
+    const int tile = (int)(k >> (db + tb));
+    for (int b = 0; b < pair_nb[p]; ++b) btype[pair_base[p] + rb * tile + b] = type;
+}
+__global__ void k_t_scatter(const unsigned long long* __restrict__ key, const int* __restrict__ eid_sorted, const int64_t* __restrict__ src,
+                            int64_t e, const int* __restrict__ run_idx, const int* __restrict__ run_pos, const int* __restrict__ run_g,
+                            const int* __restrict__ run_pair, const int* __restrict__ pair_base, int tb, int db, int rb,
+                            int* __restrict__ t_src, unsigned short* __restrict__ t_dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const int r = run_idx[i] - 1, p = (int)i - run_pos[r], g = run_g[r];
+    const unsigned long long k = key[i];
+    const int tile = (int)(k >> (db + tb)), q = (int)((k >> (db - 2)) & 3ull);
+    const int dl = (int)((k & ((1ull << (db - 2)) - 1ull)) << 2) | q;
+    const int64_t slot = ((int64_t)pair_base[run_pair[r]] + (int64_t)rb * tile + (p % g)) * 128 + 32 * q + p / g;
+    t_src[slot] = (int)src[eid_sorted[i]];
+    t_dst[slot] = (unsigned short)dl;
+}
+// root blocks (the x_i . root term as rb more blocks of edge type n_types, src = dst = the tile's own rows)
+__global__ void k_t_roots(const int* __restrict__ bptr, int n_tiles, int rt, int rb, int n_own, int n_types,
+                          int* __restrict__ btype, int* __restrict__ t_src, unsigned short* __restrict__ t_dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_tiles * rt) return;
+    const int tile = (int)(i / rt), r = (int)(i % rt);
+    const int block = bptr[tile + 1] - rb + (r >> 7), rr = r & 127;
+    const int64_t slot = (int64_t)block * 128 + 32 * (rr & 3) + (rr >> 2);
+    const int node = tile * rt + r;
+    if (node < n_own) { t_src[slot] = node; t_dst[slot] = (unsigned short)r; }
+    if (rr == 0) btype[block] = n_types;
+}
+__global__ void k_fill_u16(unsigned short* __restrict__ p, int64_t n, unsigned short v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 int bits_for(unsigned long long v) { int b = 1; while ((v >> b) != 0 && b < 64) ++b; return b; }
 
 template <class K, class V>
@@ -344,7 +443,7 @@ int read_int(const int* dptr, cudaStream_t st) {
 
 void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
-                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, int want_s, int wn, cudaStream_t st) {
+                 int64_t e_col, const int64_t* col_src, const int64_t* col_dst, int want_s, int wn, int want_t, cudaStream_t st) {
     TGNN_CHECK(wn == WN_SMALL || wn == WN_BIG, "internal: bad warp-tile height");
     const int db = wn == WN_BIG ? 7 : 6;
     g.wn = wn;
@@ -466,8 +565,59 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
             g.s_max_pass = read_int(s_maxlen, st);
             g.has_s = g.s_max_pass <= 160;          // four passes in flight must fit the kernel's 640-row ring
         }
+        // ---------------- adjacency: T format (tcgen05 edge-block kernel) --------------------------------
+        g.has_t = false;
+        if (want_t > 0) {
+            const int rt = want_t, tdb = rt == 1024 ? 10 : (rt == 512 ? 9 : 8), rb = rt / 128;
+            g.t_rows = rt; g.t_tiles = (int)((n_own + rt - 1) / rt);
+            k_t_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, tb, tdb, k0, id0);
+            const int t_end_bit = tdb + tb + bits_for((unsigned long long)g.t_tiles);
+            TGNN_CHECK(t_end_bit <= 64, "tgnn_set_graph: sort key overflow (super-tiles x edge types)");
+            sort_pairs(sc, k0, k1, id0, id1, e_adj, t_end_bit, st);
+            int* pair_head = sc.get<int>(e_adj);
+            int* pair_idx = sc.get<int>(e_adj);
+            k_t_flags<<<nblk(e_adj), TPB, 0, st>>>(k1, e_adj, tdb, run_head, pair_head, grp_seed);
+            incl_sum(sc, run_head, run_idx, e_adj, st);
+            incl_sum(sc, pair_head, pair_idx, e_adj, st);
+            incl_max(sc, grp_seed, grp_start, e_adj, st);
+            const int t_runs = read_int(run_idx + (e_adj - 1), st), t_pairs = read_int(pair_idx + (e_adj - 1), st);
+            int* t_run_pos = sc.get<int>(t_runs + 1);
+            int* t_run_pair = sc.get<int>(t_runs);
+            int* t_run_mm = sc.get<int>(t_runs);
+            int* t_run_g = sc.get<int>(t_runs);
+            int* pair_pos = sc.get<int>(t_pairs + 1);
+            int* pair_nb = sc.get<int>(t_pairs);
+            int* pair_base = sc.get<int>(t_pairs + 1);
+            TGNN_CUDA(cudaMemsetAsync(t_run_mm, 0, (size_t)t_runs * sizeof(int), st));
+            TGNN_CUDA(cudaMemsetAsync(pair_nb, 0, (size_t)t_pairs * sizeof(int), st));
+            k_t_runs<<<nblk(e_adj), TPB, 0, st>>>(e_adj, run_idx, run_head, pair_idx, pair_head, grp_start, t_run_pos, t_run_pair, t_run_mm, pair_pos);
+            k_t_groups<<<nblk(t_runs), TPB, 0, st>>>(t_run_pos, t_run_pair, t_run_mm, t_runs, (int)e_adj, t_run_g, pair_nb);
+            excl_sum(sc, pair_nb, pair_base, t_pairs, st);
+            const int64_t edge_blocks = (int64_t)read_int(pair_base + (t_pairs - 1), st) + read_int(pair_nb + (t_pairs - 1), st);
+            const int64_t n_blocks = edge_blocks + (int64_t)rb * g.t_tiles;
+            TGNN_CHECK(n_blocks * 128 < (1ll << 31) - 64, "tgnn_set_graph: edge blocks exceed 2^31 slots");
+            g.t_blocks = (int)n_blocks;
+            g.t_bptr.reserve((size_t)(g.t_tiles + 1) * sizeof(int));
+            g.t_btype.reserve((size_t)n_blocks * sizeof(int));
+            g.t_src.reserve((size_t)n_blocks * 128 * sizeof(int));
+            g.t_dst.reserve((size_t)n_blocks * 128 * sizeof(unsigned short));
+            k_fill_int<<<nblk(n_blocks * 128), TPB, 0, st>>>(g.t_src.as<int>(), n_blocks * 128, -1);
+            k_fill_u16<<<nblk(n_blocks * 128), TPB, 0, st>>>(g.t_dst.as<unsigned short>(), n_blocks * 128, (unsigned short)0xFFFF);
+            int* t_tile_end = sc.get<int>(g.t_tiles);
+            int* t_cum = sc.get<int>(g.t_tiles);
+            TGNN_CUDA(cudaMemsetAsync(t_tile_end, 0, (size_t)g.t_tiles * sizeof(int), st));
+            k_t_pairs<<<nblk(t_pairs), TPB, 0, st>>>(k1, pair_pos, pair_nb, pair_base, t_pairs, tb, tdb, t_tile_end);
+            incl_max(sc, t_tile_end, t_cum, g.t_tiles, st);
+            k_t_bptr<<<nblk(g.t_tiles), TPB, 0, st>>>(t_cum, g.t_tiles, rb, g.t_bptr.as<int>());
+            k_t_btype<<<nblk(t_pairs), TPB, 0, st>>>(k1, pair_pos, pair_nb, pair_base, t_pairs, tb, tdb, rb, g.t_btype.as<int>());
+            k_t_scatter<<<nblk(e_adj), TPB, 0, st>>>(k1, id1, adj_src, e_adj, run_idx, t_run_pos, t_run_g, t_run_pair, pair_base, tb, tdb, rb,
+                                                      g.t_src.as<int>(), g.t_dst.as<unsigned short>());
+            k_t_roots<<<nblk((int64_t)g.t_tiles * rt), TPB, 0, st>>>(g.t_bptr.as<int>(), g.t_tiles, rt, rb, (int)n_own, n_types,
+                                                                    g.t_btype.as<int>(), g.t_src.as<int>(), g.t_dst.as<unsigned short>());
+            g.has_t = true;
+        }
     } else {
-        g.has_s = false;
+        g.has_s = false; g.has_t = false;
         TGNN_CUDA(cudaMemsetAsync(g.cptr.p, 0, (size_t)(g.n_tiles + 1) * sizeof(int), st));
     }
     k_inv_deg<<<nblk(n_own), TPB, 0, st>>>(deg, n_own, g.inv_deg.as<float>());

@@ -145,7 +145,9 @@ k_gin(GinArgs A) {
             *reinterpret_cast<float4*>(xs + r * XS + 4 * q) = sum;
         }
         __syncwarp();
-        gin_mlp_chunk<HMLP>(xs, Wt, node0, A.n_own, A.out, s1, s2, lane);
+        float a1[4][4];
+        gin_load_a1(xs, lane, a1);
+        gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane);
         __syncwarp();
     }
     // fold the eight row groups (lanes with equal t) in a fixed order; lanes 0..3 publish channels 8t..8t+7

@@ -63,6 +63,24 @@ __device__ __forceinline__ void hfrag_store(__half* tab, int k, int n, float w, 
     if (flag && !(fabsf(w) <= limit)) *flag = 1;
 }
 
+// ---- tcgen05 edge-block kernel (conv_t.cu): the [64 rows n][64 halves k] K-major SWIZZLE_128B IMAGE of a type's weights.
+// k runs in the storage order of a split activation row (hsplit.cuh): 16-byte piece p = xh_pos(c >> 2) holds
+// {hi(4q..4q+3), lo(4q..4q+3)} of channels 4q + i.  Rows  0..31 ("main",  out channel n): hi-slot = Whi, lo-slot = 0;
+// rows 32..63 ("small", out channel n - 32): hi-slot = Wlo (scaled 2^11), lo-slot = Whi  ->  D = A . B^T gives
+//   D[:, n] = hi . Whi      D[:, 32 + n] = hi . Wlo + lo . Whi      message = D[:, n] + 2^-11 D[:, 32 + n].
+__host__ __device__ __forceinline__ int timg_half_index(int row, int k) { return row * 64 + ((((k >> 3) ^ (row & 7)) << 3) | (k & 7)); }
+__device__ __forceinline__ void timg_store(__half* img, int kin, int n, float w, int* flag, float limit) {
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
+    const int q = kin >> 2, i = kin & 3, p = 2 * (q & 3) + (q >> 2);          // p = xh_pos(q)
+    const int k_hi = 8 * p + i, k_lo = 8 * p + 4 + i;
+    img[timg_half_index(n, k_hi)] = hi;
+    img[timg_half_index(n, k_lo)] = __float2half_rn(0.f);
+    img[timg_half_index(32 + n, k_hi)] = lo;
+    img[timg_half_index(32 + n, k_lo)] = hi;
+    if (flag && !(fabsf(w) <= limit)) *flag = 1;
+}
+
 // ---- fp16 hi|lo fragment table of a k-major [K][N] matrix in NATURAL k order (k = 16 ks + 8 reg + 2 tt + e), for
 // the chained GIN layers whose A fragments are the previous layer's C fragments (k_gin<true>; kernels.cu) ----------
 //   uint4 index ((ks*2 + hl) * (N/16) + j)*32 + lane ; component 2(nt&1) + reg ; half e

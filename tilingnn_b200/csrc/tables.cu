@@ -5,7 +5,8 @@
 // (PyG NNConv: weight.view(-1, in, out)).  Equal rows give equal weights, so the MLP is evaluated once per distinct
 // row ("edge type") and layer -- in fp64, rounded once to fp32 -- and stored in the layouts the three adjacency
 // kernels read (layouts.cuh): 3xTF32 fragments (k_conv_adj), the pre-swizzled tcgen05 operand image (k_conv_s) and
-// fp16 hi|lo fragments (k_conv_h).  Entry K of every layer is nnConv.root.  grid = (K + 1, L), block = 256.
+// fp16 hi|lo fragments (k_conv_h), the pre-swizzled [64 x 64] fp16 image of the tcgen05 edge-block kernel (k_conv_t) and plain
+// fp32 (its wide-range stand-in).  Entry K of every layer is nnConv.root.  grid = (K + 1, L), block = 256.
 #include "layouts.cuh"
 #include "tgnn_internal.h"
 
@@ -14,7 +15,8 @@ namespace {
 
 __global__ void __launch_bounds__(256)
 k_edge_tables(const float* __restrict__ rows, int K, int d_e, const TableLayer* __restrict__ layers,
-              float* __restrict__ tabF, float* __restrict__ tabS, uint32_t* __restrict__ tabH, int* __restrict__ wflags) {
+              float* __restrict__ tabF, float* __restrict__ tabS, uint32_t* __restrict__ tabH, uint32_t* __restrict__ tabT,
+              float* __restrict__ tab32, int* __restrict__ wflags) {
     __shared__ double h1[32], h2[64];
     const int t = blockIdx.x, layer = blockIdx.y, tid = threadIdx.x;
     const TableLayer L = layers[layer];
@@ -22,6 +24,8 @@ k_edge_tables(const float* __restrict__ rows, int K, int d_e, const TableLayer* 
     float* outF = tabF ? tabF + slot * TG_FRAG32 : nullptr;
     float* outS = tabS ? tabS + slot * 2048 : nullptr;
     __half* outH = tabH ? reinterpret_cast<__half*>(tabH + slot * TG_HFRAG32) : nullptr;
+    __half* outT = tabT ? reinterpret_cast<__half*>(tabT + slot * TG_TIMG32) : nullptr;
+    float* out32 = tab32 ? tab32 + slot * (F * F) : nullptr;
     const bool is_root = t == K;
     if (!is_root) {
         const float* e = rows + (size_t)t * d_e;
@@ -57,14 +61,16 @@ k_edge_tables(const float* __restrict__ rows, int K, int d_e, const TableLayer* 
         }
         // a sigmoid is always inside the fp16 range; a root weight may not be (then k_conv_adj takes the layer)
         if (outH) hfrag_store(outH, kin, n, (float)w, is_root ? wflags + layer : nullptr, TG_H_LIMIT);
+        if (outT) timg_store(outT, kin, n, (float)w, is_root ? wflags + layer : nullptr, TG_H_LIMIT);
+        if (out32) out32[o] = (float)w;
     }
 }
 
 }  // namespace
 
 void launch_edge_tables(const float* type_rows, int n_types, int d_e, int n_layers, const TableLayer* layers_dev,
-                        float* tabF, float* tabS, uint32_t* tabH, int* wflags, cudaStream_t st) {
-    k_edge_tables<<<dim3(n_types + 1, n_layers), 256, 0, st>>>(type_rows, n_types, d_e, layers_dev, tabF, tabS, tabH, wflags);
+                        float* tabF, float* tabS, uint32_t* tabH, uint32_t* tabT, float* tab32, int* wflags, cudaStream_t st) {
+    k_edge_tables<<<dim3(n_types + 1, n_layers), 256, 0, st>>>(type_rows, n_types, d_e, layers_dev, tabF, tabS, tabH, tabT, tab32, wflags);
     TGNN_CUDA(cudaGetLastError());
 }
 

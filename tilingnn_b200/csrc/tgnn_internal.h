@@ -105,6 +105,15 @@ struct Graph {
     DevBuf s_pbase;           // int32  [s_passes + 1]     first edge of the pass in s_src
     DevBuf s_off;             // uint16 [s_passes * 136]   per pass: edge offset of row r (r = 0..128) inside the pass
     DevBuf s_src;             // int32  [e_adj]            source rows in (tile, type, row) order
+    // "T" format for the tcgen05 edge-block kernel (conv_t.cu): super-tiles of t_rows destinations; blocks of 128 same-type
+    // slots; quarter q of a block holds destinations with dst % 4 == q, all distinct inside a quarter; every super-tile ends
+    // with t_rows / 128 root blocks (type n_types, src = dst = the tile's own rows)
+    bool has_t = false;
+    int t_rows = 0, t_tiles = 0, t_blocks = 0;
+    DevBuf t_bptr;            // int32  [t_tiles + 1]     block range per super-tile
+    DevBuf t_btype;           // int32  [t_blocks]        edge type of the block (n_types = root)
+    DevBuf t_src;             // int32  [t_blocks * 128]  source row, -1 = empty slot
+    DevBuf t_dst;             // uint16 [t_blocks * 128]  destination row inside the super-tile, 0xFFFF = empty slot
     // collision CSR by destination (self loops removed)
     DevBuf col_ptr;           // int32 [n_own + 1]
     DevBuf col_src;           // int32 [e_col]
@@ -135,7 +144,7 @@ struct Scratch {
 void build_graph(Graph& g, Scratch& scratch, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
                  int64_t e_col, const int64_t* col_src, const int64_t* col_dst, int want_s /* 0 no, 1 auto, 2 force */,
-                 int wn, cudaStream_t st);
+                 int wn, int want_t /* 0 = no T format, else its super-tile rows: 256 | 512 | 1024 */, cudaStream_t st);
 constexpr int S_BM = 128;         // destination rows per tile of the S format
 constexpr int S_OFF_STRIDE = 136; // uint16 per pass (129 used; 272 B keeps 16-byte alignment)
 constexpr double S_EDGES_PER_PASS_BREAK_EVEN = 164.0;   // measured: S pass ~5.9 ns, fp16 edge-chunk kernel ~36 ps per edge
@@ -172,6 +181,11 @@ void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
 constexpr float TG_H_LIMIT = 60000.f;    // |x| above this (or NaN) raises the range flag: fp16 max is 65504
 constexpr int TG_HFRAG32 = 1024;         // 32-bit words of one fp16 hi|lo fragment table of a 32x32 matrix
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
+// tcgen05 edge-block kernel (conv_t.cu) + its fp32 stand-by for the range guard; tabT: [K+1][2048] words, tab32: [K+1][1024]
+constexpr int TG_TIMG32 = 2048;          // 32-bit words of one pre-swizzled [64 x 64] fp16 weight image
+int conv_t_blocks(int t_tiles, int sm_count);
+inline int conv_t_num_parts(int t_tiles, int sm_count) { return conv_t_blocks(t_tiles, sm_count) * 4; }
+void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, const float* tab32, int* err, int sm_count, cudaStream_t st);
 // tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st);
 
@@ -197,7 +211,8 @@ struct GinArgs {
 int gin_num_parts(int n_own, int sm_count);
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st);
 int gin_w_blocks(int gw_tiles, int sm_count);
-inline int gin_w_num_parts(int gw_tiles, int sm_count) { return gin_w_blocks(gw_tiles, sm_count) * 4; }
+constexpr int GW_MLP_WARPS = 11;  // MLP warps per CTA of k_gin_w = BatchNorm partial rows per CTA
+inline int gin_w_num_parts(int gw_tiles, int sm_count) { return gin_w_blocks(gw_tiles, sm_count) * GW_MLP_WARPS; }
 void launch_gin_w(const GinArgs& a, int sm_count, cudaStream_t st);
 
 // b1_new = BN(pre1) * BN(pre2) + residual
@@ -265,7 +280,7 @@ void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gam
 // per-type edge weight tables of all layers in one launch (tables.cu); null table pointers are skipped
 struct TableLayer { const float *a1, *c1, *a2, *c2, *a3, *c3, *root; };   // edge MLP (weight, bias) x 3 and nnConv.root
 void launch_edge_tables(const float* type_rows, int n_types, int d_e, int n_layers, const TableLayer* layers_dev,
-                        float* tabF, float* tabS, uint32_t* tabH, int* wflags, cudaStream_t st);
+                        float* tabF, float* tabS, uint32_t* tabH, uint32_t* tabT, float* tab32, int* wflags, cudaStream_t st);
 
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);  // out[c][r] = in[r][c]
 // frag table (tensor-core B fragments, hi|lo TF32 split) of a k-major [K][N] matrix; maps: see kernels.cu

@@ -376,3 +376,17 @@ class TilinGNN(nn.Module):
         rc = _lib.load().tgnn_debug_graph(nat.h, *[_ptr(t[k]) for k in order], C.c_void_p(0))
         _lib.check(nat.h, rc, "tgnn_debug_graph")
         return t
+
+    def debug_graph_t(self):
+        """The edge-block format of the tcgen05 adjacency kernel as CPU tensors (tests)."""
+        nat = self._ensure_handle()
+        inf = self.info()
+        if not inf["t_rows"]:
+            raise RuntimeError("debug_graph_t: the edge-block format was not built for this graph")
+        n_tiles = (inf["n_own"] + inf["t_rows"] - 1) // inf["t_rows"]
+        t = dict(bptr=torch.zeros(n_tiles + 1, dtype=torch.int32), btype=torch.zeros(inf["t_blocks"], dtype=torch.int32),
+                 tsrc=torch.zeros(inf["t_blocks"] * 128, dtype=torch.int32), tdst=torch.zeros(inf["t_blocks"] * 128, dtype=torch.int16))
+        rc = _lib.load().tgnn_debug_graph_t(nat.h, *[_ptr(t[k]) for k in ("bptr", "btype", "tsrc", "tdst")], C.c_void_p(0))
+        _lib.check(nat.h, rc, "tgnn_debug_graph_t")
+        t["tdst"] = t["tdst"].to(torch.int32) & 0xFFFF
+        return t
