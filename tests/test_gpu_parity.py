@@ -427,3 +427,59 @@ def test_edge_block_format_is_a_faithful_reencoding(dev, monkeypatch):
         want = [(int(a), int(b), tuple(f)) for (a, b), f in zip(ai.t().tolist(), af.numpy())]
         assert sorted(got) == sorted(want)
         assert sorted(roots) == [(i, i) for i in range(n)]
+
+
+def test_graph_replay_of_repeated_forwards(dev):
+    """Forwards on a resident graph: the first runs eagerly, the second is captured into a CUDA graph, later ones replay it
+    (one submission instead of ~75 launches for a real layout).  All of them must be bit-identical, follow a new x, and
+    survive a change of graph, of parameters and of BatchNorm mode."""
+    from tilingnn_b200 import synthetic as syn
+    z, x, ai, af, ci = load_graph("c1_heart.npz")
+    net = make_net(load_ckpt(), 3, 19, 20, dev, "train")
+    xd, aid, afd, cid = x.to(dev), ai.to(dev), af.to(dev), ci.to(dev)
+    net.set_graph(x.shape[0], aid, afd, cid)
+    outs = [net.score(xd).clone() for _ in range(4)]           # eager, capture + replay, replay, replay
+    torch.cuda.synchronize()
+    assert all(torch.equal(outs[0], o) for o in outs[1:])
+    assert np.abs(outs[0].double().cpu().numpy() - z["ref_train_f64"]).max() <= 1e-3
+    x2 = xd.clone(); x2[:, -1] *= 0.5                          # another input through the SAME captured sequence
+    a = net.score(x2).clone()
+    net2 = make_net(load_ckpt(), 3, 19, 20, dev, "train")
+    net2.set_graph(x.shape[0], aid, afd, cid)
+    assert torch.equal(a, net2.score(x2)), "replay must read the caller's x, not the captured one"
+    assert not torch.equal(a, outs[0])
+    net.eval()                                                  # mode change: new key, eager again, then capture
+    e = [net.score(xd).clone() for _ in range(3)]
+    assert all(torch.equal(e[0], o) for o in e[1:])
+    assert np.abs(e[0].double().cpu().numpy() - z["ref_eval_f64"]).max() <= 3.5e-4
+    net.train()
+    xs, ais, afs, cis = syn.lattice_graph(3000, 8, 8, seed=0)   # other graph, other parameters on the same handle
+    p = orc.make_params(3, 19, 20, seed=0)
+    net.load_state_dict(p, strict=True)
+    gold = orc.forward(p, xs, ais, afs, cis, depth=20, dtype=torch.float64)[:, 0].numpy()
+    net.set_graph(3000, ais.to(dev), afs.to(dev), cis.to(dev))
+    for _ in range(3):
+        s = net.score(xs.to(dev))
+        assert np.abs(s.double().cpu().numpy() - gold).max() <= TOL
+
+
+@pytest.mark.parametrize("var,val", [("TGNN_GINW", "1"), ("TGNN_CONV", "t")])
+def test_persistent_pipelines_over_many_tiles(dev, var, val, monkeypatch):
+    """k_gin_w and k_conv_t are persistent kernels whose mbarrier pipelines run for dozens of tiles per CTA at benchmark
+    sizes (the small parity cases give every CTA a single tile).  Size-independent property on a 300k-node graph the
+    oracle would not finish: the staged-window / tcgen05 kernel must agree with the per-lane-gather / mma.sync kernel."""
+    from tilingnn_b200 import synthetic as syn
+    x, ai, af, ci = syn.lattice_graph(300000, 16, 16, seed=0, device=dev)
+    p = orc.make_params(3, 19, 3, seed=0)
+    monkeypatch.setenv("TGNN_GINW", "0"); monkeypatch.setenv("TGNN_CONV", "h")
+    base = make_net(p, 3, 19, 3, dev)
+    a = base(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci)[0].clone()
+    monkeypatch.setenv(var, val)
+    net = make_net(p, 3, 19, 3, dev)
+    b = net(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci)[0].clone()
+    net.check_errors()
+    info = net.info()
+    assert (info["gin_kernel"] == 1) if var == "TGNN_GINW" else (info["conv_kernel"] == 3)
+    err = (a - b).abs().max().item()
+    print(f"{var}={val} vs baseline kernels on 300k nodes: max diff {err:.2e}")
+    assert torch.isfinite(b).all() and err <= 2e-5

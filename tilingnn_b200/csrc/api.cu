@@ -144,6 +144,22 @@ struct tgnn_handle {
         int64_t halo_slot = -1;
     } px;
 
+    // One-submit forward (CUDA graph replay).  The launch sequence of a forward depends only on the resident graph
+    // structures, the parameters and the BatchNorm mode -- not on x.  The first forward with a given key runs eagerly
+    // (one-shot topologies, as in the reference's greedy loop, never pay for a capture), the second is captured on a
+    // private stream with x / scores redirected to staging buffers, later ones are memcpy + cudaGraphLaunch + memcpy
+    // on the caller's stream: ~75 launches of a 600-node, 20-layer forward become three submissions.
+    struct Replay {
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t cap_stream = nullptr;
+        uint64_t key = 0; int seen = 0;
+        DevBuf x_stage, s_stage;
+        int64_t launches = 0;
+        bool disabled = getenv("TGNN_GRAPH") && std::string(getenv("TGNN_GRAPH")) == "0";
+        void drop() { if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; } seen = 0; }
+    } replay;
+    uint64_t graph_gen = 0, param_gen = 0;
+
     // bookkeeping
     int64_t launches = 0, collectives = 0;
     int stop_layer = -1;
@@ -153,6 +169,7 @@ struct tgnn_handle {
     std::vector<ProfEntry> prof;
     std::map<std::string, std::pair<float, int>> prof_result;
 
+    bool train_mode_forward() const { return cfg.bn_mode == TGNN_BN_TRAIN; }
     float* P(const std::string& k) {
         auto it = params.find(k);
         TGNN_CHECK(it != params.end(), "internal: unknown parameter " + k);
@@ -573,11 +590,13 @@ void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t s
     lz.end(2);
 }
 
-void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st) {
+void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st, bool capturing = false) {
     TGNN_CHECK(h->graph_set, "tgnn_forward: no graph set (call tgnn_set_graph first)");
-    check_device_error(h, "tgnn_forward (reported by an earlier forward)");
-    pack_params(h, st);
-    build_tables(h, st);
+    if (!capturing) {
+        check_device_error(h, "tgnn_forward (reported by an earlier forward)");
+        pack_params(h, st);
+        build_tables(h, st);
+    }
     const int L = h->cfg.depth;
     const bool train = h->cfg.bn_mode == TGNN_BN_TRAIN;
     const int n_own = (int)h->g.n_own;
@@ -753,7 +772,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     // Device-side errors are ALWAYS surfaced: synchronously here when that is cheap or asked for (small graphs: the
     // callers read the scores back at once anyway), otherwise at the next API call / tgnn_check_error (the error word
     // lives in mapped host memory, so reading it needs no CUDA call and no stall of the launch queue).
-    if (h->profiling || h->check_errors || h->g.n_own <= SYNC_CHECK_MAX_NODES) {
+    if (!capturing && (h->profiling || h->check_errors || h->g.n_own <= SYNC_CHECK_MAX_NODES)) {
         TGNN_CUDA(cudaStreamSynchronize(st));
         check_device_error(h, "tgnn_forward");
     }
@@ -763,6 +782,57 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             cudaEventElapsedTime(&ms, e.a, e.b);
             h->prof_result[e.fam].first += ms;
         }
+    }
+}
+
+constexpr int64_t REPLAY_MAX_NODES = 262144;     // above this a forward is milliseconds of kernels: launch overhead is noise
+
+// tgnn_forward: replay the captured launch sequence when there is one, capture on the second use of a key, else eager.
+void forward_entry(tgnn_handle* h, const float* x, float* scores, cudaStream_t st) {
+    TGNN_CHECK(h->graph_set, "tgnn_forward: no graph set (call tgnn_set_graph first)");
+    tgnn_handle::Replay& R = h->replay;
+    const bool can = !R.disabled && h->world == 1 && !h->profiling && h->stop_layer < 0 && scores != nullptr &&
+                     h->g.n_own <= REPLAY_MAX_NODES;
+    if (!can) { forward_impl(h, x, scores, st); return; }
+    check_device_error(h, "tgnn_forward (reported by an earlier forward)");
+    if (h->params_dirty || h->tables_dirty) R.drop();                    // derived buffers may move: the captured pointers die
+    pack_params(h, st);
+    build_tables(h, st);
+    if (h->tables_streamed) { forward_impl(h, x, scores, st); return; }   // per-layer table builds: not worth capturing
+    const uint64_t key = (h->graph_gen << 20) ^ (h->param_gen << 2) ^ (uint64_t)h->cfg.bn_mode;
+    if (key != R.key) { R.drop(); R.key = key; }
+    const size_t xb = (size_t)h->g.n_own * h->cfg.d_x * sizeof(float), sb = (size_t)h->g.n_own * sizeof(float);
+    if (!R.exec) {
+        if (++R.seen < 2) { forward_impl(h, x, scores, st); return; }
+        // second forward on the same structures: capture it
+        R.x_stage.reserve(xb); R.s_stage.reserve(sb);
+        if (!R.cap_stream) TGNN_CUDA(cudaStreamCreateWithFlags(&R.cap_stream, cudaStreamNonBlocking));
+        TGNN_CUDA(cudaStreamSynchronize(st));                             // table builds etc. issued on st are done
+        cudaGraph_t graph = nullptr;
+        bool ok = cudaStreamBeginCapture(R.cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+        if (ok) {
+            try { forward_impl(h, R.x_stage.as<float>(), R.s_stage.as<float>(), R.cap_stream, true); }
+            catch (const std::exception&) { ok = false; }
+            if (cudaStreamEndCapture(R.cap_stream, &graph) != cudaSuccess) ok = false;
+        }
+        if (ok && graph) ok = cudaGraphInstantiate(&R.exec, graph, 0) == cudaSuccess;
+        if (graph) cudaGraphDestroy(graph);
+        if (!ok) {                                                        // something in the sequence cannot be captured: stay eager
+            cudaGetLastError();
+            R.exec = nullptr; R.disabled = true;
+            forward_impl(h, x, scores, st);
+            return;
+        }
+        R.launches = h->launches;
+    }
+    TGNN_CUDA(cudaMemcpyAsync(R.x_stage.p, x, xb, cudaMemcpyDeviceToDevice, st));
+    TGNN_CUDA(cudaGraphLaunch(R.exec, st));
+    TGNN_CUDA(cudaMemcpyAsync(scores, R.s_stage.p, sb, cudaMemcpyDeviceToDevice, st));
+    h->launches = R.launches; h->collectives = 0;
+    if (h->train_mode_forward()) h->eval_coefs_valid = false;
+    if (h->check_errors || h->g.n_own <= SYNC_CHECK_MAX_NODES) {
+        TGNN_CUDA(cudaStreamSynchronize(st));
+        check_device_error(h, "tgnn_forward");
     }
 }
 
@@ -834,6 +904,8 @@ int tgnn_destroy(tgnn_handle* h) {
     {
         DeviceGuard dg(h->cfg.device);
         for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        h->replay.drop();
+        if (h->replay.cap_stream) cudaStreamDestroy(h->replay.cap_stream);
         peer_close(h);
         if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
         if (h->err_host) cudaFreeHost(h->err_host);
@@ -866,6 +938,7 @@ int tgnn_set_param(tgnn_handle* h, const char* ref_key, const void* data, const 
         TGNN_CUDA(cudaMemcpy(p.buf.p, data, bytes, cudaMemcpyDefault));
         p.set = true;
         h->params_dirty = true;
+        h->param_gen++;
     });
 }
 
@@ -903,6 +976,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         choose_gin_kernel(h, st);
         alloc_workspace(h);
         h->tables_dirty = true;
+        h->graph_gen++;
         h->graph_set = true;
     });
 }
@@ -911,7 +985,7 @@ int tgnn_forward(tgnn_handle* h, const float* x, float* scores_out, void* stream
     return guarded(h, [&] {
         TGNN_CHECK(h && x && (scores_out || h->stop_layer >= 0), "tgnn_forward: null argument");
         DeviceGuard dg(h->cfg.device);
-        forward_impl(h, x, scores_out, (cudaStream_t)stream);
+        forward_entry(h, x, scores_out, (cudaStream_t)stream);
     });
 }
 

@@ -11,7 +11,8 @@
 // and the gather warps read neighbour rows with LDS.128 at shared-memory latency:
 //   L2 -> SM traffic / 3.3, no dependent global load in the gather loop, indices 2 B instead of 4 B per edge.
 // Warp roles (16 warps = 512 threads x 128 registers, one CTA per SM, persistent over tiles):
-//   warps 0-10  node MLP on tensor cores (mma.sync): the four 16-node chunks of a tile go round-robin over the 11 warps,
+//   warps 0-10  node MLP on tensor cores (mma.sync): the four 16-node chunks of a tile go round-robin over the 11 warps
+//               (each has its own chunk buffer and barrier pair),
 //               so three tiles' MLPs are in flight (one chunk is ~6000 cycles of dependent MMAs and sigmoids; the
 //               gather delivers a tile every ~2600) -- measured: with 4 MLP warps the kernel was MLP-latency-bound
 //   warps 11-14 gather-sum from the window (8 lanes per 128-byte row, 8 rows in flight per lane): shared-memory
@@ -38,8 +39,8 @@ constexpr int PTR_INTS = 68;                                    // 65 row pointe
 constexpr int OFF_WIN = 0;                                      // [2][GW_WMAX][128 B]
 constexpr int OFF_LOC = OFF_WIN + 2 * GW_WMAX * 128;            // [2][GW_CAP] uint16
 constexpr int OFF_PTR = OFF_LOC + 2 * GW_CAP * 2;               // [2][PTR_INTS] int
-constexpr int OFF_S = OFF_PTR + 2 * PTR_INTS * 4;               // [2][GW_T][XS] float
-constexpr int OFF_W = OFF_S + 2 * GW_T * XS * 4;                // MLP weights
+constexpr int OFF_S = OFF_PTR + 2 * PTR_INTS * 4;               // [MLP_WARPS][CH][XS] float: one 16-node chunk buffer per MLP warp
+constexpr int OFF_W = OFF_S + MLP_WARPS * CH * XS * 4;          // MLP weights
 template <bool HMLP> constexpr int gw_smem_bytes() { return OFF_W + (HMLP ? GIN_WFLOATS_H : GIN_WFLOATS) * 4 + 128; }
 
 __device__ __forceinline__ float4 lds_row(uint32_t addr) { return lds128f(addr); }
@@ -48,18 +49,18 @@ template <bool HMLP>
 __global__ void __launch_bounds__(GW_THREADS, 1)
 k_gin_w(GinArgs A) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[8];                   // win_full[2], win_empty[2], s_full[2], s_empty[2]
+    __shared__ __align__(8) uint64_t bars[4 + 2 * MLP_WARPS];   // win_full[2], win_empty[2], chunk_full[MLP_WARPS], chunk_empty[MLP_WARPS]
     __shared__ int meta_s[2][4];                                // per window buffer: {nseg (0 = direct), self_loc, -, -}
     __shared__ int timeout_flag;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t bar_wf = smem_u32(&bars[0]), bar_we = smem_u32(&bars[2]), bar_sf = smem_u32(&bars[4]), bar_se = smem_u32(&bars[6]);
+    const uint32_t bar_wf = smem_u32(&bars[0]), bar_we = smem_u32(&bars[2]), bar_cf = smem_u32(&bars[4]), bar_ce = smem_u32(&bars[4 + MLP_WARPS]);
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(bar_wf + 8 * i, 1); mbar_init(bar_we + 8 * i, GATHER_WARPS);
-            mbar_init(bar_sf + 8 * i, GATHER_WARPS); mbar_init(bar_se + 8 * i, CHUNKS_PER_TILE);
-        }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_wf + 8 * i, 1); mbar_init(bar_we + 8 * i, GATHER_WARPS); }
+        // chunk ci of the CTA (ci = 4 * tile iteration + chunk in tile) belongs to MLP warp ci % MLP_WARPS and is that warp's
+        // (ci / MLP_WARPS)-th chunk: every party of a chunk barrier sees every one of its phases (a parity wait must not skip one)
+        for (int i = 0; i < MLP_WARPS; ++i) { mbar_init(bar_cf + 8 * i, GATHER_WARPS); mbar_init(bar_ce + 8 * i, 1); }
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -107,16 +108,18 @@ k_gin_w(GinArgs A) {
             const int b = it & 1;
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
             if (!mbar_wait(bar_wf + 8 * b, ph)) { timeout_flag = 1; break; }
-            if (!mbar_wait(bar_se + 8 * b, ph ^ 1)) { timeout_flag = 1; break; }       // the MLP warps are done with S[b]
             const int nseg = meta_s[b][0], self_loc = meta_s[b][1];
             const int* ptr = reinterpret_cast<const int*>(smem + OFF_PTR + b * (PTR_INTS * 4));
             const uint16_t* loc = reinterpret_cast<const uint16_t*>(smem + OFF_LOC + b * (GW_CAP * 2));
             const uint32_t win = sbase + OFF_WIN + (uint32_t)b * (GW_WMAX * 128) + (uint32_t)q * 16u;
-            float* S = reinterpret_cast<float*>(smem + OFF_S + b * (GW_T * XS * 4));
             const int node0 = tile * GW_T, e_base = ptr[0];
+            bool ok = true;
 #pragma unroll 1
-            for (int qd = gw; qd < GW_T / 4; qd += GATHER_WARPS) {
-                const int r = 4 * qd + a, node = node0 + r;
+            for (int c = 0; c < CHUNKS_PER_TILE; ++c) {
+                // rows 4 gw .. 4 gw + 3 of chunk c (this warp's quad) go into the chunk buffer of the MLP warp that owns it
+                const int ci = it * CHUNKS_PER_TILE + c, mw = ci % MLP_WARPS, use = ci / MLP_WARPS;
+                float* S = reinterpret_cast<float*>(smem + OFF_S) + mw * (CH * XS);
+                const int r = CH * c + 4 * gw + a, node = node0 + r;
                 const bool live = node < A.n_own;
                 const int e0 = live ? ptr[r] : e_base, n_mine = live ? ptr[r + 1] - e0 : 0;
                 int n_max = max(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 8));       // warp-uniform trip count
@@ -164,10 +167,14 @@ k_gin_w(GinArgs A) {
                         for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
                     }
                 }
-                *reinterpret_cast<float4*>(S + r * XS + 4 * q) = sum;
+                if (!mbar_wait(bar_ce + 8 * mw, (uint32_t)((use & 1) ^ 1))) { timeout_flag = 1; ok = false; break; }   // its previous chunk is in registers
+                *reinterpret_cast<float4*>(S + (4 * gw + a) * XS + 4 * q) = sum;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_cf + 8 * mw);
             }
+            if (!ok) break;
             __syncwarp();
-            if (lane == 0) { mbar_arrive(bar_we + 8 * b); mbar_arrive(bar_sf + 8 * b); }
+            if (lane == 0) mbar_arrive(bar_we + 8 * b);
         }
     } else {
         // ===================== node MLP: chunk c of the CTA's it-th tile goes to warp (4 it + c) % 11 =====================
@@ -175,17 +182,17 @@ k_gin_w(GinArgs A) {
         double s1[8], s2[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
-        for (int ci = warp;; ci += MLP_WARPS) {
+        const float* S = reinterpret_cast<const float*>(smem + OFF_S) + warp * (CH * XS);
+        int use = 0;
+        for (int ci = warp;; ci += MLP_WARPS, ++use) {
             const int it = ci / CHUNKS_PER_TILE, c = ci % CHUNKS_PER_TILE;
             const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
             if (tile >= n_tiles) break;
-            const int b = it & 1;
-            if (!mbar_wait(bar_sf + 8 * b, (uint32_t)((it >> 1) & 1))) { timeout_flag = 1; break; }
-            const float* S = reinterpret_cast<const float*>(smem + OFF_S + b * (GW_T * XS * 4)) + c * CH * XS;
+            if (!mbar_wait(bar_cf + 8 * warp, (uint32_t)(use & 1))) { timeout_flag = 1; break; }
             float a1[4][4];
             gin_load_a1(S, lane, a1);              // into registers, then the buffer goes back to the gather warps
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_se + 8 * b);
+            if (lane == 0) mbar_arrive(bar_ce + 8 * warp);
             const int node0 = (int)tile * GW_T + c * CH;
             if (node0 < A.n_own) gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane);
         }

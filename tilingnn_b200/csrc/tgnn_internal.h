@@ -192,7 +192,7 @@ void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* er
 constexpr int GW_T = 64;          // destination rows per window tile
 constexpr int GW_MAXSEG = 32;     // contiguous runs per window (one bulk copy each, one producer lane each)
 constexpr int GW_WMAX = 656;      // window rows (82 KB; two buffers per SM)
-constexpr int GW_CAP = 4096;      // sorted items per tile in the builder = edges + own rows
+constexpr int GW_CAP = 3072;      // sorted items per tile in the builder = edges + own rows
 constexpr int GW_GAP = 2;         // runs closer than this many rows are merged (the gap rows are loaded)
 int build_gin_windows(Graph& g, Scratch& sc, cudaStream_t st);
 
