@@ -154,6 +154,10 @@ int tgnn_debug_graph(tgnn_handle* h, int32_t* cptr, int32_t* ctype, int32_t* csr
 /* the edge-block format of kernel 3: bptr[ceil(n_own/t_rows)+1] btype[t_blocks] tsrc[t_blocks*128] tdst[t_blocks*128] */
 int tgnn_debug_graph_t(tgnn_handle* h, int32_t* bptr, int32_t* btype, int32_t* tsrc, uint16_t* tdst, void* stream);
 
+/* TGNN_ROLE_DBG=1 (environment, read at tgnn_create): per-warp {cycles, wait 0, wait 1, wait 2} of CTA 0 in the last
+ * launch of the warp-specialised kernels: out256[0..127] k_conv_t (4 per warp), out256[128..255] k_gin_w. */
+int tgnn_debug_role_cycles(tgnn_handle* h, int64_t* out256);
+
 /* Per-kernel-family device time of the last forward (ms), measured with CUDA events on `stream`
  * when enabled.  names: "init","conv","gin","bnfin","combine","final","score","halo". */
 int tgnn_set_profiling(tgnn_handle* h, int32_t enabled);

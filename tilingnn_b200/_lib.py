@@ -51,6 +51,7 @@ SIGNATURES = {
     "tgnn_debug_read": (C.c_int, [_vp, C.c_char_p, _vp, _vp]),
     "tgnn_debug_graph": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tgnn_debug_graph_t": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "tgnn_debug_role_cycles": (C.c_int, [_vp, C.POINTER(_i64)]),
     "tgnn_set_profiling": (C.c_int, [_vp, _i32]),
     "tgnn_get_profile": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "tgnn_last_error": (C.c_char_p, [_vp]),

@@ -160,6 +160,9 @@ struct tgnn_handle {
     } replay;
     uint64_t graph_gen = 0, param_gen = 0;
 
+    DevBuf role_dbg;                                // TGNN_ROLE_DBG=1: [2 kernels][32 warps][4] cycle counters of CTA 0 (k_conv_t, k_gin_w)
+    bool role_dbg_on = getenv("TGNN_ROLE_DBG") != nullptr;
+
     // bookkeeping
     int64_t launches = 0, collectives = 0;
     int stop_layer = -1;
@@ -606,6 +609,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     h->prof.clear(); h->prof_result.clear();
     Launcher lz{h, st};
     double* sums = h->sums.as<double>();
+    if (h->role_dbg_on && !h->role_dbg.p) { h->role_dbg.reserve(256 * sizeof(long long)); TGNN_CUDA(cudaMemset(h->role_dbg.p, 0, 256 * sizeof(long long))); }
     if (!train && !h->eval_coefs_valid) { lz.begin("bnfin"); eval_coefs(h, st); lz.end(2 + 2 * L + 4); h->eval_coefs_valid = true; }
     if (train) h->eval_coefs_valid = false;          // train-mode forwards overwrite the coefficient blocks
     if (h->need_xh()) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
@@ -667,7 +671,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             ca.xh = h->xh.as<uint4>();
             ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
             launch_conv_t(ca, h->g, h->tabT.as<uint32_t>() + tslot * TG_TIMG32, h->tab32.as<float>() + tslot * F * F, h->err_dev,
-                          h->sm_count, st);
+                          h->sm_count, st, h->role_dbg_on ? h->role_dbg.as<long long>() : nullptr);
             lz.end(2, 1);
         } else if (h->use_h) {
             // fp16-split kernel; falls through to the 3xTF32 arithmetic itself when a range flag is raised
@@ -694,6 +698,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         if (gw) {
             ga.gw_meta = h->g.gw_meta.as<int>(); ga.gw_seg = h->g.gw_seg.as<int>(); ga.gw_loc = h->g.gw_loc.as<uint16_t>();
             ga.gw_tiles = h->g.gw_tiles; ga.err = h->err_dev;
+            ga.dbg = h->role_dbg_on ? h->role_dbg.as<long long>() + 128 : nullptr;
             launch_gin_w(ga, h->sm_count, st);
         } else launch_gin(ga, h->sm_count, st);
         lz.end(1);
@@ -1165,6 +1170,17 @@ int tgnn_debug_graph_t(tgnn_handle* h, int32_t* bptr, int32_t* btype, int32_t* t
         cp(tsrc, h->g.t_src, (size_t)h->g.t_blocks * 128 * 4);
         cp(tdst, h->g.t_dst, (size_t)h->g.t_blocks * 128 * 2);
         TGNN_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int tgnn_debug_role_cycles(tgnn_handle* h, int64_t* out256) {
+    // TGNN_ROLE_DBG=1: per-warp {cycles, wait 0, wait 1, wait 2} of CTA 0 in the last launch of k_conv_t ([0,128)) and of
+    // k_gin_w ([128,256)); synchronises the device
+    return guarded(h, [&] {
+        TGNN_CHECK(h && out256 && h->role_dbg.p, "tgnn_debug_role_cycles: role timing is off (set TGNN_ROLE_DBG=1 before tgnn_create)");
+        DeviceGuard dg(h->cfg.device);
+        TGNN_CUDA(cudaDeviceSynchronize());
+        TGNN_CUDA(cudaMemcpy(out256, h->role_dbg.p, 256 * sizeof(long long), cudaMemcpyDeviceToHost));
     });
 }
 

@@ -191,6 +191,7 @@ __device__ __forceinline__ void conv_adj_body(const ConvArgs& A, float* smem) {
             int node = node0 + r;
             if (node < A.n_own) {
                 float v = leaky(acc[r * XS + lane] + bias_c);
+                if (!row_kept(A.mask, node)) v = 0.f;
                 A.out[(size_t)node * F + lane] = v;
                 s1 += (double)v;
                 s2 += (double)v * (double)v;

@@ -213,6 +213,7 @@ k_conv_h(ConvArgs A) {
             int node = node0 + r;
             if (node < A.n_own) {
                 float v = leaky(tile_acc[r * XS + lane] + bias_c);
+                if (!row_kept(A.mask, node)) v = 0.f;
                 A.out[(size_t)node * F + lane] = v;
                 s1 += (double)v;
                 s2 += (double)v * (double)v;

@@ -64,6 +64,7 @@ struct ConvSArgs {
     const int* pptr; const int* ptype; const int* pbase; const unsigned short* off; const int* ssrc;
     const float* inv_deg; const float* bias;
     float* out; double* part; int* error_flag;
+    const uint8_t* mask;
     long long* dbg;              // optional per-role wait/total cycle counters of CTA 0 (TGNN_CONVS_DBG=1)
     int n_own, n_tiles, d_eff;   // d_eff: passes in flight such that d_eff * (longest pass) <= RING_ROWS
 };
@@ -374,11 +375,12 @@ k_conv_s(ConvSArgs A) {
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ce + 8 * ab);          // accumulator buffer free for the tile after next
             const float idg = live ? __ldg(A.inv_deg + row) : 0.f;
+            const bool kept = live && row_kept(A.mask, row);
             float o[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const float t = np > 0 ? __uint_as_float(vt[j]) : 0.f;
-                o[j] = leaky(fmaf(t, idg, __uint_as_float(vr[j])) + __ldg(A.bias + j));
+                o[j] = kept ? leaky(fmaf(t, idg, __uint_as_float(vr[j])) + __ldg(A.bias + j)) : 0.f;
             }
             if (live) {
                 float4* dst = reinterpret_cast<float4*>(A.out + (size_t)row * F);
@@ -430,7 +432,7 @@ void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* er
     a.xin = c.xin; a.tabS = tabS; a.n_types = g.n_types;
     a.pptr = g.s_pptr.as<int>(); a.ptype = g.s_ptype.as<int>(); a.pbase = g.s_pbase.as<int>();
     a.off = g.s_off.as<unsigned short>(); a.ssrc = g.s_src.as<int>();
-    a.inv_deg = c.inv_deg; a.bias = c.bias; a.out = c.out; a.part = c.part; a.error_flag = error_flag;
+    a.inv_deg = c.inv_deg; a.bias = c.bias; a.out = c.out; a.part = c.part; a.error_flag = error_flag; a.mask = c.mask;
     a.n_own = c.n_own; a.n_tiles = g.s_tiles;
     a.d_eff = D_SLOTS;
     static long long* dbg = nullptr;

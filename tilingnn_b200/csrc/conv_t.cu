@@ -82,6 +82,8 @@ struct ConvTArgs {
     const float* inv_deg; const float* bias;
     float* out; double* part;
     const int* flag_x; const int* flag_w; int* err;
+    const uint8_t* mask;
+    long long* dbg;              // optional: per-warp {cycles, wait 0, wait 1, wait 2} of CTA 0 (TGNN_ROLE_DBG=1)
     int n_own, n_tiles, rt;      // rt: destination rows per super-tile (256 | 512 | 1024)
 };
 
@@ -93,7 +95,8 @@ __device__ __forceinline__ void finish_tile(const ConvTArgs& A, uint32_t acc_bas
     const int rows = min(A.rt, A.n_own - node0);
     for (int r = q; r < rows; r += EPI_WARPS) {
         const uint32_t a = acc_base + (uint32_t)r * 128u + (uint32_t)lane * 4u;
-        const float v = leaky(lds_f32(a) + bias_c);
+        float v = leaky(lds_f32(a) + bias_c);
+        if (!row_kept(A.mask, node0 + r)) v = 0.f;
         sts_f32(a, 0.f);
         A.out[(size_t)(node0 + r) * F + lane] = v;
         s1 += (double)v;
@@ -130,6 +133,8 @@ k_conv_t(ConvTArgs A) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    long long w0 = 0, w1 = 0, w2 = 0;
+    const long long t_start = clock64();
 
     if (warp >= W_PROD0 && warp < W_MMA) {
         // ===================== producers: gather the block's 128 split rows into the swizzled A tile =====================
@@ -155,7 +160,7 @@ k_conv_t(ConvTArgs A) {
                     ntype = __ldg(A.btype + blk + 1);
                 }
                 const int s = g % NS;
-                if (!mbar_wait_relaxed(bar_empty + 8 * s, (uint32_t)(((g / NS) & 1) ^ 1))) { timeout_flag = 1; ok = false; break; }
+                if (!TGNN_TIMED(w0, mbar_wait_relaxed(bar_empty + 8 * s, (uint32_t)(((g / NS) & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }
                 const uint32_t a_tile = stage_base + (uint32_t)s * STAGE_BYTES, bar = bar_full + 8 * s;
                 if (pw == 0 && lane == 0) {
                     mbar_arrive_expect_tx(bar, B_BYTES);
@@ -178,8 +183,8 @@ k_conv_t(ConvTArgs A) {
             const int b0 = __ldg(A.bptr + tile), b1 = __ldg(A.bptr + tile + 1);
             for (int blk = b0; blk < b1; ++blk, ++g) {
                 const int s = g % NS, tb = g % NT;
-                if (!mbar_wait(bar_acce + 8 * tb, (uint32_t)(((g / NT) & 1) ^ 1))) { timeout_flag = 1; ok = false; break; }
-                if (!mbar_wait(bar_full + 8 * s, (uint32_t)((g / NS) & 1))) { timeout_flag = 1; ok = false; break; }
+                if (!TGNN_TIMED(w0, mbar_wait(bar_acce + 8 * tb, (uint32_t)(((g / NT) & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }
+                if (!TGNN_TIMED(w1, mbar_wait(bar_full + 8 * s, (uint32_t)((g / NS) & 1)))) { timeout_flag = 1; ok = false; break; }
                 fence_proxy_async();                      // the A tile was written through the generic proxy (cp.async)
                 tc_fence_after();
                 if (lane == 0) {
@@ -214,7 +219,7 @@ k_conv_t(ConvTArgs A) {
                 float inv = 0.f;
                 if (root && live) inv = __ldg(A.inv_deg + node0 + dst);
                 const int tb = g % NT;
-                if (!mbar_wait(bar_accf + 8 * tb, (uint32_t)((g / NT) & 1))) { timeout_flag = 1; ok = false; break; }
+                if (!TGNN_TIMED(w0, mbar_wait(bar_accf + 8 * tb, (uint32_t)((g / NT) & 1)))) { timeout_flag = 1; ok = false; break; }
                 tc_fence_after();
                 float m[32], sm[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(tb * 64);
@@ -259,14 +264,20 @@ k_conv_t(ConvTArgs A) {
                 dst = ndst; type = ntype;
             }
             if (!ok) break;
+            const long long t_fin = clock64();
             named_bar_sync(1, EPI_WARPS * 32);                                // every message of the tile is in
             finish_tile(A, acc_base, tile, q, lane, bias_c, s1, s2);
             named_bar_sync(1, EPI_WARPS * 32);                                // zeroed before the next tile's first add
+            w1 += clock64() - t_fin;
         }
         if (A.part) {
             A.part[((size_t)blockIdx.x * EPI_WARPS + q) * 64 + lane] = s1;
             A.part[((size_t)blockIdx.x * EPI_WARPS + q) * 64 + 32 + lane] = s2;
         }
+    }
+    if (A.dbg && blockIdx.x == 0 && lane == 0) {
+        long long* d = A.dbg + warp * 4;
+        d[0] = clock64() - t_start; d[1] = w0; d[2] = w1; d[3] = w2;
     }
     tc_fence_before();
     __syncthreads();
@@ -318,7 +329,8 @@ k_conv_t_wide(ConvTArgs A) {
         }
         const int rows = min(A.rt, A.n_own - node0);
         for (int r = warp; r < rows; r += TBS / 32) {
-            const float v = leaky(acc[r * WS + lane] + bias_c);
+            float v = leaky(acc[r * WS + lane] + bias_c);
+            if (!row_kept(A.mask, node0 + r)) v = 0.f;
             acc[r * WS + lane] = 0.f;
             A.out[(size_t)(node0 + r) * F + lane] = v;
             s1 += (double)v;
@@ -338,7 +350,8 @@ size_t conv_t_smem(int rt) { return (size_t)rt * 128 + (size_t)NS * STAGE_BYTES 
 
 int conv_t_blocks(int t_tiles, int sm_count) { return t_tiles < sm_count ? (t_tiles < 1 ? 1 : t_tiles) : sm_count; }
 
-void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, const float* tab32, int* err, int sm_count, cudaStream_t st) {
+void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, const float* tab32, int* err, int sm_count, cudaStream_t st,
+                   long long* dbg) {
     static PerDeviceOnce once;
     once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(1024)));
@@ -348,7 +361,7 @@ void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, cons
     a.xh = c.xh; a.xin = c.xin; a.tabT = tabT; a.tab32 = tab32; a.n_types = c.n_types;
     a.bptr = g.t_bptr.as<int>(); a.btype = g.t_btype.as<int>(); a.tsrc = g.t_src.as<int>(); a.tdst = g.t_dst.as<unsigned short>();
     a.inv_deg = c.inv_deg; a.bias = c.bias; a.out = c.out; a.part = c.part;
-    a.flag_x = c.flag_x; a.flag_w = c.flag_w; a.err = err;
+    a.flag_x = c.flag_x; a.flag_w = c.flag_w; a.err = err; a.mask = c.mask; a.dbg = dbg;
     a.n_own = c.n_own; a.n_tiles = g.t_tiles; a.rt = g.t_rows;
     const int blocks = conv_t_blocks(g.t_tiles, sm_count);
     k_conv_t<<<blocks, CT_THREADS, conv_t_smem(g.t_rows), st>>>(a);

@@ -43,6 +43,7 @@ struct DenseTcArgs {
     int* error_flag;
     long long* dbg;             // optional per-role wait counters of CTA 0 (TGNN_DENSE_DBG=1)
     int n, K;
+    const uint8_t* mask;        // node mask or null: masked rows are written as 0 (and add nothing to the column sums)
 };
 
 template <int NOUT> struct DenseCfg {
@@ -268,6 +269,7 @@ k_dense_tc(DenseTcArgs A) {
                     for (int u = 0; u < 4; ++u) {
                         float o = lds_f32(sc + 4 * ((r + u) * 36 + lane)) + bias_c;
                         o = fmaxf(o, o * LEAKY);
+                        if (!row_kept(A.mask, row0 + 32 * q + r + u)) o = 0.f;
                         orow[(size_t)(r + u) * NOUT] = o;
                         s1f[u] += o; s2f[u] = fmaf(o, o, s2f[u]);
                     }
@@ -275,6 +277,7 @@ k_dense_tc(DenseTcArgs A) {
                 for (; r < nv; ++r) {
                     float o = lds_f32(sc + 4 * (r * 36 + lane)) + bias_c;
                     o = fmaxf(o, o * LEAKY);
+                    if (!row_kept(A.mask, row0 + 32 * q + r)) o = 0.f;
                     orow[(size_t)r * NOUT] = o;
                     s1f[0] += o; s2f[0] = fmaf(o, o, s2f[0]);
                 }
@@ -366,7 +369,7 @@ void launch_dense_tc(const DenseArgs& d, const float* w_img, int* error_flag, in
     TGNN_CHECK(d.K % BK == 0, "dense stage: K must be a multiple of 32");
     DenseTcArgs a{};
     a.slabs = d.slabs; a.a = d.a; a.virtual_concat = d.virtual_concat; a.in_coef = d.in_coef;
-    a.w_img = w_img; a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag;
+    a.w_img = w_img; a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag; a.mask = d.mask;
     a.n = d.n; a.K = d.K;
     switch (d.n_out) {
         case 256: launch_one<256>(a, sm_count, st); break;

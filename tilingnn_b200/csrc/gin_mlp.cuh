@@ -75,7 +75,7 @@ __device__ __forceinline__ void gin_load_a1(const float* xs, int lane, float (&a
 // and stays on 3xTF32.
 template <bool HMLP>
 __device__ __forceinline__ void gin_mlp_chunk(const float (&a1)[4][4], const GinW<HMLP>& Wt, int node0, int n_own, float* __restrict__ out,
-                                              double (&s1)[8], double (&s2)[8], int lane) {
+                                              double (&s1)[8], double (&s2)[8], int lane, const uint8_t* __restrict__ mask = nullptr) {
     const float4 *W1 = Wt.W1, *W2 = Wt.W2, *W3 = Wt.W3;
     const float *b1 = Wt.b1, *b2 = Wt.b2, *b3 = Wt.b3;
     const int g = lane >> 2, t = lane & 3;
@@ -204,6 +204,10 @@ __device__ __forceinline__ void gin_mlp_chunk(const float (&a1)[4][4], const Gin
             for (int e = 0; e < 2; ++e)
                 o[2 * nt + e] = leaky(sigmoidf_nr(c3[nt][2 * half + e] + b3[8 * t + 2 * nt + e]));
         if (node < n_own) {
+            if (!row_kept(mask, node)) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = 0.f;
+            }
             float4* dst = reinterpret_cast<float4*>(out + (size_t)node * F + 8 * t);
             dst[0] = make_float4(o[0], o[1], o[2], o[3]);
             dst[1] = make_float4(o[4], o[5], o[6], o[7]);

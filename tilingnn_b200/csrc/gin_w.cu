@@ -68,13 +68,15 @@ k_gin_w(GinArgs A) {
     gin_load_weights<HMLP>(wsm, A.wfrag, tid, GW_THREADS);
     __syncthreads();
     const int n_tiles = A.gw_tiles;
+    long long w0 = 0, w1 = 0, w2 = 0;
+    const long long t_start = clock64();
 
     if (warp == W_PROD) {
         // ===================== producer: window runs, indices and row pointers by TMA bulk copy =====================
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
-            if (!mbar_wait_relaxed(bar_we + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1))) { timeout_flag = 1; break; }
+            if (!TGNN_TIMED(w0, mbar_wait_relaxed(bar_we + 8 * b, (uint32_t)(((it >> 1) & 1) ^ 1)))) { timeout_flag = 1; break; }
             const int4 m0 = __ldg(reinterpret_cast<const int4*>(A.gw_meta) + 2 * tile);       // {nseg, rows, loc offset, self_loc}
             const int ne = __ldg(A.gw_meta + 8 * tile + 4);
             const int nseg = m0.x, rows = m0.y;
@@ -107,7 +109,7 @@ k_gin_w(GinArgs A) {
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
             const uint32_t ph = (uint32_t)((it >> 1) & 1);
-            if (!mbar_wait(bar_wf + 8 * b, ph)) { timeout_flag = 1; break; }
+            if (!TGNN_TIMED(w0, mbar_wait(bar_wf + 8 * b, ph))) { timeout_flag = 1; break; }
             const int nseg = meta_s[b][0], self_loc = meta_s[b][1];
             const int* ptr = reinterpret_cast<const int*>(smem + OFF_PTR + b * (PTR_INTS * 4));
             const uint16_t* loc = reinterpret_cast<const uint16_t*>(smem + OFF_LOC + b * (GW_CAP * 2));
@@ -167,7 +169,7 @@ k_gin_w(GinArgs A) {
                         for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
                     }
                 }
-                if (!mbar_wait(bar_ce + 8 * mw, (uint32_t)((use & 1) ^ 1))) { timeout_flag = 1; ok = false; break; }   // its previous chunk is in registers
+                if (!TGNN_TIMED(w1, mbar_wait(bar_ce + 8 * mw, (uint32_t)((use & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }   // its previous chunk is in registers
                 *reinterpret_cast<float4*>(S + (4 * gw + a) * XS + 4 * q) = sum;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_cf + 8 * mw);
@@ -188,13 +190,13 @@ k_gin_w(GinArgs A) {
             const int it = ci / CHUNKS_PER_TILE, c = ci % CHUNKS_PER_TILE;
             const long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
             if (tile >= n_tiles) break;
-            if (!mbar_wait(bar_cf + 8 * warp, (uint32_t)(use & 1))) { timeout_flag = 1; break; }
+            if (!TGNN_TIMED(w0, mbar_wait(bar_cf + 8 * warp, (uint32_t)(use & 1)))) { timeout_flag = 1; break; }
             float a1[4][4];
             gin_load_a1(S, lane, a1);              // into registers, then the buffer goes back to the gather warps
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_ce + 8 * warp);
             const int node0 = (int)tile * GW_T + c * CH;
-            if (node0 < A.n_own) gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane);
+            if (node0 < A.n_own) gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane, A.mask);
         }
         const int g = lane >> 2, t = lane & 3;
 #pragma unroll
@@ -213,6 +215,10 @@ k_gin_w(GinArgs A) {
                 A.part[row * 64 + 32 + 8 * t + j] = s2[j];
             }
         }
+    }
+    if (A.dbg && blockIdx.x == 0 && lane == 0) {
+        long long* d = A.dbg + warp * 4;
+        d[0] = clock64() - t_start; d[1] = w0; d[2] = w1; d[3] = w2;
     }
     __syncthreads();
     if (timeout_flag && tid == 0 && A.err) { *reinterpret_cast<volatile int*>(A.err) = TGNN_DEVERR_PIPELINE; __threadfence_system(); }

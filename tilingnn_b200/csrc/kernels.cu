@@ -147,7 +147,7 @@ k_gin(GinArgs A) {
         __syncwarp();
         float a1[4][4];
         gin_load_a1(xs, lane, a1);
-        gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane);
+        gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane, A.mask);
         __syncwarp();
     }
     // fold the eight row groups (lanes with equal t) in a fixed order; lanes 0..3 publish channels 8t..8t+7
@@ -179,7 +179,7 @@ template <bool FIN>
 __global__ void __launch_bounds__(256) k_combine(const float4* __restrict__ pre1, const float* __restrict__ coef1,
                           const float4* __restrict__ pre2, const float* __restrict__ coef2,
                           const float4* __restrict__ res, float4* __restrict__ out, uint4* __restrict__ xh,
-                          int* __restrict__ flag, float4* __restrict__ g2out, int64_t n4, CombineFin fin) {
+                          int* __restrict__ flag, float4* __restrict__ g2out, int64_t n4, CombineFin fin, const uint8_t* __restrict__ mask) {
     __shared__ float c1[128], c2[128];
     bool bad = false;
     if (FIN) {
@@ -198,8 +198,9 @@ __global__ void __launch_bounds__(256) k_combine(const float4* __restrict__ pre1
         __syncthreads();
         if (threadIdx.x < 64) {
             const int w = threadIdx.x >> 5, c = threadIdx.x & 31;
-            const double mean = ssum[w * 64 + c] / fin.count;
-            double var = ssum[w * 64 + 32 + c] / fin.count - mean * mean;
+            const double cnt = fin.count_ptr ? *fin.count_ptr : fin.count;
+            const double mean = ssum[w * 64 + c] / cnt;
+            double var = ssum[w * 64 + 32 + c] / cnt - mean * mean;
             if (var < 0.0) var = 0.0;
             const double rstd = 1.0 / sqrt(var + BN_EPS);
             const float mh = (float)mean, ml = (float)(mean - (double)mh);
@@ -225,6 +226,10 @@ __global__ void __launch_bounds__(256) k_combine(const float4* __restrict__ pre1
         o.z = bn_apply(p.z, c1, c + 2, 32) * g2.z;
         o.w = bn_apply(p.w, c1, c + 3, 32) * g2.w;
         if (res) { float4 r = __ldg(res + i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+        if (!row_kept(mask, (int)(i >> 3))) {                   // masked node: zero rows, so every gather of them adds nothing
+            o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g2out) g2out[i] = o;
+        }
         out[i] = o;
         if (xh) xh[(i & ~(int64_t)7) + xh_pos((int)(i & 7))] = split_h4(o, bad);     // float4 q of a row -> uint4 xh_pos(q)
     }
@@ -304,9 +309,10 @@ k_init(InitArgs A) {
         __syncwarp();
         const int n_here = min(32, A.n_own - base);
         for (int j = 0; j < n_here; ++j) {
-            const float val = tl[j * 33 + lane];
+            const bool kept = row_kept(A.mask, base + j);
+            const float val = kept ? tl[j * 33 + lane] : 0.f;
             if (MODE == 2) {
-                const float o2 = fmaf((val - cf[1][lane]) - cf[1][32 + lane], cf[1][64 + lane], cf[1][96 + lane]);
+                const float o2 = kept ? fmaf((val - cf[1][lane]) - cf[1][32 + lane], cf[1][64 + lane], cf[1][96 + lane]) : 0.f;
                 A.out[(size_t)(base + j) * F + lane] = o2;
                 if (A.xh) {
                     // lane = channel -> word w of the split row: q = w>>2, {hi(4q,4q+1), hi(4q+2,4q+3), lo(..), lo(..)}[w&3]
@@ -351,14 +357,16 @@ k_init_wide(InitArgs A) {
         float v = b0;
         for (int d = 0; d < A.d_x; ++d) v = fmaf(__ldg(A.x + (size_t)node * A.d_x + d), __ldg(A.w0 + lane * A.d_x + d), v);
         v = leaky(v);
+        const bool kept = row_kept(A.mask, node);
+        if (!kept) v = 0.f;
         if (MODE >= 1) {
             float y = bn_apply(v, A.coef0, lane, 32);
             float o = b1;
 #pragma unroll
             for (int k = 0; k < 32; ++k) o = fmaf(__shfl_sync(0xffffffffu, y, k), w1t[k * 33 + lane], o);
-            v = leaky(o);
+            v = kept ? leaky(o) : 0.f;
             if (MODE == 2) {
-                const float o2 = bn_apply(v, A.coef1, lane, 32);
+                const float o2 = kept ? bn_apply(v, A.coef1, lane, 32) : 0.f;
                 A.out[(size_t)node * F + lane] = o2;
                 if (A.xh) {
                     __half hi, lo;
@@ -458,6 +466,7 @@ k_dense(DenseArgs A) {
             for (int j = 0; j < TN; ++j) {
                 const int col = col0 + tx * TN + j;
                 float v = leaky(acc[i][j] + __ldg(A.bias + col));
+                if (!row_kept(A.mask, row)) v = 0.f;
                 A.out[(size_t)row * A.n_out + col] = v;
                 cs1[j] += (double)v; cs2[j] += (double)v * (double)v;
             }
@@ -480,7 +489,7 @@ k_dense(DenseArgs A) {
 
 // final Linear(32 -> 1) + Sigmoid on BN(a3)   (TilinGNN.py:47)
 __global__ void k_score(const float* __restrict__ a3, const float* __restrict__ coef, const float* __restrict__ w,
-                        float b, float* __restrict__ out, int64_t n) {
+                        float b, float* __restrict__ out, int64_t n, const uint8_t* __restrict__ mask) {
     const int lane = threadIdx.x & 31;
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -489,7 +498,7 @@ __global__ void k_score(const float* __restrict__ a3, const float* __restrict__ 
         float v = bn_apply(__ldg(a3 + node * F + lane), coef, lane, 32) * wl;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) out[node] = sigmoidf_acc(v + b);
+        if (lane == 0) out[node] = row_kept(mask, (int)node) ? sigmoidf_acc(v + b) : 0.f;
     }
 }
 
@@ -555,8 +564,9 @@ __global__ void k_bn_finish(BnFinishArgs A) {
     for (int i = threadIdx.x; i < nb * A.C; i += 256) {
         const int w = i / A.C, c = i - w * A.C;
         const volatile double* sums = A.sums + (size_t)w * C2;
-        const double mean = sums[c] / A.count;
-        double var = sums[A.C + c] / A.count - mean * mean;
+        const double cnt = A.count_ptr ? *A.count_ptr : A.count;
+        const double mean = sums[c] / cnt;
+        double var = sums[A.C + c] / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
         const double rstd = 1.0 / sqrt(var + BN_EPS);
         const float mh = (float)mean;
@@ -647,8 +657,9 @@ __global__ void k_bn_finish_x(BnFinishArgs A, PeerPtrs P, unsigned epoch) {
     for (int i = threadIdx.x; i < nb * A.C; i += 256) {
         const int w = i / A.C, c = i - w * A.C;
         const volatile double* sums = A.sums + (size_t)w * C2;
-        const double mean = sums[c] / A.count;
-        double var = sums[A.C + c] / A.count - mean * mean;
+        const double cnt = A.count_ptr ? *A.count_ptr : A.count;
+        const double mean = sums[c] / cnt;
+        double var = sums[A.C + c] / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
         const double rstd = 1.0 / sqrt(var + BN_EPS);
         const float mh = (float)mean;
@@ -842,7 +853,7 @@ void launch_frag_pack_h16(const float* w_kn, int K, int N, int nmap, float* out,
 
 void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
                     const float* residual, float* out, uint4* xh, int* flag, float* g2out, int64_t n_own, cudaStream_t st,
-                    const CombineFin* fin) {
+                    const CombineFin* fin, const uint8_t* mask) {
     int64_t n4 = n_own * (F / 4);
     int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
     if (blocks < 1) blocks = 1;
@@ -850,7 +861,7 @@ void launch_combine(const float* pre1, const float* coef1, const float* pre2, co
     kern<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(pre1), coef1,
                                       reinterpret_cast<const float4*>(pre2), coef2,
                                       reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), xh, flag,
-                                      reinterpret_cast<float4*>(g2out), n4, fin ? *fin : CombineFin{});
+                                      reinterpret_cast<float4*>(g2out), n4, fin ? *fin : CombineFin{}, mask);
     TGNN_CUDA(cudaGetLastError());
 }
 
@@ -877,10 +888,10 @@ void launch_dense(const DenseArgs& a, cudaStream_t st) {
     TGNN_CUDA(cudaGetLastError());
 }
 
-void launch_score(const float* a3, const float* coef, const float* w, float b, float* out, int64_t n, cudaStream_t st) {
+void launch_score(const float* a3, const float* coef, const float* w, float b, float* out, int64_t n, cudaStream_t st, const uint8_t* mask) {
     int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
     if (blocks < 1) blocks = 1;
-    k_score<<<blocks, 256, 0, st>>>(a3, coef, w, b, out, n);
+    k_score<<<blocks, 256, 0, st>>>(a3, coef, w, b, out, n, mask);
     TGNN_CUDA(cudaGetLastError());
 }
 

@@ -168,7 +168,11 @@ struct ConvArgs {
     const uint32_t* tabH;    // [K+1][1024]   fp16 hi|lo fragment tables; entry K = nnConv.root
     const int* flag_x;       // raised by the producer of xin when a value is outside the fp16 range
     const int* flag_w;       // raised at table build when a root weight is outside the fp16 range
+    const uint8_t* mask;     // node mask (tgnn_set_node_mask) or null: rows with mask 0 are written as 0 and stay out of the statistics
 };
+// Node mask (sub-layout on the resident structures): masked rows are stored as ZERO by every producer, so gathers and
+// sums over all neighbours equal sums over the kept ones, and a zero row adds nothing to the BatchNorm sums.
+__device__ __forceinline__ bool row_kept(const uint8_t* __restrict__ mask, int node) { return !mask || __ldg(mask + node) != 0; }
 // launch geometry shared by k_conv_adj and k_conv_h (same grid => same BatchNorm partial layout):
 //   wn = 64 : 8 warps per CTA, 2 CTAs per SM; few tiles (small graphs) => one CTA per tile, k_conv_h splits its chunks
 //   wn = 128: 12 warps per CTA (216 KB of accumulator tiles), 1 CTA per SM
@@ -185,7 +189,10 @@ void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
 constexpr int TG_TIMG32 = 2048;          // 32-bit words of one pre-swizzled [64 x 64] fp16 weight image
 int conv_t_blocks(int t_tiles, int sm_count);
 inline int conv_t_num_parts(int t_tiles, int sm_count) { return conv_t_blocks(t_tiles, sm_count) * 4; }
-void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, const float* tab32, int* err, int sm_count, cudaStream_t st);
+void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, const float* tab32, int* err, int sm_count, cudaStream_t st,
+                   long long* dbg = nullptr);
+// role timing (TGNN_ROLE_DBG=1): acc += cycles spent in expr
+#define TGNN_TIMED(acc, expr) ([&]() { const long long _t = clock64(); const bool _r = (expr); (acc) += clock64() - _t; return _r; })()
 // tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st);
 
@@ -200,6 +207,8 @@ struct GinArgs {
     const float* xin;        // [n_rows][32]  output of the previous CollConv (written by k_combine), or h0
     const int* col_ptr; const int* col_src;
     // k_gin_w only (null / 0 -> k_gin): windows built by build_gin_windows, and the mapped error word for timeouts
+    const uint8_t* mask = nullptr;   // node mask or null
+    long long* dbg = nullptr;        // optional: per-warp {cycles, wait 0, wait 1, wait 2} of CTA 0 (TGNN_ROLE_DBG=1)
     const int* gw_meta = nullptr; const int* gw_seg = nullptr; const uint16_t* gw_loc = nullptr; int gw_tiles = 0; int* err = nullptr;
     const float* wfrag;      // 3xTF32 frag tables W1[2048] W2[4096] W3[4096], b1[32] b2[64] b3[32], then fp16 tables W2h[2048] W3h[2048]
     int hmlp;                // layers 2, 3 of the MLP on the fp16 tables (their weights are inside the fp16 range)
@@ -221,11 +230,12 @@ void launch_gin_w(const GinArgs& a, int sm_count, cudaStream_t st);
 // its prologue (and block 0 stores them to coef_out) instead of reading coef1 / coef2.
 struct CombineFin {
     const double* part[2] = {nullptr, nullptr}; int n_part[2] = {0, 0}; double count = 1.0;
+    const double* count_ptr = nullptr;       // node mask: number of kept nodes (device), overrides count
     const float* gamma[2] = {nullptr, nullptr}; const float* beta[2] = {nullptr, nullptr}; float* coef_out[2] = {nullptr, nullptr};
 };
 void launch_combine(const float* pre1, const float* coef1, const float* pre2, const float* coef2,
                     const float* residual, float* out, uint4* xh, int* flag, float* g2out, int64_t n_own, cudaStream_t st,
-                    const CombineFin* fin = nullptr);
+                    const CombineFin* fin = nullptr, const uint8_t* mask = nullptr);
 
 // init MLP: mode 0 = stats of layer 0, 1 = stats of layer 1, 2 = write h0
 struct InitArgs {
@@ -235,6 +245,7 @@ struct InitArgs {
     const float* coef0; const float* coef1;
     float* out; double* part; int n_own;
     uint32_t* xh; int* flag;             // mode 2: fp16-split copy of h0 and its range flag (optional)
+    const uint8_t* mask;                 // node mask or null
 };
 int init_num_parts(int n_own, int sm_count);
 void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st);
@@ -250,6 +261,7 @@ struct DenseArgs {
     float* out;                 // [n][N_out]
     double* part;               // [row_blocks][2][N_out]
     int n, K, n_out;
+    const uint8_t* mask;        // node mask or null
 };
 int dense_row_blocks(int n);
 void launch_dense(const DenseArgs& a, cudaStream_t st);
@@ -259,7 +271,7 @@ void launch_weight_image(const float* w, float* img, int n_out, int K, cudaStrea
 void launch_dense_tc(const DenseArgs& a, const float* w_img, int* error_flag, int sm_count, cudaStream_t st);
 
 void launch_score(const float* a3, const float* coef, const float* w, float b, float* out,
-                  int64_t n, cudaStream_t st);
+                  int64_t n, cudaStream_t st, const uint8_t* mask = nullptr);
 
 // BatchNorm statistics: reduce partials (fixed order, fp64) and turn them into coefficients.
 // part layout: [n_part][2*C] (sum[C], sumsq[C]).  sums_out: [2*C] doubles.
@@ -271,6 +283,7 @@ struct BnFinishArgs {
     const double* part[2]; int n_part[2]; int C; double count;
     const float* gamma[2]; const float* beta[2]; float* coef[2];
     double* sums; unsigned* ticket;
+    const double* count_ptr;    // node mask: number of kept nodes (device), overrides count; else null
 };
 void launch_bn_finish(const BnFinishArgs& a, int n_bn, cudaStream_t st);
 // eval mode: coefficients from running statistics

@@ -390,3 +390,11 @@ class TilinGNN(nn.Module):
         _lib.check(nat.h, rc, "tgnn_debug_graph_t")
         t["tdst"] = t["tdst"].to(torch.int32) & 0xFFFF
         return t
+
+    def debug_role_cycles(self):
+        """TGNN_ROLE_DBG=1: {kernel: [[cycles, wait0, wait1, wait2] per warp]} of CTA 0 in the last forward."""
+        nat = self._ensure_handle()
+        buf = (C.c_int64 * 256)()
+        _lib.check(nat.h, _lib.load().tgnn_debug_role_cycles(nat.h, buf), "tgnn_debug_role_cycles")
+        v = list(buf)
+        return {"k_conv_t": [v[4 * w: 4 * w + 4] for w in range(9)], "k_gin_w": [v[128 + 4 * w: 128 + 4 * w + 4] for w in range(16)]}
