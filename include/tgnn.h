@@ -83,6 +83,17 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes,
  * x: [n_nodes, d_x] fp32 device; scores_out: [n_nodes] fp32 device (the [N,1] column). */
 int tgnn_forward(tgnn_handle* h, const float* x, float* scores_out, void* stream);
 
+/* BrickLayout.compute_sub_layout (tiling/brick_layout.py:248-286) WITHOUT re-indexing: the sub-layout of the resident
+ * graph induced by the nodes with keep[i] != 0 (uint8 [n_nodes], host or device pointer; NULL = all nodes again).
+ * The next forwards score exactly that sub-graph on the structures already in HBM: masked rows are zero in every
+ * tensor a neighbour gathers (so sums over all neighbours are sums over the kept ones), mean aggregation divides by
+ * the kept in-degree, BatchNorm statistics run over the kept nodes only.  scores_out[i] of a masked node is 0.
+ * A greedy round (util/algorithms.py:27-31) is then n_nodes bytes of upload + one forward, no rebuild.
+ * counts3 (host, optional; synchronises): {kept nodes, adjacency edges, collision edges with both endpoints kept} --
+ * what ML_Solver.predict's early-out (solver/ml_solver/ml_solver.py:31-32) needs.  Single-GPU handles only; a new
+ * tgnn_set_graph clears the mask. */
+int tgnn_set_node_mask(tgnn_handle* h, const uint8_t* keep, int64_t* counts3, void* stream);
+
 /* Device-side failures (a tcgen05 pipeline timeout, a peer-exchange wait that timed out) are recorded by
  * the kernels in a word of mapped host memory.  They are always surfaced: by tgnn_forward itself when the
  * graph is small (it then synchronises `stream`, the callers read the scores back at once anyway), otherwise

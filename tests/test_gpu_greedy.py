@@ -149,3 +149,63 @@ def test_config5_bunny_layouts(dev):
         print(f"bunny layout {i}: N={sg.node_feature.shape[0]} -> {int(solved.predict.sum())} tiles, {solved.greedy_rounds} rounds, "
               f"score {score:.4f}, {dt:.3f} s")
     print(f"config 5 scoring + greedy assembly, 4 layouts: {total:.3f} s")
+
+
+def test_node_mask_scores_equal_the_reindexed_sub_layout(dev):
+    """f2: ``tgnn_set_node_mask`` scores the sub-layout induced by the kept nodes on the RESIDENT structures; the result must
+    be what the reference's flow gives -- ``compute_sub_layout`` (re-index, brick_layout.py:248-286), upload, rebuild,
+    forward -- on the kept nodes: the same kernels on the same edges, only the summation order differs."""
+    from tilingnn_b200 import TilinGNN, greedy, synthetic as syn
+    from tilingnn_b200.tile_graph_io import SuperGraph
+    rng = np.random.RandomState(5)
+    # (a) conditioned synthetic network on a lattice: tight tolerance
+    x, ai, af, ci = syn.lattice_graph(3000, 8, 8, seed=1)
+    p = orc.make_params(3, 19, 6, seed=1)
+    net = TilinGNN(19, 6, 32, node_features_dim=3)
+    net.load_state_dict(p, strict=True)
+    net = net.to(dev).train()
+    keep = np.sort(rng.choice(3000, 2100, replace=False))
+    sg = SuperGraph(x.numpy().astype(np.float64), ci.numpy(), np.zeros((ci.shape[1], 19)), ai.numpy(), af.numpy().astype(np.float64),
+                    np.arange(3000))
+    sub, _ = greedy.compute_sub_layout(sg, keep, collide_features=False)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    ref = net(x=t(sub.node_feature, torch.float32), adj_e_index=t(sub.align_edge_index, torch.long),
+              adj_e_features=t(sub.align_edge_features, torch.float32), col_e_idx=t(sub.collide_edge_index, torch.long))[0][:, 0].clone()
+    gold = orc.forward(p, t(sub.node_feature, torch.float64).cpu(), t(sub.align_edge_index, torch.long).cpu(),
+                       t(sub.align_edge_features, torch.float64).cpu(), t(sub.collide_edge_index, torch.long).cpu(), depth=6,
+                       dtype=torch.float64)[:, 0]
+    net.set_graph(3000, ai.to(dev), af.to(dev), ci.to(dev))
+    mask = np.zeros(3000, np.uint8); mask[keep] = 1
+    counts = net.set_node_mask(mask)
+    assert counts == (len(keep), sub.align_edge_index.shape[1], sub.collide_edge_index.shape[1])
+    for _ in range(3):                                           # eager, captured, replayed
+        s = net.score(x.to(dev))
+    assert float(s[torch.from_numpy(mask == 0).to(dev)].abs().max()) == 0.0, "masked nodes score 0"
+    got = s[torch.from_numpy(keep).to(dev)]
+    e_ref, e_gold = float((got - ref).abs().max()), float((got.double().cpu() - gold).abs().max())
+    print(f"node mask, synthetic: vs re-indexed CUDA forward {e_ref:.2e}, vs fp64 oracle of the sub-layout {e_gold:.2e}")
+    assert e_ref <= 2e-5 and e_gold <= 1e-4
+    counts = net.set_node_mask(None)                             # back to the full graph
+    full = net.score(x.to(dev))
+    assert counts[0] == 3000 and float((full.double().cpu() - orc.forward(p, x, ai, af, ci, depth=6, dtype=torch.float64)[:, 0]).abs().max()) <= 1e-4
+    # (b) the shipped checkpoint on the heart layout, train-BN (ill-conditioned): masked vs re-indexed, and the whole greedy
+    # assembly through the mask path against the re-index path (same seed)
+    z = dict(np.load(os.path.join(GOLDEN, "greedy_heart.npz")))
+    sgh, graph = load_layout(z)
+    solver = make_solver(load_ckpt(), 3, sgh.align_edge_features.shape[1], graph, dev)
+    n = sgh.node_feature.shape[0]
+    keep = np.sort(rng.choice(n, int(0.7 * n), replace=False))
+    a = solver.predict_sub_layout(sgh, keep)
+    b = solver.predict(greedy.compute_sub_layout(sgh, keep, collide_features=False)[0])
+    print(f"node mask, heart / shipped checkpoint, train-BN: masked vs re-indexed {np.abs(a - b).max():.2e}")
+    assert np.abs(a - b).max() <= 1e-3
+    tr_m, tr_r = [], []
+    rm = greedy.solve_by_probablistic_greedy(solver, sgh, rng=np.random.RandomState(2), trace=tr_m, sub_layout="mask")
+    rr = greedy.solve_by_probablistic_greedy(solver, sgh, rng=np.random.RandomState(2), trace=tr_r, sub_layout="reindex")
+    same = np.array_equal(rm.selection, rr.selection)
+    print(f"greedy through the mask path: {int(rm.selection.sum())} tiles in {rm.rounds} rounds; re-index path: "
+          f"{int(rr.selection.sum())} tiles in {rr.rounds} rounds; identical: {same}")
+    if not same:
+        k = next(i for i, (u, v) in enumerate(zip(tr_m, tr_r)) if u[1] != v[1] or u[4] != v[4])
+        u, v = tr_m[k], tr_r[k]
+        assert (abs(u[2] - u[3]) < 1e-3 and abs(v[2] - v[3]) < 1e-3) if u[1] == v[1] else abs(u[2] - v[2]) < 1e-3, (u, v)

@@ -49,6 +49,26 @@ def test_greedy_makes_the_reference_decisions(heart):
     assert greedy.solve_by_probablistic_greedy(FakeSolver(), sg).order == z["order"].tolist()
 
 
+def test_greedy_through_the_node_mask_path_makes_the_reference_decisions(heart):
+    """a solver that offers ``predict_sub_layout(origin, keep)`` (the GPU solver does: node mask on the resident graph) is
+    handed the kept node ids instead of a re-indexed layout; the loop around it must make the same decisions."""
+    z, sg = heart
+
+    class MaskSolver(FakeSolver):
+        supports_node_mask = True
+
+        def predict_sub_layout(self, origin, keep):
+            sub, back = greedy.compute_sub_layout(origin, keep, collide_features=False)
+            assert np.array_equal(back, keep)
+            return self.predict(sub)
+    solver = MaskSolver()
+    res = greedy.solve_by_probablistic_greedy(solver, sg, rng=np.random.RandomState(2), sub_layout="mask")
+    assert solver.sizes == z["round_sizes"].tolist() and res.order == z["order"].tolist()
+    assert np.array_equal(res.selection, z["selection"])
+    ref = greedy.solve_by_probablistic_greedy(MaskSolver(), sg, rng=np.random.RandomState(2), sub_layout="reindex")
+    assert ref.order == res.order
+
+
 def test_greedy_solution_is_a_maximal_independent_set(heart):
     _, sg = heart
     res = greedy.solve_by_probablistic_greedy(FakeSolver(), sg, rng=np.random.RandomState(7))

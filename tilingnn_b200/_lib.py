@@ -42,6 +42,7 @@ SIGNATURES = {
     "tgnn_set_bn_mode": (C.c_int, [_vp, _i32]),
     "tgnn_set_graph": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "tgnn_forward": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "tgnn_set_node_mask": (C.c_int, [_vp, _vp, C.POINTER(_i64), _vp]),
     "tgnn_check_error": (C.c_int, [_vp, _vp, _i32]),
     "tgnn_nccl_unique_id": (C.c_int, [_vp]),
     "tgnn_shard_init": (C.c_int, [_vp, _vp, _i32, _i32]),

@@ -160,6 +160,11 @@ struct tgnn_handle {
     } replay;
     uint64_t graph_gen = 0, param_gen = 0;
 
+    // node mask (tgnn_set_node_mask): sub-layout on the resident structures
+    bool mask_on = false;
+    DevBuf mask_buf, inv_deg_m, mask_cnt;           // uint8 [n_own] | float [n_own] kept in-degree reciprocals | {int[3] counters, pad, double kept nodes}
+    const uint8_t* mask() const { return mask_on ? mask_buf.as<uint8_t>() : nullptr; }
+    const double* count_ptr() const { return mask_on ? reinterpret_cast<const double*>(mask_cnt.as<char>() + 16) : nullptr; }
     DevBuf role_dbg;                                // TGNN_ROLE_DBG=1: [2 kernels][32 warps][4] cycle counters of CTA 0 (k_conv_t, k_gin_w)
     bool role_dbg_on = getenv("TGNN_ROLE_DBG") != nullptr;
 
@@ -399,8 +404,8 @@ void choose_conv_kernel(tgnn_handle* h) {
 int want_t_rows(tgnn_handle* h, int64_t n_own) {
     if (h->conv_t_only) return 256;
     if (h->conv_h_only || h->conv_s_only || h->conv_chunk_only) return 0;
-    if (getenv("TGNN_CONV_T_ROWS")) { const int r = atoi(getenv("TGNN_CONV_T_ROWS")); if (r == 256 || r == 512 || r == 1024) return r; }
-    for (int rt : {1024, 512}) if (n_own >= (int64_t)2 * h->sm_count * rt) return rt;
+    if (getenv("TGNN_CONV_T_ROWS")) { const int r = atoi(getenv("TGNN_CONV_T_ROWS")); if (r == 256 || r == 512) return r; }
+    if (n_own >= (int64_t)2 * h->sm_count * 512) return 512;
     return 0;
 }
 
@@ -619,7 +624,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             BnFinishArgs fa{};
             fa.part[0] = part; fa.n_part[0] = n_part; fa.C = c; fa.count = count;
             fa.gamma[0] = bn.w; fa.beta[0] = bn.b; fa.coef[0] = h->C(coef_off);
-            fa.sums = sums; fa.ticket = h->bn_ticket();
+            fa.sums = sums; fa.ticket = h->bn_ticket(); fa.count_ptr = h->count_ptr();
             if (h->world == 1) launch_bn_finish(fa, 1, st);
             else { launch_bn_finish_x(fa, 1, peer_ptrs(h), ++h->px.epoch_bn, st); h->collectives += 1; }
             return;
@@ -637,6 +642,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     ia.coef0 = h->C(h->coef_init[0]); ia.coef1 = h->C(h->coef_init[1]);
     ia.out = h->mid[0]->as<float>(); ia.part = h->partA.as<double>(); ia.n_own = n_own;
     ia.xh = h->need_xh() ? h->xh.as<uint32_t>() : nullptr; ia.flag = h->need_xh() ? h->rflag(0) : nullptr;
+    ia.mask = h->mask();
     const int np_init = init_num_parts(n_own, h->sm_count);
     if (train) {
         lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
@@ -659,7 +665,8 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.tabF = h->tab.as<float>() + tslot * TG_FRAG32;
         ca.n_types = h->g.n_types; ca.bias = P.conv_bias;
         ca.cptr = h->g.cptr.as<int>(); ca.ctype = h->g.ctype.as<int>(); ca.csrc = h->g.csrc.as<int>();
-        ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->g.inv_deg.as<float>();
+        ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->mask_on ? h->inv_deg_m.as<float>() : h->g.inv_deg.as<float>();
+        ca.mask = h->mask();
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn;
         lz.begin("conv");
@@ -692,6 +699,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ga.wfrag = h->gin_wt[i]->as<float>();
         ga.eps = h->gin_eps[i]; ga.hmlp = h->gin_hmlp[i];
         ga.out = h->pre2[0].as<float>(); ga.part = train ? h->partB.as<double>() : nullptr; ga.n_own = n_own;
+        ga.mask = h->mask();
         const bool gw = h->use_gw && ga.hmlp;        // layers whose GIN weights are outside the fp16 range stay on k_gin
         const int np_gin = gw ? gin_w_num_parts(h->g.gw_tiles, h->sm_count) : gin_num_parts(n_own, h->sm_count);
         lz.begin("gin");
@@ -709,7 +717,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         CombineFin cf{};
         if (fin_in_combine) {
             cf.part[0] = h->partA.as<double>(); cf.n_part[0] = np_a; cf.part[1] = h->partB.as<double>(); cf.n_part[1] = np_gin;
-            cf.count = count;
+            cf.count = count; cf.count_ptr = h->count_ptr();
             cf.gamma[0] = P.bn_a_w; cf.beta[0] = P.bn_a_b; cf.gamma[1] = P.bn_c_w; cf.beta[1] = P.bn_c_b;
             cf.coef_out[0] = h->C(h->coef_a[i]); cf.coef_out[1] = h->C(h->coef_c[i]);
         }
@@ -722,7 +730,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
                 fa.C = 32; fa.count = count;
                 fa.gamma[0] = P.bn_a_w; fa.beta[0] = P.bn_a_b; fa.coef[0] = h->C(h->coef_a[i]);
                 fa.gamma[1] = P.bn_c_w; fa.beta[1] = P.bn_c_b; fa.coef[1] = h->C(h->coef_c[i]);
-                fa.sums = sums; fa.ticket = h->bn_ticket();
+                fa.sums = sums; fa.ticket = h->bn_ticket(); fa.count_ptr = h->count_ptr();
                 if (h->world == 1) launch_bn_finish(fa, 2, st);
                 else { launch_bn_finish_x(fa, 2, peer_ptrs(h), ++h->px.epoch_bn, st); h->collectives += 1; }
                 lz.end(1);
@@ -739,7 +747,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         launch_combine(h->pre1.as<float>(), h->C(h->coef_a[i]), h->pre2[0].as<float>(), h->C(h->coef_c[i]),
                        i >= 2 ? h->mid[i - 2]->as<float>() : nullptr, h->mid[i + 1]->as<float>(),
                        h->need_xh() ? h->xh.as<uint4>() : nullptr, h->rflag(i + 1), h->pre2[1].as<float>(), n_own, st,
-                       fin_in_combine ? &cf : nullptr);
+                       fin_in_combine ? &cf : nullptr, h->mask());
         lz.end(1);
         if (i + 1 < n_layers) halo_exchange(h, h->mid[i + 1]->as<float>(), h->pre2[1].as<float>(), h->rflag(i + 1), st, lz);
         h->last_layer_run = i;
@@ -756,7 +764,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             da.in_coef = k == 0 ? nullptr : h->C(h->coef_fin[k - 1]);
             da.wt = h->fin_wt[k]->as<float>(); da.bias = h->fin_bias[k];
             da.out = h->fa[k].as<float>(); da.part = train ? h->partA.as<double>() : nullptr;
-            da.n = n_own; da.K = dims[k]; da.n_out = dims[k + 1];
+            da.n = n_own; da.K = dims[k]; da.n_out = dims[k + 1]; da.mask = h->mask();
             lz.begin("final");
             if (h->dense_ffma) launch_dense(da, st);
             else {
@@ -771,7 +779,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         }
         lz.begin("score");
         launch_score(h->fa[3].as<float>(), h->C(h->coef_fin[3]), h->score_w, h->fin_last_bias, scores,
-                     n_own, st);
+                     n_own, st, h->mask());
         lz.end(1);
     }
     // Device-side errors are ALWAYS surfaced: synchronously here when that is cheap or asked for (small graphs: the
@@ -804,7 +812,7 @@ void forward_entry(tgnn_handle* h, const float* x, float* scores, cudaStream_t s
     pack_params(h, st);
     build_tables(h, st);
     if (h->tables_streamed) { forward_impl(h, x, scores, st); return; }   // per-layer table builds: not worth capturing
-    const uint64_t key = (h->graph_gen << 20) ^ (h->param_gen << 2) ^ (uint64_t)h->cfg.bn_mode;
+    const uint64_t key = (h->graph_gen << 20) ^ (h->param_gen << 3) ^ ((uint64_t)h->mask_on << 1) ^ (uint64_t)h->cfg.bn_mode;
     if (key != R.key) { R.drop(); R.key = key; }
     const size_t xb = (size_t)h->g.n_own * h->cfg.d_x * sizeof(float), sb = (size_t)h->g.n_own * sizeof(float);
     if (!R.exec) {
@@ -982,6 +990,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         alloc_workspace(h);
         h->tables_dirty = true;
         h->graph_gen++;
+        h->mask_on = false;
         h->graph_set = true;
     });
 }
@@ -1077,6 +1086,34 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
             TGNN_CUDA(cudaDeviceSynchronize());
             TGNN_CUDA(cudaMemcpy(f.data(), h->hflags.p, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
             for (int i = 0; i < L; ++i) out->range_fallback_layers += (f[i] | f[L + 1 + i]) ? 1 : 0;
+        }
+    });
+}
+
+int tgnn_set_node_mask(tgnn_handle* h, const uint8_t* keep, int64_t* counts3, void* stream) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && h->graph_set, "tgnn_set_node_mask: no graph set");
+        TGNN_CHECK(h->world == 1, "tgnn_set_node_mask: not supported on a sharded handle");
+        DeviceGuard dg(h->cfg.device);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (!keep) {
+            h->mask_on = false;
+            if (counts3) { counts3[0] = h->g.n_own; counts3[1] = h->g.e_adj; counts3[2] = h->g.e_col; }
+            return;
+        }
+        const size_t n = (size_t)h->g.n_own;
+        const void *b0 = h->mask_buf.p, *b1 = h->inv_deg_m.p, *b2 = h->mask_cnt.p;
+        h->mask_buf.reserve(n); h->inv_deg_m.reserve(n * sizeof(float)); h->mask_cnt.reserve(32);
+        if (b0 != h->mask_buf.p || b1 != h->inv_deg_m.p || b2 != h->mask_cnt.p) h->replay.drop();     // captured pointers moved
+        TGNN_CUDA(cudaMemcpyAsync(h->mask_buf.p, keep, n, cudaMemcpyDefault, st));
+        launch_node_mask(h->g, h->mask_buf.as<uint8_t>(), h->inv_deg_m.as<float>(), h->mask_cnt.as<int>(),
+                         reinterpret_cast<double*>(h->mask_cnt.as<char>() + 16), st);
+        h->mask_on = true;
+        if (counts3) {
+            int c[3];
+            TGNN_CUDA(cudaMemcpyAsync(c, h->mask_cnt.p, sizeof(c), cudaMemcpyDeviceToHost, st));
+            TGNN_CUDA(cudaStreamSynchronize(st));
+            counts3[0] = c[0]; counts3[1] = c[1]; counts3[2] = c[2];
         }
     });
 }

@@ -16,8 +16,15 @@
 //     row are visited in a lane-rotated order (conflict-free for ANY destinations); the data is rotated to match with
 //     three select stages.  Quarter q of a block only holds destinations with dst % 4 == q and no destination twice
 //     (graph_build.cu), so the four warps never touch the same row: no atomics, deterministic sums.
-//   * x_i . root runs as the super-tile's last blocks (type K, src = dst = own rows): acc = acc / deg + root message.
-// Persistent CTAs (one per SM), 9 warps: 0-3 epilogue (TMEM lane quarters), 4-7 gather producers, 8 MMA issuer.
+//   * x_i . root runs as the super-tile's last blocks (type K, src = dst = own rows); edge messages are scaled by 1 / deg(dst)
+//     as they are added (mean aggregation), the root message is added as it is.
+//   * measured (role cycle counters): one epilogue warp per TMEM lane quarter is the bottleneck (~900 busy cycles per block,
+//     a single warp per scheduler cannot hide its own tcgen05.ld -> FMA -> select -> FADD -> STS chain).  So there are TWO
+//     epilogue groups of four warps; group e takes the blocks with (block counter & 1) == e and accumulates into its OWN
+//     plane of the super-tile accumulator (two groups adding into one plane would race on rows of the same class); the
+//     planes are added when the tile is finished.  The accumulator rows are fetched BEFORE the wait for the MMAs.
+// Persistent CTAs (one per SM), 13 warps: 0-7 epilogue (warp & 3 = TMEM lane quarter, warp >> 2 = group), 8-11 gather
+// producers, 12 MMA issuer.  Super-tiles of 512 rows: 2 x 64 KB of accumulator planes + 4 stages of 24 KB.
 // Range guard: fp16 operands overflow at 65504; when a range flag is raised (an activation or a root weight above
 // 60000) the kernel exits at once and k_conv_t_wide redoes the layer on the same blocks with plain fp32 FMAs.
 #include <algorithm>
@@ -31,10 +38,10 @@ namespace {
 using namespace tc;
 
 constexpr int TBS = 128;                        // slots (edges) per block = UMMA M
-constexpr int NS = 3;                           // shared-memory stages (A tile + weight image)
+constexpr int NS = 4;                           // shared-memory stages (A tile + weight image)
 constexpr int NT = 4;                           // TMEM accumulator buffers (64 columns each)
 constexpr int A_BYTES = TBS * 128, B_BYTES = 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 4, PROD_WARPS = 4;
+constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS, PROD_WARPS = 4;
 constexpr int W_PROD0 = EPI_WARPS, W_MMA = EPI_WARPS + PROD_WARPS;
 constexpr int CT_THREADS = (W_MMA + 1) * 32;
 constexpr float LO_INV = 1.0f / 2048.f;
@@ -87,17 +94,19 @@ struct ConvTArgs {
     int n_own, n_tiles, rt;      // rt: destination rows per super-tile (256 | 512 | 1024)
 };
 
-// out = LeakyReLU(acc + bias), statistics, and the tile's accumulator is zeroed for the next tile.  Called by the four
-// epilogue warps (warp q takes rows q, q+4, ...; lane = channel) between two named barriers.
-__device__ __forceinline__ void finish_tile(const ConvTArgs& A, uint32_t acc_base, int tile, int q, int lane, float bias_c,
+// out = LeakyReLU(plane 0 + plane 1 + bias), statistics, and the tile's accumulator planes are zeroed for the next tile.
+// Called by the eight epilogue warps (warp w takes rows w, w+8, ...; lane = channel) between two named barriers.
+__device__ __forceinline__ void finish_tile(const ConvTArgs& A, uint32_t acc_base, int tile, int w, int lane, float bias_c,
                                             double& s1, double& s2) {
     const int node0 = tile * A.rt;
     const int rows = min(A.rt, A.n_own - node0);
-    for (int r = q; r < rows; r += EPI_WARPS) {
+    const uint32_t plane = (uint32_t)A.rt * 128u;
+    for (int r = w; r < rows; r += EPI_WARPS) {
         const uint32_t a = acc_base + (uint32_t)r * 128u + (uint32_t)lane * 4u;
-        float v = leaky(lds_f32(a) + bias_c);
+        float v = leaky((lds_f32(a) + lds_f32(a + plane)) + bias_c);
         if (!row_kept(A.mask, node0 + r)) v = 0.f;
         sts_f32(a, 0.f);
+        sts_f32(a + plane, 0.f);
         A.out[(size_t)(node0 + r) * F + lane] = v;
         s1 += (double)v;
         s2 += (double)v * (double)v;
@@ -113,14 +122,14 @@ k_conv_t(ConvTArgs A) {
     __shared__ int timeout_flag;
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t acc_base = sbase;                                          // [rt][32] fp32, row stride 128 B
-    const uint32_t stage_base = sbase + (uint32_t)A.rt * 128u;                // [NS][A tile | weight image]
+    const uint32_t acc_base = sbase;                                          // [2 planes][rt][32] fp32, row stride 128 B
+    const uint32_t stage_base = sbase + (uint32_t)EPI_GROUPS * (uint32_t)A.rt * 128u;   // [NS][A tile | weight image]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NS]);
     const uint32_t bar_accf = smem_u32(&bars[2 * NS]), bar_acce = smem_u32(&bars[2 * NS + NT]);
     if (tid == 0) {
         for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, PROD_WARPS * 32 + 1); mbar_init(bar_empty + 8 * i, 1); }
-        for (int i = 0; i < NT; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, EPI_WARPS); }
+        for (int i = 0; i < NT; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 4); }     // the 4 warps of the owning group
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -128,7 +137,7 @@ k_conv_t(ConvTArgs A) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_smem)), "n"(NT * 64));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (uint32_t i = tid; i < (uint32_t)A.rt * 8u; i += CT_THREADS) sts128f(acc_base + i * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (uint32_t i = tid; i < (uint32_t)EPI_GROUPS * (uint32_t)A.rt * 8u; i += CT_THREADS) sts128f(acc_base + i * 16u, make_float4(0.f, 0.f, 0.f, 0.f));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -200,24 +209,37 @@ k_conv_t(ConvTArgs A) {
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> message -> destination row of the tile accumulator =====================
-        const int q = warp;                               // TMEM lanes 32q .. 32q+31 = slots 32q .. 32q+31 of the block
+        // ===================== epilogue: TMEM -> message -> destination row of the group's accumulator plane =====================
+        const int q = warp & 3, grp = warp >> 2;          // TMEM lanes 32q .. 32q+31 = slots 32q .. 32q+31 of the block
         const float bias_c = __ldg(A.bias + lane);
         const int rot = lane & 7;
+        const uint32_t my_acc = acc_base + (uint32_t)grp * (uint32_t)A.rt * 128u;
         double s1 = 0.0, s2 = 0.0;
-        int g = 0;
+        int g0 = 0;                                       // block counter of the CTA at the start of the tile
         bool ok = true;
         for (int tile = blockIdx.x; ok && tile < A.n_tiles; tile += gridDim.x) {
             const int b0 = __ldg(A.bptr + tile), b1 = __ldg(A.bptr + tile + 1);
             const int node0 = tile * A.rt;
+            const int first = b0 + ((grp - g0) & 1);      // this group's blocks: (g0 + blk - b0) & 1 == grp
             int dst = 0xFFFF, type = 0;
-            if (b0 < b1) { dst = __ldg(A.tdst + (size_t)b0 * TBS + 32 * q + lane); type = __ldg(A.btype + b0); }
-            for (int blk = b0; blk < b1; ++blk, ++g) {
+            if (first < b1) { dst = __ldg(A.tdst + (size_t)first * TBS + 32 * q + lane); type = __ldg(A.btype + first); }
+            for (int blk = first; blk < b1; blk += 2) {
+                const int g = g0 + (blk - b0);
                 int ndst = 0xFFFF, ntype = 0;
-                if (blk + 1 < b1) { ndst = __ldg(A.tdst + (size_t)(blk + 1) * TBS + 32 * q + lane); ntype = __ldg(A.btype + blk + 1); }
+                if (blk + 2 < b1) { ndst = __ldg(A.tdst + (size_t)(blk + 2) * TBS + 32 * q + lane); ntype = __ldg(A.btype + blk + 2); }
                 const bool root = type == A.n_types, live = dst != 0xFFFF;
-                float inv = 0.f;
-                if (root && live) inv = __ldg(A.inv_deg + node0 + dst);
+                // mean aggregation: every edge message is scaled by 1 / deg(dst) as it is added (two planes and no order between
+                // the groups: a final scaling pass would have to know which part of a row is the root term)
+                float inv = 1.f;
+                if (!root && live) inv = __ldg(A.inv_deg + node0 + dst);
+                // the destination row's eight float4 pieces, in this lane's rotated order, BEFORE the wait for the MMAs: step
+                // st touches piece (st + lane) & 7 -- the eight lanes of a quarter-warp are on eight different bank groups
+                // whatever their rows are.  (No other warp touches this row: one class per quarter, one plane per group.)
+                const uint32_t row = my_acc + (uint32_t)(live ? dst : 0) * 128u;
+                __syncwarp();                                                 // the previous block's stores of OTHER lanes to this row
+                float4 a[8];
+#pragma unroll
+                for (int st = 0; st < 8; ++st) a[st] = lds128f(row + (uint32_t)(((st + rot) & 7) << 4));
                 const int tb = g % NT;
                 if (!TGNN_TIMED(w0, mbar_wait(bar_accf + 8 * tb, (uint32_t)((g / NT) & 1)))) { timeout_flag = 1; ok = false; break; }
                 tc_fence_after();
@@ -243,20 +265,10 @@ k_conv_t(ConvTArgs A) {
                     for (int i = 0; i < 32; ++i) m[i] = u[i];
                 }
                 if (live) {
-                    // step st touches float4 piece (st + lane) & 7 of row dst: the eight lanes of a quarter-warp are on
-                    // eight different bank groups whatever their rows are
-                    const uint32_t row = acc_base + (uint32_t)dst * 128u;
-                    float4 a[8];
-#pragma unroll
-                    for (int st = 0; st < 8; ++st) a[st] = lds128f(row + (uint32_t)(((st + rot) & 7) << 4));
 #pragma unroll
                     for (int st = 0; st < 8; ++st) {
-                        if (root) {                                           // mean over the in-edges, then the root term
-                            a[st].x = fmaf(a[st].x, inv, m[4 * st]); a[st].y = fmaf(a[st].y, inv, m[4 * st + 1]);
-                            a[st].z = fmaf(a[st].z, inv, m[4 * st + 2]); a[st].w = fmaf(a[st].w, inv, m[4 * st + 3]);
-                        } else {
-                            a[st].x += m[4 * st]; a[st].y += m[4 * st + 1]; a[st].z += m[4 * st + 2]; a[st].w += m[4 * st + 3];
-                        }
+                        a[st].x = fmaf(m[4 * st], inv, a[st].x); a[st].y = fmaf(m[4 * st + 1], inv, a[st].y);
+                        a[st].z = fmaf(m[4 * st + 2], inv, a[st].z); a[st].w = fmaf(m[4 * st + 3], inv, a[st].w);
                     }
 #pragma unroll
                     for (int st = 0; st < 8; ++st) sts128f(row + (uint32_t)(((st + rot) & 7) << 4), a[st]);
@@ -264,15 +276,16 @@ k_conv_t(ConvTArgs A) {
                 dst = ndst; type = ntype;
             }
             if (!ok) break;
+            g0 += b1 - b0;
             const long long t_fin = clock64();
             named_bar_sync(1, EPI_WARPS * 32);                                // every message of the tile is in
-            finish_tile(A, acc_base, tile, q, lane, bias_c, s1, s2);
+            finish_tile(A, acc_base, tile, warp, lane, bias_c, s1, s2);
             named_bar_sync(1, EPI_WARPS * 32);                                // zeroed before the next tile's first add
             w1 += clock64() - t_fin;
         }
         if (A.part) {
-            A.part[((size_t)blockIdx.x * EPI_WARPS + q) * 64 + lane] = s1;
-            A.part[((size_t)blockIdx.x * EPI_WARPS + q) * 64 + 32 + lane] = s2;
+            A.part[((size_t)blockIdx.x * EPI_WARPS + warp) * 64 + lane] = s1;
+            A.part[((size_t)blockIdx.x * EPI_WARPS + warp) * 64 + 32 + lane] = s2;
         }
     }
     if (A.dbg && blockIdx.x == 0 && lane == 0) {
@@ -316,14 +329,9 @@ k_conv_t_wide(ConvTArgs A) {
                     for (int n = 0; n < 32; ++n) m[n] = fmaf(xv, __ldg(W + k * 32 + n), m[n]);
                 }
                 float* row = acc + dst * WS;
-                if (type == A.n_types) {
-                    const float inv = __ldg(A.inv_deg + node0 + dst);
+                const float inv = type == A.n_types ? 1.f : __ldg(A.inv_deg + node0 + dst);
 #pragma unroll
-                    for (int n = 0; n < 32; ++n) row[n] = fmaf(row[n], inv, m[n]);
-                } else {
-#pragma unroll
-                    for (int n = 0; n < 32; ++n) row[n] += m[n];
-                }
+                for (int n = 0; n < 32; ++n) row[n] = fmaf(m[n], inv, row[n]);
             }
             __syncthreads();
         }
@@ -338,13 +346,15 @@ k_conv_t_wide(ConvTArgs A) {
         }
         __syncthreads();
     }
-    if (A.part) {
-        A.part[((size_t)blockIdx.x * (TBS / 32) + warp) * 64 + lane] = s1;
-        A.part[((size_t)blockIdx.x * (TBS / 32) + warp) * 64 + 32 + lane] = s2;
+    if (A.part) {                                     // same partial layout as k_conv_t (8 rows per CTA; this kernel fills 4)
+        A.part[((size_t)blockIdx.x * EPI_WARPS + warp) * 64 + lane] = s1;
+        A.part[((size_t)blockIdx.x * EPI_WARPS + warp) * 64 + 32 + lane] = s2;
+        A.part[((size_t)blockIdx.x * EPI_WARPS + 4 + warp) * 64 + lane] = 0.0;
+        A.part[((size_t)blockIdx.x * EPI_WARPS + 4 + warp) * 64 + 32 + lane] = 0.0;
     }
 }
 
-size_t conv_t_smem(int rt) { return (size_t)rt * 128 + (size_t)NS * STAGE_BYTES + 1024; }
+size_t conv_t_smem(int rt) { return (size_t)EPI_GROUPS * rt * 128 + (size_t)NS * STAGE_BYTES + 1024; }
 
 }  // namespace
 
@@ -354,8 +364,8 @@ void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, cons
                    long long* dbg) {
     static PerDeviceOnce once;
     once.run([&] {
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(1024)));
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * 33 * 4));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(512)));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 33 * 4));
     });
     ConvTArgs a{};
     a.xh = c.xh; a.xin = c.xin; a.tabT = tabT; a.tab32 = tab32; a.n_types = c.n_types;

@@ -134,20 +134,22 @@ k_gin_w(GinArgs A) {
                         sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
                     }
                     const uint16_t* lp = loc + (e0 - e_base);
-                    for (int o = 0; o < n_max; o += 8) {
-                        uint32_t ad[8];
-                        // the four lane groups walk a batch in rotated order (k + 2a): with equal degrees their index lists
-                        // are a fixed distance apart and the same position would fall on one bank
+                    // 16 rows in flight per lane (one gather warp per scheduler: the loads of a batch must cover the
+                    // LDS -> address -> LDS.128 -> FADD chain of the previous one); same summation order as k_gin: batches of
+                    // 8, each walked in the lane group's rotated order (k + 2a) -- with equal degrees the four groups' index
+                    // lists are a fixed distance apart and the same position would fall on one bank
+                    for (int o = 0; o < n_max; o += 16) {
+                        uint32_t ad[16];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) ad[k] = win + (uint32_t)lp[min(o + ((k + 2 * a) & 7), last)] * 128u;
-                        float4 v[8];
+                        for (int k = 0; k < 16; ++k) ad[k] = win + (uint32_t)lp[min(o + (k & 8) + ((k + 2 * a) & 7), last)] * 128u;
+                        float4 v[16];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
+                        for (int k = 0; k < 16; ++k) {
                             v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (o + ((k + 2 * a) & 7) < n_mine) v[k] = lds_row(ad[k]);
+                            if (o + (k & 8) + ((k + 2 * a) & 7) < n_mine) v[k] = lds_row(ad[k]);
                         }
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                        for (int k = 0; k < 16; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
                     }
                 } else {
                     // "direct" tile (sources not local enough for a window): rows and indices from global memory

@@ -568,7 +568,8 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         // ---------------- adjacency: T format (tcgen05 edge-block kernel) --------------------------------
         g.has_t = false;
         if (want_t > 0) {
-            const int rt = want_t, tdb = rt == 1024 ? 10 : (rt == 512 ? 9 : 8), rb = rt / 128;
+            const int rt = want_t, tdb = rt == 512 ? 9 : 8, rb = rt / 128;
+            TGNN_CHECK(rt == 256 || rt == 512, "internal: bad super-tile height");
             g.t_rows = rt; g.t_tiles = (int)((n_own + rt - 1) / rt);
             k_t_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, tb, tdb, k0, id0);
             const int t_end_bit = tdb + tb + bits_for((unsigned long long)g.t_tiles);

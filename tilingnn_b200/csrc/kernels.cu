@@ -787,6 +787,51 @@ __global__ void k_halo_unpack(const float4* __restrict__ recv, int world, int ra
     } else if (b) b[(size_t)(n_own + r) * 8 + (c - 8)] = v;
 }
 
+// ---- node mask (tgnn_set_node_mask): what changes when only the nodes with keep != 0 are part of the graph ---------
+// per 64/128-row warp tile: kept in-degree of every destination (mean aggregation divides by it) and the number of
+// adjacency edges with both endpoints kept
+__global__ void __launch_bounds__(128)
+k_mask_adj(const int* __restrict__ cptr, const int* __restrict__ csrc, const uint8_t* __restrict__ cdst, int wn, int n_own,
+           const uint8_t* __restrict__ keep, float* __restrict__ inv_deg, int* __restrict__ counters) {
+    __shared__ int deg[WN_BIG];
+    const int tile = blockIdx.x;
+    for (int i = threadIdx.x; i < wn; i += 128) deg[i] = 0;
+    __syncthreads();
+    const int64_t s0 = (int64_t)cptr[tile] * CH, s1 = (int64_t)cptr[tile + 1] * CH;
+    int both = 0;
+    for (int64_t s = s0 + threadIdx.x; s < s1; s += 128) {
+        const int src = csrc[s];
+        if (src >= 0 && keep[src]) {
+            const int d = cdst[s];
+            atomicAdd(&deg[d], 1);
+            both += keep[tile * wn + d] ? 1 : 0;
+        }
+    }
+    if (both) atomicAdd(counters + 1, both);
+    __syncthreads();
+    for (int i = threadIdx.x; i < wn; i += 128) {
+        const int node = tile * wn + i;
+        if (node < n_own) inv_deg[node] = 1.0f / (float)(deg[i] > 1 ? deg[i] : 1);
+    }
+}
+// kept nodes and collision edges with both endpoints kept
+__global__ void k_mask_count(const int* __restrict__ col_ptr, const int* __restrict__ col_src, int n_own,
+                             const uint8_t* __restrict__ keep, int* __restrict__ counters) {
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    int kept = 0, both = 0;
+    if (node < n_own && keep[node]) {
+        kept = 1;
+        for (int e = col_ptr[node]; e < col_ptr[node + 1]; ++e) both += keep[col_src[e]] ? 1 : 0;
+    }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    both = __reduce_add_sync(0xffffffffu, both);
+    if ((threadIdx.x & 31) == 0) {
+        if (kept) atomicAdd(counters, kept);
+        if (both) atomicAdd(counters + 2, both);
+    }
+}
+__global__ void k_mask_finish(const int* __restrict__ counters, double* __restrict__ count) { *count = (double)counters[0]; }
+
 int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_per_sm) {
     int want = work_items_per_block_unit;
     int cap = sm_count * blocks_per_sm;
@@ -843,6 +888,15 @@ void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st) {
     });
     if (a.hmlp) k_gin<true><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(true), st>>>(a);
     else k_gin<false><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(false), st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+void launch_node_mask(const Graph& g, const uint8_t* keep, float* inv_deg_masked, int* counters3, double* count, cudaStream_t st) {
+    TGNN_CUDA(cudaMemsetAsync(counters3, 0, 3 * sizeof(int), st));
+    if (g.n_tiles > 0) k_mask_adj<<<g.n_tiles, 128, 0, st>>>(g.cptr.as<int>(), g.csrc.as<int>(), g.cdst.as<uint8_t>(), g.wn, (int)g.n_own, keep,
+                                                            inv_deg_masked, counters3);
+    k_mask_count<<<(int)((g.n_own + 255) / 256), 256, 0, st>>>(g.col_ptr.as<int>(), g.col_src.as<int>(), (int)g.n_own, keep, counters3);
+    k_mask_finish<<<1, 1, 0, st>>>(counters3, count);
     TGNN_CUDA(cudaGetLastError());
 }
 

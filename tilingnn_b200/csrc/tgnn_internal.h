@@ -144,7 +144,7 @@ struct Scratch {
 void build_graph(Graph& g, Scratch& scratch, int d_e, int64_t n_own, int64_t n_rows,
                  int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
                  int64_t e_col, const int64_t* col_src, const int64_t* col_dst, int want_s /* 0 no, 1 auto, 2 force */,
-                 int wn, int want_t /* 0 = no T format, else its super-tile rows: 256 | 512 | 1024 */, cudaStream_t st);
+                 int wn, int want_t /* 0 = no T format, else its super-tile rows: 256 | 512 */, cudaStream_t st);
 constexpr int S_BM = 128;         // destination rows per tile of the S format
 constexpr int S_OFF_STRIDE = 136; // uint16 per pass (129 used; 272 B keeps 16-byte alignment)
 constexpr double S_EDGES_PER_PASS_BREAK_EVEN = 164.0;   // measured: S pass ~5.9 ns, fp16 edge-chunk kernel ~36 ps per edge
@@ -188,7 +188,7 @@ void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
 // tcgen05 edge-block kernel (conv_t.cu) + its fp32 stand-by for the range guard; tabT: [K+1][2048] words, tab32: [K+1][1024]
 constexpr int TG_TIMG32 = 2048;          // 32-bit words of one pre-swizzled [64 x 64] fp16 weight image
 int conv_t_blocks(int t_tiles, int sm_count);
-inline int conv_t_num_parts(int t_tiles, int sm_count) { return conv_t_blocks(t_tiles, sm_count) * 4; }
+inline int conv_t_num_parts(int t_tiles, int sm_count) { return conv_t_blocks(t_tiles, sm_count) * 8; }
 void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, const float* tab32, int* err, int sm_count, cudaStream_t st,
                    long long* dbg = nullptr);
 // role timing (TGNN_ROLE_DBG=1): acc += cycles spent in expr
@@ -324,6 +324,10 @@ void launch_halo_push(const float* a, const float* b, const int* rows, int n_sen
 // waits for the peers' flags of `epoch`, then unpacks this rank's halo buffer (as launch_halo_unpack)
 void launch_halo_unpack_x(const PeerPtrs& p, unsigned epoch, int64_t halo_slot, int64_t n_own, float* a, float* b,
                           uint4* xh, int* flag, cudaStream_t st);
+
+// node mask: kept in-degrees -> inv_deg_masked[n_own]; counters3 = {kept nodes, adjacency edges, collision edges with both
+// endpoints kept}; *count = kept nodes as a double (the BatchNorm population)
+void launch_node_mask(const Graph& g, const uint8_t* keep, float* inv_deg_masked, int* counters3, double* count, cudaStream_t st);
 
 // halo pack / unpack (sharded mode)
 void launch_halo_pack(const float* a, const float* b, const int* rows, int n_send, float* sendbuf, cudaStream_t st);

@@ -83,10 +83,17 @@ class GreedyResult:
     labels: np.ndarray = field(default=None, repr=False)   # [N] int8: 1 selected, 0 knocked out by a collision
 
 
-def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_graph=None, max_rounds=None, trace=None):
+def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_graph=None, max_rounds=None, trace=None,
+                                 sub_layout="mask"):
     """algorithms.py:18-62.  ``ml_solver.predict(layout) -> np.ndarray[N]`` is the only network access.
     ``trace`` (optional list) receives one ``(round, node, accept threshold exp(p-1), uniform draw, accepted)`` tuple per
-    visited node -- the tests use it to locate the first decision at which two score sources part ways."""
+    visited node -- the tests use it to locate the first decision at which two score sources part ways.
+    ``sub_layout``: "mask" scores a round's sub-layout through ``ml_solver.predict_sub_layout(origin_layout, keep)`` when the
+    solver has it (the origin layout stays resident on the GPU, a node mask selects the sub-graph); "reindex" always builds
+    the re-indexed sub-layout as the reference does (brick_layout.py:248-286) and calls ``predict`` on it."""
+    masked_predict = None
+    if sub_layout == "mask" and getattr(ml_solver, "supports_node_mask", False):
+        masked_predict = ml_solver.predict_sub_layout
     rng = np.random if rng is None else rng
     n = origin_layout.node_feature.shape[0]
     col = _edges(origin_layout.collide_edge_index)
@@ -103,8 +110,12 @@ def solve_by_probablistic_greedy(ml_solver, origin_layout, rng=None, complete_gr
         if max_rounds is not None and round_cnt > max_rounds:
             raise RuntimeError(f"greedy assembly did not finish in {max_rounds} rounds")
         keep = np.flatnonzero(label < 0)
-        temp_layout, node_re_index = compute_sub_layout(origin_layout, keep, collide_features=False)
-        prob = np.asarray(ml_solver.predict(temp_layout))
+        if masked_predict is not None:
+            node_re_index = keep
+            prob = np.asarray(masked_predict(origin_layout, keep))
+        else:
+            temp_layout, node_re_index = compute_sub_layout(origin_layout, keep, collide_features=False)
+            prob = np.asarray(ml_solver.predict(temp_layout))
         previous_prob = saved[keep]
         prob_per_node = np.power(np.power(previous_prob, round_cnt - 1) * prob, 1 / round_cnt)
         saved[keep] = prob_per_node

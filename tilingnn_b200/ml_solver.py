@@ -55,23 +55,64 @@ class ML_Solver:
         self.random_network = deepcopy(self.network)      # ml_solver.py:26
         self.num_prob_maps = num_prob_maps
 
+    # ---- resident layout: the greedy loop scores sub-layouts of ONE origin layout (util/algorithms.py:27-31) ---------
+    @property
+    def supports_node_mask(self):
+        """True when ``predict_sub_layout`` can run: the network is a ``tilingnn_b200.TilinGNN`` (subclasses that replace
+        ``predict`` with something else, e.g. a CPU checker, do not have one)."""
+        return hasattr(getattr(self, "network", None), "set_node_mask")
+
+    def _make_resident(self, layout):
+        """Upload ``layout`` once and build its device structures; later calls with the same object are free."""
+        res = getattr(self, "_resident", None)
+        if res is not None and res[0] is layout:
+            return res[1]
+        x, ai, af, ci, _ = to_torch_tensor(self.device, layout.node_feature, layout.align_edge_index,
+                                           layout.align_edge_features, layout.collide_edge_index)
+        self.network.set_graph(x.shape[0], ai, af, ci)
+        self._resident = (layout, x)
+        return x
+
+    def predict_sub_layout(self, origin_layout, keep):
+        """Scores of the sub-layout of ``origin_layout`` induced by the nodes ``keep`` (ascending original indices) -- what
+        ``predict(origin_layout.compute_sub_layout(...))`` returns in the reference (util/algorithms.py:27-31,
+        tiling/brick_layout.py:248-286), computed WITHOUT re-indexing or re-uploading anything: the origin layout stays
+        resident on the GPU and a node mask selects the sub-graph (``tgnn_set_node_mask``)."""
+        keep = np.asarray(keep, dtype=np.int64)
+        n = origin_layout.node_feature.shape[0]
+        if np.size(origin_layout.collide_edge_index) == 0 or np.size(origin_layout.align_edge_index) == 0:
+            return np.ones(len(keep), dtype=np.float32)
+        x = self._make_resident(origin_layout)
+        mask = np.zeros(n, dtype=np.uint8)
+        mask[keep] = 1
+        _, e_adj, e_col = self.network.set_node_mask(mask)
+        if e_col == 0 or e_adj == 0:                                              # ml_solver.py:31-32 on the sub-layout
+            return np.ones(len(keep), dtype=np.float32)
+        scores = self.network.score(x)
+        return scores.detach().cpu().numpy()[keep]
+
     def predict(self, brick_layout):
         """ml_solver.py:29-49.  Returns ``np.ndarray[N]`` float32."""
         n = brick_layout.node_feature.shape[0]
         # the reference's empty edge set is ``np.array([])`` (len 0); a [2, 0] array means the same here
         if np.size(brick_layout.collide_edge_index) == 0 or np.size(brick_layout.align_edge_index) == 0:
             return np.ones(n, dtype=np.float32)                                   # :31-32
+        res = getattr(self, "_resident", None)
+        if res is not None and res[0] is brick_layout:                            # the layout the greedy rounds just ran on
+            self.network.set_node_mask(None)
+            return self.network.score(res[1]).detach().cpu().numpy()
         x, ai, af, ci, _ = to_torch_tensor(self.device, brick_layout.node_feature, brick_layout.align_edge_index,
                                            brick_layout.align_edge_features, brick_layout.collide_edge_index)
         predictions, *_ = self.network(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci, col_e_features=None)
         # get_best_prob_map (:46,133-136) is argsort over num_prob_maps = 1 losses: always column 0
         return predictions[:, 0].detach().cpu().numpy()
 
-    def solve(self, brick_layout, rng=None):
+    def solve(self, brick_layout, rng=None, sub_layout="mask"):
         """ml_solver.py:59-67: greedy assembly, then one more scoring pass of the full layout.  Returns
         ``(output_layout, score)``; the layout copy carries ``predict``, ``predict_order``, ``predict_probs``."""
         from . import greedy
-        res = greedy.solve_by_probablistic_greedy(self, brick_layout, rng=rng, complete_graph=self.complete_graph)
+        res = greedy.solve_by_probablistic_greedy(self, brick_layout, rng=rng, complete_graph=self.complete_graph,
+                                                  sub_layout=sub_layout)
         output_layout = copy(brick_layout)          # the reference deep-copies; nothing mutates the arrays afterwards
         output_layout.predict_order = res.order
         output_layout.predict = res.selection

@@ -260,6 +260,31 @@ class TilinGNN(nn.Module):
         _lib.check(nat.h, rc, "tgnn_forward")
         return out
 
+    def set_node_mask(self, keep):
+        """Sub-layout on the RESIDENT graph (tgnn_set_node_mask; reference: BrickLayout.compute_sub_layout,
+        tiling/brick_layout.py:248-286, without the re-indexing): ``keep`` is a bool / uint8 vector [N] (torch, CPU or
+        CUDA, or numpy), ``None`` restores the full graph.  The next ``score(x)`` calls score the sub-graph induced by the
+        kept nodes; masked nodes get score 0.  Returns ``(kept nodes, adjacency edges, collision edges)`` of the sub-graph."""
+        nat = self._sync()
+        lib = _lib.load()
+        dev = self._device()
+        counts = (C.c_int64 * 3)()
+        st = torch.cuda.current_stream(dev).cuda_stream
+        if keep is None:
+            ptr, hold = C.c_void_p(0), None
+        else:
+            hold = torch.as_tensor(keep)
+            if hold.dtype != torch.uint8:
+                hold = hold.to(torch.uint8)
+            hold = hold.contiguous()
+            if hold.numel() != getattr(nat, "num_nodes", None):
+                raise ValueError("set_node_mask: keep must have one entry per node of the resident graph")
+            ptr = _ptr(hold)
+        with torch.cuda.device(dev):
+            rc = lib.tgnn_set_node_mask(nat.h, ptr, counts, C.c_void_p(st))      # synchronises (the counts come back)
+        _lib.check(nat.h, rc, "tgnn_set_node_mask")
+        return int(counts[0]), int(counts[1]), int(counts[2])
+
     def check_errors(self, synchronize=True):
         """Raise if a kernel of an earlier forward reported a device-side failure (tcgen05 pipeline or peer-exchange
         timeout).  ``tgnn_forward`` checks by itself for small graphs and at the next call for large ones; call this
