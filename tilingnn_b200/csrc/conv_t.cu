@@ -128,7 +128,7 @@ k_conv_t(ConvTArgs A) {
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NS]);
     const uint32_t bar_accf = smem_u32(&bars[2 * NS]), bar_acce = smem_u32(&bars[2 * NS + NT]);
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, PROD_WARPS * 32 + 1); mbar_init(bar_empty + 8 * i, 1); }
+        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, 32 + 1); mbar_init(bar_empty + 8 * i, 1); }      // one producer warp + its expect_tx
         for (int i = 0; i < NT; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 4); }     // the 4 warps of the owning group
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -147,42 +147,47 @@ k_conv_t(ConvTArgs A) {
 
     if (warp >= W_PROD0 && warp < W_MMA) {
         // ===================== producers: gather the block's 128 split rows into the swizzled A tile =====================
-        // instruction k of warp w covers rows 16k + 4w + (lane >> 3), 8 lanes per 128-byte row (whole lines per request);
-        // the source indices of the NEXT block are fetched before this block's copies are issued
+        // Producer warp pw takes the blocks with (block counter % 4) == pw -- a WHOLE block per warp, so four blocks'
+        // gathers are in flight and a warp has four block periods to cover the L2 latency of its index loads (measured:
+        // four warps sharing every block were bound by exactly that latency).  Indices: one coalesced 128-bit-per-4-lanes
+        // load per lane (rows 4 lane .. 4 lane + 3), fetched one own block ahead, handed out with shuffles.  Copy
+        // instruction k covers rows 4k .. 4k+3, 8 lanes per 128-byte row (whole lines per request).
         const int pw = warp - W_PROD0, c = lane & 7, sub = lane >> 3;
-        const int row0 = 4 * pw + sub;
-        int g = 0;                                        // blocks issued by this CTA
+        int g0 = 0;
         bool ok = true;
         for (int tile = blockIdx.x; ok && tile < A.n_tiles; tile += gridDim.x) {
             const int b0 = __ldg(A.bptr + tile), b1 = __ldg(A.bptr + tile + 1);
-            int idx[8], type = 0;
-            if (b0 < b1) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) idx[k] = __ldg(A.tsrc + (size_t)b0 * TBS + 16 * k + row0);
-                type = __ldg(A.btype + b0);
-            }
-            for (int blk = b0; blk < b1; ++blk, ++g) {
-                int nidx[8], ntype = 0;
-                if (blk + 1 < b1) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) nidx[k] = __ldg(A.tsrc + (size_t)(blk + 1) * TBS + 16 * k + row0);
-                    ntype = __ldg(A.btype + blk + 1);
+            const int first = b0 + ((pw - g0) & (PROD_WARPS - 1));
+            int4 idx = make_int4(-1, -1, -1, -1);
+            int type = 0;
+            if (first < b1) { idx = __ldg(reinterpret_cast<const int4*>(A.tsrc + (size_t)first * TBS) + lane); type = __ldg(A.btype + first); }
+            for (int blk = first; blk < b1; blk += PROD_WARPS) {
+                const int g = g0 + (blk - b0);
+                int4 nidx = make_int4(-1, -1, -1, -1);
+                int ntype = 0;
+                if (blk + PROD_WARPS < b1) {
+                    nidx = __ldg(reinterpret_cast<const int4*>(A.tsrc + (size_t)(blk + PROD_WARPS) * TBS) + lane);
+                    ntype = __ldg(A.btype + blk + PROD_WARPS);
                 }
                 const int s = g % NS;
                 if (!TGNN_TIMED(w0, mbar_wait_relaxed(bar_empty + 8 * s, (uint32_t)(((g / NS) & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }
                 const uint32_t a_tile = stage_base + (uint32_t)s * STAGE_BYTES, bar = bar_full + 8 * s;
-                if (pw == 0 && lane == 0) {
+                if (lane == 0) {
                     mbar_arrive_expect_tx(bar, B_BYTES);
                     bulk_g2s(a_tile + A_BYTES, A.tabT + (size_t)type * (B_BYTES / 4), B_BYTES, bar);
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (idx[k] >= 0) cp_async16(a_tile + sw128_off(16 * k + row0, c), A.xh + (size_t)idx[k] * 8 + c);
+                for (int k = 0; k < 32; ++k) {
+                    // row 4k + sub lives in component sub of lane k's int4
+                    const int sx = __shfl_sync(0xffffffffu, idx.x, k), sy = __shfl_sync(0xffffffffu, idx.y, k);
+                    const int sz = __shfl_sync(0xffffffffu, idx.z, k), sw = __shfl_sync(0xffffffffu, idx.w, k);
+                    const int src = sub == 0 ? sx : (sub == 1 ? sy : (sub == 2 ? sz : sw));
+                    if (src >= 0) cp_async16(a_tile + sw128_off(4 * k + sub, c), A.xh + (size_t)src * 8 + c);
+                }
                 cp_async_arrive(bar);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) idx[k] = nidx[k];
-                type = ntype;
+                idx = nidx; type = ntype;
             }
+            g0 += b1 - b0;
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer: four tcgen05.mma per block into TMEM buffer g % NT =====================

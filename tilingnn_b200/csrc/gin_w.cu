@@ -48,11 +48,13 @@ __device__ __forceinline__ float4 lds_row(uint32_t addr) { return lds128f(addr);
 template <bool HMLP>
 __global__ void __launch_bounds__(GW_THREADS, 1)
 k_gin_w(GinArgs A) {
-    extern __shared__ uint8_t smem_raw[];
+    // (no manual alignment of the dynamic shared memory: a pointer that went through an integer cast loses its address
+    // space and every access through it becomes a generic 64-bit LD/ST -- measured: the gather warps were bound by exactly
+    // that address arithmetic.  16-byte alignment is all the bulk copies and the 128-bit accesses need.)
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bars[4 + 2 * MLP_WARPS];   // win_full[2], win_empty[2], chunk_full[MLP_WARPS], chunk_empty[MLP_WARPS]
     __shared__ int meta_s[2][4];                                // per window buffer: {nseg (0 = direct), self_loc, -, -}
     __shared__ int timeout_flag;
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const uint32_t sbase = smem_u32(smem);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t bar_wf = smem_u32(&bars[0]), bar_we = smem_u32(&bars[2]), bar_cf = smem_u32(&bars[4]), bar_ce = smem_u32(&bars[4 + MLP_WARPS]);
@@ -105,6 +107,9 @@ k_gin_w(GinArgs A) {
         const int gw = warp - W_GATHER0;
         const int a = lane >> 3, q = lane & 7;
         const float self_w = 1.0f + A.eps;
+        int rk[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rk[k] = (k + 2 * a) & 7;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int b = it & 1;
@@ -112,7 +117,7 @@ k_gin_w(GinArgs A) {
             if (!TGNN_TIMED(w0, mbar_wait(bar_wf + 8 * b, ph))) { timeout_flag = 1; break; }
             const int nseg = meta_s[b][0], self_loc = meta_s[b][1];
             const int* ptr = reinterpret_cast<const int*>(smem + OFF_PTR + b * (PTR_INTS * 4));
-            const uint16_t* loc = reinterpret_cast<const uint16_t*>(smem + OFF_LOC + b * (GW_CAP * 2));
+            const uint32_t loc_s = sbase + OFF_LOC + (uint32_t)b * (GW_CAP * 2);
             const uint32_t win = sbase + OFF_WIN + (uint32_t)b * (GW_WMAX * 128) + (uint32_t)q * 16u;
             const int node0 = tile * GW_T, e_base = ptr[0];
             bool ok = true;
@@ -126,27 +131,27 @@ k_gin_w(GinArgs A) {
                 const int e0 = live ? ptr[r] : e_base, n_mine = live ? ptr[r + 1] - e0 : 0;
                 int n_max = max(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 8));       // warp-uniform trip count
                 n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, 16));
-                const int last = max(n_mine - 1, 0);
                 float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (nseg > 0) {
                     if (live) {
                         const float4 c = lds_row(win + (uint32_t)(self_loc + r) * 128u);
                         sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
                     }
-                    const uint16_t* lp = loc + (e0 - e_base);
                     // 16 rows in flight per lane (one gather warp per scheduler: the loads of a batch must cover the
                     // LDS -> address -> LDS.128 -> FADD chain of the previous one); same summation order as k_gin: batches of
                     // 8, each walked in the lane group's rotated order (k + 2a) -- with equal degrees the four groups' index
-                    // lists are a fixed distance apart and the same position would fall on one bank
+                    // lists are a fixed distance apart and the same position would fall on one bank.  Positions past the
+                    // row's last neighbour read a stale index (still inside the staging buffer) that is never used.
+                    const uint32_t lp = loc_s + 2u * (uint32_t)(e0 - e_base);
                     for (int o = 0; o < n_max; o += 16) {
                         uint32_t ad[16];
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) ad[k] = win + (uint32_t)lp[min(o + (k & 8) + ((k + 2 * a) & 7), last)] * 128u;
+                        for (int k = 0; k < 16; ++k) ad[k] = win + lds_u16(lp + 2u * (uint32_t)(o + (k & 8) + rk[k & 7])) * 128u;
                         float4 v[16];
 #pragma unroll
                         for (int k = 0; k < 16; ++k) {
                             v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (o + (k & 8) + ((k + 2 * a) & 7) < n_mine) v[k] = lds_row(ad[k]);
+                            if (o + (k & 8) + rk[k & 7] < n_mine) v[k] = lds_row(ad[k]);
                         }
 #pragma unroll
                         for (int k = 0; k < 16; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
@@ -157,6 +162,7 @@ k_gin_w(GinArgs A) {
                         const float4 c = ld_row4(A.xin, node, q);
                         sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
                     }
+                    const int last = max(n_mine - 1, 0);
                     for (int o = 0; o < n_max; o += 8) {
                         int idx[8];
 #pragma unroll

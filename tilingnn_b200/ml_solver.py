@@ -64,14 +64,18 @@ class ML_Solver:
 
     def _make_resident(self, layout):
         """Upload ``layout`` once and build its device structures; later calls with the same object are free."""
-        res = getattr(self, "_resident", None)
-        if res is not None and res[0] is layout:
-            return res[1]
+        if self._is_resident(layout):
+            return self._resident[1]
         x, ai, af, ci, _ = to_torch_tensor(self.device, layout.node_feature, layout.align_edge_index,
                                            layout.align_edge_features, layout.collide_edge_index)
         self.network.set_graph(x.shape[0], ai, af, ci)
-        self._resident = (layout, x)
+        self._resident = (layout, x, self.network._native.graph_serial)
         return x
+
+    def _is_resident(self, layout):
+        """``layout``'s structures are the ones on the GPU right now (no other graph was set on the network since)."""
+        res = getattr(self, "_resident", None)
+        return res is not None and res[0] is layout and res[2] == getattr(self.network._native, "graph_serial", None)
 
     def predict_sub_layout(self, origin_layout, keep):
         """Scores of the sub-layout of ``origin_layout`` induced by the nodes ``keep`` (ascending original indices) -- what
@@ -97,10 +101,9 @@ class ML_Solver:
         # the reference's empty edge set is ``np.array([])`` (len 0); a [2, 0] array means the same here
         if np.size(brick_layout.collide_edge_index) == 0 or np.size(brick_layout.align_edge_index) == 0:
             return np.ones(n, dtype=np.float32)                                   # :31-32
-        res = getattr(self, "_resident", None)
-        if res is not None and res[0] is brick_layout:                            # the layout the greedy rounds just ran on
+        if self.supports_node_mask and self._is_resident(brick_layout):          # the layout the greedy rounds just ran on
             self.network.set_node_mask(None)
-            return self.network.score(res[1]).detach().cpu().numpy()
+            return self.network.score(self._resident[1]).detach().cpu().numpy()
         x, ai, af, ci, _ = to_torch_tensor(self.device, brick_layout.node_feature, brick_layout.align_edge_index,
                                            brick_layout.align_edge_features, brick_layout.collide_edge_index)
         predictions, *_ = self.network(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci, col_e_features=None)

@@ -238,6 +238,7 @@ class TilinGNN(nn.Module):
         nat.graph_key = None
         _lib.check(nat.h, rc, "tgnn_set_graph")
         nat.num_nodes = int(num_nodes)
+        nat.graph_serial = getattr(nat, "graph_serial", 0) + 1      # lets callers notice that their resident graph was replaced
 
     def score(self, x, out=None):
         """One scoring pass on the resident graph: x [N, d_x] (CUDA) -> scores [N] fp32."""
@@ -422,4 +423,4 @@ class TilinGNN(nn.Module):
         buf = (C.c_int64 * 256)()
         _lib.check(nat.h, _lib.load().tgnn_debug_role_cycles(nat.h, buf), "tgnn_debug_role_cycles")
         v = list(buf)
-        return {"k_conv_t": [v[4 * w: 4 * w + 4] for w in range(9)], "k_gin_w": [v[128 + 4 * w: 128 + 4 * w + 4] for w in range(16)]}
+        return {"k_conv_t": [v[4 * w: 4 * w + 4] for w in range(13)], "k_gin_w": [v[128 + 4 * w: 128 + 4 * w + 4] for w in range(16)]}
