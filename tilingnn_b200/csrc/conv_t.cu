@@ -4,11 +4,12 @@
 // the per-edge product is executed by the SM's warps any more:
 //   * the A operand of one tcgen05.mma (M = 128) is a BLOCK of 128 same-type edges: their split rows (xh: 64 fp16 =
 //     128 B = exactly one SWIZZLE_128B row, written by the producers of b1) are gathered straight into the swizzled
-//     operand tile by the TMA engine: cp.async.bulk.tensor.2d ... tile::gather4 (UTMALDG.2D.GATHER4) takes FOUR row
-//     indices per instruction, so one producer warp (lane k = rows 4k .. 4k+3, indices from one coalesced load) puts a
-//     whole block in flight with a single warp instruction; empty slots carry row -1 = out of bounds = zero fill.
-//     (Measured first with per-lane cp.async: a thread can keep only a few 16-byte copies outstanding -- four warps
-//     per block were bound by the L2 latency of their index loads, one warp per block by the copy issue itself.)
+//     operand tile by cp.async (16 B x 8 per row, 8 lanes per row = whole 128-byte lines per request, completion on an
+//     mbarrier) -- no registers held across L2 latency, no fragment shuffling.  Producer TEAMS of four warps share a
+//     block (8 copies per thread); the source indices are fetched three blocks ahead.  Measured alternatives, all
+//     slower: one warp per block (32 copies per thread: the warp's outstanding-copy window serialises them, ~9000
+//     cycles per block), TMA tile::gather4 (UTMALDG.2D.GATHER4, correct, but ~75 cycles of TMA service per 512-byte
+//     instruction = 2400 cycles per block), indices only one block ahead (~950 cycles per block: L2 latency).
 //   * the B operand is the type's pre-swizzled [64 x 64] fp16 image (tables.cu), one TMA bulk copy per block:
 //       columns  0..31 : hi . Whi                       ("main")
 //       columns 32..63 : hi . Wlo + lo . Whi            ("small", scaled by 2^-11 in the epilogue)
@@ -30,9 +31,8 @@
 // producers, 12 MMA issuer.  Super-tiles of 512 rows: 2 x 64 KB of accumulator planes + 4 stages of 24 KB.
 // Range guard: fp16 operands overflow at 65504; when a range flag is raised (an activation or a root weight above
 // 60000) the kernel exits at once and k_conv_t_wide redoes the layer on the same blocks with plain fp32 FMAs.
-#include <cuda.h>
-
 #include <algorithm>
+#include <cstdlib>
 
 #include "hsplit.cuh"
 #include "tc_common.cuh"
@@ -46,9 +46,9 @@ constexpr int TBS = 128;                        // slots (edges) per block = UMM
 constexpr int NS = 4;                           // shared-memory stages (A tile + weight image)
 constexpr int NT = 4;                           // TMEM accumulator buffers (64 columns each)
 constexpr int A_BYTES = TBS * 128, B_BYTES = 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS, PROD_WARPS = 1;
-constexpr int W_PROD0 = EPI_WARPS, W_MMA = EPI_WARPS + PROD_WARPS;
-constexpr int CT_THREADS = (W_MMA + 1) * 32;
+constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS, TEAM_WARPS = 4;
+constexpr int W_PROD0 = EPI_WARPS;
+constexpr int ct_threads(int teams) { return (EPI_WARPS + teams * TEAM_WARPS + 1) * 32; }
 constexpr float LO_INV = 1.0f / 2048.f;
 
 // instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = 64
@@ -62,11 +62,9 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-// four rows (r.x .. r.w; out of range = zero fill) of the 2-D tensor behind `tmap` -> four consecutive 128-byte rows at dst
-// in the tensor map's SWIZZLE_128B pattern; completion = 512 transaction bytes on the mbarrier
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tmap, const int4& r, uint32_t bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
-                 ::"r"(dst), "l"(tmap), "r"(0), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w), "r"(bar) : "memory");
+// arrive on the mbarrier once all of this thread's earlier cp.async have landed (does not change the pending count)
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -120,8 +118,10 @@ __device__ __forceinline__ void finish_tile(const ConvTArgs& A, uint32_t acc_bas
     }
 }
 
-__global__ void __launch_bounds__(CT_THREADS, 1)
-k_conv_t(const __grid_constant__ CUtensorMap tmap_xh, ConvTArgs A) {
+template <int TEAMS>
+__global__ void __launch_bounds__(ct_threads(TEAMS), 1)
+k_conv_t(ConvTArgs A) {
+    constexpr int CT_THREADS = ct_threads(TEAMS), W_MMA = EPI_WARPS + TEAMS * TEAM_WARPS;
     if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) return;          // out of the fp16 range: k_conv_t_wide takes the layer
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * NS + 2 * NT];                  // full[NS], empty[NS], accf[NT], acce[NT]
@@ -135,7 +135,7 @@ k_conv_t(const __grid_constant__ CUtensorMap tmap_xh, ConvTArgs A) {
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NS]);
     const uint32_t bar_accf = smem_u32(&bars[2 * NS]), bar_acce = smem_u32(&bars[2 * NS + NT]);
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }           // the producer's expect_tx
+        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, TEAM_WARPS * 32 + 1); mbar_init(bar_empty + 8 * i, 1); }   // a team + its expect_tx
         for (int i = 0; i < NT; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 4); }     // the 4 warps of the owning group
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,45 +153,60 @@ k_conv_t(const __grid_constant__ CUtensorMap tmap_xh, ConvTArgs A) {
     const long long t_start = clock64();
 
     if (warp >= W_PROD0 && warp < W_MMA) {
-        // ===================== producer: one warp, one warp-wide gather4 per block =====================
-        // lane k owns rows 4k .. 4k+3 of every block: its four source indices come with ONE 16-byte load (the warp's load
-        // is a contiguous 512 bytes), fetched PREF blocks ahead so the TMA instructions never wait for L2
-        constexpr int PREF = 4;
-        int g = 0;
+        // ===================== producers: team t (4 warps) gathers the blocks with (block counter % TEAMS) == t =====================
+        // copy instruction k of team warp w covers rows 16k + 4w + (lane >> 3), 8 lanes per 128-byte row; every lane keeps the
+        // source indices of its 8 rows for the next PREF own blocks in registers (fetched that far ahead: nothing waits on L2)
+        constexpr int PREF = 3;
+        const int team = (warp - W_PROD0) / TEAM_WARPS, pw = (warp - W_PROD0) % TEAM_WARPS, c = lane & 7, sub = lane >> 3;
+        const int row0 = 4 * pw + sub;
+        int g0 = 0;
         bool ok = true;
         for (int tile = blockIdx.x; ok && tile < A.n_tiles; tile += gridDim.x) {
             const int b0 = __ldg(A.bptr + tile), b1 = __ldg(A.bptr + tile + 1);
-            const int4* src4 = reinterpret_cast<const int4*>(A.tsrc) + lane;
-            int4 idx[PREF];
-            int type[PREF];
+            const int first = b0 + ((team - g0) % TEAMS + TEAMS) % TEAMS;
+            int idx[PREF][8], type[PREF];
 #pragma unroll
             for (int j = 0; j < PREF; ++j) {
-                idx[j] = make_int4(-1, -1, -1, -1); type[j] = 0;
-                if (b0 + j < b1) { idx[j] = __ldg(src4 + (size_t)(b0 + j) * 32); type[j] = __ldg(A.btype + b0 + j); }
+                const int blk = first + j * TEAMS;
+                type[j] = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) idx[j][k] = -1;
+                if (blk < b1) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) idx[j][k] = __ldg(A.tsrc + (size_t)blk * TBS + 16 * k + row0);
+                    type[j] = __ldg(A.btype + blk);
+                }
             }
-            for (int blk = b0; blk < b1; blk += PREF) {
+            for (int base = first; base < b1; base += PREF * TEAMS) {
 #pragma unroll
                 for (int j = 0; j < PREF; ++j) {
-                    if (blk + j >= b1) break;
-                    const int4 cur = idx[j];
+                    const int blk = base + j * TEAMS;
+                    if (blk >= b1) break;
+                    int cur[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) cur[k] = idx[j][k];
                     const int ctype = type[j];
-                    if (blk + j + PREF < b1) {
-                        idx[j] = __ldg(src4 + (size_t)(blk + j + PREF) * 32);
-                        type[j] = __ldg(A.btype + blk + j + PREF);
+                    const int nblk = blk + PREF * TEAMS;
+                    if (nblk < b1) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) idx[j][k] = __ldg(A.tsrc + (size_t)nblk * TBS + 16 * k + row0);
+                        type[j] = __ldg(A.btype + nblk);
                     }
-                    const int s = g % NS;
+                    const int g = g0 + (blk - b0), s = g % NS;
                     if (!TGNN_TIMED(w0, mbar_wait_relaxed(bar_empty + 8 * s, (uint32_t)(((g / NS) & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }
                     const uint32_t a_tile = stage_base + (uint32_t)s * STAGE_BYTES, bar = bar_full + 8 * s;
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(bar, A_BYTES + B_BYTES);
+                    if (pw == 0 && lane == 0) {
+                        mbar_arrive_expect_tx(bar, B_BYTES);
                         bulk_g2s(a_tile + A_BYTES, A.tabT + (size_t)ctype * (B_BYTES / 4), B_BYTES, bar);
                     }
-                    __syncwarp();
-                    tma_gather4(a_tile + (uint32_t)lane * 512u, &tmap_xh, cur, bar);
-                    ++g;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (cur[k] >= 0) cp_async16(a_tile + sw128_off(16 * k + row0, c), A.xh + (size_t)cur[k] * 8 + c);
+                    cp_async_arrive(bar);
                 }
                 if (!ok) break;
             }
+            g0 += b1 - b0;
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer: four tcgen05.mma per block into TMEM buffer g % NT =====================
@@ -203,6 +218,7 @@ k_conv_t(const __grid_constant__ CUtensorMap tmap_xh, ConvTArgs A) {
                 const int s = g % NS, tb = g % NT;
                 if (!TGNN_TIMED(w0, mbar_wait(bar_acce + 8 * tb, (uint32_t)(((g / NT) & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }
                 if (!TGNN_TIMED(w1, mbar_wait(bar_full + 8 * s, (uint32_t)((g / NS) & 1)))) { timeout_flag = 1; ok = false; break; }
+                fence_proxy_async();                      // the A tile was written through the generic proxy (cp.async)
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_tile = stage_base + (uint32_t)s * STAGE_BYTES;
@@ -362,34 +378,6 @@ k_conv_t_wide(ConvTArgs A) {
     }
 }
 
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-        return reinterpret_cast<EncodeTiledFn>(p);
-    }();
-    return fn;
-}
-// xh as a 2-D tensor [n_rows][64 x 16-bit], rows of 128 bytes, box = ONE row (tile::gather4 brings four of them per
-// instruction), SWIZZLE_128B = the layout the UMMA descriptor of the A tile expects; out-of-range rows read as zero
-CUtensorMap make_xh_tensor_map(const uint4* xh, int64_t n_rows) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    TGNN_CHECK(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-    CUtensorMap m;
-    const cuuint64_t dims[2] = {64, (cuuint64_t)n_rows}, strides[1] = {128};
-    const cuuint32_t box[2] = {64, 1}, estr[2] = {1, 1};
-    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<uint4*>(xh), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    TGNN_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the split activation rows (code " + std::to_string((int)r) + ")");
-    return m;
-}
-
 size_t conv_t_smem(int rt) { return (size_t)EPI_GROUPS * rt * 128 + (size_t)NS * STAGE_BYTES + 1024; }
 
 }  // namespace
@@ -400,7 +388,8 @@ void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, cons
                    long long* dbg) {
     static PerDeviceOnce once;
     once.run([&] {
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(512)));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(512)));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(512)));
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_t_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 33 * 4));
     });
     ConvTArgs a{};
@@ -410,8 +399,9 @@ void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, cons
     a.flag_x = c.flag_x; a.flag_w = c.flag_w; a.err = err; a.mask = c.mask; a.dbg = dbg;
     a.n_own = c.n_own; a.n_tiles = g.t_tiles; a.rt = g.t_rows;
     const int blocks = conv_t_blocks(g.t_tiles, sm_count);
-    const CUtensorMap tmap = make_xh_tensor_map(c.xh, g.n_rows);
-    k_conv_t<<<blocks, CT_THREADS, conv_t_smem(g.t_rows), st>>>(tmap, a);
+    static const int teams = getenv("TGNN_CONV_T_TEAMS") ? atoi(getenv("TGNN_CONV_T_TEAMS")) : 1;
+    if (teams == 2) k_conv_t<2><<<blocks, ct_threads(2), conv_t_smem(g.t_rows), st>>>(a);
+    else k_conv_t<1><<<blocks, ct_threads(1), conv_t_smem(g.t_rows), st>>>(a);
     TGNN_CUDA(cudaGetLastError());
     // stand-by for the range guard: same grid (same BatchNorm partial layout), exits at once unless a flag is raised
     k_conv_t_wide<<<blocks, TBS, (size_t)g.t_rows * 33 * 4, st>>>(a);

@@ -11,12 +11,13 @@
 // and the gather warps read neighbour rows with LDS.128 at shared-memory latency:
 //   L2 -> SM traffic / 3.3, no dependent global load in the gather loop, indices 2 B instead of 4 B per edge.
 // Warp roles (16 warps = 512 threads x 128 registers, one CTA per SM, persistent over tiles):
-//   warps 0-10  node MLP on tensor cores (mma.sync): the four 16-node chunks of a tile go round-robin over the 11 warps
+//   warps 0-8   node MLP on tensor cores (mma.sync): the four 16-node chunks of a tile go round-robin over the 9 warps
 //               (each has its own chunk buffer and barrier pair),
 //               so three tiles' MLPs are in flight (one chunk is ~6000 cycles of dependent MMAs and sigmoids; the
 //               gather delivers a tile every ~2600) -- measured: with 4 MLP warps the kernel was MLP-latency-bound
-//   warps 11-14 gather-sum from the window (8 lanes per 128-byte row, 8 rows in flight per lane): shared-memory
-//               bandwidth bound, four warps keep 16 KB of LDS in flight
+//   warps 9-14  gather-sum from the window (8 lanes per 128-byte row, 16 rows in flight per lane; quads of 4 destination rows
+//               round-robin over the six warps).  This is the role that bounds the kernel: ~4100 shared-memory wavefronts
+//               per tile (2112 gathered rows + their indices + the MLP's weight fragments + the TMA fill)
 //   warp  15    producer: per tile <= 32 bulk copies (window runs), 1 for the uint16 indices, 1 for the row pointers
 // Tiles whose sources are not local (window > 656 rows / > 32 runs / > 4032 edges) are marked "direct" by the
 // builder and gathered from global memory by the same warps; graphs that are mostly direct keep k_gin.
@@ -32,7 +33,7 @@ namespace {
 using namespace ginx;
 using namespace tc;
 
-constexpr int GATHER_WARPS = 4, MLP_WARPS = GW_MLP_WARPS, CHUNKS_PER_TILE = GW_T / CH;
+constexpr int GATHER_WARPS = 6, MLP_WARPS = GW_MLP_WARPS, CHUNKS_PER_TILE = GW_T / CH, QUADS_PER_TILE = GW_T / 4;
 constexpr int W_GATHER0 = MLP_WARPS, W_PROD = MLP_WARPS + GATHER_WARPS;
 constexpr int GW_THREADS = (W_PROD + 1) * 32;
 constexpr int PTR_INTS = 68;                                    // 65 row pointers, padded to a multiple of 16 bytes
@@ -62,7 +63,7 @@ k_gin_w(GinArgs A) {
         for (int i = 0; i < 2; ++i) { mbar_init(bar_wf + 8 * i, 1); mbar_init(bar_we + 8 * i, GATHER_WARPS); }
         // chunk ci of the CTA (ci = 4 * tile iteration + chunk in tile) belongs to MLP warp ci % MLP_WARPS and is that warp's
         // (ci / MLP_WARPS)-th chunk: every party of a chunk barrier sees every one of its phases (a parity wait must not skip one)
-        for (int i = 0; i < MLP_WARPS; ++i) { mbar_init(bar_cf + 8 * i, GATHER_WARPS); mbar_init(bar_ce + 8 * i, 1); }
+        for (int i = 0; i < MLP_WARPS; ++i) { mbar_init(bar_cf + 8 * i, CH / 4); mbar_init(bar_ce + 8 * i, 1); }       // one arrival per quad of the chunk
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -122,11 +123,13 @@ k_gin_w(GinArgs A) {
             const int node0 = tile * GW_T, e_base = ptr[0];
             bool ok = true;
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS_PER_TILE; ++c) {
-                // rows 4 gw .. 4 gw + 3 of chunk c (this warp's quad) go into the chunk buffer of the MLP warp that owns it
-                const int ci = it * CHUNKS_PER_TILE + c, mw = ci % MLP_WARPS, use = ci / MLP_WARPS;
+            for (int qd = 0; qd < QUADS_PER_TILE; ++qd) {
+                // quads (4 destination rows, one per 8-lane group) go round-robin over the gather warps ACROSS tiles; a quad's
+                // sums go into the chunk buffer of the MLP warp that owns its chunk
+                if ((it * QUADS_PER_TILE + qd) % GATHER_WARPS != gw) continue;
+                const int c = qd >> 2, ci = it * CHUNKS_PER_TILE + c, mw = ci % MLP_WARPS, use = ci / MLP_WARPS;
                 float* S = reinterpret_cast<float*>(smem + OFF_S) + mw * (CH * XS);
-                const int r = CH * c + 4 * gw + a, node = node0 + r;
+                const int r = 4 * qd + a, node = node0 + r;
                 const bool live = node < A.n_own;
                 const int e0 = live ? ptr[r] : e_base, n_mine = live ? ptr[r + 1] - e0 : 0;
                 int n_max = max(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 8));       // warp-uniform trip count
@@ -178,7 +181,7 @@ k_gin_w(GinArgs A) {
                     }
                 }
                 if (!TGNN_TIMED(w1, mbar_wait(bar_ce + 8 * mw, (uint32_t)((use & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }   // its previous chunk is in registers
-                *reinterpret_cast<float4*>(S + (4 * gw + a) * XS + 4 * q) = sum;
+                *reinterpret_cast<float4*>(S + (4 * (qd & 3) + a) * XS + 4 * q) = sum;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_cf + 8 * mw);
             }
@@ -187,7 +190,7 @@ k_gin_w(GinArgs A) {
             if (lane == 0) mbar_arrive(bar_we + 8 * b);
         }
     } else {
-        // ===================== node MLP: chunk c of the CTA's it-th tile goes to warp (4 it + c) % 11 =====================
+        // ===================== node MLP: chunk c of the CTA's it-th tile goes to warp (4 it + c) % 9 =====================
         const GinW<HMLP> Wt(wsm);
         double s1[8], s2[8];
 #pragma unroll
