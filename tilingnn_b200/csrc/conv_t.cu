@@ -4,12 +4,12 @@
 // the per-edge product is executed by the SM's warps any more:
 //   * the A operand of one tcgen05.mma (M = 128) is a BLOCK of 128 same-type edges: their split rows (xh: 64 fp16 =
 //     128 B = exactly one SWIZZLE_128B row, written by the producers of b1) are gathered straight into the swizzled
-//     operand tile by cp.async (16 B x 8 per row, 8 lanes per row = whole 128-byte lines per request, completion on an
-//     mbarrier) -- no registers held across L2 latency, no fragment shuffling.  Producer TEAMS of four warps share a
-//     block (8 copies per thread); the source indices are fetched three blocks ahead.  Measured alternatives, all
-//     slower: one warp per block (32 copies per thread: the warp's outstanding-copy window serialises them, ~9000
-//     cycles per block), TMA tile::gather4 (UTMALDG.2D.GATHER4, correct, but ~75 cycles of TMA service per 512-byte
-//     instruction = 2400 cycles per block), indices only one block ahead (~950 cycles per block: L2 latency).
+//     operand tile by six producer warps: 16-byte loads into REGISTERS (8 lanes per 128-byte row = whole lines per
+//     request), three blocks of loads in flight per thread (~55 KB per SM), then swizzled 128-bit stores into the stage --
+//     the registers are the latency buffer, the loads run ahead of the shared-memory stages.  Measured alternatives on
+//     B200, all bound by the gather: cp.async (LDGSTS) keeps only ~8 copies per WARP outstanding (four warps per block:
+//     ~1000 cycles per block; one warp per block: ~9000); TMA tile::gather4 (UTMALDG.2D.GATHER4: correct, but ~75 cycles
+//     of TMA service per 512-byte instruction = 2400 cycles per block).
 //   * the B operand is the type's pre-swizzled [64 x 64] fp16 image (tables.cu), one TMA bulk copy per block:
 //       columns  0..31 : hi . Whi                       ("main")
 //       columns 32..63 : hi . Wlo + lo . Whi            ("small", scaled by 2^-11 in the epilogue)
@@ -46,9 +46,11 @@ constexpr int TBS = 128;                        // slots (edges) per block = UMM
 constexpr int NS = 4;                           // shared-memory stages (A tile + weight image)
 constexpr int NT = 4;                           // TMEM accumulator buffers (64 columns each)
 constexpr int A_BYTES = TBS * 128, B_BYTES = 64 * 128, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS, TEAM_WARPS = 4;
-constexpr int W_PROD0 = EPI_WARPS;
-constexpr int ct_threads(int teams) { return (EPI_WARPS + teams * TEAM_WARPS + 1) * 32; }
+constexpr int EPI_GROUPS = 2, EPI_WARPS = 4 * EPI_GROUPS, PROD_WARPS = 6, PROD_THREADS = PROD_WARPS * 32;
+constexpr int W_PROD0 = EPI_WARPS, W_MMA = EPI_WARPS + PROD_WARPS;
+constexpr int CT_THREADS = (W_MMA + 1) * 32;                     // 15 warps
+constexpr int CPB = (TBS * 8 + PROD_THREADS - 1) / PROD_THREADS;   // 16-byte pieces per producer thread per block (6)
+constexpr int PDEPTH = 3;                                       // blocks of row loads in flight per producer thread
 constexpr float LO_INV = 1.0f / 2048.f;
 
 // instruction descriptor: D = F32, A = B = F16, both K-major, M = 128, N = 64
@@ -118,10 +120,8 @@ __device__ __forceinline__ void finish_tile(const ConvTArgs& A, uint32_t acc_bas
     }
 }
 
-template <int TEAMS>
-__global__ void __launch_bounds__(ct_threads(TEAMS), 1)
+__global__ void __launch_bounds__(CT_THREADS, 1)
 k_conv_t(ConvTArgs A) {
-    constexpr int CT_THREADS = ct_threads(TEAMS), W_MMA = EPI_WARPS + TEAMS * TEAM_WARPS;
     if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) return;          // out of the fp16 range: k_conv_t_wide takes the layer
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * NS + 2 * NT];                  // full[NS], empty[NS], accf[NT], acce[NT]
@@ -135,7 +135,7 @@ k_conv_t(ConvTArgs A) {
     const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[NS]);
     const uint32_t bar_accf = smem_u32(&bars[2 * NS]), bar_acce = smem_u32(&bars[2 * NS + NT]);
     if (tid == 0) {
-        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, TEAM_WARPS * 32 + 1); mbar_init(bar_empty + 8 * i, 1); }   // a team + its expect_tx
+        for (int i = 0; i < NS; ++i) { mbar_init(bar_full + 8 * i, PROD_THREADS + 1); mbar_init(bar_empty + 8 * i, 1); }   // the producers + the expect_tx
         for (int i = 0; i < NT; ++i) { mbar_init(bar_accf + 8 * i, 1); mbar_init(bar_acce + 8 * i, 4); }     // the 4 warps of the owning group
         timeout_flag = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -153,60 +153,68 @@ k_conv_t(ConvTArgs A) {
     const long long t_start = clock64();
 
     if (warp >= W_PROD0 && warp < W_MMA) {
-        // ===================== producers: team t (4 warps) gathers the blocks with (block counter % TEAMS) == t =====================
-        // copy instruction k of team warp w covers rows 16k + 4w + (lane >> 3), 8 lanes per 128-byte row; every lane keeps the
-        // source indices of its 8 rows for the next PREF own blocks in registers (fetched that far ahead: nothing waits on L2)
-        constexpr int PREF = 3;
-        const int team = (warp - W_PROD0) / TEAM_WARPS, pw = (warp - W_PROD0) % TEAM_WARPS, c = lane & 7, sub = lane >> 3;
-        const int row0 = 4 * pw + sub;
-        int g0 = 0;
+        // ===================== producers: 16-byte piece id = k * 192 + p of the block's 128 x 8 pieces -> row id >> 3, piece id & 7 =====================
+        // Per tile: slot j of the register ring holds the pieces of block j, j + 3, ...; a block is retired (stored into its
+        // stage, fence, arrive) and the slot refilled with the loads of the block three ahead, whose source rows were fetched
+        // three blocks before that.
+        const int p = (warp - W_PROD0) * 32 + lane;
+        int g = 0;
         bool ok = true;
         for (int tile = blockIdx.x; ok && tile < A.n_tiles; tile += gridDim.x) {
-            const int b0 = __ldg(A.bptr + tile), b1 = __ldg(A.bptr + tile + 1);
-            const int first = b0 + ((team - g0) % TEAMS + TEAMS) % TEAMS;
-            int idx[PREF][8], type[PREF];
+            const int b0 = __ldg(A.bptr + tile), n = __ldg(A.bptr + tile + 1) - b0;
+            const int* tsrc = A.tsrc + (size_t)b0 * TBS;
+            uint4 buf[PDEPTH][CPB];
+            int idx[PDEPTH][CPB], type[PDEPTH];
+            auto load_idx = [&](int (&ix)[CPB], int& ty, int blk) {
 #pragma unroll
-            for (int j = 0; j < PREF; ++j) {
-                const int blk = first + j * TEAMS;
-                type[j] = 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) idx[j][k] = -1;
-                if (blk < b1) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) idx[j][k] = __ldg(A.tsrc + (size_t)blk * TBS + 16 * k + row0);
-                    type[j] = __ldg(A.btype + blk);
+                for (int k = 0; k < CPB; ++k) {
+                    const int id = k * PROD_THREADS + p;
+                    ix[k] = id < TBS * 8 ? __ldg(tsrc + (size_t)blk * TBS + (id >> 3)) : -1;
                 }
+                ty = __ldg(A.btype + b0 + blk);
+            };
+            auto load_rows = [&](uint4 (&bf)[CPB], const int (&ix)[CPB]) {
+#pragma unroll
+                for (int k = 0; k < CPB; ++k) {
+                    bf[k] = make_uint4(0u, 0u, 0u, 0u);                       // empty slot: a zero row (its result is never used)
+                    if (ix[k] >= 0) bf[k] = __ldg(A.xh + (size_t)ix[k] * 8 + ((k * PROD_THREADS + p) & 7));
+                }
+            };
+#pragma unroll
+            for (int j = 0; j < PDEPTH; ++j) if (j < n) load_idx(idx[j], type[j], j);
+            int cur_type[PDEPTH];                          // type of the block whose pieces sit in slot j
+#pragma unroll
+            for (int j = 0; j < PDEPTH; ++j) {
+                cur_type[j] = 0;
+                if (j < n) { load_rows(buf[j], idx[j]); cur_type[j] = type[j]; if (j + PDEPTH < n) load_idx(idx[j], type[j], j + PDEPTH); }
             }
-            for (int base = first; base < b1; base += PREF * TEAMS) {
+            for (int base = 0; ok && base < n; base += PDEPTH) {
 #pragma unroll
-                for (int j = 0; j < PREF; ++j) {
-                    const int blk = base + j * TEAMS;
-                    if (blk >= b1) break;
-                    int cur[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) cur[k] = idx[j][k];
-                    const int ctype = type[j];
-                    const int nblk = blk + PREF * TEAMS;
-                    if (nblk < b1) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) idx[j][k] = __ldg(A.tsrc + (size_t)nblk * TBS + 16 * k + row0);
-                        type[j] = __ldg(A.btype + nblk);
-                    }
-                    const int g = g0 + (blk - b0), s = g % NS;
+                for (int j = 0; j < PDEPTH; ++j) {
+                    const int i = base + j;
+                    if (i >= n) break;
+                    const int s = g % NS;
                     if (!TGNN_TIMED(w0, mbar_wait_relaxed(bar_empty + 8 * s, (uint32_t)(((g / NS) & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }
                     const uint32_t a_tile = stage_base + (uint32_t)s * STAGE_BYTES, bar = bar_full + 8 * s;
-                    if (pw == 0 && lane == 0) {
+                    if (p == 0) {
                         mbar_arrive_expect_tx(bar, B_BYTES);
-                        bulk_g2s(a_tile + A_BYTES, A.tabT + (size_t)ctype * (B_BYTES / 4), B_BYTES, bar);
+                        bulk_g2s(a_tile + A_BYTES, A.tabT + (size_t)cur_type[j] * (B_BYTES / 4), B_BYTES, bar);
                     }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        if (cur[k] >= 0) cp_async16(a_tile + sw128_off(16 * k + row0, c), A.xh + (size_t)cur[k] * 8 + c);
-                    cp_async_arrive(bar);
+                    for (int k = 0; k < CPB; ++k) {
+                        const int id = k * PROD_THREADS + p;
+                        if (id < TBS * 8) sts128(a_tile + sw128_off(id >> 3, id & 7), buf[j][k]);
+                    }
+                    fence_proxy_async();                                      // generic-proxy stores -> visible to the tensor core's reads
+                    mbar_arrive(bar);
+                    ++g;
+                    if (i + PDEPTH < n) {
+                        load_rows(buf[j], idx[j]);                            // idx[j] holds the rows of block i + PDEPTH
+                        cur_type[j] = type[j];
+                        if (i + 2 * PDEPTH < n) load_idx(idx[j], type[j], i + 2 * PDEPTH);
+                    }
                 }
-                if (!ok) break;
             }
-            g0 += b1 - b0;
         }
     } else if (warp == W_MMA) {
         // ===================== MMA issuer: four tcgen05.mma per block into TMEM buffer g % NT =====================
@@ -218,7 +226,6 @@ k_conv_t(ConvTArgs A) {
                 const int s = g % NS, tb = g % NT;
                 if (!TGNN_TIMED(w0, mbar_wait(bar_acce + 8 * tb, (uint32_t)(((g / NT) & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }
                 if (!TGNN_TIMED(w1, mbar_wait(bar_full + 8 * s, (uint32_t)((g / NS) & 1)))) { timeout_flag = 1; ok = false; break; }
-                fence_proxy_async();                      // the A tile was written through the generic proxy (cp.async)
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_tile = stage_base + (uint32_t)s * STAGE_BYTES;
@@ -388,8 +395,7 @@ void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, cons
                    long long* dbg) {
     static PerDeviceOnce once;
     once.run([&] {
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(512)));
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(512)));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_t_smem(512)));
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_t_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 33 * 4));
     });
     ConvTArgs a{};
@@ -399,9 +405,7 @@ void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, cons
     a.flag_x = c.flag_x; a.flag_w = c.flag_w; a.err = err; a.mask = c.mask; a.dbg = dbg;
     a.n_own = c.n_own; a.n_tiles = g.t_tiles; a.rt = g.t_rows;
     const int blocks = conv_t_blocks(g.t_tiles, sm_count);
-    static const int teams = getenv("TGNN_CONV_T_TEAMS") ? atoi(getenv("TGNN_CONV_T_TEAMS")) : 1;
-    if (teams == 2) k_conv_t<2><<<blocks, ct_threads(2), conv_t_smem(g.t_rows), st>>>(a);
-    else k_conv_t<1><<<blocks, ct_threads(1), conv_t_smem(g.t_rows), st>>>(a);
+    k_conv_t<<<blocks, CT_THREADS, conv_t_smem(g.t_rows), st>>>(a);
     TGNN_CUDA(cudaGetLastError());
     // stand-by for the range guard: same grid (same BatchNorm partial layout), exits at once unless a flag is raised
     k_conv_t_wide<<<blocks, TBS, (size_t)g.t_rows * 33 * 4, st>>>(a);

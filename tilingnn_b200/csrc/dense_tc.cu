@@ -248,6 +248,7 @@ k_dense_tc(DenseTcArgs A) {
             const bool live = row < A.n;
             int nv = A.n - (row0 + 32 * q);
             nv = nv < 0 ? 0 : (nv > 32 ? 32 : nv);
+            const unsigned keepbits = __ballot_sync(0xffffffffu, !live || row_kept(A.mask, row));   // bit r: row 32 q + r is kept
 #pragma unroll 1
             for (int c0 = 0; c0 < NOUT; c0 += 32) {
                 uint32_t v[32];
@@ -264,20 +265,21 @@ k_dense_tc(DenseTcArgs A) {
                 float s1f[4] = {0.f, 0.f, 0.f, 0.f}, s2f[4] = {0.f, 0.f, 0.f, 0.f};
                 float* orow = A.out + (size_t)(row0 + 32 * q) * NOUT + c0 + lane;
                 int r = 0;
-                for (; r + 4 <= nv; r += 4) {
+                if (keepbits == 0xffffffffu) {                                // no masked row in this 32-row block: the plain loop
+                    for (; r + 4 <= nv; r += 4) {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float o = lds_f32(sc + 4 * ((r + u) * 36 + lane)) + bias_c;
-                        o = fmaxf(o, o * LEAKY);
-                        if (!row_kept(A.mask, row0 + 32 * q + r + u)) o = 0.f;
-                        orow[(size_t)(r + u) * NOUT] = o;
-                        s1f[u] += o; s2f[u] = fmaf(o, o, s2f[u]);
+                        for (int u = 0; u < 4; ++u) {
+                            float o = lds_f32(sc + 4 * ((r + u) * 36 + lane)) + bias_c;
+                            o = fmaxf(o, o * LEAKY);
+                            orow[(size_t)(r + u) * NOUT] = o;
+                            s1f[u] += o; s2f[u] = fmaf(o, o, s2f[u]);
+                        }
                     }
                 }
                 for (; r < nv; ++r) {
                     float o = lds_f32(sc + 4 * (r * 36 + lane)) + bias_c;
                     o = fmaxf(o, o * LEAKY);
-                    if (!row_kept(A.mask, row0 + 32 * q + r)) o = 0.f;
+                    if (!((keepbits >> r) & 1u)) o = 0.f;                     // node mask: the row is stored as zero
                     orow[(size_t)r * NOUT] = o;
                     s1f[0] += o; s2f[0] = fmaf(o, o, s2f[0]);
                 }

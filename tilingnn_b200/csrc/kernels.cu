@@ -308,8 +308,9 @@ k_init(InitArgs A) {
         for (int c = 0; c < 32; ++c) tl[lane * 33 + c] = v[c];
         __syncwarp();
         const int n_here = min(32, A.n_own - base);
+        const unsigned keepbits = __ballot_sync(0xffffffffu, node >= A.n_own || row_kept(A.mask, node));    // bit j: node base + j is kept
         for (int j = 0; j < n_here; ++j) {
-            const bool kept = row_kept(A.mask, base + j);
+            const bool kept = (keepbits >> j) & 1u;
             const float val = kept ? tl[j * 33 + lane] : 0.f;
             if (MODE == 2) {
                 const float o2 = kept ? fmaf((val - cf[1][lane]) - cf[1][32 + lane], cf[1][64 + lane], cf[1][96 + lane]) : 0.f;
