@@ -398,15 +398,15 @@ void choose_conv_kernel(tgnn_handle* h) {
     h->use_h = !h->use_s && !h->use_t && !h->conv_chunk_only;
 }
 
-// The tcgen05 edge-block kernel (conv_t.cu) wants long same-type runs per super-tile (blocks of 128 slots, four
-// destination classes): worth building for large graphs with few edge types.  Rows per super-tile: as many as still
-// give every SM two tiles.  0 = do not build the format.
+// The tcgen05 edge-block kernel (conv_t.cu) is OPT-IN (TGNN_CONV=t, 256-row super-tiles; TGNN_CONV_T_ROWS=512 for large
+// graphs).  Measured on B200 at 1M nodes x deg 32 (profiles/r2): its MMA and epilogue side runs at ~450 cycles per
+// 128-edge block, but every way of gathering the blocks' rows (cp.async, TMA gather4, register-staged loads) delivers
+// only ~2.6-3.2 TB/s of scattered 128-byte rows out of L2, i.e. 1.3-2.7 ms per launch against the 1.14 ms of k_conv_h,
+// whose dst-tile-local walk gets 28 % of its rows from L1.  0 = do not build the format.
 int want_t_rows(tgnn_handle* h, int64_t n_own) {
-    if (h->conv_t_only) return 256;
-    if (h->conv_h_only || h->conv_s_only || h->conv_chunk_only) return 0;
+    if (!h->conv_t_only) return 0;
     if (getenv("TGNN_CONV_T_ROWS")) { const int r = atoi(getenv("TGNN_CONV_T_ROWS")); if (r == 256 || r == 512) return r; }
-    if (n_own >= (int64_t)2 * h->sm_count * 512) return 512;
-    return 0;
+    return n_own >= (int64_t)2 * h->sm_count * 512 ? 512 : 256;
 }
 
 // Staged-window collision kernel (gin_w.cu): worth it when the graph is large enough to fill the SMs with 64-row tiles
