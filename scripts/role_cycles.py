@@ -22,4 +22,4 @@ for k, rows in net.debug_role_cycles().items():
     print(k)
     for w, r in enumerate(rows):
         if r[0]:
-            print(f"  warp {w:2d}: cycles {r[0]:>10d}  wait0 {r[1]:>10d} ({100 * r[1] / r[0]:5.1f}%)  wait1 {r[2]:>10d} ({100 * r[2] / r[0]:5.1f}%)")
+            print(f"  warp {w:2d}: cycles {r[0]:>10d}  wait0 {r[1]:>10d} ({100 * r[1] / r[0]:5.1f}%)  wait1 {r[2]:>10d} ({100 * r[2] / r[0]:5.1f}%)  wait2 {r[3]:>10d} ({100 * r[3] / r[0]:5.1f}%)")

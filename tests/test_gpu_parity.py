@@ -158,9 +158,10 @@ def test_synthetic_configs_vs_oracle(dev, n, deg, mode):
     assert err <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["chunk", "s", "h", "t"])
+@pytest.mark.parametrize("kernel", ["chunk", "s", "h", "t", "z"])
 def test_all_adjacency_kernels(dev, kernel, monkeypatch):
-    """The fp16-split edge-chunk kernel, its 3xTF32 twin, the tcgen05 S kernel and the tcgen05 edge-block kernel are
+    """The fp16-split edge-chunk kernel, its 3xTF32 twin, the tcgen05 S kernel, the tcgen05 edge-block kernel and the
+    windowed tcgen05 kernel (A operand in tensor memory) are
     selected per graph by size / a cost model; force each (TGNN_CONV) on the shipped checkpoint (20 edge types) and on a
     synthetic graph (51 types)."""
     monkeypatch.setenv("TGNN_CONV", kernel)
@@ -178,7 +179,33 @@ def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     print(f"TGNN_CONV={kernel}: max err {err:.2e}")
     assert err <= TOL
     info = net.info()
-    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2, "t": 3}[kernel] and info["range_fallback_layers"] == 0
+    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2, "t": 3, "z": 4}[kernel] and info["range_fallback_layers"] == 0
+
+
+def test_conv_z_multi_edges_isolated_rows_and_mask(dev, monkeypatch):
+    """k_conv_z builds one A row per (destination, edge type): duplicate edges and several same-type in-edges are summed
+    in fp32 by the gather thread, destinations without in-edges give zero rows (mean -> 0, root term only), self loops
+    are ordinary adjacency edges.  Lattice graph with all of these added, against the fp64 oracle."""
+    monkeypatch.setenv("TGNN_CONV", "z")
+    from tilingnn_b200 import synthetic as syn
+    n = 5000
+    x, ai, af, ci = syn.lattice_graph(n, 16, 16, seed=5)
+    g = torch.Generator().manual_seed(7)
+    keep = (ai[1] % 37 != 3)                                    # destinations 3, 40, 77, ... lose all in-edges
+    ai, af = ai[:, keep], af[keep]
+    dup = torch.randint(0, ai.shape[1], (4000,), generator=g)   # duplicate edges (same feature row -> same type)
+    loops = torch.arange(0, n, 11)
+    ai = torch.cat([ai, ai[:, dup], torch.stack([loops, loops])], 1)
+    af = torch.cat([af, af[dup], af[:loops.numel()]], 0)
+    p = orc.make_params(3, 19, 4, seed=5)
+    for mode in ("train", "eval"):
+        q = orc.calibrate_running_stats(p, x, ai, af, ci, depth=4) if mode == "eval" else p
+        gold = orc.forward(q, x, ai, af, ci, depth=4, bn_mode=mode, dtype=torch.float64)[:, 0].numpy()
+        net = make_net(q, 3, 19, 4, dev, mode)
+        err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
+        net.check_errors()
+        print(f"k_conv_z multi-edge lattice {mode}: max err {err:.2e}")
+        assert net.info()["conv_kernel"] == 4 and err <= TOL
 
 
 def test_gin_mlp_on_3xtf32(dev, monkeypatch):
@@ -463,7 +490,7 @@ def test_graph_replay_of_repeated_forwards(dev):
         assert np.abs(s.double().cpu().numpy() - gold).max() <= TOL
 
 
-@pytest.mark.parametrize("var,val", [("TGNN_GINW", "1"), ("TGNN_CONV", "t")])
+@pytest.mark.parametrize("var,val", [("TGNN_GINW", "1"), ("TGNN_CONV", "t"), ("TGNN_CONV", "z")])
 def test_persistent_pipelines_over_many_tiles(dev, var, val, monkeypatch):
     """k_gin_w and k_conv_t are persistent kernels whose mbarrier pipelines run for dozens of tiles per CTA at benchmark
     sizes (the small parity cases give every CTA a single tile).  Size-independent property on a 300k-node graph the
@@ -479,7 +506,7 @@ def test_persistent_pipelines_over_many_tiles(dev, var, val, monkeypatch):
     b = net(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci)[0].clone()
     net.check_errors()
     info = net.info()
-    assert (info["gin_kernel"] == 1) if var == "TGNN_GINW" else (info["conv_kernel"] == 3)
+    assert (info["gin_kernel"] == 1) if var == "TGNN_GINW" else (info["conv_kernel"] == {"t": 3, "z": 4}[val])
     err = (a - b).abs().max().item()
     print(f"{var}={val} vs baseline kernels on 300k nodes: max diff {err:.2e}")
     assert torch.isfinite(b).all() and err <= 2e-5

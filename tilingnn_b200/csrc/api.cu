@@ -112,7 +112,8 @@ struct tgnn_handle {
     bool conv_s_only = false;                       // TGNN_CONV=s forces the tcgen05 S kernel whenever its format exists
     bool conv_h_only = false;                       // TGNN_CONV=h forces the fp16-split edge-chunk kernel (never S)
     bool conv_t_only = false;                       // TGNN_CONV=t forces the tcgen05 edge-block kernel (any graph size, 256-row super-tiles)
-    bool use_s = false, use_h = false, use_t = false;   // decided per graph in set_graph
+    bool conv_z_only = false;                       // TGNN_CONV=z forces the windowed tcgen05 kernel whenever every tile gets a window
+    bool use_s = false, use_h = false, use_t = false, use_z = false;   // decided per graph in set_graph
     bool need_xh() const { return use_h || use_t; }  // the fp16-split copy of b1 is an operand of both kernels
     DevBuf tabT, tab32;                             // [L][K+1] pre-swizzled fp16 weight images / plain fp32 tables of k_conv_t (+ stand-by)
     int tile_rows_forced = 0;                       // TGNN_TILE=64|128 (A/B runs)
@@ -380,9 +381,9 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
         h->tabT.reserve(slots * TG_TIMG32 * sizeof(uint32_t));
         h->tab32.reserve(slots * F * F * sizeof(float));
     }
-    if (h->use_s) h->tabS.reserve(slots * TG_FRAG32 * sizeof(float));
+    if (h->use_s || h->use_z) h->tabS.reserve(slots * TG_FRAG32 * sizeof(float));
     launch_edge_tables(h->g.type_rows.as<float>(), K, h->cfg.d_e, nl, h->table_layers.as<TableLayer>() + l0, h->tab.as<float>(),
-                       h->use_s ? h->tabS.as<float>() : nullptr, h->use_h ? h->tabH.as<uint32_t>() : nullptr,
+                       (h->use_s || h->use_z) ? h->tabS.as<float>() : nullptr, h->use_h ? h->tabH.as<uint32_t>() : nullptr,
                        h->use_t ? h->tabT.as<uint32_t>() : nullptr, h->use_t ? h->tab32.as<float>() : nullptr,
                        h->need_xh() ? h->wflag(l0) : nullptr, st);
     if (layer < 0) h->tables_dirty = false;
@@ -391,11 +392,22 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
 // Cost model from B200 measurements (1M nodes, deg 32, 51 types): the edge-chunk mma.sync kernel costs ~72 ps per
 // adjacency edge, the tcgen05 S kernel ~5.9 ns per (128-row tile, edge type) pass -> S pays off when the tiles see
 // few types relative to their edge count (the shipped tile graphs: 20-41 types), chunk when types are many.
-void choose_conv_kernel(tgnn_handle* h) {
-    h->use_s = h->g.has_s && !h->conv_h_only && (h->conv_s_only || (double)h->g.s_passes * S_EDGES_PER_PASS_BREAK_EVEN < (double)h->g.e_adj);
-    h->use_t = h->g.has_t && !h->conv_h_only && !h->conv_s_only && !h->conv_chunk_only;
+// The windowed tcgen05 kernel (conv_z.cu) works on the same S format with ~0.2 us per pass: it takes over when a pass
+// carries more than ~24 edges, every tile gets a window and there are enough 128-row tiles for the SMs.
+void choose_conv_kernel(tgnn_handle* h, cudaStream_t st) {
+    h->use_z = false; h->g.has_z = false;
+    const bool others_forced = h->conv_h_only || h->conv_s_only || h->conv_chunk_only || h->conv_t_only;
+    if (h->g.s_built && !others_forced && h->g.s_max_pass <= ZW_MAX_PASS &&
+        (h->conv_z_only || (h->g.n_own >= Z_MIN_NODES && h->g.s_tiles >= h->sm_count &&
+                            (double)h->g.s_passes * Z_EDGES_PER_PASS_BREAK_EVEN < (double)h->g.e_adj))) {
+        h->g.has_z = build_z_windows(h->g, h->scratch, st) == 0;
+        h->use_z = h->g.has_z;
+    }
+    h->use_s = !h->use_z && h->g.has_s && !h->conv_h_only && !h->conv_z_only &&
+               (h->conv_s_only || (double)h->g.s_passes * S_EDGES_PER_PASS_BREAK_EVEN < (double)h->g.e_adj);
+    h->use_t = h->g.has_t && !h->conv_h_only && !h->conv_s_only && !h->conv_chunk_only && !h->use_z;
     if (h->use_t) h->use_s = false;
-    h->use_h = !h->use_s && !h->use_t && !h->conv_chunk_only;
+    h->use_h = !h->use_s && !h->use_t && !h->use_z && !h->conv_chunk_only;
 }
 
 // The tcgen05 edge-block kernel (conv_t.cu) is OPT-IN (TGNN_CONV=t, 256-row super-tiles; TGNN_CONV_T_ROWS=512 for large
@@ -424,7 +436,7 @@ void choose_gin_kernel(tgnn_handle* h, cudaStream_t st) {
 // 128-row warp tiles give longer same-type runs (half the weight-table reloads, ~10 % fewer padded slots) but only 12
 // resident warps per SM instead of 16; measured on B200 at 1M nodes x deg 32 the two cancel (7.5 vs 7.3 ms per forward),
 // so 64 stays the default and TGNN_TILE=128 is kept for A/B runs.
-int want_s_mode(tgnn_handle* h) { return h->conv_s_only ? 2 : ((h->conv_chunk_only || h->conv_h_only || h->conv_t_only) ? 0 : 1); }
+int want_s_mode(tgnn_handle* h) { return (h->conv_s_only || h->conv_z_only) ? 2 : ((h->conv_chunk_only || h->conv_h_only || h->conv_t_only) ? 0 : 1); }
 int tile_rows_for(tgnn_handle* h, int64_t) { return h->tile_rows_forced ? h->tile_rows_forced : WN_SMALL; }
 
 void alloc_workspace(tgnn_handle* h) {
@@ -670,7 +682,11 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn;
         lz.begin("conv");
-        if (h->use_s) {
+        if (h->use_z) {
+            launch_conv_z(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->err_dev, h->sm_count, st,
+                          h->role_dbg_on ? h->role_dbg.as<long long>() : nullptr);
+            lz.end(1);
+        } else if (h->use_s) {
             launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->err_dev, h->sm_count, st);
             lz.end(1);
         } else if (h->use_t) {
@@ -711,7 +727,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         } else launch_gin(ga, h->sm_count, st);
         lz.end(1);
 
-        const int np_a = h->use_s ? h->g.s_tiles : (h->use_t ? conv_t_num_parts(h->g.t_tiles, h->sm_count) : np_conv);
+        const int np_a = (h->use_s || h->use_z) ? h->g.s_tiles : (h->use_t ? conv_t_num_parts(h->g.t_tiles, h->sm_count) : np_conv);
         // small graphs: k_combine finishes the two BatchNorms in its prologue (one launch less per layer)
         const bool fin_in_combine = train && h->world == 1 && np_a + np_gin <= 1024;
         CombineFin cf{};
@@ -898,6 +914,7 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->conv_s_only = csel && std::string(csel) == "s";
         h->conv_h_only = csel && std::string(csel) == "h";
         h->conv_t_only = csel && std::string(csel) == "t";
+        h->conv_z_only = csel && std::string(csel) == "z";
         const char* tsel = getenv("TGNN_TILE");
         if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
         h->hflags.reserve((size_t)(2 * cfg->depth + 3) * sizeof(int));
@@ -985,7 +1002,7 @@ int tgnn_set_graph(tgnn_handle* h, int64_t n_nodes, int64_t e_adj, const int64_t
         build_graph(h->g, h->scratch, h->cfg.d_e, n_nodes, n_nodes, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src,
                     col_dst, want_s_mode(h), tile_rows_for(h, n_nodes), want_t_rows(h, n_nodes), st);
         h->g.n_global = n_nodes; h->g.halo_slot = 0; h->g.n_send = 0;
-        choose_conv_kernel(h);
+        choose_conv_kernel(h, st);
         choose_gin_kernel(h, st);
         alloc_workspace(h);
         h->tables_dirty = true;
@@ -1039,7 +1056,7 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
         build_graph(h->g, h->scratch, h->cfg.d_e, n_own, n_rows, e_adj, adj_src, adj_dst, adj_feat, e_col, col_src, col_dst,
                     want_s_mode(h), tile_rows_for(h, n_own), want_t_rows(h, n_own), st);
         h->g.n_global = n_global; h->g.halo_slot = halo_slot; h->g.n_send = n_send;
-        choose_conv_kernel(h);
+        choose_conv_kernel(h, st);
         choose_gin_kernel(h, st);
         if (n_send > 0) {
             std::vector<int64_t> rows64(n_send);
@@ -1070,7 +1087,7 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         out->launches_per_forward = h->launches;
         out->workspace_bytes = (int64_t)h->workspace_bytes;
         out->collectives_per_forward = h->collectives;
-        out->conv_kernel = h->use_s ? 1 : (h->use_t ? 3 : (h->use_h ? 2 : 0));
+        out->conv_kernel = h->use_z ? 4 : (h->use_s ? 1 : (h->use_t ? 3 : (h->use_h ? 2 : 0)));
         out->tile_rows = h->g.wn;
         out->peer_exchange = h->px.ok ? 1 : 0;
         out->t_rows = h->g.has_t ? h->g.t_rows : 0;

@@ -534,12 +534,14 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
                                                     chunk_base, db, g.csrc.as<int>(), g.cdst.as<uint8_t>());
         k_pair_parity<<<nblk(n_chunks * (CH / GRP)), TPB, 0, st>>>(g.csrc.as<int>(), g.cdst.as<uint8_t>(), n_chunks * (CH / GRP));
         // ---------------- adjacency: S format (tcgen05 kernel) -----------------------------------------
-        g.has_s = false;
+        g.has_s = false; g.s_built = false; g.has_z = false;
         // the S format costs a 64-bit sort; in "auto" mode (want_s == 1) it is only built when the tcgen05 kernel could be
         // chosen at all: it needs ~164 edges per (128-row tile, type) pass to beat the fp16 edge-chunk kernel
         const double passes_est = 0.8 * (double)((n_own + S_BM - 1) / S_BM) *
                                   std::min<double>((double)n_types, (double)e_adj * S_BM / (double)n_own);
-        const bool s_may_win = want_s >= 2 || passes_est * S_EDGES_PER_PASS_BREAK_EVEN < (double)e_adj;
+        // (k_conv_z, which works on the same format, breaks even at far fewer edges per pass, but needs enough tiles)
+        const bool s_may_win = want_s >= 2 || passes_est * S_EDGES_PER_PASS_BREAK_EVEN < (double)e_adj ||
+                               (n_own >= Z_MIN_NODES && passes_est * Z_EDGES_PER_PASS_BREAK_EVEN < (double)e_adj);
         if (want_s && s_may_win && n_types <= S_MAX_TYPES) {
             g.s_tiles = (int)((n_own + S_BM - 1) / S_BM);
             k_s_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, k0, id0);
@@ -563,6 +565,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
             k_cptr_first<<<1, 32, 0, st>>>(g.s_pptr.as<int>());
             incl_max(sc, s_tile_end, g.s_pptr.as<int>() + 1, g.s_tiles, st);
             g.s_max_pass = read_int(s_maxlen, st);
+            g.s_built = true;
             g.has_s = g.s_max_pass <= 160;          // four passes in flight must fit the kernel's 640-row ring
         }
         // ---------------- adjacency: T format (tcgen05 edge-block kernel) --------------------------------
@@ -618,7 +621,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
             g.has_t = true;
         }
     } else {
-        g.has_s = false; g.has_t = false;
+        g.has_s = false; g.has_t = false; g.s_built = false; g.has_z = false;
         TGNN_CUDA(cudaMemsetAsync(g.cptr.p, 0, (size_t)(g.n_tiles + 1) * sizeof(int), st));
     }
     k_inv_deg<<<nblk(n_own), TPB, 0, st>>>(deg, n_own, g.inv_deg.as<float>());

@@ -423,4 +423,4 @@ class TilinGNN(nn.Module):
         buf = (C.c_int64 * 256)()
         _lib.check(nat.h, _lib.load().tgnn_debug_role_cycles(nat.h, buf), "tgnn_debug_role_cycles")
         v = list(buf)
-        return {"k_conv_t": [v[4 * w: 4 * w + 4] for w in range(15)], "k_gin_w": [v[128 + 4 * w: 128 + 4 * w + 4] for w in range(16)]}
+        return {"k_conv_t|z": [v[4 * w: 4 * w + 4] for w in range(16)], "k_gin_w": [v[128 + 4 * w: 128 + 4 * w + 4] for w in range(16)]}
