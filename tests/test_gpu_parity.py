@@ -158,7 +158,7 @@ def test_synthetic_configs_vs_oracle(dev, n, deg, mode):
     assert err <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["chunk", "s", "h", "t", "z"])
+@pytest.mark.parametrize("kernel", ["chunk", "s", "h", "t", "z", "z32"])
 def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     """The fp16-split edge-chunk kernel, its 3xTF32 twin, the tcgen05 S kernel, the tcgen05 edge-block kernel and the
     windowed tcgen05 kernel (A operand in tensor memory) are
@@ -179,14 +179,15 @@ def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     print(f"TGNN_CONV={kernel}: max err {err:.2e}")
     assert err <= TOL
     info = net.info()
-    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2, "t": 3, "z": 4}[kernel] and info["range_fallback_layers"] == 0
+    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2, "t": 3, "z": 4, "z32": 4}[kernel] and info["range_fallback_layers"] == 0
 
 
-def test_conv_z_multi_edges_isolated_rows_and_mask(dev, monkeypatch):
+@pytest.mark.parametrize("variant", ["z", "z32"])
+def test_conv_z_multi_edges_isolated_rows_and_mask(dev, variant, monkeypatch):
     """k_conv_z builds one A row per (destination, edge type): duplicate edges and several same-type in-edges are summed
     in fp32 by the gather thread, destinations without in-edges give zero rows (mean -> 0, root term only), self loops
     are ordinary adjacency edges.  Lattice graph with all of these added, against the fp64 oracle."""
-    monkeypatch.setenv("TGNN_CONV", "z")
+    monkeypatch.setenv("TGNN_CONV", variant)
     from tilingnn_b200 import synthetic as syn
     n = 5000
     x, ai, af, ci = syn.lattice_graph(n, 16, 16, seed=5)
@@ -221,11 +222,11 @@ def test_gin_mlp_on_3xtf32(dev, monkeypatch):
     assert err <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["h", "t"])
+@pytest.mark.parametrize("kernel", ["h", "t", "z"])
 def test_fp16_range_guard_hands_layers_to_the_tf32_kernel(dev, kernel, monkeypatch):
-    """k_conv_h / k_conv_t work on fp16-split operands; activations beyond +-60000 (here: a BatchNorm gain of 1e6 in
+    """k_conv_h / k_conv_t / k_conv_z<fp16> work on fp16-split operands; activations beyond +-60000 (here: a BatchNorm gain of 1e6 in
     layer 0) and root weights beyond it (layer 2) must raise the range flags so the 3xTF32 arithmetic (k_conv_h) / the
-    fp32 stand-by kernel (k_conv_t) takes those layers."""
+    fp32 stand-by kernel (k_conv_t) / the tf32 variant (k_conv_z) takes those layers."""
     monkeypatch.setenv("TGNN_CONV", kernel)
     from tilingnn_b200 import synthetic as syn
     x, ai, af, ci = syn.lattice_graph(3000, 8, 8, seed=4)
@@ -237,7 +238,7 @@ def test_fp16_range_guard_hands_layers_to_the_tf32_kernel(dev, kernel, monkeypat
     err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
     info = net.info()
     print(f"range guard: max err {err:.2e}, fallback layers {info['range_fallback_layers']}")
-    assert info["conv_kernel"] == {"h": 2, "t": 3}[kernel] and info["range_fallback_layers"] >= 2
+    assert info["conv_kernel"] == {"h": 2, "t": 3, "z": 4}[kernel] and info["range_fallback_layers"] >= 2
     assert err <= TOL
 
 

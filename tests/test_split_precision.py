@@ -41,3 +41,35 @@ def test_three_products_match_3xtf32_accuracy():
     xt = tf32(x.copy()); xtl = tf32((x - xt).copy()); wt = tf32(w.copy()); wtl = tf32((w - wt).copy())
     err_t = (np.abs(xt.astype(np.float64) @ wt + xt.astype(np.float64) @ wtl + xtl.astype(np.float64) @ wt - ref) / den).max()
     assert err_h <= 2.5e-7 and err_h <= 1.5 * err_t, (err_h, err_t)
+
+
+def test_sum_of_split_rows_in_half_precision_keeps_22_bits():
+    """k_conv_z adds the split copies of several same-type neighbour rows WITHOUT unpacking them (conv_z.cu):
+    hi' = fl16(hi_a + hi_b), err = (hi_a + hi_b) - hi' (TwoSum, exact in fp16), lo' = fl16(lo_a + lo_b + 2^11 err).
+    The new pair must carry x_a + x_b (+ x_c) as accurately as a fresh split of the fp32 sum."""
+    rng = np.random.default_rng(2)
+    f16 = np.float16
+
+    def two_sum(a, b):
+        s = (a + b).astype(f16)
+        bb = (s - a).astype(f16)
+        err = ((a - (s - bb).astype(f16)).astype(f16) + (b - bb).astype(f16)).astype(f16)
+        return s, err
+
+    n = 200000
+    xs = [(rng.standard_normal(n) * 10.0 ** rng.uniform(-2, 3.5, n)).astype(np.float32) for _ in range(3)]
+    hi, lo = split_h(xs[0])
+    exact = hi.astype(np.float64) + lo.astype(np.float64) / 2048
+    mag = np.abs(exact)
+    for x in xs[1:]:
+        h2, l2 = split_h(x)
+        exact = exact + h2.astype(np.float64) + l2.astype(np.float64) / 2048
+        mag = mag + np.abs(h2.astype(np.float64))
+        hi, err = two_sum(hi, h2)
+        # fused multiply-add in fp16: evaluate in fp64 (exact for these operands), round once
+        lo = (err.astype(np.float64) * 2048 + (lo + l2).astype(f16).astype(np.float64)).astype(f16)
+        assert np.isfinite(hi.astype(np.float32)).all() and np.isfinite(lo.astype(np.float32)).all()
+        # TwoSum is exact: hi' + err == hi_a + hi_b
+    rec = hi.astype(np.float64) + lo.astype(np.float64) / 2048
+    rel = np.abs(rec - exact) / mag                      # relative to sum |x|, as the product accuracy is stated
+    assert rel.max() <= 2.0 ** -20, rel.max()

@@ -114,7 +114,8 @@ struct tgnn_handle {
     bool conv_t_only = false;                       // TGNN_CONV=t forces the tcgen05 edge-block kernel (any graph size, 256-row super-tiles)
     bool conv_z_only = false;                       // TGNN_CONV=z forces the windowed tcgen05 kernel whenever every tile gets a window
     bool use_s = false, use_h = false, use_t = false, use_z = false;   // decided per graph in set_graph
-    bool need_xh() const { return use_h || use_t; }  // the fp16-split copy of b1 is an operand of both kernels
+    bool need_xh() const { return use_h || use_t || use_z; }  // the fp16-split copy of b1 is an operand of these kernels
+    bool conv_z32 = false;                          // TGNN_CONV=z32: k_conv_z's tf32 variant takes every layer
     DevBuf tabT, tab32;                             // [L][K+1] pre-swizzled fp16 weight images / plain fp32 tables of k_conv_t (+ stand-by)
     int tile_rows_forced = 0;                       // TGNN_TILE=64|128 (A/B runs)
     bool tables_streamed = false;                   // many edge types: one layer's weight tables at a time
@@ -127,6 +128,7 @@ struct tgnn_handle {
     DevBuf xh;                                      // [n_rows][8] uint4: fp16-split copy of the current layer's b1
     int* rflag(int i) { return hflags.as<int>() + i; }
     int* wflag(int i) { return hflags.as<int>() + cfg.depth + 1 + i; }
+    int* zflag(int i) { return hflags.as<int>() + 2 * cfg.depth + 3 + i; }   // k_conv_z: a multi-edge sum left the fp16 range (per forward)
     unsigned* bn_ticket() { return reinterpret_cast<unsigned*>(hflags.as<int>() + 2 * cfg.depth + 1); }   // k_bn_finish; +1: k_halo_push
     size_t workspace_bytes = 0;
 
@@ -377,14 +379,12 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
     h->tab.reserve(slots * TG_FRAG32 * sizeof(float));
     if (h->need_xh()) TGNN_CUDA(cudaMemsetAsync(h->wflag(l0), 0, (size_t)nl * sizeof(int), st));
     if (h->use_h) h->tabH.reserve(slots * TG_HFRAG32 * sizeof(uint32_t));
-    if (h->use_t) {
-        h->tabT.reserve(slots * TG_TIMG32 * sizeof(uint32_t));
-        h->tab32.reserve(slots * F * F * sizeof(float));
-    }
+    if (h->use_t || h->use_z) h->tabT.reserve(slots * TG_TIMG32 * sizeof(uint32_t));
+    if (h->use_t) h->tab32.reserve(slots * F * F * sizeof(float));
     if (h->use_s || h->use_z) h->tabS.reserve(slots * TG_FRAG32 * sizeof(float));
     launch_edge_tables(h->g.type_rows.as<float>(), K, h->cfg.d_e, nl, h->table_layers.as<TableLayer>() + l0, h->tab.as<float>(),
                        (h->use_s || h->use_z) ? h->tabS.as<float>() : nullptr, h->use_h ? h->tabH.as<uint32_t>() : nullptr,
-                       h->use_t ? h->tabT.as<uint32_t>() : nullptr, h->use_t ? h->tab32.as<float>() : nullptr,
+                       (h->use_t || h->use_z) ? h->tabT.as<uint32_t>() : nullptr, h->use_t ? h->tab32.as<float>() : nullptr,
                        h->need_xh() ? h->wflag(l0) : nullptr, st);
     if (layer < 0) h->tables_dirty = false;
 }
@@ -392,14 +392,13 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
 // Cost model from B200 measurements (1M nodes, deg 32, 51 types): the edge-chunk mma.sync kernel costs ~72 ps per
 // adjacency edge, the tcgen05 S kernel ~5.9 ns per (128-row tile, edge type) pass -> S pays off when the tiles see
 // few types relative to their edge count (the shipped tile graphs: 20-41 types), chunk when types are many.
-// The windowed tcgen05 kernel (conv_z.cu) works on the same S format with ~0.2 us per pass: it takes over when a pass
-// carries more than ~24 edges, every tile gets a window and there are enough 128-row tiles for the SMs.
+// The windowed tcgen05 kernel (conv_z.cu) works on the same S format.  It is OPT-IN (TGNN_CONV=z | z32): measured on B200 at
+// 1M nodes x deg 32 (profiles/r2/conv_z_*.txt) it runs at 1.5 ms per launch against the 1.2 ms of k_conv_h -- its MMA side needs
+// only ~180 cycles per (tile, type) pass, but the gather warps spend ~430 instructions per pass and warp (96 selects to undo the
+// bank-conflict-free rotated row reads, ~150 for the multi-edge rows of the synthetic graphs) and are latency/issue bound.
 void choose_conv_kernel(tgnn_handle* h, cudaStream_t st) {
     h->use_z = false; h->g.has_z = false;
-    const bool others_forced = h->conv_h_only || h->conv_s_only || h->conv_chunk_only || h->conv_t_only;
-    if (h->g.s_built && !others_forced && h->g.s_max_pass <= ZW_MAX_PASS &&
-        (h->conv_z_only || (h->g.n_own >= Z_MIN_NODES && h->g.s_tiles >= h->sm_count &&
-                            (double)h->g.s_passes * Z_EDGES_PER_PASS_BREAK_EVEN < (double)h->g.e_adj))) {
+    if (h->g.s_built && h->conv_z_only && h->g.s_max_pass <= ZW_MAX_PASS) {
         h->g.has_z = build_z_windows(h->g, h->scratch, st) == 0;
         h->use_z = h->g.has_z;
     }
@@ -630,6 +629,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     if (!train && !h->eval_coefs_valid) { lz.begin("bnfin"); eval_coefs(h, st); lz.end(2 + 2 * L + 4); h->eval_coefs_valid = true; }
     if (train) h->eval_coefs_valid = false;          // train-mode forwards overwrite the coefficient blocks
     if (h->need_xh()) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
+    if (h->use_z) TGNN_CUDA(cudaMemsetAsync(h->zflag(0), 0, (size_t)L * sizeof(int), st));
 
     auto finish_bn = [&](const double* part, int n_part, int c, const tgnn_handle::BnP& bn, size_t coef_off) {
         if (h->world == 1 || h->px.ok) {
@@ -683,9 +683,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn;
         lz.begin("conv");
         if (h->use_z) {
-            launch_conv_z(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->err_dev, h->sm_count, st,
-                          h->role_dbg_on ? h->role_dbg.as<long long>() : nullptr);
-            lz.end(1);
+            // fp16 kernel + its tf32 stand-by (exits at once unless a range flag is raised)
+            ca.xh = h->xh.as<uint4>();
+            ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
+            launch_conv_z(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->tabT.as<uint32_t>() + tslot * TG_TIMG32, h->zflag(i),
+                          h->conv_z32, h->err_dev, h->sm_count, st, h->role_dbg_on ? h->role_dbg.as<long long>() : nullptr);
+            lz.end(h->conv_z32 ? 1 : 2, 1);
         } else if (h->use_s) {
             launch_conv_s(ca, h->g, h->tabS.as<float>() + tslot * TG_FRAG32, h->err_dev, h->sm_count, st);
             lz.end(1);
@@ -914,11 +917,12 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->conv_s_only = csel && std::string(csel) == "s";
         h->conv_h_only = csel && std::string(csel) == "h";
         h->conv_t_only = csel && std::string(csel) == "t";
-        h->conv_z_only = csel && std::string(csel) == "z";
+        h->conv_z32 = csel && std::string(csel) == "z32";
+        h->conv_z_only = csel && (std::string(csel) == "z" || h->conv_z32);
         const char* tsel = getenv("TGNN_TILE");
         if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
-        h->hflags.reserve((size_t)(2 * cfg->depth + 3) * sizeof(int));
-        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(2 * cfg->depth + 3) * sizeof(int)));
+        h->hflags.reserve((size_t)(3 * cfg->depth + 3) * sizeof(int));
+        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(3 * cfg->depth + 3) * sizeof(int)));
         h->dev_error.reserve(2 * sizeof(int));                         // [1] scratch flag of pack_params
         TGNN_CUDA(cudaMemset(h->dev_error.p, 0, 2 * sizeof(int)));
         TGNN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->err_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -1099,10 +1103,10 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         if (h->need_xh() && h->graph_set) {
             DeviceGuard dg(h->cfg.device);
             const int L = h->cfg.depth;
-            std::vector<int> f(2 * L + 1);
+            std::vector<int> f(3 * L + 3);
             TGNN_CUDA(cudaDeviceSynchronize());
             TGNN_CUDA(cudaMemcpy(f.data(), h->hflags.p, f.size() * sizeof(int), cudaMemcpyDeviceToHost));
-            for (int i = 0; i < L; ++i) out->range_fallback_layers += (f[i] | f[L + 1 + i]) ? 1 : 0;
+            for (int i = 0; i < L; ++i) out->range_fallback_layers += (f[i] | f[L + 1 + i] | (h->use_z ? f[2 * L + 3 + i] : 0)) ? 1 : 0;
         }
     });
 }

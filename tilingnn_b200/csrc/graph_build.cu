@@ -539,9 +539,7 @@ void build_graph(Graph& g, Scratch& sc, int d_e, int64_t n_own, int64_t n_rows,
         // chosen at all: it needs ~164 edges per (128-row tile, type) pass to beat the fp16 edge-chunk kernel
         const double passes_est = 0.8 * (double)((n_own + S_BM - 1) / S_BM) *
                                   std::min<double>((double)n_types, (double)e_adj * S_BM / (double)n_own);
-        // (k_conv_z, which works on the same format, breaks even at far fewer edges per pass, but needs enough tiles)
-        const bool s_may_win = want_s >= 2 || passes_est * S_EDGES_PER_PASS_BREAK_EVEN < (double)e_adj ||
-                               (n_own >= Z_MIN_NODES && passes_est * Z_EDGES_PER_PASS_BREAK_EVEN < (double)e_adj);
+        const bool s_may_win = want_s >= 2 || passes_est * S_EDGES_PER_PASS_BREAK_EVEN < (double)e_adj;
         if (want_s && s_may_win && n_types <= S_MAX_TYPES) {
             g.s_tiles = (int)((n_own + S_BM - 1) / S_BM);
             k_s_keys<<<nblk(e_adj), TPB, 0, st>>>(adj_dst, type_of_edge, e_adj, n_own, k0, id0);

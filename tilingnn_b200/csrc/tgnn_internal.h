@@ -112,6 +112,7 @@ struct Graph {
     DevBuf zw_meta;           // int32  [s_tiles][4]              {runs, window rows, window row of the tile's first node, edges}
     DevBuf zw_seg;            // int32  [s_tiles][ZW_MAXSEG][2]   {first source row, first window row} per run
     DevBuf z_loc;             // uint16 [e_adj + padding]         window row of s_src[e]
+    DevBuf z_tab;             // uint16 [s_passes][128]           per (pass, row): window row of the first source | 0x8000 if several, 0xFFFF if none
     // "T" format for the tcgen05 edge-block kernel (conv_t.cu): super-tiles of t_rows destinations; blocks of 128 same-type
     // slots; quarter q of a block holds destinations with dst % 4 == q, all distinct inside a quarter; every super-tile ends
     // with t_rows / 128 root blocks (type n_types, src = dst = the tile's own rows)
@@ -157,13 +158,11 @@ constexpr int S_OFF_STRIDE = 136; // uint16 per pass (129 used; 272 B keeps 16-b
 constexpr double S_EDGES_PER_PASS_BREAK_EVEN = 164.0;   // measured: S pass ~5.9 ns, fp16 edge-chunk kernel ~36 ps per edge
 constexpr int S_MAX_TYPES = 120;  // the S path is chosen only when K + 1 (root) passes fit its per-tile tables
 // k_conv_z: tcgen05 passes with the A operand in tensor memory and the tile's neighbour rows in a shared-memory window
-constexpr int ZW_WMAX = 1280;     // window rows (160 KB)
+constexpr int ZW_WMAX = 952;      // window rows (119 KB)
 constexpr int ZW_MAXSEG = 32;     // contiguous runs per window (one bulk copy each)
 constexpr int ZW_CAP = 4608;      // sorted items per tile in the builder = in-edges + own rows
 constexpr int ZW_GAP = 2;         // runs closer than this many rows are merged (the gap rows are loaded)
-constexpr int ZW_MAX_PASS = 256;  // most edges in one (tile, type) pass
-constexpr double Z_EDGES_PER_PASS_BREAK_EVEN = 24.0;   // a Z pass costs about as much as 24 edges of k_conv_h
-constexpr int64_t Z_MIN_NODES = 16384;                 // below this the tiles do not fill the SMs
+constexpr int ZW_MAX_PASS = 216;  // most edges in one (tile, type) pass
 int build_z_windows(Graph& g, Scratch& sc, cudaStream_t st);
 int conv_z_blocks(int s_tiles, int sm_count);
 
@@ -213,8 +212,8 @@ void launch_conv_t(const ConvArgs& c, const Graph& g, const uint32_t* tabT, cons
 // tcgen05 "S" formulation of the adjacency branch (conv_s.cu); tabS: [K+1][hi|lo][32][32] transposed weights
 void launch_conv_s(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st);
 // tcgen05 passes, A in tensor memory, windowed rows (conv_z.cu); same tabS images
-void launch_conv_z(const ConvArgs& c, const Graph& g, const float* tabS, int* error_flag, int sm_count, cudaStream_t st,
-                   long long* dbg = nullptr);
+void launch_conv_z(const ConvArgs& c, const Graph& g, const float* tabS, const uint32_t* tabT, int* flag_z, bool force32,
+                   int* error_flag, int sm_count, cudaStream_t st, long long* dbg = nullptr);
 
 constexpr int GW_T = 64;          // destination rows per window tile
 constexpr int GW_MAXSEG = 32;     // contiguous runs per window (one bulk copy each, one producer lane each)
