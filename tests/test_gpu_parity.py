@@ -511,3 +511,21 @@ def test_persistent_pipelines_over_many_tiles(dev, var, val, monkeypatch):
     err = (a - b).abs().max().item()
     print(f"{var}={val} vs baseline kernels on 300k nodes: max diff {err:.2e}")
     assert torch.isfinite(b).all() and err <= 2e-5
+
+
+def test_score_stream_matches_serial_calls(dev):
+    """ScoreStream (double-buffered device slots, H2D copy of layout k+1 overlapped with the scoring of layout k) must
+    return exactly what one serial call per layout returns -- different graphs of different sizes in one stream."""
+    from tilingnn_b200 import ScoreStream, synthetic as syn
+    p = orc.make_params(3, 19, 3, seed=2)
+    net = make_net(p, 3, 19, 3, dev)
+    graphs = [syn.lattice_graph(n, d, d, seed=s) for n, d, s in ((3000, 8, 0), (5000, 16, 1), (3000, 8, 2), (777, 4, 3), (5000, 16, 1))]
+    serial = [run(net, *g, dev) for g in graphs]
+    pinned = [[t.pin_memory() for t in g] for g in graphs]
+    outs = [torch.empty(g[0].shape[0], dtype=torch.float32).pin_memory() for g in graphs]
+    ScoreStream(net)(pinned, outs)
+    torch.cuda.synchronize()
+    for a, b in zip(serial, outs):
+        assert np.array_equal(a, b.numpy())
+    gold = orc.forward(p, *graphs[1], depth=3, dtype=torch.float64)[:, 0].numpy()
+    assert np.abs(outs[1].numpy() - gold).max() <= TOL and np.array_equal(outs[1].numpy(), outs[4].numpy())
