@@ -122,6 +122,12 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
                          int64_t e_adj, const int64_t* adj_src, const int64_t* adj_dst, const float* adj_feat,
                          int64_t e_col, const int64_t* col_src, const int64_t* col_dst,
                          void* stream);
+/* Optional, after tgnn_set_graph_shard: send_mask[n_send] (host or device), bit q of byte r = rank q reads send row r.
+ * The peer-memory exchange then stores a boundary row only into the buffers of the ranks that read it (node-range shards of
+ * a spatially ordered graph have two neighbours, not world - 1); which mirrored rows THIS rank reads, and therefore whose
+ * flags it waits for, the library derives from the edge arrays itself.  Without this call every row goes to every peer.
+ * (The NCCL fallback all-gathers everything either way.)  New work: the reference is single-device. */
+int tgnn_set_halo_peers(tgnn_handle* h, const uint8_t* send_mask, int64_t n_send, void* stream);
 
 /* ---- introspection (tests, bench, profiling) --------------------------------------------- */
 typedef struct tgnn_info {

@@ -17,6 +17,14 @@ done
 timeout 900 $CS --tool racecheck --print-limit 20 --error-exitcode 3 $DRV --nodes 600 --deg 16 --depth 20 \
     > $OUT/sanitize_${TAG}_racecheck_600.log 2>&1
 echo "racecheck 600: exit $?"; tail -3 $OUT/sanitize_${TAG}_racecheck_600.log
+# the windowed tcgen05 kernel (opt-in) and the staged-window collision kernel on a graph large enough for both.  memcheck
+# only: racecheck does not model mbarrier / async-proxy ordering and slows these pipelines past their bounded waits
+# (profiles/r2/sanitize/README.txt)
+for tool in memcheck; do
+  TGNN_CONV=z TGNN_GINW=1 timeout 900 $CS --tool $tool --print-limit 20 --error-exitcode 3 $DRV --nodes 40000 --deg 16 --depth 3 \
+      > $OUT/sanitize_${TAG}_${tool}_convz_ginw.log 2>&1
+  echo "$tool conv_z + gin_w: exit $?"; tail -3 $OUT/sanitize_${TAG}_${tool}_convz_ginw.log
+done
 NG=$(nvidia-smi -L | wc -l)
 if [ "$NG" -ge 2 ]; then
   timeout 1200 $CS --tool memcheck --print-limit 20 --error-exitcode 3 --target-processes all \

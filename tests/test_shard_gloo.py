@@ -48,6 +48,24 @@ def _worker(rank, world, port, n, deg, q):
         local[plan.n_own:] = torch.cat(slots)
         assert torch.equal(local[plan.adj_src_local][:, 0], ai[0].float())
         assert torch.equal(local[plan.col_src_local][:, 0], ci[0].float())
+        # peers-only exchange (tgnn_set_halo_peers): a row goes only to the ranks whose bit is set in send_mask.  Emulate it
+        # (NaN wherever nothing was sent) -- every row the local edges read must still have arrived
+        assert plan.send_mask is not None and plan.send_mask.numel() == plan.send_rows.numel()
+        assert (plan.send_mask != 0).all() and ((plan.send_mask >> rank) & 1 == 0).all()
+        masks = [torch.zeros(plan.halo_slot, dtype=torch.uint8) for _ in range(world)]
+        mine = torch.zeros(plan.halo_slot, dtype=torch.uint8)
+        mine[: plan.send_mask.numel()] = plan.send_mask
+        dist.all_gather(masks, mine)
+        local2 = torch.full((plan.n_rows, 4), float("nan"))
+        local2[: plan.n_own] = feat
+        for qq in range(world):
+            got = ((masks[qq] >> rank) & 1).bool()
+            base = plan.n_own + qq * plan.halo_slot
+            local2[base: base + plan.halo_slot][got] = slots[qq][got]
+        assert torch.equal(local2[plan.adj_src_local][:, 0], ai[0].float())
+        assert torch.equal(local2[plan.col_src_local][:, 0], ci[0].float())
+        if world >= 3 and rank == 0:       # a 1-D lattice shard talks to its neighbours only: rank 0 sends nothing to rank 2
+            assert ((plan.send_mask >> 2) & 1 == 0).all()
         q.put((rank, "ok", int(plan.halo_slot), int(plan.n_own)))
     except Exception as e:  # pragma: no cover
         import traceback

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tgnn_nccl_unique_id": (C.c_int, [_vp]),
     "tgnn_shard_init": (C.c_int, [_vp, _vp, _i32, _i32]),
     "tgnn_set_graph_shard": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "tgnn_set_halo_peers": (C.c_int, [_vp, _vp, _i64, _vp]),
     "tgnn_get_info": (C.c_int, [_vp, C.POINTER(tgnn_info)]),
     "tgnn_debug_set_stop_layer": (C.c_int, [_vp, _i32]),
     "tgnn_debug_read": (C.c_int, [_vp, C.c_char_p, _vp, _vp]),

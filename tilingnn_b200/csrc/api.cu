@@ -594,8 +594,10 @@ void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t s
         // boundary rows go straight into the peers' buffers (NVLink stores), flags follow; the unpack waits for the flags
         const unsigned epoch = ++h->px.epoch_halo;
         const PeerPtrs pp = peer_ptrs(h);
-        launch_halo_push(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, h->g.halo_slot, pp, epoch, h->bn_ticket() + 1, st);
-        launch_halo_unpack_x(pp, epoch, h->g.halo_slot, h->g.n_own, a, b, h->need_xh() ? h->xh.as<uint4>() : nullptr, flag, st);
+        launch_halo_push(a, b, h->g.send_rows.as<int>(), (int)h->g.n_send, h->g.halo_slot, pp, epoch, h->bn_ticket() + 1,
+                         h->g.has_send_mask ? h->g.send_mask.as<uint8_t>() : nullptr, st);
+        launch_halo_unpack_x(pp, epoch, h->g.halo_slot, h->g.n_own, a, b, h->need_xh() ? h->xh.as<uint4>() : nullptr, flag,
+                             h->g.halo_used.as<uint8_t>(), h->g.need_from, st);
         h->collectives += 1;
         lz.end(2);
         return;
@@ -1075,10 +1077,44 @@ int tgnn_set_graph_shard(tgnn_handle* h, int64_t n_own, int64_t n_global, int64_
             TGNN_CUDA(cudaMemcpyAsync(h->g.send_rows.p, rows32.data(), n_send * sizeof(int), cudaMemcpyHostToDevice, st));
             TGNN_CUDA(cudaStreamSynchronize(st));
         }
+        // which mirrored rows do the local edges read, and which peers own them: the unpack waits for those peers only
+        h->g.has_send_mask = false; h->g.need_from = 0xffffffffu;
+        if (h->world > 1 && halo_slot > 0) {
+            const size_t nm = (size_t)h->world * (size_t)halo_slot;
+            h->g.halo_used.reserve(nm);
+            TGNN_CUDA(cudaMemsetAsync(h->g.halo_used.p, 0, nm, st));
+            launch_mark_halo(adj_src, e_adj, n_own, n_rows, h->g.halo_used.as<uint8_t>(), st);
+            launch_mark_halo(col_src, e_col, n_own, n_rows, h->g.halo_used.as<uint8_t>(), st);
+            std::vector<uint8_t> used(nm);
+            TGNN_CUDA(cudaMemcpyAsync(used.data(), h->g.halo_used.p, nm, cudaMemcpyDeviceToHost, st));
+            TGNN_CUDA(cudaStreamSynchronize(st));
+            unsigned nf = 0;
+            for (int q = 0; q < h->world; ++q)
+                for (int64_t i = 0; i < halo_slot; ++i)
+                    if (used[(size_t)q * halo_slot + i]) { nf |= 1u << q; break; }
+            h->g.need_from = nf;
+        }
         alloc_workspace(h);
         peer_setup(h, st);
         h->tables_dirty = true;
         h->graph_set = true;
+    });
+}
+
+int tgnn_set_halo_peers(tgnn_handle* h, const uint8_t* send_mask, int64_t n_send, void* stream) {
+    return guarded(h, [&] {
+        TGNN_CHECK(h && h->graph_set && h->world > 1, "tgnn_set_halo_peers: no sharded graph set");
+        TGNN_CHECK(n_send == h->g.n_send, "tgnn_set_halo_peers: one mask byte per send row");
+        TGNN_CHECK(h->world <= 8, "tgnn_set_halo_peers: the mask has one bit per rank (world <= 8)");
+        DeviceGuard dg(h->cfg.device);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (n_send > 0) {
+            TGNN_CHECK(send_mask, "tgnn_set_halo_peers: null mask");
+            h->g.send_mask.reserve((size_t)n_send);
+            TGNN_CUDA(cudaMemcpyAsync(h->g.send_mask.p, send_mask, (size_t)n_send, cudaMemcpyDefault, st));
+            TGNN_CUDA(cudaStreamSynchronize(st));
+        }
+        h->g.has_send_mask = n_send > 0;
     });
 }
 

@@ -594,9 +594,9 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
 // (a fast rank running on would break the "at most one exchange ahead" double-buffer invariant), so the kernel stores
 // an error code in the handle's mapped host word and ABORTS: the stream's next operation fails and tgnn_forward /
 // tgnn_check_error report it -- no NaN results, no later epochs.
-__device__ __forceinline__ void wait_peers(const unsigned* flags, int world, int rank, unsigned epoch, int* err) {
+__device__ __forceinline__ void wait_peers(const unsigned* flags, int world, int rank, unsigned epoch, int* err, unsigned peers = 0xffffffffu) {
     for (int q = 0; q < world; ++q) {
-        if (q == rank) continue;
+        if (q == rank || !((peers >> q) & 1u)) continue;
         long long t0 = clock64();
         while ((int)(ld_acquire_sys(flags + q) - epoch) < 0) {
             __nanosleep(64);
@@ -673,8 +673,10 @@ __global__ void k_bn_finish_x(BnFinishArgs A, PeerPtrs P, unsigned epoch) {
     if (threadIdx.x == 0) *A.ticket = 0u;
 }
 
+// smask (optional): bit q of smask[r] = peer q reads boundary row r -- the row then travels only to those peers (node-range
+// shards of a spatially ordered graph have 2 neighbours, not world - 1)
 __global__ void k_halo_push(const float4* __restrict__ a, const float4* __restrict__ b, const int* __restrict__ rows, int n_send,
-                            int64_t halo_slot, PeerPtrs P, unsigned epoch, unsigned* __restrict__ ticket) {
+                            int64_t halo_slot, PeerPtrs P, unsigned epoch, unsigned* __restrict__ ticket, const uint8_t* __restrict__ smask) {
     const int par = epoch & 1u;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < (int64_t)n_send * 16) {
@@ -682,8 +684,9 @@ __global__ void k_halo_push(const float4* __restrict__ a, const float4* __restri
         const int row = rows[r];
         const float4 v = c < 8 ? __ldg(a + (size_t)row * 8 + c) : (b ? __ldg(b + (size_t)row * 8 + (c - 8)) : make_float4(0.f, 0.f, 0.f, 0.f));
         const size_t off = ((size_t)par * P.world * halo_slot + (size_t)P.rank * halo_slot) * 16 + (size_t)i;     // float4 units
+        const unsigned to = smask ? (unsigned)__ldg(smask + r) : 0xffffffffu;
         for (int q = 0; q < P.world; ++q)
-            if (q != P.rank) reinterpret_cast<float4*>(P.base[q] + PX_HALO_OFF)[off] = v;
+            if (q != P.rank && ((to >> q) & 1u)) reinterpret_cast<float4*>(P.base[q] + PX_HALO_OFF)[off] = v;
     }
     // last block: everything this rank wrote is visible system-wide before the flags go up
     __shared__ bool last;
@@ -698,10 +701,13 @@ __global__ void k_halo_push(const float4* __restrict__ a, const float4* __restri
     if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// used (optional): used[r] != 0 = mirrored row r is read by a local edge; need_from: peers that own such rows -- only their
+// flags are waited for and only those rows are unpacked (rows nobody sent stay stale and are never read)
 __global__ void k_halo_unpack_x(PeerPtrs P, unsigned epoch, int64_t halo_slot, int64_t n_own,
-                                float4* __restrict__ a, float4* __restrict__ b, uint4* __restrict__ xh, int* __restrict__ flag) {
+                                float4* __restrict__ a, float4* __restrict__ b, uint4* __restrict__ xh, int* __restrict__ flag,
+                                const uint8_t* __restrict__ used, unsigned need_from) {
     const int par = epoch & 1u;
-    if (threadIdx.x == 0) wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank]) + par * PX_MAX_WORLD, P.world, P.rank, epoch, P.err);
+    if (threadIdx.x == 0) wait_peers(reinterpret_cast<const unsigned*>(P.base[P.rank]) + par * PX_MAX_WORLD, P.world, P.rank, epoch, P.err, need_from);
     __syncthreads();
     __threadfence_system();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -709,6 +715,7 @@ __global__ void k_halo_unpack_x(PeerPtrs P, unsigned epoch, int64_t halo_slot, i
     if (i >= total) return;
     const int64_t r = i >> 4; const int c = (int)(i & 15);
     if (r / halo_slot == P.rank) return;               // own slot: rows are read in place
+    if (used && !__ldg(used + r)) return;
     const float4* recv = reinterpret_cast<const float4*>(P.base[P.rank] + PX_HALO_OFF) + (size_t)par * total;
     float4 v = __ldcg(recv + i);                       // written by a peer over NVLink: L2 is the coherence point
     if (c < 8) {
@@ -969,18 +976,30 @@ void launch_bn_finish_x(const BnFinishArgs& a, int n_bn, const PeerPtrs& p, unsi
     TGNN_CUDA(cudaGetLastError());
 }
 void launch_halo_push(const float* a, const float* b, const int* rows, int n_send, int64_t halo_slot, const PeerPtrs& p,
-                      unsigned epoch, unsigned* ticket, cudaStream_t st) {
+                      unsigned epoch, unsigned* ticket, const uint8_t* send_mask, cudaStream_t st) {
     const int64_t n = (int64_t)n_send * 16;
     const int blocks = (int)std::max<int64_t>(1, (n + 255) / 256);           // at least one block: the flags must go up
     k_halo_push<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), rows, n_send,
-                                        halo_slot, p, epoch, ticket);
+                                        halo_slot, p, epoch, ticket, send_mask);
     TGNN_CUDA(cudaGetLastError());
 }
 void launch_halo_unpack_x(const PeerPtrs& p, unsigned epoch, int64_t halo_slot, int64_t n_own, float* a, float* b,
-                          uint4* xh, int* flag, cudaStream_t st) {
+                          uint4* xh, int* flag, const uint8_t* used, unsigned need_from, cudaStream_t st) {
     const int64_t n = (int64_t)p.world * halo_slot * 16;
     const int blocks = (int)std::max<int64_t>(1, (n + 255) / 256);
-    k_halo_unpack_x<<<blocks, 256, 0, st>>>(p, epoch, halo_slot, n_own, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), xh, flag);
+    k_halo_unpack_x<<<blocks, 256, 0, st>>>(p, epoch, halo_slot, n_own, reinterpret_cast<float4*>(a), reinterpret_cast<float4*>(b), xh, flag, used, need_from);
+    TGNN_CUDA(cudaGetLastError());
+}
+// used[src - n_own] = 1 for every edge source in the mirrored range
+__global__ void k_mark_halo(const int64_t* __restrict__ src, int64_t e, int64_t n_own, int64_t n_rows, uint8_t* __restrict__ used) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= e) return;
+    const long long s = src[i];
+    if (s >= n_own && s < n_rows) used[s - n_own] = 1;
+}
+void launch_mark_halo(const int64_t* src, int64_t e, int64_t n_own, int64_t n_rows, uint8_t* used, cudaStream_t st) {
+    if (e <= 0) return;
+    k_mark_halo<<<(unsigned)((e + 255) / 256), 256, 0, st>>>(src, e, n_own, n_rows, used);
     TGNN_CUDA(cudaGetLastError());
 }
 void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gamma, const float* beta, float* coef_out,

@@ -134,6 +134,10 @@ struct Graph {
     // halo (sharded mode)
     int64_t halo_slot = 0, n_send = 0;
     DevBuf send_rows;         // int32 [n_send]
+    DevBuf send_mask;         // uint8 [n_send]: bit q = peer q reads the row (tgnn_set_halo_peers); has_send_mask = false -> all peers
+    bool has_send_mask = false;
+    DevBuf halo_used;         // uint8 [world * halo_slot]: the mirrored row is read by a local edge
+    unsigned need_from = 0xffffffffu;   // peers owning at least one such row
 };
 
 struct Scratch {
@@ -339,10 +343,13 @@ enum { TGNN_DEVERR_PIPELINE = 1, TGNN_DEVERR_PEER = 2 };
 void launch_bn_finish_x(const BnFinishArgs& a, int n_bn, const PeerPtrs& p, unsigned epoch, cudaStream_t st);
 // boundary rows (a | b) -> slot `rank` of every peer's halo buffer, then the epoch flags (last block)
 void launch_halo_push(const float* a, const float* b, const int* rows, int n_send, int64_t halo_slot, const PeerPtrs& p,
-                      unsigned epoch, unsigned* ticket, cudaStream_t st);
+                      unsigned epoch, unsigned* ticket, const uint8_t* send_mask /* per row: peers that read it, or null = all */,
+                      cudaStream_t st);
 // waits for the peers' flags of `epoch`, then unpacks this rank's halo buffer (as launch_halo_unpack)
 void launch_halo_unpack_x(const PeerPtrs& p, unsigned epoch, int64_t halo_slot, int64_t n_own, float* a, float* b,
-                          uint4* xh, int* flag, cudaStream_t st);
+                          uint4* xh, int* flag, const uint8_t* used /* per mirrored row, or null = all */, unsigned need_from,
+                          cudaStream_t st);
+void launch_mark_halo(const int64_t* src, int64_t e, int64_t n_own, int64_t n_rows, uint8_t* used, cudaStream_t st);
 
 // node mask: kept in-degrees -> inv_deg_masked[n_own]; counters3 = {kept nodes, adjacency edges, collision edges with both
 // endpoints kept}; *count = kept nodes as a double (the BatchNorm population)

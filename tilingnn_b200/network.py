@@ -339,6 +339,11 @@ class TilinGNN(nn.Module):
                                           c_src.numel(), _ptr(c_src), _ptr(c_dst), C.c_void_p(st))
         nat.graph_key = None
         _lib.check(nat.h, rc, "tgnn_set_graph_shard")
+        if getattr(plan, "send_mask", None) is not None and send.numel() > 0:
+            sm = plan.send_mask.to(dev).to(torch.uint8).contiguous()
+            with torch.cuda.device(dev):
+                rc = lib.tgnn_set_halo_peers(nat.h, _ptr(sm), sm.numel(), C.c_void_p(st))
+            _lib.check(nat.h, rc, "tgnn_set_halo_peers")
         nat.num_nodes = plan.n_own
 
     # ---- the reference signature ---------------------------------------------------------------

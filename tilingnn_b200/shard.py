@@ -44,6 +44,7 @@ class ShardPlan:
     col_src_local: torch.Tensor
     col_dst_local: torch.Tensor
     publish_lists: list            # per rank: int64 global ids it publishes (sorted)
+    send_mask: torch.Tensor = None # uint8 [n_send]: bit q = rank q reads send row i (world <= 8; else None = every peer)
 
     @property
     def n_own(self):
@@ -95,6 +96,16 @@ def make_plan(n_global, bounds, adj_index, col_index, group=None) -> ShardPlan:
     publish = torch.unique(torch.cat(mine)) if mine else torch.zeros(0, dtype=torch.int64, device=dev)
     publish_lists = _all_gather_var(publish, group)
     halo_slot = max(max(p.numel() for p in publish_lists), 1)
+    # which peer reads which of my published rows: a boundary row then travels only to those ranks (tgnn_set_halo_peers)
+    send_mask = None
+    if world <= 8:
+        send_mask = torch.zeros(publish.numel(), dtype=torch.uint8, device=dev)
+        for q, nq in enumerate(needs):
+            if q == rank:
+                continue
+            ids = nq[(nq >= lo) & (nq < hi)]
+            if ids.numel():
+                send_mask[torch.searchsorted(publish, ids)] |= (1 << q)
     n_own = hi - lo
     b = torch.tensor(bounds, dtype=torch.int64, device=dev)
 
@@ -118,4 +129,4 @@ def make_plan(n_global, bounds, adj_index, col_index, group=None) -> ShardPlan:
 
     return ShardPlan(rank, world, lo, hi, int(n_global), int(halo_slot), (publish - lo).contiguous(),
                      remap(adj_index[0]).contiguous(), (adj_index[1] - lo).contiguous(),
-                     remap(col_index[0]).contiguous(), (col_index[1] - lo).contiguous(), publish_lists)
+                     remap(col_index[0]).contiguous(), (col_index[1] - lo).contiguous(), publish_lists, send_mask)
