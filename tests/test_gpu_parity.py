@@ -529,3 +529,26 @@ def test_score_stream_matches_serial_calls(dev):
         assert np.array_equal(a, b.numpy())
     gold = orc.forward(p, *graphs[1], depth=3, dtype=torch.float64)[:, 0].numpy()
     assert np.abs(outs[1].numpy() - gold).max() <= TOL and np.array_equal(outs[1].numpy(), outs[4].numpy())
+
+
+@pytest.mark.parametrize("variant", ["fp16", "tf32"])
+def test_final_mlp_variants_and_range_guard(dev, variant, monkeypatch):
+    """The final MLP's dense stages run on fp16 two-term splits (k_dense_tc<N, true>) with the 3xTF32 kernel standing by;
+    TGNN_DENSE=tf32 keeps them on 3xTF32.  A BatchNorm gain of 1e6 in the first final-MLP layer pushes the inputs of the
+    second stage outside the fp16 range: the producers must raise the range flag and the stand-by must redo that stage."""
+    if variant == "tf32":
+        monkeypatch.setenv("TGNN_DENSE", "tf32")
+    from tilingnn_b200 import synthetic as syn
+    x, ai, af, ci = syn.lattice_graph(5000, 8, 8, seed=6)
+    p = dict(orc.make_params(3, 19, 4, seed=6))
+    gold = orc.forward(p, x, ai, af, ci, depth=4, dtype=torch.float64)[:, 0].numpy()
+    err = np.abs(run(make_net(p, 3, 19, 4, dev), x, ai, af, ci, dev) - gold).max()
+    print(f"final MLP on {variant}: max err {err:.2e}")
+    assert err <= TOL
+    p["final_mlp.0.mlp.0.batch_norm.weight"] = p["final_mlp.0.mlp.0.batch_norm.weight"] * 1e6
+    gold = orc.forward(p, x, ai, af, ci, depth=4, dtype=torch.float64)[:, 0].numpy()
+    net = make_net(p, 3, 19, 4, dev)
+    err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
+    net.check_errors()
+    print(f"final MLP on {variant}, BatchNorm gain 1e6: max err {err:.2e}")
+    assert err <= TOL

@@ -82,6 +82,9 @@ struct tgnn_handle {
     std::vector<std::unique_ptr<DevBuf>> gin_wt;    // per layer: frag tables W1|W2|W3 and biases b1|b2|b3
     std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4: k-major transposes (CUDA-core path)
     std::vector<std::unique_ptr<DevBuf>> fin_whl;   // 4: pre-swizzled hi|lo slab images of the weights (tcgen05 path)
+    std::vector<std::unique_ptr<DevBuf>> fin_whh;   // 4: fp16 {hi | lo} slab images of the weights * 2^6 (k_dense_tc<N, true>)
+    bool fin_h16[4] = {false, false, false, false}; // the stage's weights fit the fp16 range (checked at pack time)
+    bool dense_tf32 = false;                        // TGNN_DENSE=tf32 keeps the final MLP on 3xTF32 (A/B, tests)
     DevBuf dev_error;                               // int[2]: [1] = scratch range flag of pack_params ([0] unused)
     // Device-side error word in MAPPED PINNED HOST memory: kernels store a code there (1 = tcgen05 pipeline timeout,
     // 2 = peer-exchange wait timeout) and the host reads it without a CUDA call -- at the start of every API call, after
@@ -128,7 +131,8 @@ struct tgnn_handle {
     DevBuf xh;                                      // [n_rows][8] uint4: fp16-split copy of the current layer's b1
     int* rflag(int i) { return hflags.as<int>() + i; }
     int* wflag(int i) { return hflags.as<int>() + cfg.depth + 1 + i; }
-    int* zflag(int i) { return hflags.as<int>() + 2 * cfg.depth + 3 + i; }   // k_conv_z: a multi-edge sum left the fp16 range (per forward)
+    int* zflag(int i) { return hflags.as<int>() + 2 * cfg.depth + 3 + i; }
+    int* dflag(int k) { return hflags.as<int>() + 3 * cfg.depth + 3 + k; }   // final MLP stage k: an input left the fp16 range (per forward)   // k_conv_z: a multi-edge sum left the fp16 range (per forward)
     unsigned* bn_ticket() { return reinterpret_cast<unsigned*>(hflags.as<int>() + 2 * cfg.depth + 1); }   // k_bn_finish; +1: k_halo_push
     size_t workspace_bytes = 0;
 
@@ -256,6 +260,9 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
     if (!h->params_dirty) return;
     for (auto& k : h->key_order) TGNN_CHECK(h->params[k].set, "parameter not set: " + k);
     const int L = h->cfg.depth;
+    const char* dsel = getenv("TGNN_DENSE");
+    h->dense_ffma = dsel && std::string(dsel) == "ffma";
+    h->dense_tf32 = dsel && std::string(dsel) == "tf32";
     h->init_w1t.reserve(32 * 32 * sizeof(float));
     launch_transpose(h->P("init_node_feature_trans.mlp.1.linear.weight"), h->init_w1t.as<float>(), 32, 32, st);
     h->gin_wt.clear(); h->gin_eps.assign(L, 0.f); h->gin_hmlp.assign(L, 0);
@@ -289,7 +296,7 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
         h->gin_hmlp[i] = out_of_range == 0 && !h->gin_tf32_only;
         TGNN_CUDA(cudaMemsetAsync(h->dev_error.as<int>() + 1, 0, sizeof(int), st));
     }
-    h->fin_wt.clear(); h->fin_whl.clear();
+    h->fin_wt.clear(); h->fin_whl.clear(); h->fin_whh.clear();
     int dims[5] = {F * (L + 1), 256, 128, 64, F};
     for (int k = 0; k < 4; ++k) {
         const float* w = h->P("final_mlp.0.mlp." + std::to_string(k) + ".linear.weight");
@@ -300,6 +307,15 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
         h->fin_whl.emplace_back(new DevBuf());
         h->fin_whl.back()->reserve(2 * ne * sizeof(float));
         launch_weight_image(w, h->fin_whl.back()->as<float>(), dims[k + 1], dims[k], st);
+        h->fin_whh.emplace_back(new DevBuf());
+        h->fin_whh.back()->reserve(2 * ne * sizeof(uint16_t));
+        TGNN_CUDA(cudaMemsetAsync(h->dev_error.as<int>() + 1, 0, sizeof(int), st));
+        launch_weight_image_h(w, h->fin_whh.back()->p, dims[k + 1], dims[k], h->dev_error.as<int>() + 1, st);
+        int out_of_range = 0;
+        TGNN_CUDA(cudaMemcpyAsync(&out_of_range, h->dev_error.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TGNN_CUDA(cudaStreamSynchronize(st));
+        h->fin_h16[k] = out_of_range == 0 && !h->dense_tf32;
+        TGNN_CUDA(cudaMemsetAsync(h->dev_error.as<int>() + 1, 0, sizeof(int), st));
     }
     {
         std::vector<TableLayer> tl(L);
@@ -331,8 +347,6 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
     h->init_w0 = h->P("init_node_feature_trans.mlp.0.linear.weight"); h->init_b0 = h->P("init_node_feature_trans.mlp.0.linear.bias");
     h->init_b1 = h->P("init_node_feature_trans.mlp.1.linear.bias"); h->score_w = h->P("final_mlp.1.linear.weight");
     h->eval_coefs_valid = false;
-    const char* dsel = getenv("TGNN_DENSE");
-    h->dense_ffma = dsel && std::string(dsel) == "ffma";
     TGNN_CUDA(cudaMemcpyAsync(&h->fin_last_bias, h->P("final_mlp.1.linear.bias"), sizeof(float), cudaMemcpyDeviceToHost, st));
     // coefficient blocks
     size_t off = 0;
@@ -632,6 +646,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     if (train) h->eval_coefs_valid = false;          // train-mode forwards overwrite the coefficient blocks
     if (h->need_xh()) TGNN_CUDA(cudaMemsetAsync(h->rflag(0), 0, (size_t)(L + 1) * sizeof(int), st));
     if (h->use_z) TGNN_CUDA(cudaMemsetAsync(h->zflag(0), 0, (size_t)L * sizeof(int), st));
+    TGNN_CUDA(cudaMemsetAsync(h->dflag(0), 0, 4 * sizeof(int), st));
 
     auto finish_bn = [&](const double* part, int n_part, int c, const tgnn_handle::BnP& bn, size_t coef_off) {
         if (h->world == 1 || h->px.ok) {
@@ -787,11 +802,14 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             da.out = h->fa[k].as<float>(); da.part = train ? h->partA.as<double>() : nullptr;
             da.n = n_own; da.K = dims[k]; da.n_out = dims[k + 1]; da.mask = h->mask();
             lz.begin("final");
+            int nl = 1;
             if (h->dense_ffma) launch_dense(da, st);
             else {
-                launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->err_dev, h->sm_count, st);
+                // fp16-split kernel + 3xTF32 stand-by (exits at once unless an input left the fp16 range)
+                nl = launch_dense_tc(da, h->fin_whl[k]->as<float>(), h->fin_h16[k] ? h->fin_whh[k]->p : nullptr, h->dflag(k), h->err_dev,
+                                     h->sm_count, st);
             }
-            lz.end(1);
+            lz.end(nl, 1);
             if (train) {
                 lz.begin("bnfin");
                 finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], h->fin_bn[k], h->coef_fin[k]);
@@ -923,8 +941,8 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         h->conv_z_only = csel && (std::string(csel) == "z" || h->conv_z32);
         const char* tsel = getenv("TGNN_TILE");
         if (tsel && (atoi(tsel) == WN_SMALL || atoi(tsel) == WN_BIG)) h->tile_rows_forced = atoi(tsel);
-        h->hflags.reserve((size_t)(3 * cfg->depth + 3) * sizeof(int));
-        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(3 * cfg->depth + 3) * sizeof(int)));
+        h->hflags.reserve((size_t)(3 * cfg->depth + 3 + 4) * sizeof(int));
+        TGNN_CUDA(cudaMemset(h->hflags.p, 0, (size_t)(3 * cfg->depth + 3 + 4) * sizeof(int)));
         h->dev_error.reserve(2 * sizeof(int));                         // [1] scratch flag of pack_params
         TGNN_CUDA(cudaMemset(h->dev_error.p, 0, 2 * sizeof(int)));
         TGNN_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->err_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));

@@ -9,11 +9,22 @@
 //                          tcgen05.commit -> mbarrier frees the smem stage / publishes the accumulator
 //   epilogue (warps 9-12): tcgen05.ld 32 columns at a time -> bias, LeakyReLU -> global, column sums in fp64.
 // 3xTF32 keeps fp32-level accuracy (single-pass TF32 would break the 1e-4 parity bar).
+//
+// k_dense_tc<N, true> is the same pipeline on fp16 two-term splits (kind::f16): x = hi + lo with hi = fp16(x),
+// lo = fp16(x - hi) (unscaled: the inputs are BatchNorm outputs / layer outputs of O(1), so lo's subnormal spacing 2^-24
+// is an ABSOLUTE error far below fp32 rounding of the sums), weights scaled by 2^6 at pack time so their lo parts stay in
+// the normal range (undone on the accumulator, exact).  A slab's A tile is ONE 128-byte-row tile {hi(32) | lo(32)} and so
+// is the weight tile: half the shared-memory bytes, and 6 MMAs (K = 16) per slab instead of 12 (K = 8) -- the tensor
+// time per tile halves (a tcgen05.mma costs max(44.6, N/2) cycles whatever the kind).  Values outside the fp16 range
+// (checked by the producers, |x| > 60000) raise a flag; the 3xTF32 kernel, launched right behind, then redoes the stage
+// (it exits at once otherwise).  Weights outside the range (checked at pack time) keep the stage on 3xTF32.
 // Every mbarrier wait is bounded: on a timeout the kernel raises a device-side error flag and exits instead of
 // hanging the GPU.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+
+#include <cuda_fp16.h>
 
 #include "tc_common.cuh"
 #include "tgnn_internal.h"
@@ -42,14 +53,18 @@ struct DenseTcArgs {
     double* part;               // [gridDim.x][2][N_out] or nullptr
     int* error_flag;
     long long* dbg;             // optional per-role wait counters of CTA 0 (TGNN_DENSE_DBG=1)
+    int* range_flag;            // fp16 variant: raised when an input value is outside the fp16 range; tf32 variant: run only if raised ...
+    int standby;                // ... when standby != 0 (else the tf32 variant always runs)
     int n, K;
     const uint8_t* mask;        // node mask or null: masked rows are written as 0 (and add nothing to the column sums)
 };
 
-template <int NOUT> struct DenseCfg {
+constexpr float H_WSCALE = 64.f, H_WSCALE_INV = 1.f / 64.f;   // fp16 variant: weights are packed as w * 2^6 (their lo parts stay normal)
+template <int NOUT, bool HALF> struct DenseCfg {
+    // tf32: A = hi tile + lo tile (16 KB each), B = hi tile + lo tile (NOUT x 128 B each);  fp16: one tile each, rows {hi | lo}
     static constexpr int B_TILE_BYTES = NOUT * BK * 4;
-    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int STAGES = NOUT >= 256 ? 2 : (NOUT >= 128 ? 3 : 4);
+    static constexpr int STAGE_BYTES = HALF ? A_TILE_BYTES + B_TILE_BYTES : 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int STAGES = HALF ? (NOUT >= 256 ? 4 : 6) : (NOUT >= 256 ? 2 : (NOUT >= 128 ? 3 : 4));
     static constexpr int EPI_BYTES = N_EPI_WARPS * SCRATCH_FLOATS * 4 + 4 * 2 * NOUT * 4 + NOUT * 4;   // scratch, red (fp32 block sums), bias
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024;
 };
@@ -62,14 +77,32 @@ template <int NOUT> struct DenseCfg {
 #define DTIMED(acc, expr) (expr)
 #endif
 
-template <int NOUT>
+__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+// two values -> packed fp16 pairs {hi(v0), hi(v1)} and {lo(v0), lo(v1)}, lo = fp16(v - hi) unscaled
+__device__ __forceinline__ void split_h2u(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(v0, v1);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v0 - f.x, v1 - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int NOUT, bool HALF>
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_dense_tc(DenseTcArgs A) {
+    if (!HALF && A.standby && !(A.range_flag && *A.range_flag)) return;      // stand-by of the fp16 variant: nothing to redo
     long long w0 = 0, w1 = 0;
     const long long t_start = clock64();
-    using Cfg = DenseCfg<NOUT>;
+    using Cfg = DenseCfg<NOUT, HALF>;
     constexpr int STAGES = Cfg::STAGES, STAGE_BYTES = Cfg::STAGE_BYTES, B_TILE_BYTES = Cfg::B_TILE_BYTES;
-    constexpr uint32_t IDESC = umma_idesc_tf32(NOUT);
+    constexpr uint32_t IDESC = HALF ? ((1u << 4) | ((uint32_t)(NOUT >> 3) << 17) | ((uint32_t)(UMMA_M >> 4) << 24)) : umma_idesc_tf32(NOUT);
     constexpr int TMEM_COLS = 2 * NOUT < 32 ? 32 : 2 * NOUT;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
@@ -141,6 +174,7 @@ k_dense_tc(DenseTcArgs A) {
             const int C4 = A.K / 4;
             nmh = __ldg(cf); nml = __ldg(cf + C4); nsc = __ldg(cf + 2 * C4); nbe = __ldg(cf + 3 * C4);
         }
+        bool bad = false;                                   // fp16 variant: a value outside the fp16 range was seen
         auto process = [&](float4 (&buf)[4]) -> bool {
             const int st = g % STAGES, row0 = tile * BM, k0 = s * BK;
             if (!DTIMED(w0, mbar_wait(bar_empty + 8 * st, ((g / STAGES) & 1) ^ 1))) return false;
@@ -163,6 +197,16 @@ k_dense_tc(DenseTcArgs A) {
                     v.z = fmaf((v.z - cmh.z) - cml.z, csc.z, cbe.z);
                     v.w = fmaf((v.w - cmh.w) - cml.w, csc.w, cbe.w);
                     if (row0 + r >= A.n) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (HALF) {
+                    // fp16 split, row layout {hi(32 halves) | lo(32 halves)}: this thread's 4 columns are 8 bytes of each half
+                    uint32_t h01, h23, l01, l23;
+                    split_h2u(v.x, v.y, h01, l01);
+                    split_h2u(v.z, v.w, h23, l23);
+                    bad |= !(fabsf(v.x) <= TG_H_LIMIT) | !(fabsf(v.y) <= TG_H_LIMIT) | !(fabsf(v.z) <= TG_H_LIMIT) | !(fabsf(v.w) <= TG_H_LIMIT);
+                    sts64(sa_hi + sw128_off(r, c >> 1) + 8u * (uint32_t)(c & 1), h01, h23);
+                    sts64(sa_hi + sw128_off(r, 4 + (c >> 1)) + 8u * (uint32_t)(c & 1), l01, l23);
+                    continue;
                 }
                 // truncation split: hi = top 19 bits (what kind::tf32 reads), lo = x - hi exact; the tensor core
                 // truncates lo to TF32 itself (relative residual ~2^-21)
@@ -191,6 +235,7 @@ k_dense_tc(DenseTcArgs A) {
             if (ok && tile < n_tiles) ok = process(pre2);
         }
         if (!ok) timeout_flag = 1;
+        if (HALF && bad && A.range_flag) *A.range_flag = 1;  // the 3xTF32 kernel launched behind this one redoes the stage
     } else if (warp == BULK_WARP) {
         // ===================== weight slabs: ONE TMA bulk copy per slab (hi and lo tiles are adjacent) =============
         if (lane == 0) {
@@ -199,8 +244,9 @@ k_dense_tc(DenseTcArgs A) {
                 for (int s = 0; s < n_slabs; ++s, ++g) {
                     const int st = g % STAGES;
                     if (!DTIMED(w0, mbar_wait_relaxed(bar_empty + 8 * st, ((g / STAGES) & 1) ^ 1))) { timeout_flag = 1; break; }
-                    mbar_arrive_expect_tx(bar_full + 8 * st, 2 * B_TILE_BYTES);
-                    bulk_g2s(smem_base + st * STAGE_BYTES + 2 * A_TILE_BYTES, A.w_img + (size_t)s * 2 * NOUT * BK, 2 * B_TILE_BYTES,
+                    constexpr int NB = HALF ? 1 : 2, NA = HALF ? 1 : 2;      // weight / A tiles per slab
+                    mbar_arrive_expect_tx(bar_full + 8 * st, NB * B_TILE_BYTES);
+                    bulk_g2s(smem_base + st * STAGE_BYTES + NA * A_TILE_BYTES, A.w_img + (size_t)s * NB * NOUT * BK, NB * B_TILE_BYTES,
                              bar_full + 8 * st);
                 }
             }
@@ -220,7 +266,18 @@ k_dense_tc(DenseTcArgs A) {
                     if (!DTIMED(w0, mbar_wait(bar_full + 8 * st, (g / STAGES) & 1))) { timeout_flag = 1; ok = false; break; }
                     tc_fence_after();
                     const uint32_t a_hi = smem_base + st * STAGE_BYTES, a_lo = a_hi + A_TILE_BYTES;
-                    const uint32_t b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+                    const uint32_t b_hi = a_hi + (HALF ? 1 : 2) * A_TILE_BYTES, b_lo = b_hi + B_TILE_BYTES;
+                    if (HALF) {
+                        // rows {hi | lo}: 16 halves = 32 bytes per K-step; steps 0, 1 = hi, steps 2, 3 = lo
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            const uint64_t dah = umma_desc_sw128(a_hi + ks * 32), dal = umma_desc_sw128(a_hi + 64 + ks * 32);
+                            const uint64_t dbh = umma_desc_sw128(b_hi + ks * 32), dbl = umma_desc_sw128(b_hi + 64 + ks * 32);
+                            umma_f16_ss(tmem_d, dal, dbh, IDESC, (s > 0 || ks > 0) ? 1u : 0u);
+                            umma_f16_ss(tmem_d, dah, dbl, IDESC, 1u);
+                            umma_f16_ss(tmem_d, dah, dbh, IDESC, 1u);
+                        }
+                    } else
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
                         const uint32_t kb = ks * 32;   // 8 tf32 = 32 bytes along K inside the swizzle atom
@@ -269,7 +326,7 @@ k_dense_tc(DenseTcArgs A) {
                     for (; r + 4 <= nv; r += 4) {
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
-                            float o = lds_f32(sc + 4 * ((r + u) * 36 + lane)) + bias_c;
+                            float o = fmaf(lds_f32(sc + 4 * ((r + u) * 36 + lane)), HALF ? H_WSCALE_INV : 1.f, bias_c);
                             o = fmaxf(o, o * LEAKY);
                             orow[(size_t)(r + u) * NOUT] = o;
                             s1f[u] += o; s2f[u] = fmaf(o, o, s2f[u]);
@@ -277,7 +334,7 @@ k_dense_tc(DenseTcArgs A) {
                     }
                 }
                 for (; r < nv; ++r) {
-                    float o = lds_f32(sc + 4 * (r * 36 + lane)) + bias_c;
+                    float o = fmaf(lds_f32(sc + 4 * (r * 36 + lane)), HALF ? H_WSCALE_INV : 1.f, bias_c);
                     o = fmaxf(o, o * LEAKY);
                     if (!((keepbits >> r) & 1u)) o = 0.f;                     // node mask: the row is stored as zero
                     orow[(size_t)r * NOUT] = o;
@@ -331,12 +388,26 @@ __global__ void k_weight_image(const float* __restrict__ w, float* __restrict__ 
     img[base + (size_t)n_out * 32 + pos] = __uint_as_float(l);
 }
 
-template <int NOUT>
+// fp16 images: per 32-wide K slab ONE tile [N_out rows x 128 B], row n = {hi(w * 2^6)[32] | lo[32]} halves, SWIZZLE_128B.
+__global__ void k_weight_image_h(const float* __restrict__ w, __half* __restrict__ img, int n_out, int K, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_out * K) return;
+    const int n = i / K, k = i - n * K, slab = k >> 5, kk = k & 31;
+    const float x = w[i] * H_WSCALE;
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn(x - __half2float(hi));
+    if (!(fabsf(x) <= TG_H_LIMIT)) *flag = 1;
+    __half* tile = img + (size_t)slab * n_out * 64;
+    tile[n * 64 + ((((kk >> 3) ^ (n & 7)) << 3) | (kk & 7))] = hi;
+    tile[n * 64 + ((((4 + (kk >> 3)) ^ (n & 7)) << 3) | (kk & 7))] = lo;
+}
+
+template <int NOUT, bool HALF>
 void launch_one(const DenseTcArgs& a, int sm_count, cudaStream_t st) {
-    constexpr size_t smem = DenseCfg<NOUT>::SMEM;
+    constexpr size_t smem = DenseCfg<NOUT, HALF>::SMEM;
     static PerDeviceOnce once;
     once.run([&] {
-        TGNN_CUDA(cudaFuncSetAttribute(k_dense_tc<NOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TGNN_CUDA(cudaFuncSetAttribute((k_dense_tc<NOUT, HALF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     });
     const int n_tiles = (a.n + BM - 1) / BM;
     static long long* dbg = nullptr;
@@ -344,7 +415,7 @@ void launch_one(const DenseTcArgs& a, int sm_count, cudaStream_t st) {
     if (want_dbg && !dbg) TGNN_CUDA(cudaMalloc(&dbg, 16 * 4 * sizeof(long long)));
     DenseTcArgs b = a;
     b.dbg = dbg;
-    k_dense_tc<NOUT><<<std::min(n_tiles, sm_count), NTHREADS, smem, st>>>(b);
+    k_dense_tc<NOUT, HALF><<<std::min(n_tiles, sm_count), NTHREADS, smem, st>>>(b);
     TGNN_CUDA(cudaGetLastError());
     if (want_dbg) {
         static int calls = 0;
@@ -367,19 +438,38 @@ void launch_weight_image(const float* w, float* img, int n_out, int K, cudaStrea
 
 int dense_tc_row_blocks(int n) { return (n + BM - 1) / BM; }
 
-void launch_dense_tc(const DenseArgs& d, const float* w_img, int* error_flag, int sm_count, cudaStream_t st) {
+void launch_weight_image_h(const float* w, void* img, int n_out, int K, int* flag, cudaStream_t st) {
+    k_weight_image_h<<<(n_out * K + 255) / 256, 256, 0, st>>>(w, reinterpret_cast<__half*>(img), n_out, K, flag);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+template <bool HALF>
+static void launch_dense_variant(const DenseTcArgs& a, int n_out, int sm_count, cudaStream_t st) {
+    switch (n_out) {
+        case 256: launch_one<256, HALF>(a, sm_count, st); break;
+        case 128: launch_one<128, HALF>(a, sm_count, st); break;
+        case 64: launch_one<64, HALF>(a, sm_count, st); break;
+        case 32: launch_one<32, HALF>(a, sm_count, st); break;
+        default: TGNN_CHECK(false, "dense stage: n_out must be 32, 64, 128 or 256");
+    }
+}
+
+// w_img16 != null: the fp16 kernel runs first and the 3xTF32 kernel stands by behind it (range_flag, zeroed by the caller
+// per forward); null: 3xTF32 only.  Returns the number of launches.
+int launch_dense_tc(const DenseArgs& d, const float* w_img, const void* w_img16, int* range_flag, int* error_flag, int sm_count,
+                    cudaStream_t st) {
     TGNN_CHECK(d.K % BK == 0, "dense stage: K must be a multiple of 32");
     DenseTcArgs a{};
     a.slabs = d.slabs; a.a = d.a; a.virtual_concat = d.virtual_concat; a.in_coef = d.in_coef;
-    a.w_img = w_img; a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag; a.mask = d.mask;
-    a.n = d.n; a.K = d.K;
-    switch (d.n_out) {
-        case 256: launch_one<256>(a, sm_count, st); break;
-        case 128: launch_one<128>(a, sm_count, st); break;
-        case 64: launch_one<64>(a, sm_count, st); break;
-        case 32: launch_one<32>(a, sm_count, st); break;
-        default: TGNN_CHECK(false, "dense stage: n_out must be 32, 64, 128 or 256");
+    a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag; a.mask = d.mask;
+    a.n = d.n; a.K = d.K; a.range_flag = range_flag;
+    if (w_img16) {
+        a.w_img = reinterpret_cast<const float*>(w_img16); a.standby = 0;
+        launch_dense_variant<true>(a, d.n_out, sm_count, st);
     }
+    a.w_img = w_img; a.standby = w_img16 ? 1 : 0;
+    launch_dense_variant<false>(a, d.n_out, sm_count, st);
+    return w_img16 ? 2 : 1;
 }
 
 }  // namespace tgnn

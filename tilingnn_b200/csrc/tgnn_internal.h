@@ -291,7 +291,10 @@ void launch_dense(const DenseArgs& a, cudaStream_t st);
 
 // tcgen05 (tensor-core) version of the dense stage: w_hi / w_lo = TF32 split of the [N_out][K] weight
 void launch_weight_image(const float* w, float* img, int n_out, int K, cudaStream_t st);   // pre-swizzled hi|lo slabs
-void launch_dense_tc(const DenseArgs& a, const float* w_img, int* error_flag, int sm_count, cudaStream_t st);
+void launch_weight_image_h(const float* w, void* img, int n_out, int K, int* flag, cudaStream_t st);   // fp16 {hi | lo} slab images of w * 2^6
+// w_img16 != null: fp16 kernel + 3xTF32 stand-by (range_flag: int, zeroed per forward); null: 3xTF32 only.  Returns launches.
+int launch_dense_tc(const DenseArgs& a, const float* w_img, const void* w_img16, int* range_flag, int* error_flag, int sm_count,
+                    cudaStream_t st);
 
 void launch_score(const float* a3, const float* coef, const float* w, float b, float* out,
                   int64_t n, cudaStream_t st, const uint8_t* mask = nullptr);
