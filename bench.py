@@ -514,7 +514,7 @@ def main():
                        "nodes_per_gpu": n_own, "deg": args.deg, "depth": args.depth, "bn": args.bn,
                        "parallelism": f"node-range shards x{world}" if world > 1 else "single GPU",
                        "l2_policy": f"no flush needed: per-step working set {info['workspace_bytes'] / 1e9:.1f} GB >> 126 MB L2"},
-            "roofline": {"bound": bound, "kernel": {"conv": {0: "k_conv_adj", 1: "k_conv_s", 2: "k_conv_h", 3: "k_conv_t", 4: "k_conv_z"}[int(info["conv_kernel"])],
+            "roofline": {"bound": bound, "kernel": {"conv": {0: "k_conv_adj", 1: "k_conv_s", 2: "k_conv_h", 3: "k_conv_t", 4: "k_conv_z", 5: "k_conv_x"}[int(info["conv_kernel"])],
                                                     "gin": "k_gin_w" if int(info.get("gin_kernel", 0)) else "k_gin", "final": "k_dense_tc", "combine": "k_combine"}.get(dom, dom),
                          "achieved": achieved_tf if bound == "tensor" else achieved,
                          "peak": peak_tc if bound == "tensor" else peak,

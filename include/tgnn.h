@@ -141,7 +141,8 @@ typedef struct tgnn_info {
     int64_t conv_kernel;           /* adjacency kernel chosen for this graph: 0 = 3xTF32 edge-chunk (mma.sync),
                                       1 = tcgen05 S formulation, 2 = fp16-split edge-chunk (mma.sync.f16),
                                       3 = tcgen05 edge-block kernel (128-edge blocks, TMEM accumulators),
-                                      4 = windowed tcgen05 kernel (A operand in tensor memory, rows staged per tile)  */
+                                      4 = windowed tcgen05 kernel (A operand in tensor memory, rows staged per tile),
+                                      5 = fp16-split edge-chunk kernel with transposed MMA roles (weights = A operand)  */
     int64_t tile_rows;             /* destination rows per warp tile of the typed adjacency format (64 or 128)  */
     int64_t peer_exchange;         /* sharded mode: 1 = boundary rows and BatchNorm sums travel as direct NVLink stores into
                                       the peers' CUDA-IPC-mapped buffers (flags, no NCCL call); 0 = NCCL collectives     */

@@ -158,7 +158,7 @@ def test_synthetic_configs_vs_oracle(dev, n, deg, mode):
     assert err <= TOL
 
 
-@pytest.mark.parametrize("kernel", ["chunk", "s", "h", "t", "z", "z32"])
+@pytest.mark.parametrize("kernel", ["chunk", "s", "h", "t", "z", "z32", "x"])
 def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     """The fp16-split edge-chunk kernel, its 3xTF32 twin, the tcgen05 S kernel, the tcgen05 edge-block kernel and the
     windowed tcgen05 kernel (A operand in tensor memory) are
@@ -179,7 +179,7 @@ def test_all_adjacency_kernels(dev, kernel, monkeypatch):
     print(f"TGNN_CONV={kernel}: max err {err:.2e}")
     assert err <= TOL
     info = net.info()
-    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2, "t": 3, "z": 4, "z32": 4}[kernel] and info["range_fallback_layers"] == 0
+    assert info["conv_kernel"] == {"chunk": 0, "s": 1, "h": 2, "t": 3, "z": 4, "z32": 4, "x": 2}[kernel] and info["range_fallback_layers"] == 0
 
 
 @pytest.mark.parametrize("variant", ["z", "z32"])
@@ -491,7 +491,7 @@ def test_graph_replay_of_repeated_forwards(dev):
         assert np.abs(s.double().cpu().numpy() - gold).max() <= TOL
 
 
-@pytest.mark.parametrize("var,val", [("TGNN_GINW", "1"), ("TGNN_CONV", "t"), ("TGNN_CONV", "z")])
+@pytest.mark.parametrize("var,val", [("TGNN_GINW", "1"), ("TGNN_CONV", "t"), ("TGNN_CONV", "z"), ("TGNN_CONV", "x")])
 def test_persistent_pipelines_over_many_tiles(dev, var, val, monkeypatch):
     """k_gin_w and k_conv_t are persistent kernels whose mbarrier pipelines run for dozens of tiles per CTA at benchmark
     sizes (the small parity cases give every CTA a single tile).  Size-independent property on a 300k-node graph the
@@ -507,7 +507,7 @@ def test_persistent_pipelines_over_many_tiles(dev, var, val, monkeypatch):
     b = net(x=x, adj_e_index=ai, adj_e_features=af, col_e_idx=ci)[0].clone()
     net.check_errors()
     info = net.info()
-    assert (info["gin_kernel"] == 1) if var == "TGNN_GINW" else (info["conv_kernel"] == {"t": 3, "z": 4}[val])
+    assert (info["gin_kernel"] == 1) if var == "TGNN_GINW" else (info["conv_kernel"] == {"t": 3, "z": 4, "x": 5}[val])
     err = (a - b).abs().max().item()
     print(f"{var}={val} vs baseline kernels on 300k nodes: max diff {err:.2e}")
     assert torch.isfinite(b).all() and err <= 2e-5
@@ -552,3 +552,25 @@ def test_final_mlp_variants_and_range_guard(dev, variant, monkeypatch):
     net.check_errors()
     print(f"final MLP on {variant}, BatchNorm gain 1e6: max err {err:.2e}")
     assert err <= TOL
+
+
+def test_conv_x_transposed_roles_vs_oracle(dev, monkeypatch):
+    """k_conv_x (weights as the A operand of mma.sync, gathered rows as B, pairwise channel scatter) only runs in the
+    persistent large-graph geometry (> 2 x #SM tiles of 64 rows): a 24k-node lattice with duplicate edges and
+    destinations without in-edges, against the fp64 oracle, train and eval."""
+    monkeypatch.setenv("TGNN_CONV", "x")
+    from tilingnn_b200 import synthetic as syn
+    n = 24000
+    x, ai, af, ci = syn.lattice_graph(n, 16, 16, seed=8)
+    keep = (ai[1] % 41 != 5)
+    ai, af = ai[:, keep], af[keep]
+    dup = torch.randint(0, ai.shape[1], (5000,), generator=torch.Generator().manual_seed(3))
+    ai, af = torch.cat([ai, ai[:, dup]], 1), torch.cat([af, af[dup]], 0)
+    p = orc.make_params(3, 19, 3, seed=8)
+    for mode in ("train", "eval"):
+        q = orc.calibrate_running_stats(p, x, ai, af, ci, depth=3) if mode == "eval" else p
+        gold = orc.forward(q, x, ai, af, ci, depth=3, bn_mode=mode, dtype=torch.float64)[:, 0].numpy()
+        net = make_net(q, 3, 19, 3, dev, mode)
+        err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
+        print(f"k_conv_x 24k lattice {mode}: max err {err:.2e}")
+        assert net.info()["conv_kernel"] == 5 and err <= TOL

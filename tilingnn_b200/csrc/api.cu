@@ -119,6 +119,9 @@ struct tgnn_handle {
     bool use_s = false, use_h = false, use_t = false, use_z = false;   // decided per graph in set_graph
     bool need_xh() const { return use_h || use_t || use_z; }  // the fp16-split copy of b1 is an operand of these kernels
     bool conv_z32 = false;                          // TGNN_CONV=z32: k_conv_z's tf32 variant takes every layer
+    int conv_x_mode = -1;                           // TGNN_CONV=x forces the transposed-roles variant of k_conv_h on large graphs, =h forbids it; -1 auto
+    bool use_x = false;                             // k_conv_x instead of k_conv_h (large graphs: persistent geometry, 64-row tiles)
+    DevBuf tabX;                                    // [L][K+1][1024] fp16 hi|lo A-operand fragment tables of W^T (k_conv_x)
     DevBuf tabT, tab32;                             // [L][K+1] pre-swizzled fp16 weight images / plain fp32 tables of k_conv_t (+ stand-by)
     int tile_rows_forced = 0;                       // TGNN_TILE=64|128 (A/B runs)
     bool tables_streamed = false;                   // many edge types: one layer's weight tables at a time
@@ -393,13 +396,14 @@ void build_tables(tgnn_handle* h, cudaStream_t st, int layer = -1) {
     h->tab.reserve(slots * TG_FRAG32 * sizeof(float));
     if (h->need_xh()) TGNN_CUDA(cudaMemsetAsync(h->wflag(l0), 0, (size_t)nl * sizeof(int), st));
     if (h->use_h) h->tabH.reserve(slots * TG_HFRAG32 * sizeof(uint32_t));
+    if (h->use_x) h->tabX.reserve(slots * TG_HFRAG32 * sizeof(uint32_t));
     if (h->use_t || h->use_z) h->tabT.reserve(slots * TG_TIMG32 * sizeof(uint32_t));
     if (h->use_t) h->tab32.reserve(slots * F * F * sizeof(float));
     if (h->use_s || h->use_z) h->tabS.reserve(slots * TG_FRAG32 * sizeof(float));
     launch_edge_tables(h->g.type_rows.as<float>(), K, h->cfg.d_e, nl, h->table_layers.as<TableLayer>() + l0, h->tab.as<float>(),
                        (h->use_s || h->use_z) ? h->tabS.as<float>() : nullptr, h->use_h ? h->tabH.as<uint32_t>() : nullptr,
                        (h->use_t || h->use_z) ? h->tabT.as<uint32_t>() : nullptr, h->use_t ? h->tab32.as<float>() : nullptr,
-                       h->need_xh() ? h->wflag(l0) : nullptr, st);
+                       h->need_xh() ? h->wflag(l0) : nullptr, st, h->use_x ? h->tabX.as<uint32_t>() : nullptr);
     if (layer < 0) h->tables_dirty = false;
 }
 
@@ -421,6 +425,9 @@ void choose_conv_kernel(tgnn_handle* h, cudaStream_t st) {
     h->use_t = h->g.has_t && !h->conv_h_only && !h->conv_s_only && !h->conv_chunk_only && !h->use_z;
     if (h->use_t) h->use_s = false;
     h->use_h = !h->use_s && !h->use_t && !h->use_z && !h->conv_chunk_only;
+    // transposed MMA roles (no register moves to assemble the A operand): the persistent large-graph geometry only
+    h->use_x = h->use_h && h->conv_x_mode != 0 && h->g.wn == WN_SMALL && !conv_geom(h->g.n_tiles, h->g.wn, h->sm_count).split &&
+               (h->conv_x_mode == 1 || TGNN_CONV_X_DEFAULT);
 }
 
 // The tcgen05 edge-block kernel (conv_t.cu) is OPT-IN (TGNN_CONV=t, 256-row super-tiles; TGNN_CONV_T_ROWS=512 for large
@@ -721,7 +728,8 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             ca.xh = h->xh.as<uint4>();
             ca.tabH = h->tabH.as<uint32_t>() + tslot * TG_HFRAG32;
             ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
-            launch_conv_h(ca, h->sm_count, st);
+            if (h->use_x) { ca.tabX = h->tabX.as<uint32_t>() + tslot * TG_HFRAG32; launch_conv_x(ca, h->sm_count, st); }
+            else launch_conv_h(ca, h->sm_count, st);
             lz.end(1);
         } else {
             launch_conv_adj(ca, h->sm_count, st);
@@ -935,7 +943,8 @@ int tgnn_create(const tgnn_cfg* cfg, tgnn_handle** out) {
         const char* csel = getenv("TGNN_CONV");
         h->conv_chunk_only = csel && std::string(csel) == "chunk";
         h->conv_s_only = csel && std::string(csel) == "s";
-        h->conv_h_only = csel && std::string(csel) == "h";
+        h->conv_h_only = csel && (std::string(csel) == "h" || std::string(csel) == "x");
+        h->conv_x_mode = !csel ? -1 : (std::string(csel) == "x" ? 1 : (std::string(csel) == "h" ? 0 : -1));
         h->conv_t_only = csel && std::string(csel) == "t";
         h->conv_z32 = csel && std::string(csel) == "z32";
         h->conv_z_only = csel && (std::string(csel) == "z" || h->conv_z32);
@@ -1145,7 +1154,7 @@ int tgnn_get_info(tgnn_handle* h, tgnn_info* out) {
         out->launches_per_forward = h->launches;
         out->workspace_bytes = (int64_t)h->workspace_bytes;
         out->collectives_per_forward = h->collectives;
-        out->conv_kernel = h->use_z ? 4 : (h->use_s ? 1 : (h->use_t ? 3 : (h->use_h ? 2 : 0)));
+        out->conv_kernel = h->use_z ? 4 : (h->use_s ? 1 : (h->use_t ? 3 : (h->use_x ? 5 : (h->use_h ? 2 : 0))));
         out->tile_rows = h->g.wn;
         out->peer_exchange = h->px.ok ? 1 : 0;
         out->t_rows = h->g.has_t ? h->g.t_rows : 0;

@@ -227,6 +227,173 @@ k_conv_h(ConvArgs A) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// "X" variant: TRANSPOSED MMA roles.  In k_conv_h the gathered rows are the A operand of mma.sync.m16n8k16, whose four
+// registers interleave rows g and g+8 -- two different edges, two different loads -- so the compiler assembles every A
+// quad with register moves: 114 of the 282 instructions of the chunk loop (cuobjdump).  Here the per-type weights are
+// the A operand (W^T, fragments straight from the table) and the gathered rows are B: a lane's B registers {k = 2t, 2t+1},
+// {k = 2t+8, 2t+9} are consecutive words of ONE edge's row piece, i.e. exactly what its 256-bit load delivers -- no moves.
+// The price is the accumulator layout: a lane now holds, per edge, two ADJACENT output channels (the table's row order
+// makes MMA rows g / g+8 the channels 2g / 2g+1 of a 16-channel half), so the scatter into the warp's tile is 8 x
+// (LDS.64, 2 FADD, STS.64) per chunk instead of 4 x (LDS.128, 4 FADD, STS.128): the same 32 wavefronts when the four edges
+// a half-warp touches have destinations that differ mod 4 (row stride 40 floats; graph_build.cu arranges the slots so).
+constexpr int XSX = 40;          // row stride of the accumulator tile (floats)
+
+struct AFragX { uint4 h[2][2], l[2][2]; };       // [m-tile][k16 step]: {a0, a1, a2, a3} of W^T hi / lo
+__device__ __forceinline__ void load_afrag_x(AFragX& a, const uint32_t* __restrict__ tab, int lane) {
+    const uint4* p = reinterpret_cast<const uint4*>(tab) + lane;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            a.h[i][ks] = __ldg(p + ((i * 2 + ks) * 2 + 0) * 32);
+            a.l[i][ks] = __ldg(p + ((i * 2 + ks) * 2 + 1) * 32);
+        }
+}
+// rows[2 j + ks] = the lane's piece (k16 step ks) of the row of edge slot 8 j + g: {hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)}
+// m[i][j][c]: C fragment of (channel half i, edge group j): c = {edge 2t ch 2g, edge 2t+1 ch 2g, edge 2t ch 2g+1, edge 2t+1 ch 2g+1}
+__device__ __forceinline__ void chunk_mma_x(const uint4 (&rows)[4], const AFragX& a, float (&m)[2][2][4]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            float sm[4] = {}, mn[2][4] = {};
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint4 r = rows[2 * j + ks], wh = a.h[i][ks], wl = a.l[i][ks];
+                mma_f16(sm, wh.x, wh.y, wh.z, wh.w, r.z, r.w);          // Whi . lo
+                mma_f16(mn[ks], wh.x, wh.y, wh.z, wh.w, r.x, r.y);      // Whi . hi
+                mma_f16(sm, wl.x, wl.y, wl.z, wl.w, r.x, r.y);          // Wlo . hi
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) m[i][j][c] = fmaf(sm[c], LO_INV, mn[0][c] + mn[1][c]);
+        }
+}
+
+template <int WN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+k_conv_x(ConvArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) {            // out of the fp16 range: 3xTF32 on the fp32 rows
+        conv_adj_fallback<WN, WARPS>(A, smem);
+        return;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* acc = smem + warp * (WN * XSX);
+    const int g = lane >> 2, t = lane & 3;
+    const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
+    double s1 = 0.0, s2 = 0.0;
+    const float bias_c = __ldg(A.bias + lane);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    const uint4* __restrict__ xh = A.xh;
+    AFragX af;
+    int cur_type = -1;
+    for (int tile = gwarp; tile < A.n_tiles; tile += nwarp) {
+        for (int i = lane; i < WN * XSX / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c0 = __ldg(A.cptr + tile), c1 = __ldg(A.cptr + tile + 1);
+        // software pipeline as in k_conv_h: slot indices TWO chunks ahead, gathered rows ONE chunk ahead
+        uint4 pre[4] = {zero4, zero4, zero4, zero4};
+        int psrc = -1, pdst = 0, ptype = 0, nsrc = -1, ndst = 0, ntype = 0;
+        if (c0 < c1) {
+            psrc = __ldg(A.csrc + (size_t)c0 * CH + (lane & 15));
+            pdst = __ldg(A.cdst + (size_t)c0 * CH + (lane & 15));
+            ptype = __ldg(A.ctype + c0);
+            if (c0 + 1 < c1) {
+                nsrc = __ldg(A.csrc + (size_t)(c0 + 1) * CH + (lane & 15));
+                ndst = __ldg(A.cdst + (size_t)(c0 + 1) * CH + (lane & 15));
+                ntype = __ldg(A.ctype + c0 + 1);
+            }
+            const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
+            if (sa >= 0) ld_rowh2(xh, sa, t, pre[0], pre[1]);
+            if (sb >= 0) ld_rowh2(xh, sb, t, pre[2], pre[3]);
+        }
+        __syncwarp();
+        for (int c = c0; c < c1; ++c) {
+            const uint4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
+            const int cdst = psrc >= 0 ? pdst : -1, type = ptype;       // destination row of this lane's slot, -1 = empty slot
+            if (c + 1 < c1) {
+                const int sa = __shfl_sync(0xffffffffu, nsrc, g), sb = __shfl_sync(0xffffffffu, nsrc, g + 8);
+                pre[0] = pre[1] = pre[2] = pre[3] = zero4;
+                if (sa >= 0) ld_rowh2(xh, sa, t, pre[0], pre[1]);
+                if (sb >= 0) ld_rowh2(xh, sb, t, pre[2], pre[3]);
+            }
+            psrc = nsrc; pdst = ndst; ptype = ntype;
+            if (c + 2 < c1) {
+                nsrc = __ldg(A.csrc + (size_t)(c + 2) * CH + (lane & 15));
+                ndst = __ldg(A.cdst + (size_t)(c + 2) * CH + (lane & 15));
+                ntype = __ldg(A.ctype + c + 2);
+            }
+            if (type != cur_type) { load_afrag_x(af, A.tabX + (size_t)type * TG_HFRAG32, lane); cur_type = type; }
+            if (ptype != type && c + 1 < c1)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(A.tabX + (size_t)ptype * TG_HFRAG32) + lane * 128));
+            float m[2][2][4];
+            chunk_mma_x(cur, af, m);
+            // scatter: slot 8 j + 2 t + u; destinations are distinct inside a group of 8 slots (j), the groups are separated by
+            // a warp barrier
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int d = __shfl_sync(0xffffffffu, cdst, 8 * j + 2 * t + u);
+                    if (d >= 0) {
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            float2* p = reinterpret_cast<float2*>(acc + d * XSX + 16 * i + 2 * g);
+                            float2 v = *p;
+                            v.x += m[i][j][u]; v.y += m[i][j][2 + u];
+                            *p = v;
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        const int node0 = tile * WN;
+        // mean over in-edges and root term in one read-modify-write of the tile (as k_conv_h): acc = fma(acc, inv_deg, x_row @ root)
+        if (cur_type != A.n_types) { load_afrag_x(af, A.tabX + (size_t)A.n_types * TG_HFRAG32, lane); cur_type = A.n_types; }
+        for (int rc = 0; rc < WN / CH; ++rc) {
+            const int na = node0 + rc * CH + g, nb = na + 8;
+            uint4 cur[4] = {zero4, zero4, zero4, zero4};
+            if (na < A.n_own) ld_rowh2(xh, na, t, cur[0], cur[1]);
+            if (nb < A.n_own) ld_rowh2(xh, nb, t, cur[2], cur[3]);
+            float m[2][2][4];
+            chunk_mma_x(cur, af, m);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int r = rc * CH + 8 * j + 2 * t + u;
+                    const float id = node0 + r < A.n_own ? __ldg(A.inv_deg + node0 + r) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        float2* p = reinterpret_cast<float2*>(acc + r * XSX + 16 * i + 2 * g);
+                        float2 v = *p;
+                        v.x = fmaf(v.x, id, m[i][j][u]); v.y = fmaf(v.y, id, m[i][j][2 + u]);
+                        *p = v;
+                    }
+                }
+        }
+        __syncwarp();
+        // bias, LeakyReLU, store, statistics (lane = channel)
+        for (int r = 0; r < WN; ++r) {
+            const int node = node0 + r;
+            if (node < A.n_own) {
+                float v = leaky(acc[r * XSX + lane] + bias_c);
+                if (!row_kept(A.mask, node)) v = 0.f;
+                A.out[(size_t)node * F + lane] = v;
+                s1 += (double)v;
+                s2 += (double)v * (double)v;
+            }
+        }
+        __syncwarp();
+    }
+    if (A.part) {
+        A.part[(size_t)gwarp * 64 + lane] = s1;
+        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
+    }
+}
+
 }  // namespace
 
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
@@ -242,6 +409,19 @@ void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
     if (a.wn == WN_BIG) k_conv_h<WN_BIG, 12, false><<<g.blocks, 12 * 32, smem_big, st>>>(a);
     else if (g.split) k_conv_h<WN_SMALL, 8, true><<<g.blocks, 256, smem_small, st>>>(a);
     else k_conv_h<WN_SMALL, 8, false><<<g.blocks, 256, smem_small, st>>>(a);
+    TGNN_CUDA(cudaGetLastError());
+}
+
+// transposed-roles variant: large graphs only (the same persistent grid as k_conv_h's non-split geometry)
+void launch_conv_x(const ConvArgs& a, int sm_count, cudaStream_t st) {
+    static PerDeviceOnce once;
+    const size_t smem = (size_t)8 * WN_SMALL * XSX * sizeof(float);
+    once.run([&] {
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_x<WN_SMALL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    });
+    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
+    TGNN_CHECK(a.wn == WN_SMALL && !g.split, "internal: k_conv_x needs 64-row tiles and the persistent geometry");
+    k_conv_x<WN_SMALL, 8><<<g.blocks, 256, smem, st>>>(a);
     TGNN_CUDA(cudaGetLastError());
 }
 

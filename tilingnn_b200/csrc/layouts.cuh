@@ -63,6 +63,26 @@ __device__ __forceinline__ void hfrag_store(__half* tab, int k, int n, float w, 
     if (flag && !(fabsf(w) <= limit)) *flag = 1;
 }
 
+// ---- fp16 hi|lo A-operand fragment table of W^T for the transposed-roles kernel (k_conv_x; conv_h.cu) ----------------
+//   MMA row r of channel half i  <-> output channel 16 i + 2 (r & 7) + (r >> 3)      (rows g / g+8 = adjacent channels)
+//   MMA k index kappa of k16 step ks <-> input channel 16 ks + 4 ((kappa & 7) >> 1) + 2 (kappa >> 3) + (kappa & 1)
+//     (= the order of a split row's storage: a lane's B registers are consecutive words of its 256-bit row load)
+//   uint4 index ((i*2 + ks)*2 + hl)*32 + lane, lane = 4 (r & 7) + ((kappa & 7) >> 1); register (r >> 3) + 2 (kappa >> 3); half kappa & 1
+__host__ __device__ __forceinline__ int xfrag_half_index(int kin, int n, int hl) {
+    const int ks = kin >> 4, rem = kin & 15, tp = rem >> 2, within = rem & 3;
+    const int kappa = within < 2 ? 2 * tp + within : 8 + 2 * tp + (within - 2);
+    const int i = n >> 4, nr = n & 15, r = (nr & 1) ? 8 + (nr >> 1) : (nr >> 1);
+    const int lane = 4 * (r & 7) + ((kappa & 7) >> 1), reg = (r >> 3) + 2 * (kappa >> 3), e = kappa & 1;
+    return ((((i * 2 + ks) * 2 + hl) * 32 + lane) * 4 + reg) * 2 + e;
+}
+__device__ __forceinline__ void xfrag_store(__half* tab, int kin, int n, float w, int* flag, float limit) {
+    const __half hi = __float2half_rn(w);
+    const __half lo = __float2half_rn((w - __half2float(hi)) * 2048.f);
+    tab[xfrag_half_index(kin, n, 0)] = hi;
+    tab[xfrag_half_index(kin, n, 1)] = lo;
+    if (flag && !(fabsf(w) <= limit)) *flag = 1;
+}
+
 // ---- tcgen05 edge-block kernel (conv_t.cu): the [64 rows n][64 halves k] K-major SWIZZLE_128B IMAGE of a type's weights.
 // k runs in the storage order of a split activation row (hsplit.cuh): 16-byte piece p = xh_pos(c >> 2) holds
 // {hi(4q..4q+3), lo(4q..4q+3)} of channels 4q + i.  Rows  0..31 ("main",  out channel n): hi-slot = Whi, lo-slot = 0;

@@ -16,7 +16,7 @@ namespace {
 __global__ void __launch_bounds__(256)
 k_edge_tables(const float* __restrict__ rows, int K, int d_e, const TableLayer* __restrict__ layers,
               float* __restrict__ tabF, float* __restrict__ tabS, uint32_t* __restrict__ tabH, uint32_t* __restrict__ tabT,
-              float* __restrict__ tab32, int* __restrict__ wflags) {
+              float* __restrict__ tab32, int* __restrict__ wflags, uint32_t* __restrict__ tabX) {
     __shared__ double h1[32], h2[64];
     const int t = blockIdx.x, layer = blockIdx.y, tid = threadIdx.x;
     const TableLayer L = layers[layer];
@@ -26,6 +26,7 @@ k_edge_tables(const float* __restrict__ rows, int K, int d_e, const TableLayer* 
     __half* outH = tabH ? reinterpret_cast<__half*>(tabH + slot * TG_HFRAG32) : nullptr;
     __half* outT = tabT ? reinterpret_cast<__half*>(tabT + slot * TG_TIMG32) : nullptr;
     float* out32 = tab32 ? tab32 + slot * (F * F) : nullptr;
+    __half* outX = tabX ? reinterpret_cast<__half*>(tabX + slot * TG_HFRAG32) : nullptr;
     const bool is_root = t == K;
     if (!is_root) {
         const float* e = rows + (size_t)t * d_e;
@@ -63,14 +64,16 @@ k_edge_tables(const float* __restrict__ rows, int K, int d_e, const TableLayer* 
         if (outH) hfrag_store(outH, kin, n, (float)w, is_root ? wflags + layer : nullptr, TG_H_LIMIT);
         if (outT) timg_store(outT, kin, n, (float)w, is_root ? wflags + layer : nullptr, TG_H_LIMIT);
         if (out32) out32[o] = (float)w;
+        if (outX) xfrag_store(outX, kin, n, (float)w, is_root ? wflags + layer : nullptr, TG_H_LIMIT);
     }
 }
 
 }  // namespace
 
 void launch_edge_tables(const float* type_rows, int n_types, int d_e, int n_layers, const TableLayer* layers_dev,
-                        float* tabF, float* tabS, uint32_t* tabH, uint32_t* tabT, float* tab32, int* wflags, cudaStream_t st) {
-    k_edge_tables<<<dim3(n_types + 1, n_layers), 256, 0, st>>>(type_rows, n_types, d_e, layers_dev, tabF, tabS, tabH, tabT, tab32, wflags);
+                        float* tabF, float* tabS, uint32_t* tabH, uint32_t* tabT, float* tab32, int* wflags, cudaStream_t st,
+                        uint32_t* tabX) {
+    k_edge_tables<<<dim3(n_types + 1, n_layers), 256, 0, st>>>(type_rows, n_types, d_e, layers_dev, tabF, tabS, tabH, tabT, tab32, wflags, tabX);
     TGNN_CUDA(cudaGetLastError());
 }
 

@@ -186,6 +186,7 @@ struct ConvArgs {
     // 3xTF32 arithmetic on xin (conv_adj_body.cuh) when one is raised
     const uint4* xh;         // [n_rows][8]   split copy of xin: per 4 channels {hi01, hi23, lo01, lo23} fp16 pairs
     const uint32_t* tabH;    // [K+1][1024]   fp16 hi|lo fragment tables; entry K = nnConv.root
+    const uint32_t* tabX;    // [K+1][1024]   fp16 hi|lo A-operand fragment tables of W^T (k_conv_x); entry K = nnConv.root
     const int* flag_x;       // raised by the producer of xin when a value is outside the fp16 range
     const int* flag_w;       // raised at table build when a root weight is outside the fp16 range
     const uint8_t* mask;     // node mask (tgnn_set_node_mask) or null: rows with mask 0 are written as 0 and stay out of the statistics
@@ -205,6 +206,8 @@ void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
 constexpr float TG_H_LIMIT = 60000.f;    // |x| above this (or NaN) raises the range flag: fp16 max is 65504
 constexpr int TG_HFRAG32 = 1024;         // 32-bit words of one fp16 hi|lo fragment table of a 32x32 matrix
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st);
+void launch_conv_x(const ConvArgs& a, int sm_count, cudaStream_t st);     // transposed MMA roles (weights = A operand), large graphs
+constexpr bool TGNN_CONV_X_DEFAULT = false;   // k_conv_x is chosen automatically on large graphs (else only with TGNN_CONV=x)
 // tcgen05 edge-block kernel (conv_t.cu) + its fp32 stand-by for the range guard; tabT: [K+1][2048] words, tab32: [K+1][1024]
 constexpr int TG_TIMG32 = 2048;          // 32-bit words of one pre-swizzled [64 x 64] fp16 weight image
 int conv_t_blocks(int t_tiles, int sm_count);
@@ -319,7 +322,8 @@ void launch_bn_coef_eval(const float* rmean, const float* rvar, const float* gam
 // per-type edge weight tables of all layers in one launch (tables.cu); null table pointers are skipped
 struct TableLayer { const float *a1, *c1, *a2, *c2, *a3, *c3, *root; };   // edge MLP (weight, bias) x 3 and nnConv.root
 void launch_edge_tables(const float* type_rows, int n_types, int d_e, int n_layers, const TableLayer* layers_dev,
-                        float* tabF, float* tabS, uint32_t* tabH, uint32_t* tabT, float* tab32, int* wflags, cudaStream_t st);
+                        float* tabF, float* tabS, uint32_t* tabH, uint32_t* tabT, float* tab32, int* wflags, cudaStream_t st,
+                        uint32_t* tabX = nullptr);
 
 void launch_transpose(const float* in, float* out, int rows, int cols, cudaStream_t st);  // out[c][r] = in[r][c]
 // frag table (tensor-core B fragments, hi|lo TF32 split) of a k-major [K][N] matrix; maps: see kernels.cu
