@@ -169,6 +169,13 @@ struct tgnn_handle {
         void drop() { if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; } seen = 0; }
     } replay;
     uint64_t graph_gen = 0, param_gen = 0;
+    // small graphs: a layer's collision branch (k_gin) runs on a side stream next to the adjacency branch (k_conv_*): the two
+    // kernels are latency chains of a few CTAs each (16 + 19 us at N ~ 600), not throughput work.  Fork / join by events, so a
+    // captured forward gets two parallel branches per layer.
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool two_streams_off = getenv("TGNN_BRANCHES") && std::string(getenv("TGNN_BRANCHES")) == "0";
+    bool fin_off = getenv("TGNN_BNFIN") && std::string(getenv("TGNN_BNFIN")) == "launch";       // A/B: BatchNorm statistics by k_bn_finish launches
 
     // node mask (tgnn_set_node_mask): sub-layout on the resident structures
     bool mask_on = false;
@@ -477,7 +484,8 @@ void alloc_workspace(tgnn_handle* h) {
                           (size_t)init_num_parts((int)own, h->sm_count)});
     size_t part_bytes = std::max(np * 64, (size_t)dense_row_blocks((int)own) * 2 * 256) * sizeof(double);
     res(h->partA, part_bytes);
-    res(h->partB, np * 64 * sizeof(double));
+    res(h->partB, part_bytes);                       // (stages alternate between the two: a consumer that finishes a BatchNorm
+                                                     //  itself reads one while its CTAs write the other)
     res(h->sums, 2 * 512 * sizeof(double));
     res(h->slab_ptrs, (size_t)(L + 1) * sizeof(float*));
     std::vector<const float*> slabs(L + 1);
@@ -632,6 +640,9 @@ void halo_exchange(tgnn_handle* h, float* a, float* b, int* flag, cudaStream_t s
     lz.end(2);
 }
 
+constexpr int64_t FIN_MAX_NODES = 32768;          // up to here the consumers finish the BatchNorm statistics themselves (bn_fin.cuh)
+constexpr int64_t BRANCH_MAX_NODES = 65536;       // above this either branch fills the GPU on its own
+
 void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st, bool capturing = false) {
     TGNN_CHECK(h->graph_set, "tgnn_forward: no graph set (call tgnn_set_graph first)");
     if (!capturing) {
@@ -680,7 +691,22 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     ia.xh = h->need_xh() ? h->xh.as<uint32_t>() : nullptr; ia.flag = h->need_xh() ? h->rflag(0) : nullptr;
     ia.mask = h->mask();
     const int np_init = init_num_parts(n_own, h->sm_count);
-    if (train) {
+    // small graphs: no k_bn_finish launches -- every consumer of a BatchNorm'd tensor finishes the statistic in its prologue
+    const bool fin_small = train && h->world == 1 && n_own <= FIN_MAX_NODES && !h->fin_off;
+    auto make_fin = [&](const double* part, int n_part, const tgnn_handle::BnP& bn, size_t coef_off) {
+        BnFin f{};
+        f.part = part; f.n_part = n_part; f.count = count; f.count_ptr = h->count_ptr();
+        f.gamma = bn.w; f.beta = bn.b; f.coef_out = h->C(coef_off);
+        return f;
+    };
+    if (train && fin_small) {
+        lz.begin("init");
+        launch_init(ia, 0, h->sm_count, st);                                                         // partials -> partA
+        ia.fin = make_fin(h->partA.as<double>(), np_init, h->init_bn[0], h->coef_init[0]); ia.part = h->partB.as<double>();
+        launch_init(ia, 1, h->sm_count, st);                                                         // finishes BN 0; partials -> partB
+        ia.fin = make_fin(h->partB.as<double>(), np_init, h->init_bn[1], h->coef_init[1]); ia.part = nullptr;
+        lz.end(2);
+    } else if (train) {
         lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
         lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[0], h->coef_init[0]); lz.end(h->world == 1 || h->px.ok ? 1 : 2);
         lz.begin("init"); launch_init(ia, 1, h->sm_count, st); lz.end(1);
@@ -692,6 +718,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     // ---- message-passing layers ----------------------------------------------------------------
     const int n_layers = h->stop_layer >= 0 ? std::min(L, h->stop_layer + 1) : L;
     const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count);
+    const bool fork = !h->two_streams_off && h->world == 1 && !h->profiling && !h->role_dbg_on && h->g.n_own <= BRANCH_MAX_NODES;
+    if (fork && !h->side_stream) {
+        TGNN_CUDA(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+        TGNN_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        TGNN_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
     for (int i = 0; i < n_layers; ++i) {
         const tgnn_handle::LayerP& P = h->lp[i];
         if (h->tables_streamed) { lz.begin("conv"); build_tables(h, st, i); lz.end(1); }
@@ -705,6 +737,10 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.mask = h->mask();
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
         ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn;
+        if (fork) {                                   // everything the two branches read is complete at this point of st
+            TGNN_CUDA(cudaEventRecord(h->ev_fork, st));
+            TGNN_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        }
         lz.begin("conv");
         if (h->use_z) {
             // fp16 kernel + its tf32 stand-by (exits at once unless a range flag is raised)
@@ -747,17 +783,22 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         const bool gw = h->use_gw && ga.hmlp;        // layers whose GIN weights are outside the fp16 range stay on k_gin
         const int np_gin = gw ? gin_w_num_parts(h->g.gw_tiles, h->sm_count) : gin_num_parts(n_own, h->sm_count);
         lz.begin("gin");
+        cudaStream_t st_gin = fork ? h->side_stream : st;
         if (gw) {
             ga.gw_meta = h->g.gw_meta.as<int>(); ga.gw_seg = h->g.gw_seg.as<int>(); ga.gw_loc = h->g.gw_loc.as<uint16_t>();
             ga.gw_tiles = h->g.gw_tiles; ga.err = h->err_dev;
             ga.dbg = h->role_dbg_on ? h->role_dbg.as<long long>() + 128 : nullptr;
-            launch_gin_w(ga, h->sm_count, st);
-        } else launch_gin(ga, h->sm_count, st);
+            launch_gin_w(ga, h->sm_count, st_gin);
+        } else launch_gin(ga, h->sm_count, st_gin);
         lz.end(1);
+        if (fork) {
+            TGNN_CUDA(cudaEventRecord(h->ev_join, h->side_stream));
+            TGNN_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));
+        }
 
         const int np_a = (h->use_s || h->use_z) ? h->g.s_tiles : (h->use_t ? conv_t_num_parts(h->g.t_tiles, h->sm_count) : np_conv);
         // small graphs: k_combine finishes the two BatchNorms in its prologue (one launch less per layer)
-        const bool fin_in_combine = train && h->world == 1 && np_a + np_gin <= 1024;
+        const bool fin_in_combine = fin_small && np_a + np_gin <= 1024;
         CombineFin cf{};
         if (fin_in_combine) {
             cf.part[0] = h->partA.as<double>(); cf.n_part[0] = np_a; cf.part[1] = h->partB.as<double>(); cf.n_part[1] = np_gin;
@@ -807,8 +848,12 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             da.virtual_concat = k == 0;
             da.in_coef = k == 0 ? nullptr : h->C(h->coef_fin[k - 1]);
             da.wt = h->fin_wt[k]->as<float>(); da.bias = h->fin_bias[k];
-            da.out = h->fa[k].as<float>(); da.part = train ? h->partA.as<double>() : nullptr;
+            double* part_k = (k & 1) ? h->partB.as<double>() : h->partA.as<double>();
+            double* part_prev = (k & 1) ? h->partA.as<double>() : h->partB.as<double>();
+            const bool fin_k = fin_small && !h->dense_ffma;
+            da.out = h->fa[k].as<float>(); da.part = train ? (fin_k ? part_k : h->partA.as<double>()) : nullptr;
             da.n = n_own; da.K = dims[k]; da.n_out = dims[k + 1]; da.mask = h->mask();
+            if (fin_k && k > 0) da.fin = make_fin(part_prev, dense_row_blocks(n_own), h->fin_bn[k - 1], h->coef_fin[k - 1]);
             lz.begin("final");
             int nl = 1;
             if (h->dense_ffma) launch_dense(da, st);
@@ -818,15 +863,17 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
                                      h->sm_count, st);
             }
             lz.end(nl, 1);
-            if (train) {
+            if (train && !fin_k) {
                 lz.begin("bnfin");
                 finish_bn(h->partA.as<double>(), dense_row_blocks(n_own), dims[k + 1], h->fin_bn[k], h->coef_fin[k]);
                 lz.end(h->world == 1 || h->px.ok ? 1 : 2);
             }
         }
+        BnFin score_fin{};
+        if (fin_small && !h->dense_ffma) score_fin = make_fin(h->partB.as<double>(), dense_row_blocks(n_own), h->fin_bn[3], h->coef_fin[3]);
         lz.begin("score");
         launch_score(h->fa[3].as<float>(), h->C(h->coef_fin[3]), h->score_w, h->fin_last_bias, scores,
-                     n_own, st, h->mask());
+                     n_own, st, h->mask(), score_fin.part ? &score_fin : nullptr);
         lz.end(1);
     }
     // Device-side errors are ALWAYS surfaced: synchronously here when that is cheap or asked for (small graphs: the
@@ -969,6 +1016,9 @@ int tgnn_destroy(tgnn_handle* h) {
         for (auto& e : h->prof) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         h->replay.drop();
         if (h->replay.cap_stream) cudaStreamDestroy(h->replay.cap_stream);
+        if (h->side_stream) cudaStreamDestroy(h->side_stream);
+        if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+        if (h->ev_join) cudaEventDestroy(h->ev_join);
         peer_close(h);
         if (h->comm && nccl().CommDestroy) nccl().CommDestroy(h->comm);
         if (h->err_host) cudaFreeHost(h->err_host);

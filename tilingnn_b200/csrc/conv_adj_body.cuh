@@ -2,6 +2,7 @@
 // stand-in taken when a range flag is raised -- by k_conv_h (conv_h.cu); also the mma.sync 3xTF32 building block of k_gin.
 #pragma once
 
+#include "bn_fin.cuh"
 #include "tgnn_internal.h"
 
 namespace tgnn {
@@ -199,10 +200,7 @@ __device__ __forceinline__ void conv_adj_body(const ConvArgs& A, float* smem) {
         }
         __syncwarp();
     }
-    if (A.part) {
-        A.part[(size_t)gwarp * 64 + lane] = s1;
-        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
-    }
+    if (A.part) block_part_store(A.part, s1, s2, reinterpret_cast<double*>(smem), NW);      // one partial row per CTA
 }
 
 

@@ -221,10 +221,7 @@ k_conv_h(ConvArgs A) {
         }
         if (SPLIT) __syncthreads(); else __syncwarp();
     }
-    if (A.part) {
-        A.part[(size_t)gwarp * 64 + lane] = s1;
-        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
-    }
+    if (A.part) block_part_store(A.part, s1, s2, reinterpret_cast<double*>(smem), WARPS);    // one partial row per CTA
 }
 
 
@@ -388,10 +385,7 @@ k_conv_x(ConvArgs A) {
         }
         __syncwarp();
     }
-    if (A.part) {
-        A.part[(size_t)gwarp * 64 + lane] = s1;
-        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
-    }
+    if (A.part) block_part_store(A.part, s1, s2, reinterpret_cast<double*>(smem), WARPS);    // one partial row per CTA
 }
 
 }  // namespace

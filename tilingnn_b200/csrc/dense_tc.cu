@@ -26,6 +26,7 @@
 
 #include <cuda_fp16.h>
 
+#include "bn_fin.cuh"
 #include "tc_common.cuh"
 #include "tgnn_internal.h"
 
@@ -57,6 +58,7 @@ struct DenseTcArgs {
     int standby;                // ... when standby != 0 (else the tf32 variant always runs)
     int n, K;
     const uint8_t* mask;        // node mask or null: masked rows are written as 0 (and add nothing to the column sums)
+    BnFin fin;                  // fin.part != null: finish the input's BatchNorm (C = K) in the prologue, publish it to in_coef
 };
 
 constexpr float H_WSCALE = 64.f, H_WSCALE_INV = 1.f / 64.f;   // fp16 variant: weights are packed as w * 2^6 (their lo parts stay normal)
@@ -109,6 +111,7 @@ k_dense_tc(DenseTcArgs A) {
     __shared__ uint32_t tmem_base_smem;
     __shared__ int timeout_flag;
     __shared__ const float* slab_ptr[32];              // virtual concat: slab base pointers (no dependent global load per slab)
+    __shared__ __align__(16) float coef_s[4 * 256];    // input BatchNorm coefficients when this launch finishes them itself (A.fin)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (A.virtual_concat && tid < A.K / BK && tid < 32) slab_ptr[tid] = A.slabs[tid];
@@ -138,6 +141,13 @@ k_dense_tc(DenseTcArgs A) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_smem;
+    // small graphs: the previous stage's BatchNorm is finished here (every CTA the same fixed-order sums) instead of by a
+    // k_bn_finish launch in between; the stage ring is idle until the producers start, so it serves as the scratch space
+    const float* in_coef = A.in_coef;
+    if (A.fin.part) {
+        bn_finish_block(A.fin, A.K, coef_s, reinterpret_cast<double*>(smem));
+        in_coef = coef_s;
+    }
 
     if (warp < N_PROD_WARPS) {
         // ===================== producers: 256 threads, item (row = tid/8 + 32 j, chunk = tid%8) =====================
@@ -169,10 +179,10 @@ k_dense_tc(DenseTcArgs A) {
         };
         int g = 0, tile = blockIdx.x, s = 0;
         float4 nmh = make_float4(0.f, 0.f, 0.f, 0.f), nml = nmh, nsc = nmh, nbe = nmh;
-        if (A.in_coef) {
-            const float4* cf = reinterpret_cast<const float4*>(A.in_coef) + c;
+        if (in_coef) {
+            const float4* cf = reinterpret_cast<const float4*>(in_coef) + c;
             const int C4 = A.K / 4;
-            nmh = __ldg(cf); nml = __ldg(cf + C4); nsc = __ldg(cf + 2 * C4); nbe = __ldg(cf + 3 * C4);
+            nmh = cf[0]; nml = cf[C4]; nsc = cf[2 * C4]; nbe = cf[3 * C4];
         }
         bool bad = false;                                   // fp16 variant: a value outside the fp16 range was seen
         auto process = [&](float4 (&buf)[4]) -> bool {
@@ -181,17 +191,17 @@ k_dense_tc(DenseTcArgs A) {
             const uint32_t sa_hi = smem_base + st * STAGE_BYTES, sa_lo = sa_hi + A_TILE_BYTES;
             // BatchNorm coefficients of this thread's 4 columns (lazy BN of the input), fetched one slab ahead
             const float4 cmh = nmh, cml = nml, csc = nsc, cbe = nbe;
-            if (A.in_coef) {
+            if (in_coef) {
                 const int ns = (s + 1 == n_slabs) ? 0 : s + 1;
-                const float4* cf = reinterpret_cast<const float4*>(A.in_coef + ns * BK) + c;
+                const float4* cf = reinterpret_cast<const float4*>(in_coef + ns * BK) + c;
                 const int C4 = A.K / 4;
-                nmh = __ldg(cf); nml = __ldg(cf + C4); nsc = __ldg(cf + 2 * C4); nbe = __ldg(cf + 3 * C4);
+                nmh = cf[0]; nml = cf[C4]; nsc = cf[2 * C4]; nbe = cf[3 * C4];
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int r = rbase + 32 * j;
                 float4 v = buf[j];
-                if (A.in_coef) {
+                if (in_coef) {
                     v.x = fmaf((v.x - cmh.x) - cml.x, csc.x, cbe.x);
                     v.y = fmaf((v.y - cmh.y) - cml.y, csc.y, cbe.y);
                     v.z = fmaf((v.z - cmh.z) - cml.z, csc.z, cbe.z);
@@ -463,9 +473,11 @@ int launch_dense_tc(const DenseArgs& d, const float* w_img, const void* w_img16,
     a.slabs = d.slabs; a.a = d.a; a.virtual_concat = d.virtual_concat; a.in_coef = d.in_coef;
     a.bias = d.bias; a.out = d.out; a.part = d.part; a.error_flag = error_flag; a.mask = d.mask;
     a.n = d.n; a.K = d.K; a.range_flag = range_flag;
+    a.fin = d.fin;                           // the kernel that runs first finishes the input's BatchNorm and publishes in_coef ...
     if (w_img16) {
         a.w_img = reinterpret_cast<const float*>(w_img16); a.standby = 0;
         launch_dense_variant<true>(a, d.n_out, sm_count, st);
+        a.fin = BnFin{};                     // ... the stand-by behind it reads the published coefficients
     }
     a.w_img = w_img; a.standby = w_img16 ? 1 : 0;
     launch_dense_variant<false>(a, d.n_out, sm_count, st);

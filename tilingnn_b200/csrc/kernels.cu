@@ -159,12 +159,17 @@ k_gin(GinArgs A) {
             s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
         }
     }
-    if (A.part && g == 0) {
+    if (A.part) {                                 // one partial row per CTA: the warps' rows are added in warp order
+        double* scratch = reinterpret_cast<double*>(smem);            // (the weight tables: no warp reads them any more)
+        __syncthreads();
+        if (g == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            A.part[(size_t)gwarp * 64 + 8 * t + j] = s1[j];
-            A.part[(size_t)gwarp * 64 + 32 + 8 * t + j] = s2[j];
+            for (int j = 0; j < 8; ++j) {
+                scratch[warp * 64 + 8 * t + j] = s1[j];
+                scratch[warp * 64 + 32 + 8 * t + j] = s2[j];
+            }
         }
+        block_part_finish(A.part, scratch, WARPS);
     }
 }
 
@@ -176,7 +181,7 @@ __device__ __forceinline__ float bn_apply(float x, const float* __restrict__ coe
 }
 
 template <bool FIN>
-__global__ void __launch_bounds__(256) k_combine(const float4* __restrict__ pre1, const float* __restrict__ coef1,
+__global__ void __launch_bounds__(FIN ? 1024 : 256) k_combine(const float4* __restrict__ pre1, const float* __restrict__ coef1,
                           const float4* __restrict__ pre2, const float* __restrict__ coef2,
                           const float4* __restrict__ res, float4* __restrict__ out, uint4* __restrict__ xh,
                           int* __restrict__ flag, float4* __restrict__ g2out, int64_t n4, CombineFin fin, const uint8_t* __restrict__ mask) {
@@ -184,23 +189,35 @@ __global__ void __launch_bounds__(256) k_combine(const float4* __restrict__ pre1
     bool bad = false;
     if (FIN) {
         // small graphs: every block finishes the two BatchNorms itself (same fixed order everywhere, so all blocks
-        // get identical coefficients) instead of waiting for a separate k_bn_finish launch; block 0 publishes them
-        __shared__ double ssum[128];
-        if (threadIdx.x < 128) {
-            const int w = threadIdx.x >> 6, col = threadIdx.x & 63;
+        // get identical coefficients) instead of waiting for a separate k_bn_finish launch; block 0 publishes them.
+        // The block's (blockDim / 128) thread slices each sum every nsl-th partial row of a column with all their loads in
+        // flight at once (the prologue is one L2 latency, not one per 8 rows); the slices are added in a fixed order.
+        __shared__ double ssum[8][128];
+        const int nsl = blockDim.x >> 7;                                       // 8 at the launch width of 1024 threads
+        double cnt = fin.count;
+        if (fin.count_ptr && threadIdx.x < 64) cnt = *fin.count_ptr;           // (in flight with the partial rows)
+        {
+            const int col128 = threadIdx.x & 127, slice = threadIdx.x >> 7;
+            const int w = col128 >> 6, col = col128 & 63;
             const double* p = (w == 0 ? fin.part[0] : fin.part[1]) + col;      // (no dynamic indexing of the parameter struct)
             const int nr = w == 0 ? fin.n_part[0] : fin.n_part[1];
             double s = 0.0;
-#pragma unroll 8
-            for (int r = 0; r < nr; ++r) s += p[(size_t)r * 64];
-            ssum[threadIdx.x] = s;
+            for (int r0 = slice; r0 < nr; r0 += 16 * nsl) {                    // 16 rows in flight, then their adds (row order)
+                double v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) { const int r = r0 + k * nsl; v[k] = 0.0; if (r < nr) v[k] = p[(size_t)r * 64]; }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) s += v[k];
+            }
+            ssum[slice][col128] = s;
         }
         __syncthreads();
         if (threadIdx.x < 64) {
             const int w = threadIdx.x >> 5, c = threadIdx.x & 31;
-            const double cnt = fin.count_ptr ? *fin.count_ptr : fin.count;
-            const double mean = ssum[w * 64 + c] / cnt;
-            double var = ssum[w * 64 + 32 + c] / cnt - mean * mean;
+            double t1 = 0.0, t2 = 0.0;
+            for (int k = 0; k < nsl; ++k) { t1 += ssum[k][w * 64 + c]; t2 += ssum[k][w * 64 + 32 + c]; }
+            const double mean = t1 / cnt;
+            double var = t2 / cnt - mean * mean;
             if (var < 0.0) var = 0.0;
             const double rstd = 1.0 / sqrt(var + BN_EPS);
             const float mh = (float)mean, ml = (float)(mean - (double)mh);
@@ -251,14 +268,16 @@ k_init(InitArgs A) {
     __shared__ __align__(16) float w0t[INIT_MAX_DX * 32];      // [d][c]
     __shared__ __align__(16) float w1t[32 * 32];               // [k][c]
     __shared__ float cf[2][128];
-    __shared__ float tile[WARPS][32 * 33];
+    __shared__ __align__(16) float tile[WARPS][32 * 33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < A.d_x * 32; i += TPB) w0t[i] = __ldg(A.w0 + (i & 31) * A.d_x + (i >> 5));
+    const bool fin = MODE >= 1 && A.fin.part != nullptr;      // small graphs: this launch finishes the BatchNorm it needs fresh
     if (MODE >= 1) {
         for (int i = threadIdx.x; i < 32 * 32; i += TPB) w1t[i] = __ldg(A.w1t + i);
-        if (threadIdx.x < 128) cf[0][threadIdx.x] = A.coef0[threadIdx.x];
+        if (threadIdx.x < 128 && !(fin && MODE == 1)) cf[0][threadIdx.x] = A.coef0[threadIdx.x];
     }
-    if (MODE == 2 && threadIdx.x < 128) cf[1][threadIdx.x] = A.coef1[threadIdx.x];
+    if (MODE == 2 && threadIdx.x < 128 && !fin) cf[1][threadIdx.x] = A.coef1[threadIdx.x];
+    if (fin) bn_finish_block(A.fin, 32, cf[MODE == 1 ? 0 : 1], reinterpret_cast<double*>(&tile[0][0]));
     __syncthreads();
     const float b0 = __ldg(A.b0 + lane), b1 = MODE >= 1 ? __ldg(A.b1 + lane) : 0.f;
     const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
@@ -334,18 +353,20 @@ k_init(InitArgs A) {
         }
     }
     if (MODE == 2 && bad) *A.flag = 1;
-    if (MODE < 2 && A.part) {
-        A.part[(size_t)gwarp * 64 + lane] = s1;
-        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
-    }
+    if (MODE < 2 && A.part) block_part_store(A.part, s1, s2, reinterpret_cast<double*>(&tile[0][0]), WARPS);     // one partial row per CTA
 }
 
 // the same for d_x > 64: lane = channel, one warp per node
 template <int MODE>
 __global__ void __launch_bounds__(TPB)
 k_init_wide(InitArgs A) {
-    __shared__ float w1t[32 * 33];
+    __shared__ __align__(16) float w1t[32 * 33];
+    __shared__ float cfs[128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool fin = MODE >= 1 && A.fin.part != nullptr;      // small graphs: this launch finishes the BatchNorm it needs fresh
+    if (fin) bn_finish_block(A.fin, 32, cfs, reinterpret_cast<double*>(w1t));
+    const float* coef0 = (fin && MODE == 1) ? cfs : A.coef0;
+    const float* coef1 = (fin && MODE == 2) ? cfs : A.coef1;
     if (MODE >= 1) {
         for (int i = threadIdx.x; i < 32 * 32; i += TPB) w1t[(i >> 5) * 33 + (i & 31)] = __ldg(A.w1t + i);
         __syncthreads();
@@ -361,13 +382,13 @@ k_init_wide(InitArgs A) {
         const bool kept = row_kept(A.mask, node);
         if (!kept) v = 0.f;
         if (MODE >= 1) {
-            float y = bn_apply(v, A.coef0, lane, 32);
+            float y = bn_apply(v, coef0, lane, 32);
             float o = b1;
 #pragma unroll
             for (int k = 0; k < 32; ++k) o = fmaf(__shfl_sync(0xffffffffu, y, k), w1t[k * 33 + lane], o);
             v = kept ? leaky(o) : 0.f;
             if (MODE == 2) {
-                const float o2 = kept ? bn_apply(v, A.coef1, lane, 32) : 0.f;
+                const float o2 = kept ? bn_apply(v, coef1, lane, 32) : 0.f;
                 A.out[(size_t)node * F + lane] = o2;
                 if (A.xh) {
                     __half hi, lo;
@@ -386,10 +407,7 @@ k_init_wide(InitArgs A) {
         s1 += (double)v;
         s2 += (double)v * (double)v;
     }
-    if (MODE < 2 && A.part) {
-        A.part[(size_t)gwarp * 64 + lane] = s1;
-        A.part[(size_t)gwarp * 64 + 32 + lane] = s2;
-    }
+    if (MODE < 2 && A.part) block_part_store(A.part, s1, s2, reinterpret_cast<double*>(w1t), WARPS);            // one partial row per CTA
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -490,8 +508,11 @@ k_dense(DenseArgs A) {
 
 // final Linear(32 -> 1) + Sigmoid on BN(a3)   (TilinGNN.py:47)
 __global__ void k_score(const float* __restrict__ a3, const float* __restrict__ coef, const float* __restrict__ w,
-                        float b, float* __restrict__ out, int64_t n, const uint8_t* __restrict__ mask) {
+                        float b, float* __restrict__ out, int64_t n, const uint8_t* __restrict__ mask, BnFin fin) {
     const int lane = threadIdx.x & 31;
+    __shared__ float cfs[128];
+    __shared__ double fin_scratch[8 * 64];
+    if (fin.part) { bn_finish_block(fin, 32, cfs, fin_scratch); coef = cfs; }     // small graphs: the last BatchNorm is finished here
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float wl = __ldg(w + lane);
@@ -871,8 +892,8 @@ static int gin_blocks(int n_own, int sm_count) {
 }
 static int init_blocks(int n_own, int sm_count) { return persistent_blocks((n_own + WARPS * 32 - 1) / (WARPS * 32), sm_count, 4); }
 
-int gin_num_parts(int n_own, int sm_count) { return gin_blocks(n_own, sm_count) * WARPS; }
-int init_num_parts(int n_own, int sm_count) { return init_blocks(n_own, sm_count) * WARPS; }
+int gin_num_parts(int n_own, int sm_count) { return gin_blocks(n_own, sm_count); }          // one partial row per CTA
+int init_num_parts(int n_own, int sm_count) { return init_blocks(n_own, sm_count); }
 int dense_row_blocks(int n) { return (n + DM - 1) / DM; }
 
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st) {
@@ -917,10 +938,11 @@ void launch_combine(const float* pre1, const float* coef1, const float* pre2, co
                     const float* residual, float* out, uint4* xh, int* flag, float* g2out, int64_t n_own, cudaStream_t st,
                     const CombineFin* fin, const uint8_t* mask) {
     int64_t n4 = n_own * (F / 4);
-    int blocks = (int)std::min<int64_t>((n4 + 255) / 256, 148 * 16);
+    const int tpb = fin ? 1024 : 256;       // the BatchNorm-finishing prologue wants many loads in flight (see the kernel)
+    int blocks = (int)std::min<int64_t>((n4 + tpb - 1) / tpb, 148 * 16);
     if (blocks < 1) blocks = 1;
     auto kern = fin ? k_combine<true> : k_combine<false>;
-    kern<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(pre1), coef1,
+    kern<<<blocks, tpb, 0, st>>>(reinterpret_cast<const float4*>(pre1), coef1,
                                       reinterpret_cast<const float4*>(pre2), coef2,
                                       reinterpret_cast<const float4*>(residual), reinterpret_cast<float4*>(out), xh, flag,
                                       reinterpret_cast<float4*>(g2out), n4, fin ? *fin : CombineFin{}, mask);
@@ -950,10 +972,11 @@ void launch_dense(const DenseArgs& a, cudaStream_t st) {
     TGNN_CUDA(cudaGetLastError());
 }
 
-void launch_score(const float* a3, const float* coef, const float* w, float b, float* out, int64_t n, cudaStream_t st, const uint8_t* mask) {
+void launch_score(const float* a3, const float* coef, const float* w, float b, float* out, int64_t n, cudaStream_t st, const uint8_t* mask,
+                  const BnFin* fin) {
     int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
     if (blocks < 1) blocks = 1;
-    k_score<<<blocks, 256, 0, st>>>(a3, coef, w, b, out, n, mask);
+    k_score<<<blocks, 256, 0, st>>>(a3, coef, w, b, out, n, mask, fin ? *fin : BnFin{});
     TGNN_CUDA(cudaGetLastError());
 }
 

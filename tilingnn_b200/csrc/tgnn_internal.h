@@ -179,7 +179,7 @@ struct ConvArgs {
     const int* cptr; const int* ctype; const int* csrc; const uint8_t* cdst;
     const float* inv_deg;
     float* out;              // pre1 [n_own][32]  LeakyReLU(conv), before BatchNorm
-    double* part;            // [n_part][64]  per-warp partial sums (sum, sum of squares)
+    double* part;            // [n_part][64]  per-CTA partial sums (sum, sum of squares)
     int n_own, n_tiles;
     int wn;                  // rows per warp tile: WN_SMALL or WN_BIG
     // fp16-split operands of k_conv_h (conv_h.cu) and the range flags: k_conv_h uses them when both flags are 0 and the
@@ -199,7 +199,7 @@ __device__ __forceinline__ bool row_kept(const uint8_t* __restrict__ mask, int n
 //   wn = 128: 12 warps per CTA (216 KB of accumulator tiles), 1 CTA per SM
 struct ConvGeom { int blocks, warps; bool split; };
 ConvGeom conv_geom(int n_tiles, int wn, int sm_count);
-inline int conv_adj_num_parts(int n_tiles, int wn, int sm_count) { ConvGeom g = conv_geom(n_tiles, wn, sm_count); return g.blocks * g.warps; }
+inline int conv_adj_num_parts(int n_tiles, int wn, int sm_count) { ConvGeom g = conv_geom(n_tiles, wn, sm_count); return g.blocks; }   // one partial row per CTA
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
 
 // fp16-split edge-chunk kernel (conv_h.cu)
@@ -252,6 +252,15 @@ void launch_gin_w(const GinArgs& a, int sm_count, cudaStream_t st);
 
 // b1_new = BN(pre1) * BN(pre2) + residual
 // xh / flag (optional): fp16-split copy of the result for k_conv_h and its range flag; g2out (optional): BN(pre2).
+// A train-mode BatchNorm that the CONSUMER of the normalised tensor finishes in its own prologue (bn_fin.cuh; small graphs:
+// no k_bn_finish launch between producer and consumer).  part: [n_part][2 C] doubles (sum[C] | sum of squares[C]).
+struct BnFin {
+    const double* part = nullptr; int n_part = 0;
+    double count = 1.0; const double* count_ptr = nullptr;      // node mask: number of kept nodes (device), overrides count
+    const float* gamma = nullptr; const float* beta = nullptr;
+    float* coef_out = nullptr;                                   // [4][C] {mean hi, mean lo, gamma / sqrt(var + eps), beta}; CTA 0 writes it
+};
+
 // fin (optional, small graphs): BatchNorm partials of the two branches -- the kernel then computes the coefficients in
 // its prologue (and block 0 stores them to coef_out) instead of reading coef1 / coef2.
 struct CombineFin {
@@ -272,6 +281,7 @@ struct InitArgs {
     float* out; double* part; int n_own;
     uint32_t* xh; int* flag;             // mode 2: fp16-split copy of h0 and its range flag (optional)
     const uint8_t* mask;                 // node mask or null
+    BnFin fin;                           // fin.part != null: mode 1 finishes stage 0's BatchNorm (coef0) itself, mode 2 stage 1's (coef1)
 };
 int init_num_parts(int n_own, int sm_count);
 void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st);
@@ -288,6 +298,7 @@ struct DenseArgs {
     double* part;               // [row_blocks][2][N_out]
     int n, K, n_out;
     const uint8_t* mask;        // node mask or null
+    BnFin fin;                  // fin.part != null: the kernel finishes the input's BatchNorm (C = K) itself and publishes in_coef
 };
 int dense_row_blocks(int n);
 void launch_dense(const DenseArgs& a, cudaStream_t st);
@@ -300,7 +311,7 @@ int launch_dense_tc(const DenseArgs& a, const float* w_img, const void* w_img16,
                     cudaStream_t st);
 
 void launch_score(const float* a3, const float* coef, const float* w, float b, float* out,
-                  int64_t n, cudaStream_t st, const uint8_t* mask = nullptr);
+                  int64_t n, cudaStream_t st, const uint8_t* mask = nullptr, const BnFin* fin = nullptr);
 
 // BatchNorm statistics: reduce partials (fixed order, fp64) and turn them into coefficients.
 // part layout: [n_part][2*C] (sum[C], sumsq[C]).  sums_out: [2*C] doubles.
