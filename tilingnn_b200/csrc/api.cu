@@ -764,6 +764,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
             ca.xh = h->xh.as<uint4>();
             ca.tabH = h->tabH.as<uint32_t>() + tslot * TG_HFRAG32;
             ca.flag_x = h->rflag(i); ca.flag_w = h->wflag(i);
+            ca.dbg = h->role_dbg_on ? h->role_dbg.as<long long>() : nullptr;
             if (h->use_x) { ca.tabX = h->tabX.as<uint32_t>() + tslot * TG_HFRAG32; launch_conv_x(ca, h->sm_count, st); }
             else launch_conv_h(ca, h->sm_count, st);
             lz.end(1);

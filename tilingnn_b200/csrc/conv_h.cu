@@ -12,7 +12,11 @@
 //     is 2^-22 relative -- the same as 3xTF32 (measured: 1.0e-7 vs 1.2e-7 of sum|x||w|).
 // fp16 has a narrow exponent range, so the producers raise a per-tensor flag when |x| > 60000 (or NaN); this kernel
 // then runs the layer with the 3xTF32 arithmetic of k_conv_adj on the fp32 rows instead (conv_adj_body.cuh).  Values below 2^-14 keep an absolute accuracy of 2^-35, far under fp32 rounding of the O(1) sums.
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
+
+#include <cstdlib>
+#include <string>
 
 #include "conv_adj_body.cuh"
 #include "hsplit.cuh"
@@ -20,6 +24,8 @@
 
 namespace tgnn {
 namespace {
+
+namespace cg = cooperative_groups;
 
 using tfx::XS;                  // padded shared-memory row stride (floats)
 constexpr float LO_INV = 1.0f / 2048.f;
@@ -95,20 +101,43 @@ __device__ __forceinline__ void ld_rowh2(const uint4* __restrict__ xh, int row, 
 template <int WN, int WARPS>
 __device__ __noinline__ void conv_adj_fallback(const ConvArgs& A, float* smem) { tfx::conv_adj_body<WN, WARPS>(A, smem); }
 
-// SPLIT = false: persistent, one warp per 64-row tile (large graphs).  SPLIT = true: one CTA per tile, its 8 warps take
-// every 8th chunk into private partial tiles that are summed in a fixed order -- the real layouts have ~10 tiles
-// (N ~ 600), where one warp walking ~60 latency-bound chunks per tile would leave the GPU idle.
+// SPLIT = false: persistent, one warp per 64-row tile (large graphs).  SPLIT = true: one CTA per tile, its warps take
+// contiguous ranges of the tile's chunks into private partial tiles that are summed in a fixed order -- the real layouts
+// have ~10 tiles (N ~ 600), where one warp walking ~80 latency-bound chunks per tile would leave the GPU idle.  That geometry
+// is a chain of dependent L2 accesses (measured with TGNN_ROLE_DBG: ~1350 cycles per chunk and warp, of which the MMAs and
+// the scatter are ~300 each), so everything that can be requested early is: the range flags and the tile's chunk range
+// together, the tile's slot indices staged in shared memory by the whole CTA in one pass (the loop then reads them at
+// shared-memory latency), the root pass operands before the partial tiles are summed; and 16 warps share a tile when the
+// graph has no more tiles than the GPU has SMs.
+constexpr int SPLIT_CAP = 256;                     // chunks of a tile staged in shared memory (larger tiles read global memory)
+constexpr int SPLIT_STAGE_BYTES = SPLIT_CAP * (CH * 4 + CH + 4);
 template <int WN, int WARPS, bool SPLIT>
-__global__ void __launch_bounds__(WARPS * 32, WN == WN_BIG ? 1 : 2)
+__global__ void __launch_bounds__(WARPS * 32, (WN == WN_BIG || WARPS > 8) ? 1 : 2)
 k_conv_h(ConvArgs A) {
     constexpr int TPB = WARPS * 32;
     extern __shared__ __align__(16) float smem[];
-    if ((A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w)) {            // out of the fp16 range: 3xTF32 on the fp32 rows
+    const long long t_start = SPLIT ? clock64() : 0ll;
+    long long t_loop0 = 0, t_loop1 = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // SPLIT: S CTAs of one thread-block cluster share a tile (S = 1 without a cluster launch)
+    const int S = SPLIT ? (int)cg::this_cluster().num_blocks() : 1;
+    const int crank = SPLIT ? (int)cg::this_cluster().block_rank() : 0;
+    const int tile_first = SPLIT ? (int)blockIdx.x / S : blockIdx.x * WARPS + warp;
+    bool out_of_range;
+    int c0s = 0, c1s = 0;
+    if (SPLIT) {     // (requested together: a short-circuit `||` of the two flags would serialise two L2 accesses)
+        const int fx = A.flag_x ? *A.flag_x : 0, fw = A.flag_w ? *A.flag_w : 0;
+        if (tile_first < A.n_tiles) { c0s = __ldg(A.cptr + tile_first); c1s = __ldg(A.cptr + tile_first + 1); }
+        out_of_range = (fx | fw) != 0;
+    } else out_of_range = (A.flag_x && *A.flag_x) || (A.flag_w && *A.flag_w);
+    if (out_of_range) {                                                       // out of the fp16 range: 3xTF32 on the fp32 rows
         conv_adj_fallback<WN, WARPS>(A, smem);                           // (same grid, same BatchNorm partial layout)
         return;
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* acc = smem + warp * (WN * XS);
+    int* s_src = reinterpret_cast<int*>(smem + WARPS * (WN * XS));       // SPLIT: [SPLIT_CAP][16] staged slot sources ...
+    int* s_type = s_src + SPLIT_CAP * CH;                                // ... [SPLIT_CAP] chunk types ...
+    uint8_t* s_dst = reinterpret_cast<uint8_t*>(s_type + SPLIT_CAP);     // ... [SPLIT_CAP][16] slot destinations
     const int g = lane >> 2, t = lane & 3;
     const int gwarp = blockIdx.x * WARPS + warp, nwarp = gridDim.x * WARPS;
     double s1 = 0.0, s2 = 0.0;
@@ -117,35 +146,64 @@ k_conv_h(ConvArgs A) {
     const uint4* __restrict__ xh = A.xh;
     BFragH bf;
     int cur_type = -1;
-    const int tile_first = SPLIT ? blockIdx.x : gwarp, tile_step = SPLIT ? gridDim.x : nwarp;
-    const int cstep = SPLIT ? WARPS : 1;
+    const int tile_step = SPLIT ? (int)gridDim.x / S : nwarp;
 
     for (int tile = tile_first; tile < A.n_tiles; tile += tile_step) {
         for (int i = lane; i < WN * XS / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int c0 = __ldg(A.cptr + tile) + (SPLIT ? warp : 0), c1 = __ldg(A.cptr + tile + 1);
+        int c0, c1;
+        const int* srcp = A.csrc; const uint8_t* dstp = A.cdst; const int* typep = A.ctype;
+        if (SPLIT) {
+            const int tt0 = tile == tile_first ? c0s : __ldg(A.cptr + tile), t1 = tile == tile_first ? c1s : __ldg(A.cptr + tile + 1);
+            // this CTA's share of the tile's chunks (contiguous; the whole tile without a cluster)
+            const int per_cta = (t1 - tt0 + S - 1) / S;
+            const int t0 = min(tt0 + crank * per_cta, t1), t1c = min(t0 + per_cta, t1);
+            const int nch = t1c - t0;
+            if (nch <= SPLIT_CAP) {                                     // (CTA-uniform)
+                if (tile != tile_first) __syncthreads();                // the previous tile's readers are done
+                const int4* gs = reinterpret_cast<const int4*>(A.csrc + (size_t)t0 * CH);
+                const uint32_t* gd = reinterpret_cast<const uint32_t*>(A.cdst + (size_t)t0 * CH);
+                for (int i = threadIdx.x; i < nch * (CH / 4); i += TPB) {
+                    reinterpret_cast<int4*>(s_src)[i] = __ldg(gs + i);
+                    reinterpret_cast<uint32_t*>(s_dst)[i] = __ldg(gd + i);
+                }
+                for (int i = threadIdx.x; i < nch; i += TPB) s_type[i] = __ldg(A.ctype + t0 + i);
+                __syncthreads();
+                srcp = s_src - (size_t)t0 * CH; dstp = s_dst - (size_t)t0 * CH; typep = s_type - t0;
+            }
+            // the tile's chunks go to the CTA's warps in CONTIGUOUS ranges (chunks are sorted by type: neighbours in the list
+            // mostly share their weight fragments)
+            const int per = (nch + WARPS - 1) / WARPS;
+            c0 = min(t0 + warp * per, t1c); c1 = min(c0 + per, t1c);
+        } else { c0 = __ldg(A.cptr + tile); c1 = __ldg(A.cptr + tile + 1); }
+        // (the persistent geometry reads the kernel parameters' arrays directly: no pointer registers in its hot loop)
+        auto ld_src = [&](int c) -> int { return SPLIT ? srcp[(size_t)c * CH + (lane & 15)] : __ldg(A.csrc + (size_t)c * CH + (lane & 15)); };
+        auto ld_dst = [&](int c) -> int { return SPLIT ? dstp[(size_t)c * CH + (lane & 15)] : __ldg(A.cdst + (size_t)c * CH + (lane & 15)); };
+        auto ld_type = [&](int c) -> int { return SPLIT ? typep[c] : __ldg(A.ctype + c); };
         // software pipeline: slot indices run TWO chunks ahead of the MMAs, gathered rows ONE chunk ahead, so neither
         // the index load nor the dependent row loads are waited for in the iteration that issues them
         uint4 pre[4] = {zero4, zero4, zero4, zero4};
         int psrc = -1, pdst = 0, ptype = 0;            // chunk c
-        int nsrc = -1, ndst = 0, ntype = 0;            // chunk c + cstep
+        int nsrc = -1, ndst = 0, ntype = 0;            // chunk c + 1
         if (c0 < c1) {
-            psrc = __ldg(A.csrc + (size_t)c0 * CH + (lane & 15));
-            pdst = __ldg(A.cdst + (size_t)c0 * CH + (lane & 15));
-            ptype = __ldg(A.ctype + c0);
-            if (c0 + cstep < c1) {
-                nsrc = __ldg(A.csrc + (size_t)(c0 + cstep) * CH + (lane & 15));
-                ndst = __ldg(A.cdst + (size_t)(c0 + cstep) * CH + (lane & 15));
-                ntype = __ldg(A.ctype + c0 + cstep);
+            psrc = ld_src(c0);
+            pdst = ld_dst(c0);
+            ptype = ld_type(c0);
+            if (c0 + 1 < c1) {
+                nsrc = ld_src(c0 + 1);
+                ndst = ld_dst(c0 + 1);
+                ntype = ld_type(c0 + 1);
             }
             const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
             if (sa >= 0) ld_rowh2(xh, sa, t, pre[0], pre[1]);
             if (sb >= 0) ld_rowh2(xh, sb, t, pre[2], pre[3]);
+            if (SPLIT) { load_bfrag_h(bf, A.tabH + (size_t)ptype * TG_HFRAG32, lane); cur_type = ptype; }      // with the first rows
         }
         __syncwarp();
-        for (int c = c0; c < c1; c += cstep) {
+        if (SPLIT) t_loop0 = clock64();
+        for (int c = c0; c < c1; ++c) {
             const uint4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
             const int csrc = psrc, cdst = pdst, type = ptype;
-            const int cn = c + cstep, cn2 = c + 2 * cstep;
+            const int cn = c + 1, cn2 = c + 2;
             if (cn < c1) {                                 // rows of the next chunk (its indices arrived an iteration ago)
                 const int sa = __shfl_sync(0xffffffffu, nsrc, g), sb = __shfl_sync(0xffffffffu, nsrc, g + 8);
                 pre[0] = pre[1] = pre[2] = pre[3] = zero4;
@@ -154,9 +212,9 @@ k_conv_h(ConvArgs A) {
             }
             psrc = nsrc; pdst = ndst; ptype = ntype;
             if (cn2 < c1) {                                // indices of the chunk after that
-                nsrc = __ldg(A.csrc + (size_t)cn2 * CH + (lane & 15));
-                ndst = __ldg(A.cdst + (size_t)cn2 * CH + (lane & 15));
-                ntype = __ldg(A.ctype + cn2);
+                nsrc = ld_src(cn2);
+                ndst = ld_dst(cn2);
+                ntype = ld_type(cn2);
             }
             if (type != cur_type) { load_bfrag_h(bf, A.tabH + (size_t)type * TG_HFRAG32, lane); cur_type = type; }
             if (ptype != type && cn < c1)          // next type's 4 KB table towards L1 (32 lines of 128 B)
@@ -175,27 +233,63 @@ k_conv_h(ConvArgs A) {
             }
             __syncwarp();
         }
+        if (SPLIT) t_loop1 = clock64();
         const int node0 = tile * WN;
         float* tile_acc = acc;
-        int r0 = 0, r1 = WN;                                      // rows this warp finishes
+        // SPLIT: this CTA finishes rows [row_lo, row_lo + rows_per) of the tile (all 64 without a cluster).  Root pass operands are
+        // requested BEFORE the partial tiles are summed (their L2 latency hides behind the barriers); warp w owns rows
+        // row_lo + 16 w .. + 15 of them
+        const int rows_per = SPLIT ? WN / S : WN, row_lo = crank * rows_per;
+        uint4 rcur[4] = {zero4, zero4, zero4, zero4};
+        float ria = 0.f, rib = 0.f;
+        const bool root_warp = SPLIT && 16 * warp < rows_per;
+        const int rra = row_lo + 16 * warp + g, rrb = rra + 8;                      // tile rows of the lane's two MMA rows
+        const bool rva = 16 * warp + g < rows_per, rvb = 16 * warp + g + 8 < rows_per;
+        if (root_warp) {
+            load_bfrag_h(bf, A.tabH + (size_t)A.n_types * TG_HFRAG32, lane); cur_type = A.n_types;      // (the chunk loop is over: bf is free)
+            if (rva && node0 + rra < A.n_own) { ld_rowh2(xh, node0 + rra, t, rcur[0], rcur[1]); ria = __ldg(A.inv_deg + node0 + rra); }
+            if (rvb && node0 + rrb < A.n_own) { ld_rowh2(xh, node0 + rrb, t, rcur[2], rcur[3]); rib = __ldg(A.inv_deg + node0 + rrb); }
+        }
         if (SPLIT) {
             __syncthreads();
-            for (int i = threadIdx.x; i < WN * XS; i += TPB) {    // fixed-order sum of the 8 partial tiles
+            for (int i = threadIdx.x; i < WN * XS; i += TPB) {    // fixed-order sum of the warps' partial tiles
                 float v = smem[i];
 #pragma unroll
                 for (int w = 1; w < WARPS; ++w) v += smem[w * (WN * XS) + i];
                 smem[i] = v;
             }
-            __syncthreads();
-            tile_acc = smem; r0 = warp * (WN / WARPS); r1 = r0 + WN / WARPS;
+            tile_acc = smem;
+            if (S > 1) {
+                // the cluster's S partial tiles -> this CTA's rows, summed in rank order through distributed shared memory into
+                // the (now free) partial-tile region of warp 1; the second cluster barrier keeps every CTA's partial tile
+                // untouched until all its readers are done
+                cg::cluster_group cluster = cg::this_cluster();
+                cluster.sync();
+                float* fin = smem + WN * XS;
+                for (int i = threadIdx.x; i < rows_per * 32; i += TPB) {
+                    const int off = (row_lo + (i >> 5)) * XS + (i & 31);
+                    float v = 0.f;
+                    for (int q = 0; q < S; ++q) v += *cluster.map_shared_rank(smem + off, q);
+                    fin[off] = v;
+                }
+                cluster.sync();
+                tile_acc = fin;
+            } else __syncthreads();
         }
         // mean over in-edges and root term in ONE read-modify-write of the tile: the root pass visits every row exactly
         // once (four 16-row chunks of the tile's own rows against table entry n_types), so
         //   acc[row] = fma(acc[row], inv_deg[row], x_row @ root)
         // replaces a separate scaling pass: 128 shared-memory wavefronts less per tile (and one rounding less)
-        if (!SPLIT || warp < WN / CH) {
+        if (SPLIT) {
+            if (root_warp) {
+                float m[4][4];
+                chunk_mma_h(rcur, bf, m);
+                if (rva) acc_fma8(tile_acc + rra * XS + 8 * t, m, 0, ria);
+                if (rvb) acc_fma8(tile_acc + rrb * XS + 8 * t, m, 1, rib);
+            }
+        } else {
             if (cur_type != A.n_types) { load_bfrag_h(bf, A.tabH + (size_t)A.n_types * TG_HFRAG32, lane); cur_type = A.n_types; }
-            for (int rc = SPLIT ? warp : 0; rc < (SPLIT ? warp + 1 : WN / CH); ++rc) {
+            for (int rc = 0; rc < WN / CH; ++rc) {
                 const int na = node0 + rc * CH + g, nb = na + 8;
                 uint4 cur[4] = {zero4, zero4, zero4, zero4};
                 float ia = 0.f, ib = 0.f;
@@ -208,8 +302,8 @@ k_conv_h(ConvArgs A) {
             }
         }
         if (SPLIT) __syncthreads(); else __syncwarp();
-        // bias, LeakyReLU, store, statistics (lane = channel)
-        for (int r = r0; r < r1; ++r) {
+        // bias, LeakyReLU, store, statistics (lane = channel); SPLIT: the CTA's rows round-robin over its warps
+        for (int r = SPLIT ? row_lo + warp : 0; r < (SPLIT ? row_lo + rows_per : WN); r += SPLIT ? WARPS : 1) {
             int node = node0 + r;
             if (node < A.n_own) {
                 float v = leaky(tile_acc[r * XS + lane] + bias_c);
@@ -222,6 +316,11 @@ k_conv_h(ConvArgs A) {
         if (SPLIT) __syncthreads(); else __syncwarp();
     }
     if (A.part) block_part_store(A.part, s1, s2, reinterpret_cast<double*>(smem), WARPS);    // one partial row per CTA
+    if (SPLIT && A.dbg && blockIdx.x == 0 && lane == 0) {                  // TGNN_ROLE_DBG=1: where the cycles of CTA 0 went
+        long long* d = A.dbg + warp * 4;
+        const long long t_end = clock64();
+        d[0] = t_end - t_start; d[1] = t_loop0 - t_start; d[2] = t_loop1 - t_loop0; d[3] = t_end - t_loop1;
+    }
 }
 
 
@@ -393,15 +492,28 @@ k_conv_x(ConvArgs A) {
 void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
     static PerDeviceOnce once;
     const size_t smem_small = (size_t)8 * WN_SMALL * XS * sizeof(float), smem_big = (size_t)12 * WN_BIG * XS * sizeof(float);
+    const size_t smem_split8 = smem_small + SPLIT_STAGE_BYTES, smem_split16 = 2 * smem_small + SPLIT_STAGE_BYTES;
     once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
-        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_split8));
+        TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_SMALL, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_split16));
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_BIG, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
     });
     // same grid as k_conv_adj: the BatchNorm partial layout is shared by the two kernels
     const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
+    static const bool w16_off = getenv("TGNN_CONV_W16") && std::string(getenv("TGNN_CONV_W16")) == "0";
     if (a.wn == WN_BIG) k_conv_h<WN_BIG, 12, false><<<g.blocks, 12 * 32, smem_big, st>>>(a);
-    else if (g.split) k_conv_h<WN_SMALL, 8, true><<<g.blocks, 256, smem_small, st>>>(a);
+    else if (g.split && g.cluster > 1) {                       // fewer tiles than SMs: a cluster of CTAs per tile
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(g.blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = smem_split8; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = g.cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        TGNN_CUDA(cudaLaunchKernelEx(&cfg, k_conv_h<WN_SMALL, 8, true>, a));
+    }
+    else if (g.split && g.blocks <= sm_count && !w16_off) k_conv_h<WN_SMALL, 16, true><<<g.blocks, 512, smem_split16, st>>>(a);   // a tile per SM: 16 warps share it
+    else if (g.split) k_conv_h<WN_SMALL, 8, true><<<g.blocks, 256, smem_split8, st>>>(a);
     else k_conv_h<WN_SMALL, 8, false><<<g.blocks, 256, smem_small, st>>>(a);
     TGNN_CUDA(cudaGetLastError());
 }

@@ -3,6 +3,8 @@
 // Layout in HBM: every node tensor is row-major [rows][32] fp32, one 128-byte line per node, so a
 // gather of a neighbour is exactly one coalesced line.  See DESIGN.md for the per-kernel byte model.
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 
 #include "conv_adj_body.cuh"
 #include "gin_mlp.cuh"
@@ -170,6 +172,103 @@ k_gin(GinArgs A) {
             }
         }
         block_part_finish(A.part, scratch, WARPS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Collision branch on SMALL graphs ("S" variant, n_own <= GIN_S_MAX_NODES): the same arithmetic as k_gin, laid out for latency
+// instead of throughput.  At N ~ 600 k_gin is 38 warps that each walk 4 rounds x 5 batches of dependent L2 loads and then
+// the MLP (19 us per launch, a third of a depth-20 forward).  Here one CTA of four warps takes one 16-node chunk: every
+// 8-lane group owns ONE destination row (a single round), all of the row's neighbour indices are fetched at once and
+// 16 neighbour rows are in flight per lane; the MLP's weight tables arrive by cp.async while the gather runs; warp 0
+// then runs the MLP.  One BatchNorm partial row per CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int GIN_S_THREADS = 128;
+constexpr int GIN_S_MAX_NODES = 4096;           // 256 chunks (= 256 BatchNorm partial rows for the consumer's prologue); beyond that k_gin
+
+template <bool HMLP>
+__device__ __forceinline__ void gin_load_weights_async(float* smem, const float* __restrict__ wfrag, int tid, int nthreads) {
+    auto cp16 = [](float* dst, const float* src) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    };
+    if (HMLP) {
+        for (int i = tid; i < GIN_W1 / 4; i += nthreads) cp16(smem + 4 * i, wfrag + 4 * i);
+        for (int i = tid; i < (GIN_W2H + GIN_W3H) / 4; i += nthreads) cp16(smem + GIN_W1 + 4 * i, wfrag + GIN_WFLOATS + 4 * i);
+        for (int i = tid; i < 128 / 4; i += nthreads) cp16(smem + GIN_W1 + GIN_W2H + GIN_W3H + 4 * i, wfrag + GIN_W1 + GIN_W2 + GIN_W3 + 4 * i);
+    } else {
+        for (int i = tid; i < GIN_WFLOATS / 4; i += nthreads) cp16(smem + 4 * i, wfrag + 4 * i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+template <bool HMLP>
+__global__ void __launch_bounds__(GIN_S_THREADS)
+k_gin_s(GinArgs A) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int WF = HMLP ? GIN_WFLOATS_H : GIN_WFLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    gin_load_weights_async<HMLP>(smem, A.wfrag, tid, GIN_S_THREADS);
+    float* xs = smem + WF;                       // [CH][XS] neighbour sums of the chunk
+    const int a = lane >> 3, q = lane & 7;
+    const int node0 = blockIdx.x * CH;
+    const int r = 4 * warp + a, node = node0 + r;
+    const bool live = node < A.n_own;
+    int e0 = 0, e1 = 0;
+    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+        e0 = __ldg(A.col_ptr + node); e1 = __ldg(A.col_ptr + node + 1);
+        const float4 c = ld_row4(A.xin, node, q);
+        const float self_w = 1.0f + A.eps;
+        sum.x = self_w * c.x; sum.y = self_w * c.y; sum.z = self_w * c.z; sum.w = self_w * c.w;
+    }
+    const int n_mine = e1 - e0;
+    int n_max = max(n_mine, __shfl_xor_sync(0xffffffffu, n_mine, 8));       // warp-uniform trip count
+    n_max = max(n_max, __shfl_xor_sync(0xffffffffu, n_max, 16));
+    for (int o64 = 0; o64 < n_max; o64 += 64) {
+        // lane q of the row's group fetches index positions q, q + 8, ... (<= 64 per pass), all in flight together
+        int ix[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { ix[k] = 0; if (o64 + 8 * k + q < n_mine) ix[k] = __ldg(A.col_src + e0 + o64 + 8 * k + q); }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {            // 16 neighbour rows in flight per lane, then their adds (CSR order)
+            if (o64 + 16 * b >= n_max) break;
+            float4 v[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const int idx = __shfl_sync(0xffffffffu, ix[2 * b + (k >> 3)], (lane & 24) + (k & 7));
+                v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o64 + 16 * b + k < n_mine) v[k] = ld_row4(A.xin, idx, q);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) add4(sum, v[k]);
+        }
+    }
+    *reinterpret_cast<float4*>(xs + r * XS + 4 * q) = sum;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (warp != 0) return;
+    const GinW<HMLP> Wt(smem);
+    double s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s1[j] = 0.0; s2[j] = 0.0; }
+    float a1[4][4];
+    gin_load_a1(xs, lane, a1);
+    gin_mlp_chunk<HMLP>(a1, Wt, node0, A.n_own, A.out, s1, s2, lane, A.mask);
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+    }
+    if (A.part && g == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            A.part[(size_t)blockIdx.x * 64 + 8 * t + j] = s1[j];
+            A.part[(size_t)blockIdx.x * 64 + 32 + 8 * t + j] = s2[j];
+        }
     }
 }
 
@@ -876,6 +975,7 @@ static size_t gin_smem(bool hmlp) { return (size_t)((hmlp ? GIN_WFLOATS_H : GIN_
 
 ConvGeom conv_geom(int n_tiles, int wn, int sm_count) {
     ConvGeom g{};
+    g.cluster = 1;
     if (wn == WN_BIG) {
         g.warps = 12; g.split = false;
         g.blocks = persistent_blocks((n_tiles + 11) / 12, sm_count, 1);
@@ -883,6 +983,15 @@ ConvGeom conv_geom(int n_tiles, int wn, int sm_count) {
         g.warps = WARPS;
         g.split = n_tiles <= 2 * sm_count;          // few tiles (small graphs): one CTA per tile, chunks split over its warps
         g.blocks = g.split ? (n_tiles < 1 ? 1 : n_tiles) : persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2);
+        // fewer tiles than SMs: a tile's chunks are shared by a CLUSTER of 2 / 4 / 8 CTAs (one SM works through a chunk every
+        // ~135 cycles however many warps it has, so the only way to finish a tile sooner is more SMs); partial tiles are
+        // summed through distributed shared memory
+        static const bool cl_off = getenv("TGNN_CONV_CLUSTER") && std::string(getenv("TGNN_CONV_CLUSTER")) == "0";
+        if (g.split && !cl_off) {
+            const int room = sm_count / (n_tiles < 1 ? 1 : n_tiles);
+            g.cluster = room >= 8 ? 8 : (room >= 4 ? 4 : (room >= 2 ? 2 : 1));
+            g.blocks *= g.cluster;
+        }
     }
     return g;
 }
@@ -892,7 +1001,8 @@ static int gin_blocks(int n_own, int sm_count) {
 }
 static int init_blocks(int n_own, int sm_count) { return persistent_blocks((n_own + WARPS * 32 - 1) / (WARPS * 32), sm_count, 4); }
 
-int gin_num_parts(int n_own, int sm_count) { return gin_blocks(n_own, sm_count); }          // one partial row per CTA
+bool gin_small(int n_own) { return n_own <= GIN_S_MAX_NODES && !(getenv("TGNN_GIN_S") && std::string(getenv("TGNN_GIN_S")) == "0"); }
+int gin_num_parts(int n_own, int sm_count) { return gin_small(n_own) ? (n_own + CH - 1) / CH : gin_blocks(n_own, sm_count); }   // one partial row per CTA
 int init_num_parts(int n_own, int sm_count) { return init_blocks(n_own, sm_count); }
 int dense_row_blocks(int n) { return (n + DM - 1) / DM; }
 
@@ -915,6 +1025,14 @@ void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st) {
         TGNN_CUDA(cudaFuncSetAttribute(k_gin<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem(false)));
         TGNN_CUDA(cudaFuncSetAttribute(k_gin<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gin_smem(true)));
     });
+    if (gin_small(a.n_own)) {                    // small graphs: one CTA of four warps per 16-node chunk (latency layout)
+        const int chunks = (a.n_own + CH - 1) / CH;
+        const size_t sm_s = (size_t)((a.hmlp ? GIN_WFLOATS_H : GIN_WFLOATS) + CH * XS) * sizeof(float);
+        if (a.hmlp) k_gin_s<true><<<chunks, GIN_S_THREADS, sm_s, st>>>(a);
+        else k_gin_s<false><<<chunks, GIN_S_THREADS, sm_s, st>>>(a);
+        TGNN_CUDA(cudaGetLastError());
+        return;
+    }
     if (a.hmlp) k_gin<true><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(true), st>>>(a);
     else k_gin<false><<<gin_blocks(a.n_own, sm_count), TPB, gin_smem(false), st>>>(a);
     TGNN_CUDA(cudaGetLastError());
@@ -974,7 +1092,7 @@ void launch_dense(const DenseArgs& a, cudaStream_t st) {
 
 void launch_score(const float* a3, const float* coef, const float* w, float b, float* out, int64_t n, cudaStream_t st, const uint8_t* mask,
                   const BnFin* fin) {
-    int blocks = (int)std::min<int64_t>((n + 7) / 8, 148 * 8);
+    int blocks = (int)std::min<int64_t>((n + 7) / 8, fin ? 148 : 148 * 8);        // (every CTA repeats the BatchNorm-finishing prologue)
     if (blocks < 1) blocks = 1;
     k_score<<<blocks, 256, 0, st>>>(a3, coef, w, b, out, n, mask, fin ? *fin : BnFin{});
     TGNN_CUDA(cudaGetLastError());

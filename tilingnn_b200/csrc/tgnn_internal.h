@@ -190,6 +190,7 @@ struct ConvArgs {
     const int* flag_x;       // raised by the producer of xin when a value is outside the fp16 range
     const int* flag_w;       // raised at table build when a root weight is outside the fp16 range
     const uint8_t* mask;     // node mask (tgnn_set_node_mask) or null: rows with mask 0 are written as 0 and stay out of the statistics
+    long long* dbg;          // optional (TGNN_ROLE_DBG=1): per warp of CTA 0 {total, prologue, chunk loop, epilogue} cycles (k_conv_h, one tile per CTA)
 };
 // Node mask (sub-layout on the resident structures): masked rows are stored as ZERO by every producer, so gathers and
 // sums over all neighbours equal sums over the kept ones, and a zero row adds nothing to the BatchNorm sums.
@@ -197,7 +198,7 @@ __device__ __forceinline__ bool row_kept(const uint8_t* __restrict__ mask, int n
 // launch geometry shared by k_conv_adj and k_conv_h (same grid => same BatchNorm partial layout):
 //   wn = 64 : 8 warps per CTA, 2 CTAs per SM; few tiles (small graphs) => one CTA per tile, k_conv_h splits its chunks
 //   wn = 128: 12 warps per CTA (216 KB of accumulator tiles), 1 CTA per SM
-struct ConvGeom { int blocks, warps; bool split; };
+struct ConvGeom { int blocks, warps; bool split; int cluster; };   // cluster: CTAs (of one thread-block cluster) sharing a tile in the split geometry
 ConvGeom conv_geom(int n_tiles, int wn, int sm_count);
 inline int conv_adj_num_parts(int n_tiles, int wn, int sm_count) { ConvGeom g = conv_geom(n_tiles, wn, sm_count); return g.blocks; }   // one partial row per CTA
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
