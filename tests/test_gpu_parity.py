@@ -574,3 +574,47 @@ def test_conv_x_transposed_roles_vs_oracle(dev, monkeypatch):
         err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
         print(f"k_conv_x 24k lattice {mode}: max err {err:.2e}")
         assert net.info()["conv_kernel"] == 5 and err <= TOL
+
+
+# ---------------------------------------------------------------------------------------------- #
+# small-graph latency layout (round 2): cluster-split k_conv_h, k_gin_s, BatchNorm finished by the consumers, parallel branches
+@pytest.mark.parametrize("n,deg", [(600, 12), (1900, 8), (4000, 16), (8000, 8)])
+def test_small_graph_layouts_vs_oracle(dev, n, deg):
+    """n = 600 / 1900 / 4000 / 8000 -> 10 / 30 / 63 / 125 tiles of 64 rows -> thread-block clusters of 8 / 4 / 2 / 1 CTAs per
+    tile (148 SMs); k_gin_s below 4096 nodes, k_gin above; every BatchNorm finished in its consumer's prologue.  Ragged graph:
+    some destinations lose all their in-edges, duplicates are added.  Against the fp64 oracle, train and eval."""
+    from tilingnn_b200 import synthetic as syn
+    x, ai, af, ci = syn.lattice_graph(n, deg, deg, seed=5)
+    keep = (ai[1] % 37 != 3)
+    ai, af = ai[:, keep], af[keep]
+    dup = torch.randint(0, ai.shape[1], (n // 4,), generator=torch.Generator().manual_seed(1))
+    ai, af = torch.cat([ai, ai[:, dup]], 1), torch.cat([af, af[dup]], 0)
+    p = orc.make_params(3, 19, 4, seed=5)
+    for mode in ("train", "eval"):
+        q = orc.calibrate_running_stats(p, x, ai, af, ci, depth=4) if mode == "eval" else p
+        gold = orc.forward(q, x, ai, af, ci, depth=4, bn_mode=mode, dtype=torch.float64)[:, 0].numpy()
+        net = make_net(q, 3, 19, 4, dev, mode)
+        err = np.abs(run(net, x, ai, af, ci, dev) - gold).max()
+        print(f"small-graph layout n={n} {mode}: max err {err:.2e}, launches {net.info()['launches_per_forward']}")
+        assert err <= TOL
+
+
+@pytest.mark.parametrize("var,val,exact", [("TGNN_BRANCHES", "0", True), ("TGNN_BNFIN", "launch", False), ("TGNN_CONV_CLUSTER", "0", False),
+                                           ("TGNN_GIN_S", "0", False), ("TGNN_CONV_W16", "0", False)])
+def test_small_graph_switches_agree(dev, var, val, exact, monkeypatch):
+    """Each small-graph mechanism can be switched off for A/B runs; the scores must not depend on it: bit-identical for the
+    side stream (same kernels, same order of arithmetic), <= 2e-5 (eval-BN) where the order of a floating-point sum changes
+    (BatchNorm partial rows, cluster / warp partial tiles, gather order of k_gin_s)."""
+    z, x, ai, af, ci = load_graph("c1_heart.npz")
+    p = load_ckpt("ckpt_30-60-90.npz")
+    base = run(make_net(p, x.shape[1], af.shape[1], 20, dev, "eval"), x, ai, af, ci, dev)
+    base_t = run(make_net(p, x.shape[1], af.shape[1], 20, dev, "train"), x, ai, af, ci, dev)
+    monkeypatch.setenv(var, val)
+    alt = run(make_net(p, x.shape[1], af.shape[1], 20, dev, "eval"), x, ai, af, ci, dev)
+    alt_t = run(make_net(p, x.shape[1], af.shape[1], 20, dev, "train"), x, ai, af, ci, dev)
+    d = np.abs(alt - base).max()
+    print(f"{var}={val}: eval-BN max diff {d:.2e}, train-BN max diff {np.abs(alt_t - base_t).max():.2e}")
+    if exact:
+        assert d == 0.0 and np.array_equal(alt_t, base_t)
+    else:
+        assert d <= 2e-5       # (eval-BN's collapsed running variances amplify fp32 rounding by ~300; train-BN on this checkpoint amplifies rounding by ~1e3, SURVEY 8c: reported, gated by the tier-3 test)

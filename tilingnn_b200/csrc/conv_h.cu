@@ -501,7 +501,7 @@ void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
     });
     // same grid as k_conv_adj: the BatchNorm partial layout is shared by the two kernels
     const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
-    static const bool w16_off = getenv("TGNN_CONV_W16") && std::string(getenv("TGNN_CONV_W16")) == "0";
+    const bool w16_off = getenv("TGNN_CONV_W16") && std::string(getenv("TGNN_CONV_W16")) == "0";
     if (a.wn == WN_BIG) k_conv_h<WN_BIG, 12, false><<<g.blocks, 12 * 32, smem_big, st>>>(a);
     else if (g.split && g.cluster > 1) {                       // fewer tiles than SMs: a cluster of CTAs per tile
         cudaLaunchConfig_t cfg{};

@@ -986,7 +986,7 @@ ConvGeom conv_geom(int n_tiles, int wn, int sm_count) {
         // fewer tiles than SMs: a tile's chunks are shared by a CLUSTER of 2 / 4 / 8 CTAs (one SM works through a chunk every
         // ~135 cycles however many warps it has, so the only way to finish a tile sooner is more SMs); partial tiles are
         // summed through distributed shared memory
-        static const bool cl_off = getenv("TGNN_CONV_CLUSTER") && std::string(getenv("TGNN_CONV_CLUSTER")) == "0";
+        const bool cl_off = getenv("TGNN_CONV_CLUSTER") && std::string(getenv("TGNN_CONV_CLUSTER")) == "0";
         if (g.split && !cl_off) {
             const int room = sm_count / (n_tiles < 1 ? 1 : n_tiles);
             g.cluster = room >= 8 ? 8 : (room >= 4 ? 4 : (room >= 2 ? 2 : 1));
