@@ -615,11 +615,24 @@ __global__ void k_score(const float* __restrict__ a3, const float* __restrict__ 
     const int64_t gwarp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float wl = __ldg(w + lane);
-    for (int64_t node = gwarp; node < n; node += nwarp) {
-        float v = bn_apply(__ldg(a3 + node * F + lane), coef, lane, 32) * wl;
+    // lane = channel: its four BatchNorm coefficients live in registers; a warp takes 8 consecutive rows per step (8 row loads
+    // in flight, 8 interleaved shuffle trees) -- one row at a time was a chain of dependent L2 latencies (0.089 ms for 1M rows)
+    const float mh = coef[lane], ml = coef[32 + lane], sc = coef[64 + lane], be = coef[96 + lane];
+    for (int64_t base = gwarp * 8; base < n; base += nwarp * 8) {
+        float v[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) out[node] = row_kept(mask, (int)node) ? sigmoidf_acc(v + b) : 0.f;
+        for (int k = 0; k < 8; ++k) { v[k] = 0.f; if (base + k < n) v[k] = __ldg(a3 + (base + k) * F + lane); }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaf((v[k] - mh) - ml, sc, be) * wl;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        float mine = v[0];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) if (lane == k) mine = v[k];
+        const int64_t node = base + lane;
+        if (lane < 8 && node < n) out[node] = row_kept(mask, (int)node) ? sigmoidf_acc(mine + b) : 0.f;
     }
 }
 
@@ -1092,7 +1105,7 @@ void launch_dense(const DenseArgs& a, cudaStream_t st) {
 
 void launch_score(const float* a3, const float* coef, const float* w, float b, float* out, int64_t n, cudaStream_t st, const uint8_t* mask,
                   const BnFin* fin) {
-    int blocks = (int)std::min<int64_t>((n + 7) / 8, fin ? 148 : 148 * 8);        // (every CTA repeats the BatchNorm-finishing prologue)
+    int blocks = (int)std::min<int64_t>((n + 63) / 64, fin ? 148 : 148 * 8);      // 8 warps x 8 rows per step (every CTA repeats the BatchNorm-finishing prologue)
     if (blocks < 1) blocks = 1;
     k_score<<<blocks, 256, 0, st>>>(a3, coef, w, b, out, n, mask, fin ? *fin : BnFin{});
     TGNN_CUDA(cudaGetLastError());
