@@ -3,6 +3,7 @@
 #pragma once
 
 #include "bn_fin.cuh"
+#include "hsplit.cuh"
 #include "tgnn_internal.h"
 
 namespace tgnn {
@@ -102,10 +103,12 @@ __device__ __forceinline__ void chunk_mma32(const float4 (&rows)[4], const BFrag
 
 __device__ __forceinline__ void acc_add8(float* row, const float (&c)[4][4], int half) {
     float4* p = reinterpret_cast<float4*>(row);
-    float4 v0 = p[0], v1 = p[1];
-    v0.x += c[0][2 * half]; v0.y += c[0][2 * half + 1]; v0.z += c[1][2 * half]; v0.w += c[1][2 * half + 1];
-    v1.x += c[2][2 * half]; v1.y += c[2][2 * half + 1]; v1.z += c[3][2 * half]; v1.w += c[3][2 * half + 1];
-    p[0] = v0; p[1] = v1;
+    const float4 v0 = p[0], v1 = p[1];
+    const float2 a = f2add(make_float2(v0.x, v0.y), make_float2(c[0][2 * half], c[0][2 * half + 1]));       // FADD2: the C fragment's register
+    const float2 b = f2add(make_float2(v0.z, v0.w), make_float2(c[1][2 * half], c[1][2 * half + 1]));       // pairs are adjacent columns
+    const float2 d = f2add(make_float2(v1.x, v1.y), make_float2(c[2][2 * half], c[2][2 * half + 1]));
+    const float2 e = f2add(make_float2(v1.z, v1.w), make_float2(c[3][2 * half], c[3][2 * half + 1]));
+    p[0] = make_float4(a.x, a.y, b.x, b.y); p[1] = make_float4(d.x, d.y, e.x, e.y);
 }
 
 template <int WN, int NW>

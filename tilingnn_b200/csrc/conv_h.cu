@@ -67,9 +67,7 @@ __device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH
             mma_f16(sm[1], ra.x, rb.x, ra.y, rb.y, bl.z, bl.w);
         }
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) m[2 * j + u][i] = fmaf(sm[u][i], LO_INV, mn[0][u][i] + mn[1][u][i]);
+        for (int u = 0; u < 2; ++u) f4_fma_add(m[2 * j + u], sm[u], LO_INV, mn[0][u], mn[1][u]);      // FADD2 + FFMA2
     }
 }
 

@@ -125,9 +125,7 @@ __device__ __forceinline__ void gin_mlp_chunk(const float (&a1)[4][4], const Gin
                 mma_f16(mn[ks][1], ah[ks][0], ah[ks][1], ah[ks][2], ah[ks][3], bh.z, bh.w);
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) c2[2 * j + u][i] = fmaf(sm[u][i], 1.0f / 2048.f, mn[0][u][i] + mn[1][u][i]);
+            for (int u = 0; u < 2; ++u) f4_fma_add(c2[2 * j + u], sm[u], 1.0f / 2048.f, mn[0][u], mn[1][u]);
         }
         // ---- layer 3: 64 -> 32 (output channels 8t..8t+7 per lane); A = fp16 split of sigmoid(c2 + b2) ----------
         uint32_t a3h[4][4], a3l[4][4];
@@ -154,14 +152,19 @@ __device__ __forceinline__ void gin_mlp_chunk(const float (&a1)[4][4], const Gin
                 mma_f16(mn[0], a3h[ks][0], a3h[ks][1], a3h[ks][2], a3h[ks][3], bh.x, bh.y);
                 mma_f16(mn[1], a3h[ks][0], a3h[ks][1], a3h[ks][2], a3h[ks][3], bh.z, bh.w);
 #pragma unroll
-                for (int u = 0; u < 2; ++u)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[u][i] += mn[u][i];           // IEEE adds between the k16 steps
+                for (int u = 0; u < 2; ++u) {                                     // IEEE adds between the k16 steps (FADD2)
+                    const float2 a0 = f2add(make_float2(acc[u][0], acc[u][1]), make_float2(mn[u][0], mn[u][1]));
+                    const float2 a1 = f2add(make_float2(acc[u][2], acc[u][3]), make_float2(mn[u][2], mn[u][3]));
+                    acc[u][0] = a0.x; acc[u][1] = a0.y; acc[u][2] = a1.x; acc[u][3] = a1.y;
+                }
             }
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) c3[2 * j + u][i] = fmaf(sm[u][i], 1.0f / 2048.f, acc[u][i]);
+            for (int u = 0; u < 2; ++u) {
+                const float2 kk = make_float2(1.0f / 2048.f, 1.0f / 2048.f);
+                const float2 r0 = f2fma(make_float2(sm[u][0], sm[u][1]), kk, make_float2(acc[u][0], acc[u][1]));
+                const float2 r1 = f2fma(make_float2(sm[u][2], sm[u][3]), kk, make_float2(acc[u][2], acc[u][3]));
+                c3[2 * j + u][0] = r0.x; c3[2 * j + u][1] = r0.y; c3[2 * j + u][2] = r1.x; c3[2 * j + u][3] = r1.y;
+            }
         }
     } else {
     // ---- layer 2: 32 -> 64, A = sigmoid(c1 + b1) straight from the C fragments ------------------

@@ -158,7 +158,7 @@ k_gin_w(GinArgs A) {
                             if (o + (k & 8) + rk[k & 7] < n_mine) v[k] = lds_row(ad[k]);
                         }
 #pragma unroll
-                        for (int k = 0; k < 16; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                        for (int k = 0; k < 16; ++k) f4add(sum, v[k]);          // two FADD2 per row
                     }
                 } else {
                     // "direct" tile (sources not local enough for a window): rows and indices from global memory
@@ -178,7 +178,7 @@ k_gin_w(GinArgs A) {
                             if (o + k < n_mine) v[k] = ld_row4(A.xin, idx[k], q);
                         }
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) { sum.x += v[k].x; sum.y += v[k].y; sum.z += v[k].z; sum.w += v[k].w; }
+                        for (int k = 0; k < 8; ++k) f4add(sum, v[k]);
                     }
                 }
                 if (!TGNN_TIMED(w1, mbar_wait(bar_ce + 8 * mw, (uint32_t)((use & 1) ^ 1)))) { timeout_flag = 1; ok = false; break; }   // its previous chunk is in registers

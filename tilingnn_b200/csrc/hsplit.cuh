@@ -7,6 +7,23 @@
 
 namespace tgnn {
 
+// Packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest operations per instruction -- the same bits
+// as the scalar forms, half the issue slots).  The GIN kernels are bound by instruction issue, not by a data pipe.
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ void f4add(float4& a, const float4& b) {
+    const float2 lo = f2add(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = f2add(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    a = make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// c[i] = fma(s[i], k, a[i] + b[i]) for four accumulator registers
+__device__ __forceinline__ void f4_fma_add(float (&c)[4], const float (&s)[4], float k, const float (&a)[4], const float (&b)[4]) {
+    const float2 kk = make_float2(k, k);
+    const float2 r0 = f2fma(make_float2(s[0], s[1]), kk, f2add(make_float2(a[0], a[1]), make_float2(b[0], b[1])));
+    const float2 r1 = f2fma(make_float2(s[2], s[3]), kk, f2add(make_float2(a[2], a[3]), make_float2(b[2], b[3])));
+    c[0] = r0.x; c[1] = r0.y; c[2] = r1.x; c[3] = r1.y;
+}
+
 // hi = fp16(x), lo = fp16((x - hi) * 2^11); the subtraction and the scaling are exact in fp32.
 __device__ __forceinline__ void split_h(float x, __half& hi, __half& lo) {
     hi = __float2half_rn(x);
@@ -38,7 +55,9 @@ __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1,
 __device__ __forceinline__ void split_h2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(v0, v1);
     const float2 f = __half22float2(h);
-    const __half2 l = __floats2half2_rn((v0 - f.x) * 2048.f, (v1 - f.y) * 2048.f);
+    // (v - hi) * 2^11 = fma(v, 2^11, -2^11 hi): both products and the difference are exact, so the bits are those of the scalar form
+    const float2 d = f2fma(make_float2(v0, v1), make_float2(2048.f, 2048.f), f2mul(f, make_float2(-2048.f, -2048.f)));
+    const __half2 l = __floats2half2_rn(d.x, d.y);
     hi = *reinterpret_cast<const uint32_t*>(&h);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }

@@ -70,7 +70,7 @@ k_conv_adj(ConvArgs A) {
 constexpr int GIN_IDX_CAP = 1024;                                         // staged neighbour indices per 16-node chunk
 constexpr int GIN_WARP_FLOATS = CH * XS + GIN_IDX_CAP;
 
-__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void add4(float4& a, const float4& b) { f4add(a, b); }     // two FADD2
 
 // HMLP: layers 2 and 3 of the MLP on fp16-split operands (mma.sync m16n8k16: half the MMAs and half the weight-table
 // reads of 3xTF32).  Their inputs are sigmoid outputs in (0, 1), always inside the fp16 range; layer 1 sees unbounded
