@@ -19,6 +19,9 @@ __device__ __forceinline__ float sigmoidf_acc(float v) { return 1.0f / (1.0f + e
 // 128 sigmoids per node are a third of its instructions.  (the clamp keeps 1 + e finite: sigmoid(-80) = 1.8e-35 is below
 // every tolerance here)
 __device__ __forceinline__ float sigmoidf_nr(float v) {
+#ifdef TGNN_SIGMOID_ACC
+    { const float x = 1.0f + expf(-fmaxf(v, -80.f)); float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return fmaf(r, fmaf(-x, r, 1.0f), r); }
+#endif
     float e, r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf(v, -80.f) * -1.4426950408889634f));
     const float x = 1.0f + e;
@@ -26,6 +29,16 @@ __device__ __forceinline__ float sigmoidf_nr(float v) {
     return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
+
+// The MLP's OUTPUT sigmoid feeds BatchNorm directly (eval-mode BatchNorm of the shipped checkpoints amplifies its rounding by
+// up to ~300: collapsed running variances), so it keeps the accurate exponential; the two inner layers'
+// sigmoids (96 of 128 per node) go through a 32- / 64-term dot product first and use the SFU form.
+__device__ __forceinline__ float sigmoidf_out(float v) {
+    const float x = 1.0f + expf(-fmaxf(v, -80.f));
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
 
 constexpr int GIN_W1 = 2048, GIN_W2 = 4096, GIN_W3 = 4096;                 // floats (hi + lo)
 constexpr int GIN_WFLOATS = GIN_W1 + GIN_W2 + GIN_W3 + 128;                // + b1[32] b2[64] b3[32]
@@ -208,7 +221,7 @@ __device__ __forceinline__ void gin_mlp_chunk(const float (&a1)[4][4], const Gin
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-                o[2 * nt + e] = leaky(sigmoidf_nr(c3[nt][2 * half + e] + b3[8 * t + 2 * nt + e]));
+                o[2 * nt + e] = leaky(sigmoidf_out(c3[nt][2 * half + e] + b3[8 * t + 2 * nt + e]));
         if (node < n_own) {
             if (!row_kept(mask, node)) {
 #pragma unroll
