@@ -358,6 +358,8 @@ def main():
     if world > 1:
         dist.barrier()
     from tilingnn_b200 import shard as shard_mod
+    # one process per GPU: keep each rank (and the pinned buffers it allocates) on the NUMA node of its GPU
+    numa_cores = shard_mod.bind_to_gpu_numa(local) if world > 1 and os.environ.get("TGNN_NUMA_BIND", "1") != "0" else None
     warmup = max(3, args.warmup)
 
     n_global = args.nodes * world if args.scaling == "weak" else args.nodes
@@ -535,6 +537,7 @@ def main():
             "gpu_launches": int(info["launches_per_forward"]) * args.steps,
             "collectives_per_step": int(info["collectives_per_forward"]),
             "parity_max_err": parity_err,
+            "numa_bound_cores": numa_cores,
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -11,14 +11,14 @@
 // and the gather warps read neighbour rows with LDS.128 at shared-memory latency:
 //   L2 -> SM traffic / 3.3, no dependent global load in the gather loop, indices 2 B instead of 4 B per edge.
 // Warp roles (16 warps = 512 threads x 128 registers, one CTA per SM, persistent over tiles):
-//   warps 0-10  node MLP on tensor cores (mma.sync): the four 16-node chunks of a tile go round-robin over the 11 warps
-//               (each has its own chunk buffer and barrier pair),
-//               so three tiles' MLPs are in flight (one chunk is ~6000 cycles of dependent MMAs and sigmoids; the
-//               gather delivers a tile every ~2600) -- measured: with 4 MLP warps the kernel was MLP-latency-bound
-//   warps 11-14 gather-sum from the window (8 lanes per 128-byte row, 16 rows in flight per lane; quads of 4 destination rows
-//               round-robin over the four warps).  This is the role that bounds the kernel (measured: six gather warps and
-//               nine MLP warps were slower, 0.415 vs 0.39 ms per launch); ncu: 3800 shared-memory wavefronts per tile
-//               (2112 gathered rows, their indices, the MLP's weight fragments) at ~55 % of the pipe
+//   warps 0-6   node MLP on tensor cores (mma.sync): the four 16-node chunks of a tile go round-robin over the 7 warps
+//               (each has its own chunk buffer and barrier pair), so ~two tiles' MLPs are in flight (one chunk is ~6000 cycles
+//               of dependent MMAs and sigmoids)
+//   warps 7-14  gather-sum from the window (8 lanes per 128-byte row, 16 rows in flight per lane; quads of 4 destination rows
+//               round-robin over the eight warps).  This is the role that bounds the kernel.  The split is measured
+//               (TGNN_ROLE_DBG, profiles/r2/gin_w_role_cycles.txt): with 4 gather / 11 MLP warps the gather warps were busy 90 %
+//               of the time and the MLP warps waited 76 % of it (the MLP had meanwhile lost a third of its instructions: SFU
+//               sigmoid, packed fp32 adds); 6 / 9: 0.377, 8 / 7: 0.334, 9 / 6: 0.340, 10 / 5: 0.352 ms per launch (4 / 11: 0.393)
 //   warp  15    producer: per tile <= 32 bulk copies (window runs), 1 for the uint16 indices, 1 for the row pointers
 // Tiles whose sources are not local (window > 656 rows / > 32 runs / > 4032 edges) are marked "direct" by the
 // builder and gathered from global memory by the same warps; graphs that are mostly direct keep k_gin.
@@ -34,7 +34,7 @@ namespace {
 using namespace ginx;
 using namespace tc;
 
-constexpr int GATHER_WARPS = 4, MLP_WARPS = GW_MLP_WARPS, CHUNKS_PER_TILE = GW_T / CH, QUADS_PER_TILE = GW_T / 4;
+constexpr int GATHER_WARPS = 15 - GW_MLP_WARPS, MLP_WARPS = GW_MLP_WARPS, CHUNKS_PER_TILE = GW_T / CH, QUADS_PER_TILE = GW_T / 4;
 constexpr int W_GATHER0 = MLP_WARPS, W_PROD = MLP_WARPS + GATHER_WARPS;
 constexpr int GW_THREADS = (W_PROD + 1) * 32;
 constexpr int PTR_INTS = 68;                                    // 65 row pointers, padded to a multiple of 16 bytes

@@ -247,7 +247,10 @@ struct GinArgs {
 int gin_num_parts(int n_own, int sm_count);
 void launch_gin(const GinArgs& a, int sm_count, cudaStream_t st);
 int gin_w_blocks(int gw_tiles, int sm_count);
-constexpr int GW_MLP_WARPS = 11;  // MLP warps per CTA of k_gin_w = BatchNorm partial rows per CTA
+#ifndef TGNN_GW_MLP_WARPS
+#define TGNN_GW_MLP_WARPS 7
+#endif
+constexpr int GW_MLP_WARPS = TGNN_GW_MLP_WARPS;  // MLP warps per CTA of k_gin_w = BatchNorm partial rows per CTA (gather warps: 15 - this)
 inline int gin_w_num_parts(int gw_tiles, int sm_count) { return gin_w_blocks(gw_tiles, sm_count) * GW_MLP_WARPS; }
 void launch_gin_w(const GinArgs& a, int sm_count, cudaStream_t st);
 

@@ -130,3 +130,34 @@ def make_plan(n_global, bounds, adj_index, col_index, group=None) -> ShardPlan:
     return ShardPlan(rank, world, lo, hi, int(n_global), int(halo_slot), (publish - lo).contiguous(),
                      remap(adj_index[0]).contiguous(), (adj_index[1] - lo).contiguous(),
                      remap(col_index[0]).contiguous(), (col_index[1] - lo).contiguous(), publish_lists, send_mask)
+
+
+def bind_to_gpu_numa(device_index):
+    """One process per GPU: restrict this process to the CPU cores next to its GPU (NVML's CPU affinity of the device), so
+    that the pinned host buffers it allocates afterwards are placed on that NUMA node.  Eight ranks that each stream
+    3.5 GB per step out of ONE socket's memory share that socket's DRAM and the inter-socket link (round 1: end-to-end
+    efficiency 0.47 at 8 GPUs).  Returns the number of cores kept, or None when NVML / the affinity call is not available
+    (the caller carries on unbound)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = torch.cuda.get_device_properties(device_index).uuid
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if not cpus:
+                return None
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+        finally:
+            pynvml.nvmlShutdown()
+    except Exception:
+        return None
