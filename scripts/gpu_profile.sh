@@ -25,4 +25,14 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_' -c 300 -
 # full capture of the heaviest kernels (skip the warm-up forwards' launches)
 ncu --set full --clock-control none --import-source on -k regex:'k_conv_h|k_gin|k_dense_tc|k_init|k_combine' -s 24 -c 22 \
     -o $OUT/prof_${TAG} -f python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline > $OUT/ncu_full_${TAG}.log 2>&1
+# real-size layouts: forward latency (captured replay and eager), predict() breakdown, warm-cache per-kernel durations
+python scripts/small_forward.py > $OUT/small_${TAG}.log 2>&1
+python scripts/small_forward.py --eager >> $OUT/small_${TAG}.log 2>&1
+python scripts/small_forward.py --lattice 10000 8 >> $OUT/small_${TAG}.log 2>&1
+python scripts/small_forward.py --lattice 10000 32 >> $OUT/small_${TAG}.log 2>&1
+python scripts/small_latency.py >> $OUT/small_${TAG}.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -k regex:'k_' -c 900 --csv --log-file $OUT/launches_small_warm_${TAG}.csv \
+    python scripts/small_forward.py --eager --reps 2 > $OUT/ncu_small_${TAG}.log 2>&1
+python scripts/role_cycles.py 1000000 32 > $OUT/role_cycles_${TAG}.log 2>&1
+cat $OUT/small_${TAG}.log
 ls -la $OUT | tail -14
