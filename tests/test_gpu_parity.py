@@ -618,3 +618,20 @@ def test_small_graph_switches_agree(dev, var, val, exact, monkeypatch):
         assert d == 0.0 and np.array_equal(alt_t, base_t)
     else:
         assert d <= 2e-5       # (eval-BN's collapsed running variances amplify fp32 rounding by ~300; train-BN on this checkpoint amplifies rounding by ~1e3, SURVEY 8c: reported, gated by the tier-3 test)
+
+
+def test_weight_tables_survive_set_graph_with_the_same_feature_rows(dev):
+    """tgnn_set_graph keeps the per-type weight tables when the new graph has the same distinct edge-feature rows (successive
+    layouts of one tile set) and rebuilds them when it does not: a handle that walks through A (51 rows), B (same rows, other
+    size), C (continuous features: other rows), B again must score each exactly like a fresh handle does."""
+    from tilingnn_b200 import synthetic as syn
+    p = orc.make_params(3, 19, 3, seed=2)
+    graphs = [syn.lattice_graph(900, 8, 8, seed=4), syn.lattice_graph(2500, 8, 8, seed=4),
+              syn.lattice_graph(700, 8, 8, seed=4, continuous_features=True), syn.lattice_graph(2500, 8, 8, seed=4)]
+    net = make_net(p, 3, 19, 3, dev)
+    for k, (x, ai, af, ci) in enumerate(graphs):
+        got = run(net, x, ai, af, ci, dev)
+        fresh = run(make_net(p, 3, 19, 3, dev), x, ai, af, ci, dev)
+        assert np.array_equal(got, fresh), f"graph {k}: a reused handle scores differently from a fresh one"
+        gold = orc.forward(p, x, ai, af, ci, depth=3, bn_mode="train", dtype=torch.float64)[:, 0].numpy()
+        assert np.abs(got - gold).max() <= TOL
