@@ -9,9 +9,15 @@ namespace tgnn {
 
 // Packed fp32 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2, two IEEE round-to-nearest operations per instruction -- the same bits
 // as the scalar forms, half the issue slots).  The GIN kernels are bound by instruction issue, not by a data pipe.
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+#else   // (host-side layout checks include this header for the index maps and compile for the default architecture)
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y)); }
+#endif
 __device__ __forceinline__ void f4add(float4& a, const float4& b) {
     const float2 lo = f2add(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = f2add(make_float2(a.z, a.w), make_float2(b.z, b.w));
     a = make_float4(lo.x, lo.y, hi.x, hi.y);
