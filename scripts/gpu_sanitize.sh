@@ -14,9 +14,16 @@ for tool in memcheck racecheck synccheck; do
       > $OUT/sanitize_${TAG}_${tool}_10k.log 2>&1
   echo "$tool 10k: exit $?"; tail -3 $OUT/sanitize_${TAG}_${tool}_10k.log
 done
-timeout 900 $CS --tool racecheck --print-limit 20 --error-exitcode 3 $DRV --nodes 600 --deg 16 --depth 20 \
-    > $OUT/sanitize_${TAG}_racecheck_600.log 2>&1
-echo "racecheck 600: exit $?"; tail -3 $OUT/sanitize_${TAG}_racecheck_600.log
+# real-layout size: cluster-split k_conv_h (distributed-shared-memory sum of the partial tiles), k_gin_s, BatchNorm statistics
+# finished in the consumers' prologues, the collision branch on a side stream
+for tool in memcheck racecheck synccheck; do
+  timeout 900 $CS --tool $tool --print-limit 20 --error-exitcode 3 $DRV --nodes 600 --deg 16 --depth 20 \
+      > $OUT/sanitize_${TAG}_${tool}_600.log 2>&1
+  echo "$tool 600: exit $?"; tail -3 $OUT/sanitize_${TAG}_${tool}_600.log
+done
+timeout 900 $CS --tool racecheck --print-limit 20 --error-exitcode 3 $DRV --nodes 2500 --deg 8 --depth 6 \
+    > $OUT/sanitize_${TAG}_racecheck_2500.log 2>&1
+echo "racecheck 2500 (clusters of 2): exit $?"; tail -3 $OUT/sanitize_${TAG}_racecheck_2500.log
 # the windowed tcgen05 kernel (opt-in) and the staged-window collision kernel on a graph large enough for both.  memcheck
 # only: racecheck does not model mbarrier / async-proxy ordering and slows these pipelines past their bounded waits
 # (profiles/r2/sanitize/README.txt)
