@@ -438,7 +438,7 @@ void choose_conv_kernel(tgnn_handle* h, cudaStream_t st) {
     if (h->use_t) h->use_s = false;
     h->use_h = !h->use_s && !h->use_t && !h->use_z && !h->conv_chunk_only;
     // transposed MMA roles (no register moves to assemble the A operand): the persistent large-graph geometry only
-    h->use_x = h->use_h && h->conv_x_mode != 0 && h->g.wn == WN_SMALL && !conv_geom(h->g.n_tiles, h->g.wn, h->sm_count).split &&
+    h->use_x = h->use_h && h->conv_x_mode != 0 && h->g.wn == WN_SMALL && !conv_geom(h->g.n_tiles, h->g.wn, h->sm_count, h->g.n_chunks).split &&
                (h->conv_x_mode == 1 || TGNN_CONV_X_DEFAULT);
 }
 
@@ -483,7 +483,7 @@ void alloc_workspace(tgnn_handle* h) {
     res(h->pre2[0], rows * F * sizeof(float));
     res(h->pre2[1], rows * F * sizeof(float));
     for (int k = 0; k < 4; ++k) res(h->fa[k], own * FIN_DIMS[k + 1] * sizeof(float));
-    size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count), (size_t)h->g.s_tiles, (size_t)gin_num_parts((int)own, h->sm_count),
+    size_t np = std::max({(size_t)conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count, h->g.n_chunks), (size_t)h->g.s_tiles, (size_t)gin_num_parts((int)own, h->sm_count),
                           (size_t)(h->g.has_t ? conv_t_num_parts(h->g.t_tiles, h->sm_count) : 0),
                           (size_t)gin_w_num_parts(h->g.gw_tiles, h->sm_count),
                           (size_t)init_num_parts((int)own, h->sm_count)});
@@ -723,7 +723,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
 
     // ---- message-passing layers ----------------------------------------------------------------
     const int n_layers = h->stop_layer >= 0 ? std::min(L, h->stop_layer + 1) : L;
-    const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count);
+    const int np_conv = conv_adj_num_parts(h->g.n_tiles, h->g.wn, h->sm_count, h->g.n_chunks);
     static const int64_t branch_max = getenv("TGNN_BRANCH_MAX") ? atoll(getenv("TGNN_BRANCH_MAX")) : BRANCH_MAX_NODES;
     const bool fork = !h->two_streams_off && h->world == 1 && !h->profiling && !h->role_dbg_on && h->g.n_own <= branch_max;
     if (fork && !h->side_stream) {
@@ -743,7 +743,7 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
         ca.cdst = h->g.cdst.as<uint8_t>(); ca.inv_deg = h->mask_on ? h->inv_deg_m.as<float>() : h->g.inv_deg.as<float>();
         ca.mask = h->mask();
         ca.out = h->pre1.as<float>(); ca.part = train ? h->partA.as<double>() : nullptr;
-        ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn;
+        ca.n_own = n_own; ca.n_tiles = h->g.n_tiles; ca.wn = h->g.wn; ca.n_chunks = h->g.n_chunks;
         if (fork) {                                   // everything the two branches read is complete at this point of st
             TGNN_CUDA(cudaEventRecord(h->ev_fork, st));
             TGNN_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));

@@ -498,7 +498,7 @@ void launch_conv_h(const ConvArgs& a, int sm_count, cudaStream_t st) {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_h<WN_BIG, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
     });
     // same grid as k_conv_adj: the BatchNorm partial layout is shared by the two kernels
-    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
+    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count, a.n_chunks);
     const bool w16_off = getenv("TGNN_CONV_W16") && std::string(getenv("TGNN_CONV_W16")) == "0";
     if (a.wn == WN_BIG) k_conv_h<WN_BIG, 12, false><<<g.blocks, 12 * 32, smem_big, st>>>(a);
     else if (g.split && g.cluster > 1) {                       // fewer tiles than SMs: a cluster of CTAs per tile
@@ -523,7 +523,7 @@ void launch_conv_x(const ConvArgs& a, int sm_count, cudaStream_t st) {
     once.run([&] {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_x<WN_SMALL, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     });
-    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
+    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count, a.n_chunks);
     TGNN_CHECK(a.wn == WN_SMALL && !g.split, "internal: k_conv_x needs 64-row tiles and the persistent geometry");
     k_conv_x<WN_SMALL, 8><<<g.blocks, 256, smem, st>>>(a);
     TGNN_CUDA(cudaGetLastError());

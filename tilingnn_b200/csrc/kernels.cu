@@ -986,7 +986,7 @@ int persistent_blocks(int work_items_per_block_unit, int sm_count, int blocks_pe
 // ------------------------------------------------------------------------------------------------
 static size_t gin_smem(bool hmlp) { return (size_t)((hmlp ? GIN_WFLOATS_H : GIN_WFLOATS) + WARPS * GIN_WARP_FLOATS) * sizeof(float); }
 
-ConvGeom conv_geom(int n_tiles, int wn, int sm_count) {
+ConvGeom conv_geom(int n_tiles, int wn, int sm_count, int64_t n_chunks) {
     ConvGeom g{};
     g.cluster = 1;
     if (wn == WN_BIG) {
@@ -994,7 +994,14 @@ ConvGeom conv_geom(int n_tiles, int wn, int sm_count) {
         g.blocks = persistent_blocks((n_tiles + 11) / 12, sm_count, 1);
     } else {
         g.warps = WARPS;
-        g.split = n_tiles <= 2 * sm_count;          // few tiles (small graphs): one CTA per tile, chunks split over its warps
+        // few tiles per warp: one CTA per tile, its chunks split over the CTA's warps (a warp that owns a whole tile walks
+        // ~150 chunks of ~2000 cycles each at deg 32: with fewer than ~3 tiles per warp the persistent geometry is one long
+        // latency chain with idle SMs next to it)
+        // Measured (B200, forward time, split vs persistent): 50k x deg 32 (782 tiles) -12 %, 100k x deg 32 (1563 tiles) -4 %,
+        // 100k x deg 8 +4 %, 300k x deg 32 +13 %, 1M +10 % -> up to ~11 tiles per SM when the tiles are long (>= 100 chunks).
+        const bool long_tiles = n_tiles > 0 && n_chunks >= (int64_t)100 * n_tiles;
+        const int split_max = getenv("TGNN_CONV_SPLIT_MAX") ? atoi(getenv("TGNN_CONV_SPLIT_MAX")) : (long_tiles ? 11 : 2) * sm_count;
+        g.split = n_tiles <= split_max;
         g.blocks = g.split ? (n_tiles < 1 ? 1 : n_tiles) : persistent_blocks((n_tiles + WARPS - 1) / WARPS, sm_count, 2);
         // fewer tiles than SMs: a tile's chunks are shared by a CLUSTER of 2 / 4 / 8 CTAs (one SM works through a chunk every
         // ~135 cycles however many warps it has, so the only way to finish a tile sooner is more SMs); partial tiles are
@@ -1026,7 +1033,7 @@ void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st) {
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj<WN_SMALL, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_small));
         TGNN_CUDA(cudaFuncSetAttribute(k_conv_adj<WN_BIG, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_big));
     });
-    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count);
+    const ConvGeom g = conv_geom(a.n_tiles, a.wn, sm_count, a.n_chunks);
     if (a.wn == WN_BIG) k_conv_adj<WN_BIG, 12><<<g.blocks, 12 * 32, smem_big, st>>>(a);
     else k_conv_adj<WN_SMALL, WARPS><<<g.blocks, TPB, smem_small, st>>>(a);
     TGNN_CUDA(cudaGetLastError());

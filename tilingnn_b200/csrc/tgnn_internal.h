@@ -182,6 +182,7 @@ struct ConvArgs {
     double* part;            // [n_part][64]  per-CTA partial sums (sum, sum of squares)
     int n_own, n_tiles;
     int wn;                  // rows per warp tile: WN_SMALL or WN_BIG
+    int64_t n_chunks;        // 16-edge chunks of the whole graph (launch geometry)
     // fp16-split operands of k_conv_h (conv_h.cu) and the range flags: k_conv_h uses them when both flags are 0 and the
     // 3xTF32 arithmetic on xin (conv_adj_body.cuh) when one is raised
     const uint4* xh;         // [n_rows][8]   split copy of xin: per 4 channels {hi01, hi23, lo01, lo23} fp16 pairs
@@ -199,8 +200,8 @@ __device__ __forceinline__ bool row_kept(const uint8_t* __restrict__ mask, int n
 //   wn = 64 : 8 warps per CTA, 2 CTAs per SM; few tiles (small graphs) => one CTA per tile, k_conv_h splits its chunks
 //   wn = 128: 12 warps per CTA (216 KB of accumulator tiles), 1 CTA per SM
 struct ConvGeom { int blocks, warps; bool split; int cluster; };   // cluster: CTAs (of one thread-block cluster) sharing a tile in the split geometry
-ConvGeom conv_geom(int n_tiles, int wn, int sm_count);
-inline int conv_adj_num_parts(int n_tiles, int wn, int sm_count) { ConvGeom g = conv_geom(n_tiles, wn, sm_count); return g.blocks; }   // one partial row per CTA
+ConvGeom conv_geom(int n_tiles, int wn, int sm_count, int64_t n_chunks);      // n_chunks: 16-edge chunks of the whole graph
+inline int conv_adj_num_parts(int n_tiles, int wn, int sm_count, int64_t n_chunks) { ConvGeom g = conv_geom(n_tiles, wn, sm_count, n_chunks); return g.blocks; }   // one partial row per CTA
 void launch_conv_adj(const ConvArgs& a, int sm_count, cudaStream_t st);
 
 // fp16-split edge-chunk kernel (conv_h.cu)
