@@ -84,6 +84,7 @@ struct tgnn_handle {
 
     // derived parameter layouts
     DevBuf init_w1t;
+    InitW1 init_w1_host{};                          // host copy of init_w1t: passed to k_init as a kernel parameter
     std::vector<std::unique_ptr<DevBuf>> gin_wt;    // per layer: frag tables W1|W2|W3 and biases b1|b2|b3
     std::vector<std::unique_ptr<DevBuf>> fin_wt;    // 4: k-major transposes (CUDA-core path)
     std::vector<std::unique_ptr<DevBuf>> fin_whl;   // 4: pre-swizzled hi|lo slab images of the weights (tcgen05 path)
@@ -280,6 +281,8 @@ void pack_params(tgnn_handle* h, cudaStream_t st) {
     h->dense_tf32 = dsel && std::string(dsel) == "tf32";
     h->init_w1t.reserve(32 * 32 * sizeof(float));
     launch_transpose(h->P("init_node_feature_trans.mlp.1.linear.weight"), h->init_w1t.as<float>(), 32, 32, st);
+    TGNN_CUDA(cudaMemcpyAsync(h->init_w1_host.w, h->init_w1t.p, sizeof(h->init_w1_host.w), cudaMemcpyDeviceToHost, st));
+    TGNN_CUDA(cudaStreamSynchronize(st));        // (parameters change rarely; the launches below read the host copy)
     h->gin_wt.clear(); h->gin_eps.assign(L, 0.f); h->gin_hmlp.assign(L, 0);
     DevBuf tmp_t;
     for (int i = 0; i < L; ++i) {
@@ -707,18 +710,18 @@ void forward_impl(tgnn_handle* h, const float* x, float* scores, cudaStream_t st
     };
     if (train && fin_small) {
         lz.begin("init");
-        launch_init(ia, 0, h->sm_count, st);                                                         // partials -> partA
+        launch_init(ia, h->init_w1_host, 0, h->sm_count, st);                                                         // partials -> partA
         ia.fin = make_fin(h->partA.as<double>(), np_init, h->init_bn[0], h->coef_init[0]); ia.part = h->partB.as<double>();
-        launch_init(ia, 1, h->sm_count, st);                                                         // finishes BN 0; partials -> partB
+        launch_init(ia, h->init_w1_host, 1, h->sm_count, st);                                                         // finishes BN 0; partials -> partB
         ia.fin = make_fin(h->partB.as<double>(), np_init, h->init_bn[1], h->coef_init[1]); ia.part = nullptr;
         lz.end(2);
     } else if (train) {
-        lz.begin("init"); launch_init(ia, 0, h->sm_count, st); lz.end(1);
+        lz.begin("init"); launch_init(ia, h->init_w1_host, 0, h->sm_count, st); lz.end(1);
         lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[0], h->coef_init[0]); lz.end(h->world == 1 || h->px.ok ? 1 : 2);
-        lz.begin("init"); launch_init(ia, 1, h->sm_count, st); lz.end(1);
+        lz.begin("init"); launch_init(ia, h->init_w1_host, 1, h->sm_count, st); lz.end(1);
         lz.begin("bnfin"); finish_bn(h->partA.as<double>(), np_init, 32, h->init_bn[1], h->coef_init[1]); lz.end(h->world == 1 || h->px.ok ? 1 : 2);
     }
-    lz.begin("init"); launch_init(ia, 2, h->sm_count, st); lz.end(1);
+    lz.begin("init"); launch_init(ia, h->init_w1_host, 2, h->sm_count, st); lz.end(1);
     halo_exchange(h, h->mid[0]->as<float>(), nullptr, h->rflag(0), st, lz);
 
     // ---- message-passing layers ----------------------------------------------------------------

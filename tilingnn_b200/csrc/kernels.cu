@@ -363,16 +363,14 @@ constexpr int INIT_MAX_DX = 64;       // wider node features take k_init_wide (o
 
 template <int MODE>
 __global__ void __launch_bounds__(TPB)
-k_init(InitArgs A) {
+k_init(InitArgs A, const __grid_constant__ InitW1 W1) {
     __shared__ __align__(16) float w0t[INIT_MAX_DX * 32];      // [d][c]
-    __shared__ __align__(16) float w1t[32 * 32];               // [k][c]
     __shared__ float cf[2][128];
     __shared__ __align__(16) float tile[WARPS][32 * 33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < A.d_x * 32; i += TPB) w0t[i] = __ldg(A.w0 + (i & 31) * A.d_x + (i >> 5));
     const bool fin = MODE >= 1 && A.fin.part != nullptr;      // small graphs: this launch finishes the BatchNorm it needs fresh
     if (MODE >= 1) {
-        for (int i = threadIdx.x; i < 32 * 32; i += TPB) w1t[i] = __ldg(A.w1t + i);
         if (threadIdx.x < 128 && !(fin && MODE == 1)) cf[0][threadIdx.x] = A.coef0[threadIdx.x];
     }
     if (MODE == 2 && threadIdx.x < 128 && !fin) cf[1][threadIdx.x] = A.coef1[threadIdx.x];
@@ -409,13 +407,8 @@ k_init(InitArgs A) {
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 const float y = fmaf((v[k] - cf[0][k]) - cf[0][32 + k], cf[0][64 + k], cf[0][96 + k]);
-                const float4* w = reinterpret_cast<const float4*>(w1t + k * 32);
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 wv = w[c4];
-                    o[4 * c4 + 0] = fmaf(y, wv.x, o[4 * c4 + 0]); o[4 * c4 + 1] = fmaf(y, wv.y, o[4 * c4 + 1]);
-                    o[4 * c4 + 2] = fmaf(y, wv.z, o[4 * c4 + 2]); o[4 * c4 + 3] = fmaf(y, wv.w, o[4 * c4 + 3]);
-                }
+                for (int c = 0; c < 32; ++c) o[c] = fmaf(y, W1.w[k * 32 + c], o[c]);        // weight = constant-bank operand
             }
 #pragma unroll
             for (int c = 0; c < 32; ++c) v[c] = leaky(o[c]);
@@ -1087,12 +1080,12 @@ void launch_combine(const float* pre1, const float* coef1, const float* pre2, co
     TGNN_CUDA(cudaGetLastError());
 }
 
-void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st) {
+void launch_init(const InitArgs& a, const InitW1& w1, int mode, int sm_count, cudaStream_t st) {
     int blocks = init_blocks(a.n_own, sm_count);
     if (a.d_x <= INIT_MAX_DX) {
-        if (mode == 0) k_init<0><<<blocks, TPB, 0, st>>>(a);
-        else if (mode == 1) k_init<1><<<blocks, TPB, 0, st>>>(a);
-        else k_init<2><<<blocks, TPB, 0, st>>>(a);
+        if (mode == 0) k_init<0><<<blocks, TPB, 0, st>>>(a, w1);
+        else if (mode == 1) k_init<1><<<blocks, TPB, 0, st>>>(a, w1);
+        else k_init<2><<<blocks, TPB, 0, st>>>(a, w1);
     } else {
         if (mode == 0) k_init_wide<0><<<blocks, TPB, 0, st>>>(a);
         else if (mode == 1) k_init_wide<1><<<blocks, TPB, 0, st>>>(a);

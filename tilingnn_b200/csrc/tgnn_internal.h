@@ -289,7 +289,11 @@ struct InitArgs {
     BnFin fin;                           // fin.part != null: mode 1 finishes stage 0's BatchNorm (coef0) itself, mode 2 stage 1's (coef1)
 };
 int init_num_parts(int n_own, int sm_count);
-void launch_init(const InitArgs& a, int mode, int sm_count, cudaStream_t st);
+// The second Linear's 32 x 32 weights ([k][c], k-major) travel as a KERNEL PARAMETER: every FFMA then takes its weight as a
+// constant-bank operand (warp-uniform), instead of through 8 broadcast LDS.128 per 32 FFMA that kept the shared-memory pipe
+// 80 % busy (ncu: k_init<1> / <2> l1tex 84 % / 79 %)
+struct InitW1 { float w[32 * 32]; };
+void launch_init(const InitArgs& a, const InitW1& w1, int mode, int sm_count, cudaStream_t st);
 
 // dense stage of the final MLP: out = LeakyReLU( BN_in(A) @ Wt + b ), plus column statistics
 struct DenseArgs {
