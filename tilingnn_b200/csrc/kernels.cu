@@ -401,17 +401,19 @@ k_init(InitArgs A, const __grid_constant__ InitW1 W1) {
 #pragma unroll
         for (int c = 0; c < 32; ++c) v[c] = leaky(v[c]);
         if (MODE >= 1) {
-            float o[32];
+            float2 o[16];                           // channel pairs: packed FFMA2 (the same bits as 32 scalar FFMAs, half the issue slots)
 #pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = __shfl_sync(0xffffffffu, b1, c);
+            for (int c = 0; c < 16; ++c) o[c] = make_float2(__shfl_sync(0xffffffffu, b1, 2 * c), __shfl_sync(0xffffffffu, b1, 2 * c + 1));
 #pragma unroll
             for (int k = 0; k < 32; ++k) {
                 const float y = fmaf((v[k] - cf[0][k]) - cf[0][32 + k], cf[0][64 + k], cf[0][96 + k]);
+                const float2 yy = make_float2(y, y);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) o[c] = fmaf(y, W1.w[k * 32 + c], o[c]);        // weight = constant-bank operand
+                for (int c = 0; c < 16; ++c)        // weights = kernel parameter (constant cache), read as pairs
+                    o[c] = f2fma(yy, make_float2(W1.w[k * 32 + 2 * c], W1.w[k * 32 + 2 * c + 1]), o[c]);
             }
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = leaky(o[c]);
+            for (int c = 0; c < 16; ++c) { v[2 * c] = leaky(o[c].x); v[2 * c + 1] = leaky(o[c].y); }
         }
         // transpose: thread (node) major -> lane = channel
         __syncwarp();
