@@ -100,3 +100,14 @@ def test_even_bounds():
     for n, w in ((100, 4), (63, 2)):                                     # would leave trailing ranks empty: rejected everywhere
         with pytest.raises(ValueError):
             shard.even_bounds(n, w)
+
+
+def test_bind_to_gpu_numa_is_optional():
+    """``shard.bind_to_gpu_numa`` (NVML CPU affinity of the rank's GPU -> sched_setaffinity) must never get in the way: without a
+    GPU / NVML it returns None and leaves the process's affinity mask alone."""
+    import os
+    from tilingnn_b200 import shard
+    before = os.sched_getaffinity(0)
+    assert shard.bind_to_gpu_numa(0) is None or isinstance(shard.bind_to_gpu_numa(0), int)
+    if not __import__("torch").cuda.is_available():
+        assert os.sched_getaffinity(0) == before
