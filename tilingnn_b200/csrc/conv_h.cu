@@ -49,26 +49,50 @@ __device__ __forceinline__ void load_bfrag_h(BFragH& b, const uint32_t* __restri
 // rows[ks] = uint4 (4ks' + t) of row g, rows[2 + ks] = of row g+8:  {hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)}
 // Tensor cores accumulate with truncation; the main term of each k16 step gets its own zeroed accumulator and the
 // steps are combined with IEEE FADDs (same reasoning as mma3 in kernels.cu); the two small terms share one.
-__device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH& b, float (&m)[4][4]) {
+// The A operand of mma.sync.m16n8k16 is a register QUAD {row g k-lo, row g+8 k-lo, row g k-hi, row g+8 k-hi}: it interleaves the
+// pieces of two gathered rows, i.e. of two different 256-bit loads.  Left to itself the compiler keeps the rows as loaded
+// and re-assembles a quad in front of nearly every HMMA pair (the HMMA results overwrite the assembled copy): ~52 moves per
+// chunk, plus 16 for carrying the prefetched rows into the next iteration.  Here the four quads of a chunk
+// ([0] hi, k16 step 0; [1] lo, step 0; [2] hi, step 1; [3] lo, step 1) are the ONLY live form of its rows: they are assembled
+// once, when the prefetched rows are taken over at the end of the previous iteration (16 moves in all).
+struct AQuads { uint32_t q[4][4]; };
+// rows[ks] = uint4 (4ks' + t) of row g, rows[2 + ks] = of row g+8:  {hi(c0,c1), hi(c2,c3), lo(c0,c1), lo(c2,c3)}
+__device__ __forceinline__ void make_quads(const uint4 (&rows)[4], AQuads& a) {
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        const uint4 ra = rows[ks], rb = rows[2 + ks];
+        a.q[2 * ks][0] = ra.x; a.q[2 * ks][1] = rb.x; a.q[2 * ks][2] = ra.y; a.q[2 * ks][3] = rb.y;
+        a.q[2 * ks + 1][0] = ra.z; a.q[2 * ks + 1][1] = rb.z; a.q[2 * ks + 1][2] = ra.w; a.q[2 * ks + 1][3] = rb.w;
+    }
+}
+// Tensor cores accumulate with truncation; the main term of each k16 step gets its own zeroed accumulator and the
+// steps are combined with IEEE FADDs (same reasoning as mma3 in kernels.cu); the two small terms share one.
+__device__ __forceinline__ void chunk_mma_q(const AQuads& a, const BFragH& b, float (&m)[4][4]) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
         float sm[2][4] = {}, mn[2][2][4] = {};
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
-            const uint4 ra = rows[ks], rb = rows[2 + ks];
+            const uint32_t (&hi)[4] = a.q[2 * ks];
+            const uint32_t (&lo)[4] = a.q[2 * ks + 1];
             const uint4 bh = b.h[ks][j], bl = b.l[ks][j];
             // issue order: the two updates of sm[u] are four instructions apart (an HMMA's result is ready after ~4
             // issue slots of the tensor pipe), the independent main products sit between them
-            mma_f16(sm[0], ra.z, rb.z, ra.w, rb.w, bh.x, bh.y);          // lo . Whi
-            mma_f16(sm[1], ra.z, rb.z, ra.w, rb.w, bh.z, bh.w);
-            mma_f16(mn[ks][0], ra.x, rb.x, ra.y, rb.y, bh.x, bh.y);      // hi . Whi
-            mma_f16(mn[ks][1], ra.x, rb.x, ra.y, rb.y, bh.z, bh.w);
-            mma_f16(sm[0], ra.x, rb.x, ra.y, rb.y, bl.x, bl.y);          // hi . Wlo
-            mma_f16(sm[1], ra.x, rb.x, ra.y, rb.y, bl.z, bl.w);
+            mma_f16(sm[0], lo[0], lo[1], lo[2], lo[3], bh.x, bh.y);          // lo . Whi
+            mma_f16(sm[1], lo[0], lo[1], lo[2], lo[3], bh.z, bh.w);
+            mma_f16(mn[ks][0], hi[0], hi[1], hi[2], hi[3], bh.x, bh.y);      // hi . Whi
+            mma_f16(mn[ks][1], hi[0], hi[1], hi[2], hi[3], bh.z, bh.w);
+            mma_f16(sm[0], hi[0], hi[1], hi[2], hi[3], bl.x, bl.y);          // hi . Wlo
+            mma_f16(sm[1], hi[0], hi[1], hi[2], hi[3], bl.z, bl.w);
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) f4_fma_add(m[2 * j + u], sm[u], LO_INV, mn[0][u], mn[1][u]);      // FADD2 + FFMA2
     }
+}
+__device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH& b, float (&m)[4][4]) {
+    AQuads a;
+    make_quads(rows, a);
+    chunk_mma_q(a, b, m);
 }
 
 // row = row * scale + the lane's 8 message channels of C-fragment half `half`
@@ -197,9 +221,10 @@ k_conv_h(ConvArgs A) {
             if (SPLIT) { load_bfrag_h(bf, A.tabH + (size_t)ptype * TG_HFRAG32, lane); cur_type = ptype; }      // with the first rows
         }
         __syncwarp();
+        AQuads qa;                                         // the current chunk's rows as A-operand quads
+        make_quads(pre, qa);
         if (SPLIT) t_loop0 = clock64();
         for (int c = c0; c < c1; ++c) {
-            const uint4 cur[4] = {pre[0], pre[1], pre[2], pre[3]};
             const int csrc = psrc, cdst = pdst, type = ptype;
             const int cn = c + 1, cn2 = c + 2;
             if (cn < c1) {                                 // rows of the next chunk (its indices arrived an iteration ago)
@@ -218,7 +243,7 @@ k_conv_h(ConvArgs A) {
             if (ptype != type && cn < c1)          // next type's 4 KB table towards L1 (32 lines of 128 B)
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(A.tabH + (size_t)ptype * TG_HFRAG32) + lane * 128));
             float m[4][4];
-            chunk_mma_h(cur, bf, m);
+            chunk_mma_q(qa, bf, m);
             // rows 0..7 (group 0), then rows 8..15 (group 1): destinations are distinct inside a group
             {
                 const int s = __shfl_sync(0xffffffffu, csrc, g), d = __shfl_sync(0xffffffffu, cdst, g);
@@ -230,6 +255,7 @@ k_conv_h(ConvArgs A) {
                 if (s >= 0) acc_add8(acc + d * XS + 8 * t, m, 1);
             }
             __syncwarp();
+            if (cn < c1) make_quads(pre, qa);              // take the prefetched rows over (waits for their loads here)
         }
         if (SPLIT) t_loop1 = clock64();
         const int node0 = tile * WN;
