@@ -95,6 +95,26 @@ __device__ __forceinline__ void chunk_mma_h(const uint4 (&rows)[4], const BFragH
     chunk_mma_q(a, b, m);
 }
 
+// shared-memory form of acc_add8 (conv_adj_body.cuh) on a 32-bit shared address: the hot loop then forms a scatter address
+// with ONE multiply-add (lane base + destination row * row stride) instead of rebuilding the generic pointer
+__device__ __forceinline__ float4 lds4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts4(uint32_t a, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void acc_add8_s(uint32_t addr, const float (&c)[4][4], int half) {
+    const float4 v0 = lds4(addr), v1 = lds4(addr + 16);
+    const float2 a = f2add(make_float2(v0.x, v0.y), make_float2(c[0][2 * half], c[0][2 * half + 1]));
+    const float2 b = f2add(make_float2(v0.z, v0.w), make_float2(c[1][2 * half], c[1][2 * half + 1]));
+    const float2 d = f2add(make_float2(v1.x, v1.y), make_float2(c[2][2 * half], c[2][2 * half + 1]));
+    const float2 e = f2add(make_float2(v1.z, v1.w), make_float2(c[3][2 * half], c[3][2 * half + 1]));
+    sts4(addr, make_float4(a.x, a.y, b.x, b.y));
+    sts4(addr + 16, make_float4(d.x, d.y, e.x, e.y));
+}
+
 // row = row * scale + the lane's 8 message channels of C-fragment half `half`
 __device__ __forceinline__ void acc_fma8(float* row, const float (&c)[4][4], int half, float scale) {
     float4* p = reinterpret_cast<float4*>(row);
@@ -157,6 +177,8 @@ k_conv_h(ConvArgs A) {
         return;
     }
     float* acc = smem + warp * (WN * XS);
+    uint32_t acc_s = (uint32_t)__cvta_generic_to_shared(acc) + 32u * (uint32_t)(threadIdx.x & 3);    // lane's 8 channels of row 0
+    asm volatile("mov.u32 %0, %0;" : "+r"(acc_s));      // (opaque: kept in a register instead of being rebuilt from tid at every use)
     int* s_src = reinterpret_cast<int*>(smem + WARPS * (WN * XS));       // SPLIT: [SPLIT_CAP][16] staged slot sources ...
     int* s_type = s_src + SPLIT_CAP * CH;                                // ... [SPLIT_CAP] chunk types ...
     uint8_t* s_dst = reinterpret_cast<uint8_t*>(s_type + SPLIT_CAP);     // ... [SPLIT_CAP][16] slot destinations
@@ -247,12 +269,12 @@ k_conv_h(ConvArgs A) {
             // rows 0..7 (group 0), then rows 8..15 (group 1): destinations are distinct inside a group
             {
                 const int s = __shfl_sync(0xffffffffu, csrc, g), d = __shfl_sync(0xffffffffu, cdst, g);
-                if (s >= 0) acc_add8(acc + d * XS + 8 * t, m, 0);
+                if (s >= 0) acc_add8_s(acc_s + (uint32_t)d * (XS * 4), m, 0);
             }
             __syncwarp();
             {
                 const int s = __shfl_sync(0xffffffffu, csrc, g + 8), d = __shfl_sync(0xffffffffu, cdst, g + 8);
-                if (s >= 0) acc_add8(acc + d * XS + 8 * t, m, 1);
+                if (s >= 0) acc_add8_s(acc_s + (uint32_t)d * (XS * 4), m, 1);
             }
             __syncwarp();
             if (cn < c1) make_quads(pre, qa);              // take the prefetched rows over (waits for their loads here)
