@@ -191,6 +191,9 @@ k_conv_h(ConvArgs A) {
     BFragH bf;
     int cur_type = -1;
     const int tile_step = SPLIT ? (int)gridDim.x / S : nwarp;
+    const int* csrc_l = SPLIT ? nullptr : A.csrc + (lane & 15);     // persistent geometry: this lane's slot column of the chunk arrays
+    const uint8_t* cdst_l = SPLIT ? nullptr : A.cdst + (lane & 15);
+    if (!SPLIT) asm volatile("" : "+l"(csrc_l), "+l"(cdst_l));      // (opaque: kept in registers, not rebuilt from tid + parameters per load)
 
     for (int tile = tile_first; tile < A.n_tiles; tile += tile_step) {
         for (int i = lane; i < WN * XS / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -220,8 +223,8 @@ k_conv_h(ConvArgs A) {
             c0 = min(t0 + warp * per, t1c); c1 = min(c0 + per, t1c);
         } else { c0 = __ldg(A.cptr + tile); c1 = __ldg(A.cptr + tile + 1); }
         // (the persistent geometry reads the kernel parameters' arrays directly: no pointer registers in its hot loop)
-        auto ld_src = [&](int c) -> int { return SPLIT ? srcp[(size_t)c * CH + (lane & 15)] : __ldg(A.csrc + (size_t)c * CH + (lane & 15)); };
-        auto ld_dst = [&](int c) -> int { return SPLIT ? dstp[(size_t)c * CH + (lane & 15)] : __ldg(A.cdst + (size_t)c * CH + (lane & 15)); };
+        auto ld_src = [&](int c) -> int { return SPLIT ? srcp[(size_t)c * CH + (lane & 15)] : __ldg(csrc_l + (size_t)c * CH); };
+        auto ld_dst = [&](int c) -> int { return SPLIT ? dstp[(size_t)c * CH + (lane & 15)] : __ldg(cdst_l + (size_t)c * CH); };
         auto ld_type = [&](int c) -> int { return SPLIT ? typep[c] : __ldg(A.ctype + c); };
         // software pipeline: slot indices run TWO chunks ahead of the MMAs, gathered rows ONE chunk ahead, so neither
         // the index load nor the dependent row loads are waited for in the iteration that issues them
@@ -237,9 +240,11 @@ k_conv_h(ConvArgs A) {
                 ndst = ld_dst(c0 + 1);
                 ntype = ld_type(c0 + 1);
             }
+            // (an EMPTY slot gathers row 0: its product is computed and dropped -- the scatter below skips the slot -- which is
+            //  cheaper than clearing eight registers and predicating the load in every iteration)
             const int sa = __shfl_sync(0xffffffffu, psrc, g), sb = __shfl_sync(0xffffffffu, psrc, g + 8);
-            if (sa >= 0) ld_rowh2(xh, sa, t, pre[0], pre[1]);
-            if (sb >= 0) ld_rowh2(xh, sb, t, pre[2], pre[3]);
+            ld_rowh2(xh, max(sa, 0), t, pre[0], pre[1]);
+            ld_rowh2(xh, max(sb, 0), t, pre[2], pre[3]);
             if (SPLIT) { load_bfrag_h(bf, A.tabH + (size_t)ptype * TG_HFRAG32, lane); cur_type = ptype; }      // with the first rows
         }
         __syncwarp();
@@ -247,13 +252,12 @@ k_conv_h(ConvArgs A) {
         make_quads(pre, qa);
         if (SPLIT) t_loop0 = clock64();
         for (int c = c0; c < c1; ++c) {
-            const int csrc = psrc, cdst = pdst, type = ptype;
+            const int cdst = psrc >= 0 ? pdst : -1, type = ptype;       // this lane's slot: destination row, -1 = empty slot
             const int cn = c + 1, cn2 = c + 2;
             if (cn < c1) {                                 // rows of the next chunk (its indices arrived an iteration ago)
                 const int sa = __shfl_sync(0xffffffffu, nsrc, g), sb = __shfl_sync(0xffffffffu, nsrc, g + 8);
-                pre[0] = pre[1] = pre[2] = pre[3] = zero4;
-                if (sa >= 0) ld_rowh2(xh, sa, t, pre[0], pre[1]);
-                if (sb >= 0) ld_rowh2(xh, sb, t, pre[2], pre[3]);
+                ld_rowh2(xh, max(sa, 0), t, pre[0], pre[1]);
+                ld_rowh2(xh, max(sb, 0), t, pre[2], pre[3]);
             }
             psrc = nsrc; pdst = ndst; ptype = ntype;
             if (cn2 < c1) {                                // indices of the chunk after that
@@ -268,13 +272,13 @@ k_conv_h(ConvArgs A) {
             chunk_mma_q(qa, bf, m);
             // rows 0..7 (group 0), then rows 8..15 (group 1): destinations are distinct inside a group
             {
-                const int s = __shfl_sync(0xffffffffu, csrc, g), d = __shfl_sync(0xffffffffu, cdst, g);
-                if (s >= 0) acc_add8_s(acc_s + (uint32_t)d * (XS * 4), m, 0);
+                const int d = __shfl_sync(0xffffffffu, cdst, g);
+                if (d >= 0) acc_add8_s(acc_s + (uint32_t)d * (XS * 4), m, 0);
             }
             __syncwarp();
             {
-                const int s = __shfl_sync(0xffffffffu, csrc, g + 8), d = __shfl_sync(0xffffffffu, cdst, g + 8);
-                if (s >= 0) acc_add8_s(acc_s + (uint32_t)d * (XS * 4), m, 1);
+                const int d = __shfl_sync(0xffffffffu, cdst, g + 8);
+                if (d >= 0) acc_add8_s(acc_s + (uint32_t)d * (XS * 4), m, 1);
             }
             __syncwarp();
             if (cn < c1) make_quads(pre, qa);              // take the prefetched rows over (waits for their loads here)
